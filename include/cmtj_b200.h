@@ -1,0 +1,240 @@
+/*
+ * cmtj_b200.h -- C-ABI of the B200-native (s)LLGS junction integrator.
+ *
+ * This is the drop-in boundary that replaces the pybind11 translation unit of the
+ * reference (python/cmtj.cpp:291-355 `Junction`, :358-426 `stack`, :429-445 `reservoir`)
+ * for ONE path: the per-timestep (s)LLGS integration of multilayer junctions, batched
+ * across parameter-sweep instances.  Plain C types only: no C++ types, no exceptions,
+ * no Python.h, no torch types.  Every entry point returns 0 on success or a negative
+ * CMTJB_E* code; cmtjb_last_error() returns a thread-local message whose wording follows
+ * the reference's exception texts so that a Python facade can re-raise the same
+ * ValueError / RuntimeError the reference's tests match on.
+ *
+ * Data model
+ * ----------
+ *  - A *junction model* is a `cmtjb_junction_t` header plus `n_layers` `cmtjb_layer_t`
+ *    records.  It carries the RAW physical description, exactly what the reference's
+ *    `Layer<T>` / `Junction<T>` members hold (core/junction.hpp:145-260, :1139-1156);
+ *    all hoisting of reciprocals / derived coefficients happens inside the library.
+ *  - Every time-dependent quantity of a layer is a *driver slot* (`cmtjb_slot`), holding
+ *    the reference's `ScalarDriver<T>` fields (core/drivers.hpp:31-72).
+ *  - A *batch* is `n_instances` copies of the model.  Instances differ by their
+ *    magnetisation state and by optional per-instance *overrides* of driver fields
+ *    (e.g. a different external field vector or current amplitude per instance).
+ *  - State and logs are SoA with the instance index fastest:
+ *        m_state[(layer*3 + comp) * n_instances + inst]
+ *        log[(channel * n_samples + sample) * n_instances + inst]
+ *    Channels: for each layer mx,my,mz; then R (CLASSIC) or Rx,Ry,Rz (STRIP)
+ *    (core/junction.hpp:1614-1635).
+ */
+#ifndef CMTJ_B200_H_
+#define CMTJ_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMTJB_ABI_VERSION 1
+#define CMTJB_MAX_LAYERS 8
+
+/* ---- error codes --------------------------------------------------------------- */
+enum cmtjb_status {
+  CMTJB_OK = 0,
+  CMTJB_EINVAL = -1,      /* reference: std::invalid_argument -> ValueError   */
+  CMTJB_ERUNTIME = -2,    /* reference: std::runtime_error    -> RuntimeError */
+  CMTJB_ENOTSUP = -3,     /* valid in the reference, not supported by this build */
+  CMTJB_ECUDA = -4,       /* CUDA runtime failure (no device, launch error...) */
+  CMTJB_ENAN = -5         /* "NAN magnetisation" (core/junction.hpp:1037-1039) */
+};
+
+/* ---- drivers: core/drivers.hpp:18-29 (UpdateType) ------------------------------- */
+enum cmtjb_update {
+  CMTJB_UPD_CONSTANT = 0,
+  CMTJB_UPD_PULSE = 1,
+  CMTJB_UPD_SINE = 2,
+  CMTJB_UPD_STEP = 3,
+  CMTJB_UPD_POSINE = 4,
+  CMTJB_UPD_HALFSINE = 5,
+  CMTJB_UPD_TRAPEZOID = 6,
+  CMTJB_UPD_GAUSSIMPULSE = 7,
+  CMTJB_UPD_GAUSSSTEP = 8,
+  CMTJB_UPD_CUSTOM = 100 /* python callback: rejected with CMTJB_ENOTSUP */
+};
+
+/* core/drivers.hpp:34-36 (Driver fields) + :68-69 (edgeTime, steadyTime) */
+typedef struct cmtjb_driver {
+  int32_t update;
+  int32_t reserved;
+  double constantValue, amplitude, frequency, phase, period, cycle, timeStart, timeStop,
+      edgeTime, steadyTime;
+} cmtjb_driver_t;
+
+/* field selector for per-instance overrides (index into the doubles above) */
+enum cmtjb_field {
+  CMTJB_FIELD_CONSTANT = 0,
+  CMTJB_FIELD_AMPLITUDE = 1,
+  CMTJB_FIELD_FREQUENCY = 2,
+  CMTJB_FIELD_PHASE = 3,
+  CMTJB_FIELD_PERIOD = 4,
+  CMTJB_FIELD_CYCLE = 5,
+  CMTJB_FIELD_TIMESTART = 6,
+  CMTJB_FIELD_TIMESTOP = 7,
+  CMTJB_FIELD_EDGETIME = 8,
+  CMTJB_FIELD_STEADYTIME = 9
+};
+
+/* driver slots of one layer: the ScalarDriver / AxialDriver members of Layer<T>
+ * (core/junction.hpp:147-163) */
+enum cmtjb_slot {
+  CMTJB_SLOT_HEXT_X = 0, CMTJB_SLOT_HEXT_Y, CMTJB_SLOT_HEXT_Z,       /* externalFieldDriver */
+  CMTJB_SLOT_HOE_X = 3, CMTJB_SLOT_HOE_Y, CMTJB_SLOT_HOE_Z,          /* HoeDriver */
+  CMTJB_SLOT_HDMI_X = 6, CMTJB_SLOT_HDMI_Y, CMTJB_SLOT_HDMI_Z,       /* HdmiDriver */
+  CMTJB_SLOT_HRES_X = 9, CMTJB_SLOT_HRES_Y, CMTJB_SLOT_HRES_Z,       /* HreservedInteractionFieldDriver */
+  CMTJB_SLOT_K1 = 12,                                                 /* anisotropyDriver */
+  CMTJB_SLOT_K2 = 13,                                                 /* secondOrderAnisotropyDriver */
+  CMTJB_SLOT_IEC_TOP = 14, CMTJB_SLOT_IEC_BOTTOM = 15,
+  CMTJB_SLOT_IECQ_TOP = 16, CMTJB_SLOT_IECQ_BOTTOM = 17,
+  CMTJB_SLOT_IDMI_TOP_X = 18, CMTJB_SLOT_IDMI_TOP_Y, CMTJB_SLOT_IDMI_TOP_Z,
+  CMTJB_SLOT_IDMI_BOTTOM_X = 21, CMTJB_SLOT_IDMI_BOTTOM_Y, CMTJB_SLOT_IDMI_BOTTOM_Z,
+  CMTJB_SLOT_CURRENT = 24,
+  CMTJB_SLOT_FL = 25, CMTJB_SLOT_DL = 26, CMTJB_SLOT_FL2 = 27, CMTJB_SLOT_DL2 = 28,
+  CMTJB_SLOT_TEMPERATURE = 29,
+  CMTJB_NSLOTS = 30
+};
+
+/* core/junction.hpp:141 */
+enum cmtjb_reference { CMTJB_REF_NONE = 0, CMTJB_REF_FIXED = 1, CMTJB_REF_TOP = 2, CMTJB_REF_BOTTOM = 3 };
+/* core/junction.hpp:143 */
+enum cmtjb_solver { CMTJB_EULER_HEUN = 0, CMTJB_RK4 = 1, CMTJB_DORMAND_PRINCE = 2, CMTJB_HEUN = 3 };
+/* core/junction.hpp:1144 */
+enum cmtjb_mr_mode { CMTJB_MR_NONE = 0, CMTJB_MR_CLASSIC = 1, CMTJB_MR_STRIP = 2 };
+/* core/cvector.hpp:11 */
+enum cmtjb_axis { CMTJB_AXIS_X = 0, CMTJB_AXIS_Y = 1, CMTJB_AXIS_Z = 2, CMTJB_AXIS_ALL = 3, CMTJB_AXIS_NONE = 4 };
+
+/* One magnetic layer: the data members of Layer<T> (core/junction.hpp:145-260). */
+typedef struct cmtjb_layer {
+  double mag[3];  /* as stored by the reference (NOT normalised by the ctor, see SURVEY 8a note 10) */
+  double anis[3];
+  double Ms, thickness, cellSurface, damping;
+  double demagTensor[9], dipoleBottom[9], dipoleTop[9]; /* row-major */
+  double fieldLikeTorque, dampingLikeTorque;            /* static SOT (createSOTLayer) */
+  double SlonczewskiSpacerLayerParameter, beta, kappa, spinPolarisation; /* STT */
+  double referenceLayer[3], secondaryReferenceLayer[3];
+  double Rx0, Ry0, AMR_X, AMR_Y, SMR_X, SMR_Y, AHE;     /* STRIP magnetoresistance, per layer */
+  double noiseAlpha, noiseStd, noiseScale;              /* setAlphaNoise (core/junction.hpp:406-414) */
+  /* AdaptiveIntegrationParams (core/junction.hpp:125-139) */
+  double abs_tol, rel_tol, max_factor, min_factor, safety_factor, ki, kp, kd,
+      prev_error_ratio, integral_error;
+  int32_t referenceType;
+  int32_t includeSTT, includeSOT, dynamicSOT, alternativeSTT;
+  int32_t temperatureSet;
+  int32_t noiseAxis;
+  int32_t use_pid_control;
+  cmtjb_driver_t drivers[CMTJB_NSLOTS];
+} cmtjb_layer_t;
+
+/* Junction-level data (core/junction.hpp:1146-1155) + a snapshot of the mutable
+ * PhysicalConstants (core/constants.hpp:39-44), taken at call time. */
+typedef struct cmtjb_junction {
+  int32_t n_layers;
+  int32_t mr_mode;
+  double Rp, Rap;
+  double MAGNETIC_PERMEABILITY, GYRO, TtoAm, HBAR, ELECTRON_CHARGE, BOLTZMANN_CONST;
+} cmtjb_junction_t;
+
+/* Per-instance override of one driver field: values[inst] replaces
+ * layers[layer].drivers[slot].<field> for instance `inst`; layer = -1 applies the same
+ * per-instance value to every layer (the reference's layerID == "all"). */
+typedef struct cmtjb_override {
+  int32_t layer;
+  int32_t slot;
+  int32_t field;
+  int32_t reserved;
+  const double *values; /* [n_instances]; host or device pointer according to the entry point */
+} cmtjb_override_t;
+
+/* Arguments of Junction::runSimulation (core/junction.hpp:1948-1950) for a batch. */
+typedef struct cmtjb_run_args {
+  double totalTime, timeStep, writeFrequency;
+  int32_t solverMode;       /* requested cmtjb_solver; may be overridden like getSolver (:1891-1931) */
+  int32_t log_mode;         /* CMTJB_LOG_* */
+  uint64_t seed;            /* Philox key for thermal noise */
+  int64_t n_instances;
+  int64_t instance_offset;  /* global index of instance 0 (RNG stream id; multi-GPU shards) */
+  int64_t start_iteration;  /* first step index; >0 continues a run in time chunks */
+  /* Pre-generated 1/f^alpha vector noise (VectorAlphaNoise::tickVector, core/noise.hpp:291-301),
+   * already scaled; [n_layers*3][total_iterations][n_instances] or NULL.  Host or device
+   * pointer according to the entry point. */
+  const double *onef_buffer;
+} cmtjb_run_args_t;
+
+enum cmtjb_log_mode {
+  CMTJB_LOG_FULL = 0,   /* every channel at every written sample */
+  CMTJB_LOG_NONE = 1    /* final state only: m_state is updated, no samples written */
+};
+
+/* What a run will do; filled by cmtjb_plan() so the caller can size buffers. */
+typedef struct cmtjb_plan {
+  int32_t effective_solver;  /* after the thermal / 1/f-noise override */
+  int32_t solver_overridden; /* 1 if the reference would print its [WARNING] */
+  int32_t n_layers;
+  int32_t n_channels;        /* 3*n_layers + {0,1,3} */
+  int64_t total_iterations;  /* (unsigned)(totalTime/timeStep) */
+  int64_t write_every;       /* (unsigned)(writeFrequency/timeStep) */
+  int64_t n_samples;         /* fixed-step: ceil(total_iterations/write_every); DP: capacity */
+  int32_t variable_samples;  /* 1 for Dormand-Prince: per-instance n_samples_out/time_log used */
+  int32_t feature_mask;      /* kernel variant chosen (diagnostic) */
+  char variant[64];
+} cmtjb_plan_t;
+
+/* ---- entry points ---------------------------------------------------------------- */
+
+int cmtjb_abi_version(void);
+const char *cmtjb_last_error(void);
+/* number of CUDA devices visible to the library (0 when none) */
+int cmtjb_device_count(void);
+
+/* Validates the model the way the reference's constructors and runSimulation do
+ * (core/junction.hpp:1164-1243, :1952-1955, :1111-1114) and fills `plan`. */
+int cmtjb_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
+               const cmtjb_run_args_t *args, cmtjb_plan_t *plan);
+
+/* Device entry: replaces Junction::runSimulation (core/junction.hpp:1948-2056) for a batch.
+ * All pointers below are DEVICE pointers on `device`; the launch is asynchronous on
+ * `stream` (a cudaStream_t, NULL = legacy default stream).
+ *   m_state        in/out [n_layers*3][n_instances]
+ *   log            out    [n_channels][n_samples][n_instances]   (may be NULL for LOG_NONE)
+ *   status         out    [n_instances] int32: 0 ok, 1 NaN magnetisation
+ *   n_samples_out  out    [n_instances] int32 (Dormand-Prince only, else may be NULL)
+ *   time_log       out    [n_samples][n_instances]  (Dormand-Prince only, else may be NULL)
+ *   dt_state       in/out [n_instances] current adaptive step (DP only; NULL = start at timeStep)
+ */
+int cmtjb_run_device(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
+                     const cmtjb_override_t *overrides, int32_t n_overrides,
+                     const cmtjb_run_args_t *args, double *m_state, double *log,
+                     int32_t *status, int32_t *n_samples_out, double *time_log,
+                     int device, void *stream);
+
+/* Host entry: same contract with HOST pointers; the library stages inputs to the device,
+ * runs, and copies state/logs/status back before returning (synchronous).  This is the
+ * call `Junction.runSimulation` of the facade makes, and what `e2e` in bench.py times. */
+int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
+                   const cmtjb_override_t *overrides, int32_t n_overrides,
+                   const cmtjb_run_args_t *args, double *m_state, double *log,
+                   int32_t *status, int32_t *n_samples_out, double *time_log, int device);
+
+/* ScalarDriver::getCurrentScalarValue (core/drivers.hpp:262-305) evaluated on the device
+ * for n times (host pointers); used by the parity tests of the inline driver code. */
+int cmtjb_eval_driver_host(const cmtjb_driver_t *driver, const double *times, int64_t n,
+                           double *out, int device);
+
+/* FP64 FMA-pipe microbenchmark used for the roofline denominator: runs `iters` dependent
+ * DFMA chains on every SM and returns achieved FLOP/s in *flops (2 flop per DFMA). */
+int cmtjb_fp64_peak(int device, int64_t iters, double *flops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMTJ_B200_H_ */

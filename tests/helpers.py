@@ -1,0 +1,153 @@
+"""Shared test helpers: oracle loader, reference-module loader, and model builders that
+construct the SAME system against either API (the reference `_cmtj` or `cmtj_b200`)."""
+import ctypes
+import glob
+import importlib.util
+import math
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+_oracle = None
+_ref = False
+
+
+def oracle_backend():
+    global _oracle
+    if _oracle is None:
+        from cmtj_b200 import _abi
+
+        so = os.path.join(ORACLE_DIR, "liboracle.so")
+        src = os.path.join(ORACLE_DIR, "llgs_oracle.cpp")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"])
+        lib = ctypes.CDLL(so)
+        _oracle = _abi.Backend(lib, "oracle_", has_device_arg=False)
+    return _oracle
+
+
+def reference_module():
+    """Import oracle/_ref/_cmtj*.so (None when it has not been built)."""
+    global _ref
+    if _ref is False:
+        cands = glob.glob(os.path.join(ORACLE_DIR, "_ref", "_cmtj*.so"))
+        if not cands:
+            _ref = None
+        else:
+            spec = importlib.util.spec_from_file_location("_cmtj", cands[0])
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _ref = mod
+    return _ref
+
+
+# ---------------------------------------------------------------------------------------
+# model builders (mod is either the reference module or cmtj_b200)
+# ---------------------------------------------------------------------------------------
+DEMAG = [(0, 0, 0), (0, 0, 0), (0, 0, 1)]
+ALPHA = 0.005
+SURFACE = 150e-9 * 150e-9 * math.pi
+
+
+def _demag(mod, d=DEMAG):
+    return [mod.CVector(*r) for r in d]
+
+
+def two_layer_mtj(mod, mag=(0.1, 0.1, 1.0)):
+    """tests/conftest.py:104-140 of the reference (fixture two_layer_mtj)."""
+    Kdir = mod.CVector(1, 0, 0)
+    l1 = mod.Layer("free", mod.CVector(*mag), Kdir, 1.65, 3e-9, SURFACE, _demag(mod), ALPHA)
+    l2 = mod.Layer("bottom", mod.CVector(*mag), Kdir, 1.45, 4e-9, SURFACE, _demag(mod), ALPHA)
+    j = mod.Junction([l1, l2], 100, 200)
+    j.setLayerAnisotropyDriver("free", mod.ScalarDriver.getConstantDriver(1.05e3))
+    j.setLayerAnisotropyDriver("bottom", mod.ScalarDriver.getConstantDriver(50e3))
+    j.setIECDriver("free", "bottom", mod.ScalarDriver.getConstantDriver(-1.78e-3))
+    j.setQuadIECDriver("free", "bottom", mod.ScalarDriver.getConstantDriver(-1.69e-4))
+    return j
+
+
+def single_layer_mtj(mod, mag=(0.1, 0.1, 1.0)):
+    """tests/conftest.py:81-101 (single_layer_mtj_fictious)."""
+    l1 = mod.Layer("free", mod.CVector(*mag), mod.CVector(1, 0, 0), 1.65, 3e-9, SURFACE, _demag(mod), ALPHA)
+    l1.setReferenceLayer(mod.CVector(1, 0, 0))
+    j = mod.Junction([l1], 100, 200)
+    j.setLayerAnisotropyDriver("free", mod.ScalarDriver.getConstantDriver(1.05e3))
+    return j
+
+
+def tri_layer_mtj(mod, mag=(0.1, 0.1, 1.0)):
+    """tests/conftest.py:184-237 (tri_layer_mtj)."""
+    Kdir = mod.CVector(1, 0, 0)
+    l1 = mod.Layer("free", mod.CVector(*mag), Kdir, 1.65, 3e-9, SURFACE, _demag(mod), ALPHA)
+    l2 = mod.Layer("middle", mod.CVector(*mag), Kdir, 1.45, 4e-9, SURFACE, _demag(mod), ALPHA)
+    l3 = mod.Layer("bottom", mod.CVector(*mag), mod.CVector(0, 0, 1.0), 0.7, 1e-9, SURFACE, _demag(mod), ALPHA)
+    j = mod.Junction([l1, l2, l3])
+    for l, k in zip(["free", "middle", "bottom"], [1.05e3, 50e3, 1e4]):
+        j.setLayerAnisotropyDriver(l, mod.ScalarDriver.getConstantDriver(k))
+    j.setIECDriver("free", "middle", mod.ScalarDriver.getConstantDriver(-1.78e-3))
+    j.setQuadIECDriver("free", "middle", mod.ScalarDriver.getConstantDriver(-1.69e-4))
+    j.setIECDriver("middle", "bottom", mod.ScalarDriver.getConstantDriver(3e-4))
+    j.setQuadIECDriver("middle", "bottom", mod.ScalarDriver.getConstantDriver(2e-6))
+    return j
+
+
+def stt_layer_mtj(mod, mag=None, temperature=None):
+    """p-bit style STT junction (curated-examples/p-bit.py:188-227 parameters)."""
+    if mag is None:
+        mag = (math.sin(0.2) * math.cos(1.0), math.sin(0.2) * math.sin(1.0), math.cos(0.2))
+    demag = [(0.00024164288391924, 0, 0), (0, 0.000160046006320031, 0), (0, 0, 0.999598310229469)]
+    l = mod.Layer.createSTTLayer(
+        "free", mod.CVector(*mag), mod.CVector(1, 0, 0), 1.6, 2e-9, math.pi * (0.7e-9) ** 2 * 1e4,
+        _demag(mod, demag), 0.1, 1.0, 0.9, 1.0,
+    )
+    l.setReferenceLayer(mod.CVector(1, 0, 0))
+    j = mod.Junction([l], 100, 200)
+    j.setLayerAnisotropyDriver("free", mod.ScalarDriver.getConstantDriver(350e3))
+    j.setLayerCurrentDriver("free", mod.ScalarDriver.getConstantDriver(-1e10))
+    j.setLayerExternalFieldDriver("free", mod.AxialDriver(50e3, 0.0, 0.0))
+    if temperature is not None:
+        j.setLayerTemperatureDriver("free", mod.ScalarDriver.getConstantDriver(temperature))
+    return j
+
+
+def sot_layer(mod, dynamic=True, mag=(0.1, 0.1, 0.9)):
+    """1-layer SOT junction with K2 and step torque drivers (CIMS-like)."""
+    demag = [(0, 0, 0), (0, 0, 0), (0, 0, 1)]
+    if dynamic:
+        l = mod.Layer("free", mod.CVector(*mag), mod.CVector(0, 0, 1), 1.0, 1.2e-9, 1e-14, _demag(mod, demag), 0.03)
+    else:
+        l = mod.Layer.createSOTLayer(
+            "free", mod.CVector(*mag), mod.CVector(0, 0, 1), 1.0, 1.2e-9, 1e-14, _demag(mod, demag), 0.03, 2e-9, -3e-9
+        )
+    l.setReferenceLayer(mod.CVector(0, 1, 0))
+    l.setSecondaryReferenceLayer(mod.CVector(1, 0, 0))
+    j = mod.Junction([l], [100.0], [1.0], [-0.24], [0.0], [-0.46], [0.0], [-2.7])
+    j.setLayerAnisotropyDriver("free", mod.ScalarDriver.getConstantDriver(0.6e6))
+    j.setLayerSecondOrderAnisotropyDriver("free", mod.ScalarDriver.getConstantDriver(2e4))
+    j.setLayerExternalFieldDriver("free", mod.AxialDriver(20e3, 5e3, -10e3))
+    if dynamic:
+        j.setLayerFieldLikeTorqueDriver("free", mod.ScalarDriver.getStepDriver(0, 3e3, 0.2e-9, 1.5e-9))
+        j.setLayerDampingLikeTorqueDriver("free", mod.ScalarDriver.getStepDriver(100.0, -9e3, 0.2e-9, 1.5e-9))
+        j.setLayerSecondaryFieldLikeTorqueDriver("free", mod.ScalarDriver.getSineDriver(0, 1e3, 5e9, 0.3))
+        j.setLayerSecondaryDampingLikeTorqueDriver("free", mod.ScalarDriver.getConstantDriver(500.0))
+    else:
+        j.setLayerCurrentDriver("free", mod.ScalarDriver.getSineDriver(1e11, 5e11, 3e9, 0.0))
+    return j
+
+
+def log_arrays(log):
+    return {k: np.asarray(v, dtype=np.float64) for k, v in log.items()}
+
+
+def max_rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / scale)

@@ -1,0 +1,224 @@
+"""Pins the oracle (oracle/llgs_oracle.cpp, driven through the cmtj_b200 facade and its
+packing code) BIT-FOR-BIT against the unmodified reference extension (oracle/_ref), on
+deterministic runs.  CPU only.  If these pass, facade + packing + restatement reproduce
+core/junction.hpp exactly, and the restatement can stand in for the reference on the GPU box.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import cmtj_b200
+import helpers
+
+MODES = ["RK4", "Heun", "EulerHeun"]
+
+
+def _run_both(ref, build, T=1e-9, dt=1e-13, wf=1e-12, mode="RK4", tweak=None, **kw):
+    jr = build(ref, **kw)
+    jo = build(cmtj_b200, **kw)
+    if tweak:
+        tweak(ref, jr)
+        tweak(cmtj_b200, jo)
+    jr.runSimulation(T, dt, wf, solverMode=getattr(ref.SolverMode, mode))
+    jo.runSimulation(T, dt, wf, solverMode=getattr(cmtj_b200.SolverMode, mode))
+    return jr, jo
+
+
+def _assert_same_logs(jr, jo):
+    lr, lo = helpers.log_arrays(jr.getLog()), helpers.log_arrays(jo.getLog())
+    assert set(lr) == set(lo)
+    for k in lr:
+        assert lr[k].shape == lo[k].shape, k
+        assert np.array_equal(lr[k], lo[k]), (k, helpers.max_rel_err(lo[k], lr[k]))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("build", ["single_layer_mtj", "two_layer_mtj", "tri_layer_mtj", "stt_layer_mtj"])
+def test_fixtures_bit_exact(ref, on_oracle, build, mode):
+    jr, jo = _run_both(ref, getattr(helpers, build), mode=mode)
+    _assert_same_logs(jr, jo)
+    for lid in jr.getLayerIds():
+        assert jr.getLayerMagnetisation(lid).tolist() == jo.getLayerMagnetisation(lid).tolist()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_sot_strip_bit_exact(ref, on_oracle, dynamic, mode):
+    jr, jo = _run_both(ref, helpers.sot_layer, T=2e-9, mode=mode, dynamic=dynamic)
+    _assert_same_logs(jr, jo)
+    assert jr.getMagnetoresistance() == jo.getMagnetoresistance()
+
+
+def test_default_write_frequency_truncates_to_99(ref, on_oracle):
+    # SURVEY 8a note 2: 1e-11/1e-13 -> 99
+    jr = helpers.two_layer_mtj(ref)
+    jo = helpers.two_layer_mtj(cmtj_b200)
+    jr.runSimulation(2e-9)
+    jo.runSimulation(2e-9)
+    _assert_same_logs(jr, jo)
+    t = np.asarray(jo.getLog()["time"])
+    assert len(t) == 203 and t[1] == 99 * 1e-13
+
+
+def test_unnormalised_initial_mag_and_carried_state(ref, on_oracle):
+    # SURVEY 8a note 10 + section 5: state persists and the log appends until clearLog
+    jr = helpers.two_layer_mtj(ref, mag=(0.3, -0.2, 1.0))
+    jo = helpers.two_layer_mtj(cmtj_b200, mag=(0.3, -0.2, 1.0))
+    assert jo.getLayerMagnetisation("free").tolist() == [0.3, -0.2, 1.0]
+    for H in (0.0, 50e3, 100e3):
+        for j, m in ((jr, ref), (jo, cmtj_b200)):
+            j.setLayerExternalFieldDriver("all", m.AxialDriver(H, 10e3, 0.0))
+            j.runSimulation(0.5e-9, 1e-13, 1e-13)
+    _assert_same_logs(jr, jo)
+    assert len(jo.getLog()["time"]) == 3 * 5000
+    jo.clearLog()
+    assert jo.getLog() == {}
+
+
+def _all_driver_kinds(m):
+    S = m.ScalarDriver
+    return [
+        S.getConstantDriver(3.5),
+        S.getPulseDriver(1.0, 2.0, 1e-10, 0.3),
+        S.getSineDriver(10, 20, 7e9, 0.4),
+        S.getPosSineDriver(-3, 20, 7e9, 0.4),
+        S.getHalfSineDriver(-3, 20, 7e9, 0.4) if hasattr(S, "getHalfSineDriver") else None,
+        S.getStepDriver(0.5, 4.0, 1e-10, 3e-10),
+        S.getTrapezoidDriver(0.5, 4.0, 1e-10, 0.5e-10, 2e-10),
+        S.getGaussianImpulseDriver(0.1, 5.0, 3e-10, 0.4e-10),
+        S.getGaussianStepDriver(0.1, 5.0, 3e-10, 0.4e-10),
+    ]
+
+
+def test_driver_values_match_reference(ref, oracle):
+    """drivers.hpp:262-305 -- facade host evaluation, oracle evaluation and the reference agree."""
+    import ctypes as C
+
+    from cmtj_b200 import _abi
+
+    times = np.linspace(0, 6e-10, 977)
+    f = oracle.lib.oracle_eval_driver
+    f.restype = C.c_int
+    for dr, do in zip(_all_driver_kinds(ref), _all_driver_kinds(cmtj_b200)):
+        if do is None:
+            continue
+        want = np.array([dr.getCurrentScalarValue(float(t)) for t in times]) if dr is not None else None
+        got_py = np.array([do.getCurrentScalarValue(float(t)) for t in times])
+        rec = _abi.Driver()
+        do._pack(rec)
+        out = np.zeros_like(times)
+        f(C.byref(rec), times.ctypes.data_as(C.c_void_p), C.c_int64(len(times)), out.ctypes.data_as(C.c_void_p))
+        if want is not None:
+            assert np.array_equal(out, want), do
+            # the pure-Python API evaluation may differ from libm-in-C++ by an ulp
+            assert np.allclose(got_py, want, rtol=1e-14, atol=0), do
+        else:
+            assert np.array_equal(out, got_py)
+
+
+@pytest.mark.parametrize("kind", range(9))
+def test_time_dependent_drivers_in_dynamics(ref, on_oracle, kind):
+    """Every driver type on Hoe_z, K1 and IEC of a 2-layer junction."""
+
+    def tweak(m, j):
+        d = _all_driver_kinds(m)[kind]
+        if d is None:
+            pytest.skip("half-sine factory not bound in the reference")
+        j.setLayerOerstedFieldDriver("all", m.AxialDriver(m.NullDriver(), m.NullDriver(), d * 1e3))
+        j.setLayerAnisotropyDriver("free", d * 300.0)
+        j.setIECDriver("free", "bottom", d * -1e-4)
+
+    jr, jo = _run_both(ref, helpers.two_layer_mtj, T=0.7e-9, wf=1e-13, tweak=tweak)
+    _assert_same_logs(jr, jo)
+
+
+def test_idmi_dipole_hdmi_k2_terms(ref, on_oracle):
+    def tweak(m, j):
+        j.setIDMIDriver("free", "bottom", m.AxialDriver(1e-4, -2e-4, 3e-4))
+        j.setLayerHdmiDriver("free", m.AxialDriver(1e3, 2e3, -3e3))
+        j.setLayerSecondOrderAnisotropyDriver("bottom", m.ScalarDriver.getConstantDriver(7e3))
+        t = [m.CVector(1e-3, 2e-4, 0), m.CVector(2e-4, -3e-3, 1e-4), m.CVector(0, 1e-4, 2e-3)]
+        j.getLayer("free").setBottomDipoleTensor(t)
+        j.getLayer("bottom").setTopDipoleTensor(t)
+
+    for mode in MODES:
+        jr, jo = _run_both(ref, helpers.two_layer_mtj, T=0.5e-9, wf=1e-13, mode=mode, tweak=tweak)
+        _assert_same_logs(jr, jo)
+
+
+def test_reference_types_top_bottom(ref, on_oracle):
+    def build(m):
+        d = helpers._demag(m)
+        a = m.Layer.createSTTLayer("free", m.CVector(0.1, 0.2, 1), m.CVector(0, 0, 1), 1.2, 1.5e-9, 1e-14, d, 0.02, 1.3, 0.1, 0.7)
+        b = m.Layer.createSTTLayer("bottom", m.CVector(1, 0.1, 0.1), m.CVector(1, 0, 0), 1.5, 3e-9, 1e-14, d, 0.02, 1.3, 0.0, 0.7)
+        a.setReferenceLayer(m.Reference.bottom)
+        b.setReferenceLayer(m.Reference.top)
+        j = m.Junction([a, b], 100, 200)
+        j.setLayerAnisotropyDriver("free", m.ScalarDriver.getConstantDriver(4e5))
+        j.setLayerAnisotropyDriver("bottom", m.ScalarDriver.getConstantDriver(1e5))
+        j.setLayerCurrentDriver("all", m.ScalarDriver.getSineDriver(2e10, 1e10, 4e9, 0))
+        j.setLayerAlternativeSTT("bottom", True)
+        j.setIECDriver("free", "bottom", m.ScalarDriver.getConstantDriver(2e-5))
+        return j
+
+    for mode in MODES:
+        jr, jo = _run_both(ref, build, T=0.5e-9, wf=1e-13, mode=mode)
+        _assert_same_logs(jr, jo)
+
+
+def test_dormand_prince_single_layer(ref, on_oracle):
+    jr, jo = _run_both(ref, helpers.sot_layer, T=3e-9, dt=1e-12, wf=1e-11, mode="DormandPrince", dynamic=True)
+    _assert_same_logs(jr, jo)
+    assert len(jo.getLog()["time"]) > 10
+
+
+def test_dormand_prince_pid(ref, on_oracle):
+    def tweak(m, j):
+        p = m.AdaptiveIntegrationParams()
+        p.use_pid_control = True
+        p.abs_tol = 1e-7
+        j.getLayer("free").setAdaptiveParams(p)
+
+    jr, jo = _run_both(ref, helpers.single_layer_mtj, T=2e-9, dt=1e-12, wf=2e-11, mode="DormandPrince", tweak=tweak)
+    _assert_same_logs(jr, jo)
+
+
+def test_constants_snapshot(ref, on_oracle):
+    # constants.hpp:39-44 are mutable globals read at run time
+    try:
+        ref.constants.PhysicalConstants.set_gyromagnetic_ratio(2.0e5)
+        cmtj_b200.PhysicalConstants.set_gyromagnetic_ratio(2.0e5)
+        ref.constants.PhysicalConstants.set_magnetic_permeability(1.2e-6)
+        cmtj_b200.PhysicalConstants.set_magnetic_permeability(1.2e-6)
+        jr, jo = _run_both(ref, helpers.two_layer_mtj, T=0.3e-9, wf=1e-13)
+        _assert_same_logs(jr, jo)
+    finally:
+        ref.constants.PhysicalConstants.resetToDefaults()
+        cmtj_b200.PhysicalConstants.resetToDefaults()
+    assert cmtj_b200.PhysicalConstants.gyromagnetic_ratio() == 220880.0
+
+
+def test_error_contract(ref, on_oracle):
+    """Same exception types / message substrings as the reference (SURVEY 8a note 11)."""
+    for m in (ref, cmtj_b200):
+        d = helpers._demag(m)
+        l = m.Layer("free", m.CVector(0, 0, 1), m.CVector(1, 0, 0), 1.0, 1e-9, 1e-14, d, 0.01)
+        with pytest.raises(ValueError, match="must have a pinning"):
+            m.Junction([l], 100, 200)
+        with pytest.raises(ValueError, match="zero length"):
+            m.Junction([])
+        with pytest.raises(ValueError, match="unique ids"):
+            m.Junction([l, l])
+        with pytest.raises(RuntimeError, match="zero vector"):
+            m.Layer("x", m.CVector(0, 0, 0), m.CVector(1, 0, 0), 1.0, 1e-9, 1e-14, d, 0.01)
+        j = m.Junction([l])
+        with pytest.raises(RuntimeError, match="cannot be larger than write frequency"):
+            j.runSimulation(1e-9, 1e-12, 1e-13)
+        with pytest.raises(RuntimeError, match="Failed to find a layer"):
+            j.setLayerAnisotropyDriver("nope", m.ScalarDriver.getConstantDriver(1.0))
+        with pytest.raises(RuntimeError, match="Start time cannot be later"):
+            m.ScalarDriver.getStepDriver(0, 1, 2e-9, 1e-9)
+        sot = m.Layer.createSOTLayer("s", m.CVector(0, 0, 1), m.CVector(1, 0, 0), 1.0, 1e-9, 1e-14, d, 0.01, 1.0, 1.0)
+        with pytest.raises(RuntimeError, match="static SOT"):
+            sot.setFieldLikeTorqueDriver(m.ScalarDriver.getConstantDriver(1.0))
