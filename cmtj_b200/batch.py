@@ -1,0 +1,271 @@
+"""Batched parameter sweeps: ``n_instances`` copies of one :class:`~cmtj_b200.core.Junction`
+integrated by a single fused kernel launch, one GPU thread per instance.
+
+This is the entry the reference does not have: its sweeps are Python ``for`` loops over
+``runSimulation`` (cmtj/utils/procedures.py:120-141, curated-examples/*.py).  Instances
+share the junction's structure and differ by
+
+* their magnetisation state (``set_magnetisation`` / carried over between runs), and
+* per-instance *overrides* of any driver field of any layer, e.g. the external field
+  vector, a current amplitude, a sine frequency (``set_override`` and helpers).
+
+Two ways to run:
+
+``run(...)``         host (numpy) buffers through ``cmtjb_run_host``; H2D/D2H included.
+``run_device(...)``  state, overrides and logs stay on the GPU as ``torch`` tensors
+                     (``cmtjb_run_device``, asynchronous on the current torch stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _abi
+from .core import CVector, Junction, SolverMode, _next_seed
+
+_FIELD_INDEX = {n: i for i, n in enumerate(_abi.FIELD_NAMES)}
+_SLOT_BY_NAME = {
+    "Hext_x": 0, "Hext_y": 1, "Hext_z": 2,
+    "Hoe_x": 3, "Hoe_y": 4, "Hoe_z": 5,
+    "Hdmi_x": 6, "Hdmi_y": 7, "Hdmi_z": 8,
+    "Hres_x": 9, "Hres_y": 10, "Hres_z": 11,
+    "K1": 12, "K2": 13,
+    "IEC_top": 14, "IEC_bottom": 15, "IECquad_top": 16, "IECquad_bottom": 17,
+    "IDMI_top_x": 18, "IDMI_top_y": 19, "IDMI_top_z": 20,
+    "IDMI_bottom_x": 21, "IDMI_bottom_y": 22, "IDMI_bottom_z": 23,
+    "current": 24, "fieldLike": 25, "dampingLike": 26, "fieldLike2": 27, "dampingLike2": 28,
+    "temperature": 29,
+}  # fmt: skip
+
+
+class BatchLog(dict):
+    """name -> array [n_samples, n_instances] (``time``: [n_samples], or [n_samples, B] for
+    Dormand-Prince).  ``instance(i)`` gives the reference-shaped ``getLog()`` dict of one instance."""
+
+    n_samples_per_instance: Optional[np.ndarray] = None
+
+    def instance(self, i: int) -> Dict[str, np.ndarray]:
+        n = None if self.n_samples_per_instance is None else int(self.n_samples_per_instance[i])
+        out = {}
+        for k, v in self.items():
+            a = v if v.ndim == 1 else v[:, i]
+            out[k] = np.asarray(a[:n])
+        return out
+
+
+class JunctionBatch:
+    def __init__(self, junction: Junction, n_instances: int, device: int = 0, instance_offset: int = 0):
+        if n_instances < 0:
+            raise ValueError("n_instances must be non-negative")
+        self.junction = junction
+        self.B = int(n_instances)
+        self.device = int(device)
+        self.instance_offset = int(instance_offset)
+        L = junction.layerNo
+        m0 = np.array([c for l in junction._layers for c in l.mag.tolist()], dtype=np.float64)
+        # [L*3][B], instance fastest
+        self.m_state = np.repeat(m0[:, None], self.B, axis=1).copy()
+        self._m_dev = None
+        self._overrides: Dict[tuple, np.ndarray] = {}
+        self._ovr_dev: Dict[tuple, object] = {}
+        self.last_plan: Optional[_abi.Plan] = None
+
+    # ---- per-instance inputs ----------------------------------------------------------------------
+    def _layer_index(self, layer_id: str) -> int:
+        if layer_id == "all":
+            return -1
+        ids = self.junction.getLayerIds()
+        if layer_id not in ids:
+            raise RuntimeError("Failed to find a layer with a given id: " + layer_id + "!")
+        return ids.index(layer_id)
+
+    def set_override(self, layer_id: str, slot: Union[int, str], field: Union[int, str], values) -> None:
+        """values[i] replaces ``<layer>.<slot driver>.<field>`` for instance i."""
+        s = _SLOT_BY_NAME[slot] if isinstance(slot, str) else int(slot)
+        f = _FIELD_INDEX[field] if isinstance(field, str) else int(field)
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).reshape(-1))
+        if v.shape[0] != self.B:
+            raise ValueError(f"override needs {self.B} values, got {v.shape[0]}")
+        key = (self._layer_index(layer_id), s, f)
+        self._overrides[key] = v
+        self._ovr_dev.pop(key, None)
+
+    def clear_overrides(self) -> None:
+        self._overrides.clear()
+        self._ovr_dev.clear()
+
+    def set_external_field(self, layer_id: str, H) -> None:
+        """Per-instance constant external field, H: [B,3] in A/m (the batched form of
+        ``setLayerExternalFieldDriver(id, AxialDriver(Hx,Hy,Hz))``)."""
+        H = np.asarray(H, dtype=np.float64).reshape(self.B, 3)
+        for c in range(3):
+            self.set_override(layer_id, _abi.SLOT_HEXT + c, 0, H[:, c])
+
+    def set_magnetisation(self, layer_id: str, m) -> None:
+        """Per-instance magnetisation, m: [B,3]; normalised like ``Layer::setMagnetisation``."""
+        m = np.asarray(m, dtype=np.float64).reshape(self.B, 3)
+        n = np.sqrt((m * m).sum(axis=1))
+        if np.any(n == 0):
+            raise RuntimeError("Initial magnetisation was set to a zero vector!")
+        m = m / n[:, None]
+        self.sync_state_to_host()
+        for l in range(self.junction.layerNo) if layer_id == "all" else [self._layer_index(layer_id)]:
+            self.m_state[3 * l : 3 * l + 3, :] = m.T
+        self._m_dev = None
+
+    def get_magnetisation(self, layer_id: str) -> np.ndarray:
+        self.sync_state_to_host()
+        l = self._layer_index(layer_id)
+        return self.m_state[3 * l : 3 * l + 3, :].T.copy()
+
+    def sync_state_to_host(self) -> None:
+        if self._m_dev is not None:
+            self.m_state = self._m_dev.cpu().numpy()
+
+    # ---- shared plumbing -------------------------------------------------------------------------------
+    def _args(self, totalTime, timeStep, writeFrequency, solverMode, log, seed, onef) -> _abi.RunArgs:
+        a = _abi.RunArgs()
+        a.totalTime = float(totalTime)
+        a.timeStep = float(timeStep)
+        a.writeFrequency = float(writeFrequency)
+        a.solverMode = int(solverMode)
+        a.log_mode = _abi.LOG_FULL if log else _abi.LOG_NONE
+        a.seed = _next_seed() if seed is None else int(seed)
+        a.n_instances = self.B
+        a.instance_offset = self.instance_offset
+        a.start_iteration = 0
+        a.onef_buffer = onef
+        return a
+
+    def _override_table(self, pointers: Sequence[int]):
+        n = len(self._overrides)
+        tab = (_abi.Override * max(n, 1))()
+        for k, ((l, s, f), _) in enumerate(self._overrides.items()):
+            tab[k].layer, tab[k].slot, tab[k].field, tab[k].values = l, s, f, pointers[k]
+        return tab, n
+
+    def _check_onef(self):
+        if any(l.noiseScale != 0 for l in self.junction._layers):
+            raise NotImplementedError("1/f^alpha noise is only wired for single-instance Junction.runSimulation")
+
+    def _package(self, plan: _abi.Plan, log: Optional[np.ndarray], timeStep: float, tlog, nsamp) -> BatchLog:
+        out = BatchLog()
+        if log is None:
+            return out
+        for ch, name in enumerate(self.junction._channel_names()):
+            out[name] = log[ch]
+        if plan.variable_samples:
+            out["time"] = tlog
+            out.n_samples_per_instance = nsamp
+        else:
+            out["time"] = np.arange(0, int(plan.total_iterations), int(plan.write_every), dtype=np.float64) * float(
+                timeStep
+            )
+        return out
+
+    # ---- host path -----------------------------------------------------------------------------------------
+    def run(
+        self,
+        totalTime: float,
+        timeStep: float = 1e-13,
+        writeFrequency: float = 1e-11,
+        solverMode: SolverMode = SolverMode.RK4,
+        log: bool = True,
+        seed: Optional[int] = None,
+        out: Optional[np.ndarray] = None,
+    ) -> BatchLog:
+        """Integrate every instance; host buffers in, host buffers out (H2D/D2H inside).
+        ``out`` may be a preallocated (e.g. pinned) float64 array [n_channels, n_samples, B]."""
+        self._check_onef()
+        self.sync_state_to_host()
+        self._m_dev = None
+        be = _abi.backend()
+        jn, layers = self.junction._pack()
+        a = self._args(totalTime, timeStep, writeFrequency, solverMode, log, seed, None)
+        plan = be.plan(jn, layers, a)
+        self.last_plan = plan
+        n_ch, n_s = int(plan.n_channels), int(plan.n_samples)
+        buf = None
+        if log:
+            if out is not None:
+                if out.shape != (n_ch, n_s, self.B) or out.dtype != np.float64 or not out.flags.c_contiguous:
+                    raise ValueError(f"out must be C-contiguous float64 of shape {(n_ch, n_s, self.B)}")
+                buf = out
+            else:
+                buf = np.empty((n_ch, n_s, self.B), dtype=np.float64)
+        status = np.zeros(self.B, dtype=np.int32)
+        nsamp = np.zeros(self.B, dtype=np.int32) if plan.variable_samples else None
+        tlog = np.zeros((n_s, self.B), dtype=np.float64) if plan.variable_samples and log else None
+        tab, n = self._override_table([v.ctypes.data for v in self._overrides.values()])
+        rc = be.run_host(jn, layers, tab, n, a, self.m_state, buf, status, nsamp, tlog, self.device)
+        self.status = status
+        be.check(rc)
+        return self._package(plan, buf, timeStep, tlog, nsamp)
+
+    # ---- device path -----------------------------------------------------------------------------------------
+    def run_device(
+        self,
+        totalTime: float,
+        timeStep: float = 1e-13,
+        writeFrequency: float = 1e-11,
+        solverMode: SolverMode = SolverMode.RK4,
+        log: bool = True,
+        seed: Optional[int] = None,
+        out=None,
+    ):
+        """Same run with everything resident on the GPU.  Returns a dict of ``torch`` tensors
+        (views of one [n_channels, n_samples, B] tensor); asynchronous on the current stream."""
+        import torch
+
+        self._check_onef()
+        be = _abi.cuda_backend()
+        lib = be.lib
+        dev = torch.device("cuda", self.device)
+        jn, layers = self.junction._pack()
+        a = self._args(totalTime, timeStep, writeFrequency, solverMode, log, seed, None)
+        plan = be.plan(jn, layers, a)
+        self.last_plan = plan
+        n_ch, n_s = int(plan.n_channels), int(plan.n_samples)
+        if self._m_dev is None:
+            self._m_dev = torch.from_numpy(self.m_state).to(dev)
+        for key, v in self._overrides.items():
+            if key not in self._ovr_dev:
+                self._ovr_dev[key] = torch.from_numpy(v).to(dev)
+        tab, n = self._override_table([self._ovr_dev[k].data_ptr() for k in self._overrides])
+        buf = None
+        if log:
+            buf = out if out is not None else torch.empty((n_ch, n_s, self.B), dtype=torch.float64, device=dev)
+            assert tuple(buf.shape) == (n_ch, n_s, self.B) and buf.is_contiguous() and buf.dtype == torch.float64
+        status = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        nsamp = torch.zeros(self.B, dtype=torch.int32, device=dev) if plan.variable_samples else None
+        tlog = torch.zeros((n_s, self.B), dtype=torch.float64, device=dev) if plan.variable_samples and log else None
+        f = lib.cmtjb_run_device
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+
+        def p(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = f(
+            C.byref(jn), layers, tab, n, C.byref(a), p(self._m_dev), p(buf), p(status), p(nsamp), p(tlog),
+            self.device, C.c_void_p(stream),
+        )  # fmt: skip
+        be.check(rc)
+        self.status_dev = status
+        res = {}
+        if buf is not None:
+            for ch, name in enumerate(self.junction._channel_names()):
+                res[name] = buf[ch]
+            if plan.variable_samples:
+                res["time"] = tlog
+                res["n_samples"] = nsamp
+            else:
+                res["time"] = (
+                    torch.arange(0, int(plan.total_iterations), int(plan.write_every), dtype=torch.float64, device=dev)
+                    * float(timeStep)
+                )
+        res["_log"] = buf
+        return res

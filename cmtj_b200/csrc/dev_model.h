@@ -1,0 +1,94 @@
+// dev_model.h -- derived, device-resident form of a junction model.
+//
+// The raw records of include/cmtj_b200.h are turned into this struct on the host
+// (cabi.cu: derive_model) with every reciprocal and product that does not depend on the
+// magnetisation hoisted (SURVEY 7 "Target arithmetic").  The whole struct is passed to the
+// kernels BY VALUE as a __grid_constant__ parameter, so uniform parameters live in
+// constant bank 0 and reach the FP64 pipe as free c[0x0][..] operands: no registers, no
+// loads.  Only per-instance quantities (state, summed constant field, override table
+// entries) occupy registers.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/cmtj_b200.h"
+
+namespace cmtjb {
+
+// compile-time feature bits of a kernel variant (terms that are compiled in)
+enum : uint32_t {
+  F_K2 = 1u << 0,         // second-order anisotropy          (junction.hpp:645-652)
+  F_IEC = 1u << 1,        // bilinear + biquadratic IEC       (junction.hpp:654-675)
+  F_IDMI = 1u << 2,       // interlayer DMI                   (junction.hpp:677-701)
+  F_DIPOLE = 1u << 3,     // top/bottom dipole tensors        (junction.hpp:583-585)
+  F_DEMAG_FULL = 1u << 4, // off-diagonal demag entries (diagonal is always compiled in)
+  F_STT = 1u << 5,        // Slonczewski STT                  (junction.hpp:743-769)
+  F_SOT = 1u << 6,        // SOT primary + secondary          (junction.hpp:770-812)
+  F_THERMAL = 1u << 7,    // Langevin field                   (junction.hpp:1111-1128)
+  F_ONEF = 1u << 8,       // pre-generated 1/f^alpha vector   (junction.hpp:1130-1136)
+  F_DYN = 1u << 9,        // at least one time-dependent driver
+  F_OVR = 1u << 10,       // per-instance overrides other than constant field components
+  F_ALL = (1u << 11) - 1
+};
+
+struct DevDriver {
+  int32_t type;  // cmtjb_update
+  int32_t pad;
+  double amplitude, frequency, phase, period, cycle, timeStart, timeStop, edgeTime, steadyTime;
+};
+
+struct DevLayer {
+  double cst[CMTJB_NSLOTS];  // constantValue of every slot
+  double anis[3];
+  double cK1, cK2;           // 2/Ms, 4/Ms
+  double inv_Mst;            // 1/(Ms*thickness)
+  double demag[9];           // demagTensor * (Ms/mu0)
+  double dipB[9], dipT[9];   // dipole tensors * (Ms/mu0)
+  double alpha;
+  double llg;                // -gamma/(1+alpha^2)
+  double aJ_c;               // hbar/(e*Ms*thickness)
+  double lam, lam2, P, beta, kappa;
+  double flT, dlT;           // static SOT efficiencies
+  double ref[3], ref2[3];
+  double sigma_c;            // 2*alpha*kB/(Ms*V*gamma); sigma = sqrt(sigma_c*T)
+  double Rx0, Ry0, AMR_X, SMR_X, AHE_half, AMRSMR_Y;
+  // Dormand-Prince controller
+  double abs_tol, rel_tol, max_factor, min_factor, safety_factor, ki, kp, kd, prev_error_ratio,
+      integral_error;
+  int32_t refType;           // cmtjb_reference
+  int32_t stt, sot, dynamicSOT, altSTT, thermal, onef, pid;
+  uint32_t dynmask;          // bit s: slot s is time dependent
+  uint32_t ovmask;           // bit s: slot s has a per-instance override of some field
+  int8_t ovidx[CMTJB_NSLOTS][10];  // override table row of (slot, field) or -1
+  DevDriver drv[CMTJB_NSLOTS];
+};
+
+template <int NL> struct DevModel {
+  DevLayer L[NL];
+  double Rp, Rhalf;          // Rp, (Rap-Rp)/2
+  int32_t mr_mode;
+  int32_t n_layers;
+};
+
+constexpr int kMaxOverrides = 24;
+
+// run parameters (also constant bank)
+struct RunParams {
+  double *m_state;           // [NL*3][B]
+  double *log;               // [n_channels][n_samples][B] or null
+  int32_t *status;           // [B]
+  int32_t *n_samples_out;    // [B] (DP)
+  double *time_log;          // [n_samples][B] (DP)
+  const double *ovr[kMaxOverrides];  // row k: [B] values of override k
+  const double *onef;        // [NL*3][total_iterations][B] or null
+  long long B;
+  long long inst_offset;
+  long long n_samples;       // row count of the log
+  long long it_begin, it_end;  // step range of this launch
+  long long total_iterations;
+  long long write_every;
+  long long first_sample;    // sample index of the first write of this launch
+  double dt, sqrt_dt, total_time, write_frequency;
+  unsigned long long seed;
+};
+
+}  // namespace cmtjb

@@ -1,0 +1,343 @@
+// llgs_device.cuh -- FP64 device functions of the fused (s)LLGS time-loop kernels.
+//
+// One thread integrates one sweep instance; its magnetisation vectors live in registers for
+// the whole time loop.  Uniform parameters are read from the __grid_constant__ DevModel
+// (constant bank), time-dependent drivers are evaluated inline, and thermal noise comes from
+// a counter-based Philox4x32-10 stream keyed by (seed, instance, layer, step).
+//
+// Arithmetic is re-associated relative to the reference (hoisted reciprocals, -gamma/(1+a^2)
+// folded into the stage updates, FMA contraction); the parity bar is <= 1e-9 relative on m
+// and R against oracle/llgs_oracle.cpp, which itself is bit-exact against the reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "dev_model.h"
+
+namespace cmtjb {
+
+struct d3 {
+  double x, y, z;
+};
+__device__ __forceinline__ d3 mk(double x, double y, double z) { return d3{x, y, z}; }
+__device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ d3 operator*(d3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ double dot(d3 a, d3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ d3 cross(d3 a, d3 b) {
+  return mk(fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x)));
+}
+// r + a*s
+__device__ __forceinline__ d3 axpy(d3 a, double s, d3 r) { return mk(fma(a.x, s, r.x), fma(a.y, s, r.y), fma(a.z, s, r.z)); }
+__device__ __forceinline__ d3 ld3(const double *p) { return mk(p[0], p[1], p[2]); }
+// r - T*v  (row-major 3x3)
+__device__ __forceinline__ d3 sub_matvec(const double *T, d3 v, d3 r) {
+  return mk(fma(-T[0], v.x, fma(-T[1], v.y, fma(-T[2], v.z, r.x))), fma(-T[3], v.x, fma(-T[4], v.y, fma(-T[5], v.z, r.y))),
+            fma(-T[6], v.x, fma(-T[7], v.y, fma(-T[8], v.z, r.z))));
+}
+
+// CVector::normalize (cvector.hpp:185-192): no-op for the zero vector.  |m|^2 is within
+// 1e-4 of 1 on every regular step, where a 4-term series of (1+e)^(-1/2) is exact to
+// < 1e-17; anything else (first step from an un-normalised input, large stochastic kicks)
+// takes the full-precision path.
+__device__ __forceinline__ d3 normalize3(d3 v) {
+  const double l2 = fma(v.z, v.z, fma(v.y, v.y, v.x * v.x));
+  const double e = l2 - 1.0;
+  double s;
+  if (fabs(e) < 1e-4) {
+    s = fma(fma(fma(fma(0.2734375, e, -0.3125), e, 0.375), e, -0.5), e, 1.0);
+  } else {
+    if (l2 == 0.0) return v;
+    s = 1.0 / sqrt(l2);
+  }
+  return mk(v.x * s, v.y * s, v.z * s);
+}
+
+// ---------------------------------------------------------------------------------------
+// per-instance overrides
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double ovr_always(const DevLayer &Lr, const RunParams &R, int s, int field, long long i,
+                                             double dflt) {
+  if ((Lr.ovmask >> s) & 1u) {
+    const int k = Lr.ovidx[s][field];
+    if (k >= 0) return __ldg(R.ovr[k] + i);
+  }
+  return dflt;
+}
+template <uint32_t F>
+__device__ __forceinline__ double ovr_or(const DevLayer &Lr, const RunParams &R, int s, int field, long long i, double dflt) {
+  if constexpr ((F & F_OVR) != 0) return ovr_always(Lr, R, s, field, i, dflt);
+  return dflt;
+}
+
+// ---------------------------------------------------------------------------------------
+// drivers: the time-dependent part of ScalarDriver::getCurrentScalarValue
+// (drivers.hpp:262-305, helpers :73-108); constantValue is added by the caller.
+// ---------------------------------------------------------------------------------------
+template <uint32_t F>
+__device__ __noinline__ double driver_dynamic(const DevLayer &Lr, const RunParams &R, int s, double t, long long i) {
+  const DevDriver &d = Lr.drv[s];
+  const double A = ovr_or<F>(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, d.amplitude);
+  switch (d.type) {
+  case CMTJB_UPD_PULSE: {
+    const double period = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PERIOD, i, d.period);
+    const double cycle = ovr_or<F>(Lr, R, s, CMTJB_FIELD_CYCLE, i, d.cycle);
+    const int n = (int)(t / period);
+    const double nT = n * period;
+    return (nT <= t && t <= (nT + cycle * period)) ? A : 0.0;
+  }
+  case CMTJB_UPD_SINE:
+  case CMTJB_UPD_POSINE:
+  case CMTJB_UPD_HALFSINE: {
+    const double f = ovr_or<F>(Lr, R, s, CMTJB_FIELD_FREQUENCY, i, d.frequency);
+    const double ph = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PHASE, i, d.phase);
+    const double v = A * sin(2 * M_PI * t * f + ph);
+    if (d.type == CMTJB_UPD_SINE) return v;
+    if (d.type == CMTJB_UPD_POSINE) return fabs(v);
+    return v <= 0 ? v : 0.0;
+  }
+  case CMTJB_UPD_STEP: {
+    const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+    const double t1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTOP, i, d.timeStop);
+    return (t >= t0 && t <= t1) ? A : 0.0;
+  }
+  case CMTJB_UPD_TRAPEZOID: {
+    const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+    const double e = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
+    const double st = ovr_or<F>(Lr, R, s, CMTJB_FIELD_STEADYTIME, i, d.steadyTime);
+    if (t < t0) return 0.0;
+    if (t <= t0 + e) return (A / e) * (t - t0);
+    if (t <= t0 + e + st) return A;
+    if (t <= t0 + 2 * e + st) return A - (A / e) * (t - (t0 + e + st));
+    return 0.0;
+  }
+  case CMTJB_UPD_GAUSSIMPULSE: {
+    const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+    const double e = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
+    const double x = t - t0;
+    return A * exp(-(x * x) / (2 * (e * e)));
+  }
+  case CMTJB_UPD_GAUSSSTEP: {
+    const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+    const double e = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
+    return 0.5 * A * (1 + erf((t - t0) / (sqrt(2.0) * e)));
+  }
+  default:
+    return 0.0;
+  }
+}
+
+// value of a scalar slot at time t
+template <uint32_t F>
+__device__ __forceinline__ double slot_value(const DevLayer &Lr, const RunParams &R, int s, double t, long long i) {
+  double v = ovr_or<F>(Lr, R, s, CMTJB_FIELD_CONSTANT, i, Lr.cst[s]);
+  if constexpr ((F & F_DYN) != 0) {
+    if ((Lr.dynmask >> s) & 1u) v += driver_dynamic<F>(Lr, R, s, t, i);
+  }
+  return v;
+}
+template <uint32_t F>
+__device__ __forceinline__ d3 slot_vec(const DevLayer &Lr, const RunParams &R, int s0, double t, long long i) {
+  return mk(slot_value<F>(Lr, R, s0, t, i), slot_value<F>(Lr, R, s0 + 1, t, i), slot_value<F>(Lr, R, s0 + 2, t, i));
+}
+
+// Sum of the CONSTANT parts of the four plain field drivers (Hext + Hoe + Hdmi + Hreserved,
+// junction.hpp:607-620), including per-instance overrides; evaluated once per launch.
+__device__ __forceinline__ d3 constant_field(const DevLayer &Lr, const RunParams &R, long long i) {
+  double h[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double v = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) v += ovr_always(Lr, R, g * 3 + c, CMTJB_FIELD_CONSTANT, i, Lr.cst[g * 3 + c]);
+    h[c] = v;
+  }
+  return mk(h[0], h[1], h[2]);
+}
+
+// time-dependent parts of the same four drivers
+template <uint32_t F>
+__device__ __forceinline__ d3 dynamic_field(const DevLayer &Lr, const RunParams &R, double t, long long i, d3 H) {
+  if constexpr ((F & F_DYN) != 0) {
+    if (Lr.dynmask & 0xFFFu) {
+      double h[3] = {H.x, H.y, H.z};
+#pragma unroll
+      for (int g = 0; g < 4; g++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          if ((Lr.dynmask >> (g * 3 + c)) & 1u) h[c] += driver_dynamic<F>(Lr, R, g * 3 + c, t, i);
+      return mk(h[0], h[1], h[2]);
+    }
+  }
+  return H;
+}
+
+// ---------------------------------------------------------------------------------------
+// u(t, m) with dm/dt = Lr.llg * u : field assembly (calculateHeff, junction.hpp:579-622)
+// fused with solveLLG (junction.hpp:716-815).
+//   HAS_BOT / HAS_TOP: the layer has a neighbour on that side (else the reference passes 0).
+// ---------------------------------------------------------------------------------------
+template <uint32_t F, bool HAS_BOT, bool HAS_TOP>
+__device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, long long i, double t, d3 m, d3 bot, d3 top,
+                                    d3 Hc) {
+  d3 H = dynamic_field<F>(Lr, R, t, i, Hc);
+  const d3 a = ld3(Lr.anis);
+  const double am = dot(a, m);
+  {  // K1 (junction.hpp:638-643)
+    const double K = slot_value<F>(Lr, R, CMTJB_SLOT_K1, t, i);
+    H = axpy(a, (Lr.cK1 * K) * am, H);
+  }
+  if constexpr ((F & F_K2) != 0) {  // (junction.hpp:645-652)
+    const double K2 = slot_value<F>(Lr, R, CMTJB_SLOT_K2, t, i);
+    H = axpy(a, (Lr.cK2 * K2) * (am * am * am), H);
+  }
+  if constexpr ((F & F_IEC) != 0) {  // (junction.hpp:654-675)
+    if constexpr (HAS_BOT) {
+      const double J = slot_value<F>(Lr, R, CMTJB_SLOT_IEC_BOTTOM, t, i);
+      const double J2 = slot_value<F>(Lr, R, CMTJB_SLOT_IECQ_BOTTOM, t, i);
+      H = axpy(bot, fma(2 * J2, dot(bot, m), J) * Lr.inv_Mst, H);
+    }
+    if constexpr (HAS_TOP) {
+      const double J = slot_value<F>(Lr, R, CMTJB_SLOT_IEC_TOP, t, i);
+      const double J2 = slot_value<F>(Lr, R, CMTJB_SLOT_IECQ_TOP, t, i);
+      H = axpy(top, fma(2 * J2, dot(top, m), J) * Lr.inv_Mst, H);
+    }
+  }
+  if constexpr ((F & F_IDMI) != 0) {  // (junction.hpp:677-701)
+    if constexpr (HAS_BOT) {
+      const d3 D = slot_vec<F>(Lr, R, CMTJB_SLOT_IDMI_BOTTOM_X, t, i);
+      H = axpy(cross(D, bot), -Lr.inv_Mst, H);
+    }
+    if constexpr (HAS_TOP) {
+      const d3 D = slot_vec<F>(Lr, R, CMTJB_SLOT_IDMI_TOP_X, t, i);
+      H = axpy(cross(D, top), -Lr.inv_Mst, H);
+    }
+  }
+  // demag (junction.hpp:598-599); off-diagonal entries only in F_DEMAG_FULL variants
+  if constexpr ((F & F_DEMAG_FULL) != 0) {
+    H = sub_matvec(Lr.demag, m, H);
+  } else {
+    H = mk(fma(-Lr.demag[0], m.x, H.x), fma(-Lr.demag[4], m.y, H.y), fma(-Lr.demag[8], m.z, H.z));
+  }
+  if constexpr ((F & F_DIPOLE) != 0) {  // (junction.hpp:583-585)
+    if constexpr (HAS_BOT) H = sub_matvec(Lr.dipB, bot, H);
+    if constexpr (HAS_TOP) H = sub_matvec(Lr.dipT, top, H);
+  }
+
+  // --- solveLLG ------------------------------------------------------------------------
+  const d3 p = cross(m, H);
+  const d3 am3 = m * Lr.alpha;
+  d3 u = mk(fma(am3.y, p.z, fma(-am3.z, p.y, p.x)), fma(am3.z, p.x, fma(-am3.x, p.z, p.y)),
+            fma(am3.x, p.y, fma(-am3.y, p.x, p.z)));
+  if constexpr ((F & (F_STT | F_SOT)) != 0) {
+    d3 ref = mk(0, 0, 0);
+    if (Lr.refType == CMTJB_REF_FIXED) ref = ld3(Lr.ref);
+    else if (Lr.refType == CMTJB_REF_TOP) ref = top;
+    else if (Lr.refType == CMTJB_REF_BOTTOM) ref = bot;
+    if constexpr ((F & F_STT) != 0) {
+      if (Lr.stt) {
+        const double I = slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
+        const double mp = dot(m, ref);
+        double eta;
+        if (Lr.altSTT) eta = Lr.P / fma(Lr.lam, mp, 1.0);
+        else eta = (Lr.P * Lr.lam2) / fma(Lr.lam2 - 1.0, mp, Lr.lam2 + 1.0);
+        const double ae = Lr.aJ_c * I * eta;
+        const d3 fl = cross(m, ref);
+        const d3 dl = cross(m, fl);
+        u = axpy(dl, ae * Lr.kappa, u);
+        u = axpy(fl, -(ae * Lr.beta), u);
+        return u;
+      }
+    }
+    if constexpr ((F & F_SOT) != 0) {
+      if (Lr.sot) {
+        double Hdl, Hfl, Hdl2 = 0, Hfl2 = 0;
+        if (Lr.dynamicSOT) {
+          Hdl = slot_value<F>(Lr, R, CMTJB_SLOT_DL, t, i);
+          Hfl = slot_value<F>(Lr, R, CMTJB_SLOT_FL, t, i);
+          Hdl2 = slot_value<F>(Lr, R, CMTJB_SLOT_DL2, t, i);
+          Hfl2 = slot_value<F>(Lr, R, CMTJB_SLOT_FL2, t, i);
+        } else {
+          const double I = slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
+          Hdl = Lr.dlT * I;
+          Hfl = Lr.flT * I;
+        }
+        const d3 cm1 = cross(m, ref);
+        const d3 ccm1 = cross(m, cm1);
+        u = axpy(cm1, fma(-Lr.alpha, Hdl, Hfl), u);
+        u = axpy(ccm1, fma(Lr.alpha, Hfl, Hdl), u);
+        if (Lr.dynamicSOT) {
+          const d3 ref2 = ld3(Lr.ref2);
+          const d3 cm2 = cross(m, ref2);
+          const d3 ccm2 = cross(m, cm2);
+          u = axpy(cm2, fma(-Lr.alpha, Hdl2, Hfl2), u);
+          u = axpy(ccm2, fma(Lr.alpha, Hfl2, Hdl2), u);
+        }
+      }
+    }
+  }
+  return u;
+}
+
+// stochasticTorque (junction.hpp:824-831) in the same "u" units: g = Lr.llg * (m x dW + a m x (m x dW))
+__device__ __forceinline__ d3 stoch_u(const DevLayer &Lr, d3 m, d3 dW) {
+  const d3 c1 = cross(m, dW);
+  const d3 c2 = cross(m, c1);
+  return axpy(c2, Lr.alpha, c1);
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.  Normals are produced in FP32 (the
+// FP32/SFU pipes are otherwise idle) and widened to FP64; validated distributionally in
+// tests/test_stochastic_gpu.py.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__device__ __forceinline__ d3 normal3(unsigned long long seed, unsigned long long inst, unsigned int layer,
+                                      unsigned long long step) {
+  const uint4 ctr = make_uint4((uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)step,
+                               ((uint32_t)(step >> 32) << 8) | (layer & 0xFFu));
+  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = fmaf((float)r.x, k, 0.5f * k), u2 = fmaf((float)r.z, k, 0.5f * k);
+  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * ((float)r.y * k), &s0, &c0);
+  sincospif(2.0f * ((float)r.w * k), &s1, &c1);
+  (void)s1;
+  return mk((double)(r0 * c0), (double)(r0 * s0), (double)(r1 * c1));
+}
+
+// the step's noise vector dW (junction.hpp:1121-1136): Langevin + 1/f^alpha buffer
+template <uint32_t F, int NL>
+__device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, int l, long long i, long long it, double t) {
+  d3 dW = mk(0, 0, 0);
+  if constexpr ((F & F_THERMAL) != 0) {
+    if (Lr.thermal) {
+      const double T = slot_value<F>(Lr, R, CMTJB_SLOT_TEMPERATURE, t, i);
+      const double sigma = sqrt(Lr.sigma_c * T);
+      dW = normal3(R.seed, (unsigned long long)(R.inst_offset + i), (unsigned)l, (unsigned long long)it) * sigma;
+    }
+  }
+  if constexpr ((F & F_ONEF) != 0) {
+    if (Lr.onef && R.onef) {
+      const double *b = R.onef + ((long long)(l * 3) * R.total_iterations + it) * R.B + i;
+      const long long cs = R.total_iterations * R.B;
+      dW = dW + mk(__ldg(b), __ldg(b + cs), __ldg(b + 2 * cs));
+    }
+  }
+  return dW;
+}
+
+}  // namespace cmtjb

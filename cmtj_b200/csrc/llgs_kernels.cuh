@@ -1,0 +1,317 @@
+// llgs_kernels.cuh -- fused time-loop kernels: one launch integrates every step of every
+// instance of a batch (Junction::runSimulation, junction.hpp:1948-2056), one thread per
+// instance, magnetisation in registers, decimated log written with coalesced streaming
+// stores ([channel][sample][instance], instance fastest).
+#pragma once
+#include "llgs_device.cuh"
+
+namespace cmtjb {
+
+constexpr int kBlock = 128;
+
+template <int NL> struct State {
+  d3 m[NL];
+};
+
+// ---- log writer: logLayerParams (junction.hpp:1580-1636), MR :1835-1867 ---------------------
+template <int NL>
+__device__ __forceinline__ void write_sample(const DevModel<NL> &M, const RunParams &R, const State<NL> &S, long long sample,
+                                             long long i) {
+  double *p = R.log + sample * R.B + i;
+  const long long cs = R.n_samples * R.B;  // channel stride
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    __stcs(p + (3 * l + 0) * cs, S.m[l].x);
+    __stcs(p + (3 * l + 1) * cs, S.m[l].y);
+    __stcs(p + (3 * l + 2) * cs, S.m[l].z);
+  }
+  if (M.mr_mode == CMTJB_MR_CLASSIC) {
+    double c;
+    if constexpr (NL == 1) c = dot(S.m[0], ld3(M.L[0].ref));
+    else c = dot(S.m[0], S.m[1]);
+    __stcs(p + (3 * NL) * cs, fma(M.Rhalf, 1.0 - c, M.Rp));
+  } else if (M.mr_mode == CMTJB_MR_STRIP) {
+    double rx = 0.0, ry = 0.0;
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const DevLayer &Lr = M.L[l];
+      const d3 m = S.m[l];
+      const double Rx = fma(Lr.SMR_X, m.y * m.y, fma(Lr.AMR_X, m.x * m.x, Lr.Rx0));
+      const double Ry = fma(Lr.AMRSMR_Y * m.x, m.y, fma(Lr.AHE_half, m.z, Lr.Ry0));
+      rx += 1.0 / Rx;
+      ry += 1.0 / Ry;
+    }
+    __stcs(p + (3 * NL + 0) * cs, 1.0 / rx);
+    __stcs(p + (3 * NL + 1) * cs, 1.0 / ry);
+    __stcs(p + (3 * NL + 2) * cs, 0.0);
+  }
+}
+
+// ---- steppers -------------------------------------------------------------------------------------
+// Each stepper is written per layer with compile-time layer index so that every DevLayer
+// access is a constant-bank operand.
+
+template <int NL, uint32_t F, int l>
+__device__ __forceinline__ d3 layer_u(const DevModel<NL> &M, const RunParams &R, long long i, double t, d3 m,
+                                      const State<NL> &nb, const d3 *Hc) {
+  const d3 zero = mk(0, 0, 0);
+  const d3 bot = (l > 0) ? nb.m[l > 0 ? l - 1 : 0] : zero;
+  const d3 top = (l < NL - 1) ? nb.m[l < NL - 1 ? l + 1 : 0] : zero;
+  return llg_u<F, (l > 0), (l < NL - 1)>(M.L[l], R, i, t, m, bot, top, Hc[l]);
+}
+
+// RK4: Layer::rk4_step (junction.hpp:1017-1041) under runMultiLayerSolver (:1682-1696):
+// neighbours frozen at their pre-step values for all four stages (Jacobi).
+template <int NL, uint32_t F, int l>
+__device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &R, long long i, double t, const State<NL> &S0,
+                                        const d3 *Hc) {
+  const DevLayer &Lr = M.L[l];
+  const double h = Lr.llg * R.dt;  // dm = h * u
+  const d3 m0 = S0.m[l];
+  const d3 u1 = layer_u<NL, F, l>(M, R, i, t, m0, S0, Hc);
+  const d3 u2 = layer_u<NL, F, l>(M, R, i, t + 0.5 * R.dt, axpy(u1, 0.5 * h, m0), S0, Hc);
+  const d3 u3 = layer_u<NL, F, l>(M, R, i, t + 0.5 * R.dt, axpy(u2, 0.5 * h, m0), S0, Hc);
+  const d3 u4 = layer_u<NL, F, l>(M, R, i, t + R.dt, axpy(u3, h, m0), S0, Hc);
+  const d3 acc = mk(fma(2.0, u2.x + u3.x, u1.x + u4.x), fma(2.0, u2.y + u3.y, u1.y + u4.y), fma(2.0, u2.z + u3.z, u1.z + u4.z));
+  return normalize3(axpy(acc, h * (1.0 / 6.0), m0));
+}
+
+template <int NL, uint32_t F, int l = 0>
+__device__ __forceinline__ void rk4_all(const DevModel<NL> &M, const RunParams &R, long long i, double t, const State<NL> &S0,
+                                        State<NL> &S1, const d3 *Hc) {
+  S1.m[l] = rk4_layer<NL, F, l>(M, R, i, t, S0, Hc);
+  if constexpr (l + 1 < NL) rk4_all<NL, F, l + 1>(M, R, i, t, S0, S1, Hc);
+}
+
+// Euler-Heun: Junction::eulerHeunSolverStep (junction.hpp:1709-1754)
+template <int NL, uint32_t F, int l = 0>
+__device__ __forceinline__ void euler_heun_all(const DevModel<NL> &M, const RunParams &R, long long i, long long it, double t,
+                                               const State<NL> &S0, State<NL> &S1, const d3 *Hc) {
+  const DevLayer &Lr = M.L[l];
+  const d3 m0 = S0.m[l];
+  const d3 f = layer_u<NL, F, l>(M, R, i, t, m0, S0, Hc);
+  d3 mn = axpy(f, Lr.llg * R.dt, m0);
+  if constexpr ((F & (F_THERMAL | F_ONEF)) != 0) {
+    const d3 dW = noise_dW<F, NL>(Lr, R, l, i, it, t);
+    const double gs = Lr.llg * R.sqrt_dt;
+    const d3 g = stoch_u(Lr, m0, dW);
+    const d3 gp = stoch_u(Lr, axpy(g, gs, m0), dW);
+    mn = axpy(g + gp, 0.5 * gs, mn);
+  }
+  S1.m[l] = normalize3(mn);
+  if constexpr (l + 1 < NL) euler_heun_all<NL, F, l + 1>(M, R, i, it, t, S0, S1, Hc);
+}
+
+// Heun: Junction::heunSolverStep (junction.hpp:1756-1815); predictor for every layer first,
+// corrector with the PREDICTED neighbours.
+template <int NL, uint32_t F, int l = 0>
+__device__ __forceinline__ void heun_predict(const DevModel<NL> &M, const RunParams &R, long long i, long long it, double t,
+                                             const State<NL> &S0, State<NL> &P, State<NL> &Fn, State<NL> &Gn, State<NL> &dWs,
+                                             const d3 *Hc) {
+  const DevLayer &Lr = M.L[l];
+  const d3 m0 = S0.m[l];
+  const d3 f = layer_u<NL, F, l>(M, R, i, t, m0, S0, Hc);
+  Fn.m[l] = f;
+  d3 mp = axpy(f, Lr.llg * R.dt, m0);
+  if constexpr ((F & (F_THERMAL | F_ONEF)) != 0) {
+    const d3 dW = noise_dW<F, NL>(Lr, R, l, i, it, t);
+    const d3 g = stoch_u(Lr, m0, dW);
+    dWs.m[l] = dW;
+    Gn.m[l] = g;
+    mp = axpy(g, Lr.llg * R.sqrt_dt, mp);
+  }
+  P.m[l] = mp;
+  if constexpr (l + 1 < NL) heun_predict<NL, F, l + 1>(M, R, i, it, t, S0, P, Fn, Gn, dWs, Hc);
+}
+template <int NL, uint32_t F, int l = 0>
+__device__ __forceinline__ void heun_correct(const DevModel<NL> &M, const RunParams &R, long long i, double t,
+                                             const State<NL> &S0, const State<NL> &P, const State<NL> &Fn, const State<NL> &Gn,
+                                             const State<NL> &dWs, State<NL> &S1, const d3 *Hc) {
+  const DevLayer &Lr = M.L[l];
+  const d3 f2 = layer_u<NL, F, l>(M, R, i, t + R.dt, P.m[l], P, Hc);
+  d3 mn = axpy(Fn.m[l] + f2, 0.5 * (Lr.llg * R.dt), S0.m[l]);
+  if constexpr ((F & (F_THERMAL | F_ONEF)) != 0) {
+    const d3 g2 = stoch_u(Lr, P.m[l], dWs.m[l]);
+    mn = axpy(Gn.m[l] + g2, 0.5 * (Lr.llg * R.sqrt_dt), mn);
+  }
+  S1.m[l] = normalize3(mn);
+  if constexpr (l + 1 < NL) heun_correct<NL, F, l + 1>(M, R, i, t, S0, P, Fn, Gn, dWs, S1, Hc);
+}
+
+template <int NL, int SOLVER, uint32_t F>
+__device__ __forceinline__ void do_step(const DevModel<NL> &M, const RunParams &R, long long i, long long it, double t,
+                                        State<NL> &S, const d3 *Hc) {
+  State<NL> S1;
+  if constexpr (SOLVER == CMTJB_RK4) {
+    rk4_all<NL, F>(M, R, i, t, S, S1, Hc);
+  } else if constexpr (SOLVER == CMTJB_EULER_HEUN) {
+    euler_heun_all<NL, F>(M, R, i, it, t, S, S1, Hc);
+  } else {
+    State<NL> P, Fn, Gn, dWs;
+    heun_predict<NL, F>(M, R, i, it, t, S, P, Fn, Gn, dWs, Hc);
+    heun_correct<NL, F>(M, R, i, t, S, P, Fn, Gn, dWs, S1, Hc);
+  }
+  S = S1;
+}
+
+// ---- fixed-step kernel (RK4 / Heun / Euler-Heun) ------------------------------------------------
+template <int NL, int SOLVER, uint32_t F>
+__global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constant__ DevModel<NL> M,
+                                                            const __grid_constant__ RunParams R) {
+  const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= R.B) return;
+  State<NL> S;
+  d3 Hc[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    S.m[l] = mk(R.m_state[(3 * l + 0) * R.B + i], R.m_state[(3 * l + 1) * R.B + i], R.m_state[(3 * l + 2) * R.B + i]);
+    Hc[l] = constant_field(M.L[l], R, i);
+  }
+  // sample k is written after step k*write_every (junction.hpp:1973-1980)
+  long long until_write = (R.write_every - (R.it_begin % R.write_every)) % R.write_every;
+  long long sample = R.first_sample;
+  const bool logging = R.log != nullptr;
+  for (long long it = R.it_begin; it < R.it_end; ++it) {
+    const double t = (double)it * R.dt;
+    do_step<NL, SOLVER, F>(M, R, i, it, t, S, Hc);
+    if (until_write == 0) {
+      if (logging) write_sample<NL>(M, R, S, sample, i);
+      sample++;
+      until_write = R.write_every;
+    }
+    until_write--;
+  }
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    R.m_state[(3 * l + 0) * R.B + i] = S.m[l].x;
+    R.m_state[(3 * l + 1) * R.B + i] = S.m[l].y;
+    R.m_state[(3 * l + 2) * R.B + i] = S.m[l].z;
+  }
+  // RK4 throws "NAN magnetisation" on isnan(mag.x) (junction.hpp:1037-1039); NaN is absorbing,
+  // so testing the final state is equivalent.
+  if (R.status) {
+    int st = 0;
+    if constexpr (SOLVER == CMTJB_RK4) {
+#pragma unroll
+      for (int l = 0; l < NL; l++) st |= isnan(S.m[l].x) ? 1 : 0;
+    }
+    if (R.it_begin == 0 || st) R.status[i] = st;
+  }
+}
+
+// ---- Dormand-Prince (single layer): Layer::dormand_prince_step (junction.hpp:866-1002) and the
+// adaptive loop of runSimulation (:1983-2044), including its quirks: time advances by the NEW
+// step size after an accepted step, and consecutive_rejections is reset every iteration.
+template <uint32_t F>
+__global__ void __launch_bounds__(kBlock) llgs_dopri_kernel(const __grid_constant__ DevModel<1> M,
+                                                            const __grid_constant__ RunParams R) {
+  const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= R.B) return;
+  const DevLayer &Lr = M.L[0];
+  State<1> S;
+  S.m[0] = mk(R.m_state[i], R.m_state[R.B + i], R.m_state[2 * R.B + i]);
+  d3 Hc[1];
+  Hc[0] = constant_field(Lr, R, i);
+  double t = 0.0, next_write = 0.0, h = R.dt;
+  double integral_error = Lr.integral_error, prev_error_ratio = Lr.prev_error_ratio;
+  long long sample = 0;
+  int st = 0;
+  const bool logging = R.log != nullptr;
+  auto f = [&](double tt, d3 mm) { return layer_u<1, F, 0>(M, R, i, tt, mm, S, Hc) * Lr.llg; };
+  while (t < R.total_time) {
+    if (t + h > R.total_time) h = R.total_time - t;
+    if (isnan(h) || isinf(h) || h <= 0) h = R.dt;
+    const d3 m = S.m[0];
+    const d3 k1 = f(t, m) * h;
+    const d3 k2 = f(t + (1.0 / 5.0) * h, axpy(k1, 1.0 / 5.0, m)) * h;
+    const d3 k3 = f(t + (3.0 / 10.0) * h, axpy(k2, 9.0 / 40.0, axpy(k1, 3.0 / 40.0, m))) * h;
+    const d3 k4 = f(t + (4.0 / 5.0) * h, axpy(k3, 32.0 / 9.0, axpy(k2, -56.0 / 15.0, axpy(k1, 44.0 / 45.0, m)))) * h;
+    const d3 k5 = f(t + (8.0 / 9.0) * h, axpy(k4, -212.0 / 729.0,
+                                              axpy(k3, 64448.0 / 6561.0, axpy(k2, -25360.0 / 2187.0, axpy(k1, 19372.0 / 6561.0, m))))) *
+                  h;
+    const d3 k6 = f(t + h, axpy(k5, -5103.0 / 18656.0,
+                                axpy(k4, 49.0 / 176.0,
+                                     axpy(k3, 46732.0 / 5247.0, axpy(k2, -355.0 / 33.0, axpy(k1, 9017.0 / 3168.0, m)))))) *
+                  h;
+    const d3 m5 = axpy(k6, 11.0 / 84.0,
+                       axpy(k5, -2187.0 / 6784.0, axpy(k4, 125.0 / 192.0, axpy(k3, 500.0 / 1113.0, axpy(k1, 35.0 / 384.0, m)))));
+    const d3 k7 = f(t + h, m5) * h;
+    const d3 m4 = axpy(k7, 1.0 / 40.0,
+                       axpy(k6, 187.0 / 2100.0,
+                            axpy(k5, -92097.0 / 339200.0,
+                                 axpy(k4, 393.0 / 640.0, axpy(k3, 7571.0 / 16695.0, axpy(k1, 5179.0 / 57600.0, m))))));
+    const d3 e = m5 - m4;
+    const double err = sqrt(dot(e, e));
+    const double tol = fma(Lr.rel_tol, sqrt(dot(m, m)), Lr.abs_tol);
+    double ratio = err / tol;
+    if (tol < 1e-15 || isnan(ratio) || isinf(ratio)) ratio = 10.0;
+    double factor;
+    if (Lr.pid) {
+      const double e_n = log(ratio);
+      integral_error += e_n;
+      factor = exp(Lr.kp * e_n + Lr.ki * integral_error + Lr.kd * (e_n - prev_error_ratio));
+      prev_error_ratio = e_n;
+    } else {
+      factor = Lr.safety_factor * pow(1.0 / ratio, 0.2);
+    }
+    if (isnan(factor) || isinf(factor)) factor = Lr.min_factor;
+    factor = fmin(factor, Lr.max_factor);
+    factor = fmax(factor, Lr.min_factor);
+    double nh = h * factor;
+    if (isnan(nh) || isinf(nh) || nh <= 0) nh = h * Lr.min_factor;
+    bool accepted = ratio <= 1.0;
+    if (accepted) {
+      const double l2 = dot(m5, m5);
+      S.m[0] = (l2 != 0.0) ? m5 * (1.0 / sqrt(l2)) : m5;
+      if (isnan(S.m[0].x)) {
+        st = 1;
+        break;
+      }
+    }
+    h = nh;
+    if (!accepted && h < 1e-15) accepted = true;  // forced acceptance (:2020-2027)
+    if (accepted) {
+      t += h;
+      if (t >= next_write) {
+        if (logging && sample < R.n_samples) {
+          write_sample<1>(M, R, S, sample, i);
+          if (R.time_log) R.time_log[sample * R.B + i] = t;
+        }
+        sample++;
+        next_write = ((double)((unsigned int)(t / R.write_frequency) + 1u)) * R.write_frequency;
+      }
+    }
+  }
+  R.m_state[i] = S.m[0].x;
+  R.m_state[R.B + i] = S.m[0].y;
+  R.m_state[2 * R.B + i] = S.m[0].z;
+  if (R.n_samples_out) R.n_samples_out[i] = (int)(sample < R.n_samples ? sample : R.n_samples);
+  if (R.status) R.status[i] = st;
+}
+
+// ---- host-side launch shims ---------------------------------------------------------------------
+typedef cudaError_t (*LaunchFn)(const void *model, const RunParams *R, cudaStream_t stream);
+
+template <int NL, int SOLVER, uint32_t F>
+cudaError_t launch_fixed(const void *model, const RunParams *R, cudaStream_t stream) {
+  const DevModel<NL> *M = static_cast<const DevModel<NL> *>(model);
+  const long long blocks = (R->B + kBlock - 1) / kBlock;
+  llgs_fixed_kernel<NL, SOLVER, F><<<(unsigned)blocks, kBlock, 0, stream>>>(*M, *R);
+  return cudaGetLastError();
+}
+template <uint32_t F> cudaError_t launch_dopri(const void *model, const RunParams *R, cudaStream_t stream) {
+  const DevModel<1> *M = static_cast<const DevModel<1> *>(model);
+  const long long blocks = (R->B + kBlock - 1) / kBlock;
+  llgs_dopri_kernel<F><<<(unsigned)blocks, kBlock, 0, stream>>>(*M, *R);
+  return cudaGetLastError();
+}
+
+struct Variant {
+  int nl;
+  int solver;
+  uint32_t features;
+  LaunchFn launch;
+  const char *name;
+};
+
+}  // namespace cmtjb

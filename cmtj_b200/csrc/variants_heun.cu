@@ -1,0 +1,19 @@
+// Heun variants (Junction::heunSolverStep, junction.hpp:1756-1815).
+#include "variants.h"
+namespace cmtjb {
+static const Variant kTable[] = {
+    CMTJB_FIXED(1, CMTJB_HEUN, 0),
+    CMTJB_FIXED(1, CMTJB_HEUN, F_STT | F_THERMAL),
+    CMTJB_FIXED(1, CMTJB_HEUN, F_ALL),
+    CMTJB_FIXED(2, CMTJB_HEUN, F_IEC),
+    CMTJB_FIXED(2, CMTJB_HEUN, F_ALL),
+    CMTJB_FIXED(3, CMTJB_HEUN, F_IEC),
+    CMTJB_FIXED(3, CMTJB_HEUN, F_IEC | F_SOT | F_K2 | F_OVR | F_DYN),
+    CMTJB_FIXED(3, CMTJB_HEUN, F_ALL),
+    CMTJB_FIXED(4, CMTJB_HEUN, F_ALL),
+};
+int variants_heun(const Variant **out) {
+  *out = kTable;
+  return (int)(sizeof(kTable) / sizeof(kTable[0]));
+}
+}  // namespace cmtjb

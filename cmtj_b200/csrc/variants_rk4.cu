@@ -1,0 +1,22 @@
+// RK4 variants (Layer::rk4_step, junction.hpp:1017-1041).
+#include "variants.h"
+namespace cmtjb {
+static const Variant kTable[] = {
+    // lean: K1 + diagonal demag + constant fields
+    CMTJB_FIXED(1, CMTJB_RK4, 0),
+    CMTJB_FIXED(1, CMTJB_RK4, F_DYN),
+    CMTJB_FIXED(1, CMTJB_RK4, F_STT),
+    CMTJB_FIXED(1, CMTJB_RK4, F_ALL),
+    CMTJB_FIXED(2, CMTJB_RK4, F_IEC),
+    CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN),
+    CMTJB_FIXED(2, CMTJB_RK4, F_ALL),
+    CMTJB_FIXED(3, CMTJB_RK4, F_IEC),
+    CMTJB_FIXED(3, CMTJB_RK4, F_IEC | F_DYN),
+    CMTJB_FIXED(3, CMTJB_RK4, F_ALL),
+    CMTJB_FIXED(4, CMTJB_RK4, F_ALL),
+};
+int variants_rk4(const Variant **out) {
+  *out = kTable;
+  return (int)(sizeof(kTable) / sizeof(kTable[0]));
+}
+}  // namespace cmtjb

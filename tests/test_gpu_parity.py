@@ -1,0 +1,254 @@
+"""Parity tests proper: the CUDA path (through the C-ABI, libcmtj_b200.so) against the CPU
+oracle (oracle/liboracle.so, bit-exact to the reference) on identical inputs.
+
+Bar (BASELINE.json north_star): deterministic trajectories agree within 1e-9 relative on m
+and R in FP64.  Relative = max|a-b| / max|b| per log channel.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cmtj_b200
+import helpers
+from cmtj_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+MODES = ["RK4", "Heun", "EulerHeun"]
+
+
+def _both(build, T, dt, wf, mode, tweak=None, **kw):
+    """Run the same facade model once on CUDA and once on the oracle."""
+    out = []
+    for backend in (None, helpers.oracle_backend()):
+        _abi._active = backend
+        try:
+            j = build(cmtj_b200, **kw)
+            if tweak:
+                tweak(cmtj_b200, j)
+            j.runSimulation(T, dt, wf, solverMode=getattr(cmtj_b200.SolverMode, mode))
+            out.append((helpers.log_arrays(j.getLog()), j))
+        finally:
+            _abi._active = None
+    return out
+
+
+def _check(got, want, tol=TOL):
+    assert set(got) == set(want)
+    worst = 0.0
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        if k == "time":
+            assert np.array_equal(got[k], want[k])
+            continue
+        e = helpers.max_rel_err(got[k], want[k])
+        worst = max(worst, e)
+        assert e <= tol, (k, e)
+    return worst
+
+
+def test_library_loads_and_sees_gpu():
+    lib = _abi.load_library()
+    assert lib.cmtjb_device_count() >= 1
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("build", ["single_layer_mtj", "two_layer_mtj", "tri_layer_mtj", "stt_layer_mtj"])
+def test_fixtures(build, mode):
+    (g, jg), (w, jw) = _both(getattr(helpers, build), 2e-9, 1e-13, 1e-12, mode)
+    _check(g, w)
+    for lid in jw.getLayerIds():
+        assert np.allclose(jg.getLayerMagnetisation(lid).tolist(), jw.getLayerMagnetisation(lid).tolist(), rtol=0, atol=1e-9)
+
+
+def test_two_layer_rk4_full_length_pimm_like():
+    """20 ns at dt=1e-13 (2e5 steps), the headline S1 shape for one instance."""
+
+    def tweak(m, j):
+        j.setLayerExternalFieldDriver("all", m.AxialDriver(120e3, 30e3, 10e3))
+        oe = m.ScalarDriver.getStepDriver(0, 50, 0, 3e-13)
+        j.setLayerOerstedFieldDriver("all", m.AxialDriver(m.NullDriver(), m.NullDriver(), oe))
+
+    (g, _), (w, _) = _both(helpers.two_layer_mtj, 20e-9, 1e-13, 1e-11, "RK4", tweak)
+    assert len(w["time"]) == 2021
+    _check(g, w)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("dynamic", [True, False])
+def test_sot_strip(dynamic, mode):
+    (g, jg), (w, jw) = _both(helpers.sot_layer, 2e-9, 1e-13, 1e-12, mode, dynamic=dynamic)
+    _check(g, w)
+
+
+@pytest.mark.parametrize("kind", range(9))
+def test_every_driver_type_in_dynamics(kind):
+    import test_oracle_vs_ref as t
+
+    def tweak(m, j):
+        d = t._all_driver_kinds(m)[kind]
+        j.setLayerOerstedFieldDriver("all", m.AxialDriver(m.NullDriver(), m.NullDriver(), d * 1e3))
+        j.setLayerAnisotropyDriver("free", d * 300.0)
+        j.setIECDriver("free", "bottom", d * -1e-4)
+
+    (g, _), (w, _) = _both(helpers.two_layer_mtj, 0.7e-9, 1e-13, 1e-13, "RK4", tweak)
+    _check(g, w)
+
+
+def test_driver_values_on_device():
+    import test_oracle_vs_ref as t
+
+    lib = _abi.load_library()
+    f = lib.cmtjb_eval_driver_host
+    f.restype = C.c_int
+    fo = helpers.oracle_backend().lib.oracle_eval_driver
+    times = np.linspace(0, 6e-10, 2049)
+    for d in t._all_driver_kinds(cmtj_b200):
+        rec = _abi.Driver()
+        d._pack(rec)
+        got = np.zeros_like(times)
+        want = np.zeros_like(times)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert f(C.byref(rec), vp(times), C.c_int64(len(times)), vp(got), 0) == 0
+        fo(C.byref(rec), vp(times), C.c_int64(len(times)), vp(want))
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.max(np.abs(want))), d
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_idmi_dipole_hdmi_k2_terms(mode):
+    def tweak(m, j):
+        j.setIDMIDriver("free", "bottom", m.AxialDriver(1e-4, -2e-4, 3e-4))
+        j.setLayerHdmiDriver("free", m.AxialDriver(1e3, 2e3, -3e3))
+        j.setLayerSecondOrderAnisotropyDriver("bottom", m.ScalarDriver.getConstantDriver(7e3))
+        tt = [m.CVector(1e-3, 2e-4, 0), m.CVector(2e-4, -3e-3, 1e-4), m.CVector(0, 1e-4, 2e-3)]
+        j.getLayer("free").setBottomDipoleTensor(tt)
+        j.getLayer("bottom").setTopDipoleTensor(tt)
+
+    (g, _), (w, _) = _both(helpers.two_layer_mtj, 1e-9, 1e-13, 1e-12, mode, tweak)
+    _check(g, w)
+
+
+def test_full_demag_tensor_and_reference_types():
+    def build(m):
+        d = [m.CVector(0.1, 0.01, 0.02), m.CVector(0.01, 0.2, -0.03), m.CVector(0.02, -0.03, 0.7)]
+        a = m.Layer.createSTTLayer("free", m.CVector(0.1, 0.2, 1), m.CVector(0, 0, 1), 1.2, 1.5e-9, 1e-14, d, 0.02, 1.3, 0.1, 0.7)
+        b = m.Layer.createSTTLayer("bottom", m.CVector(1, 0.1, 0.1), m.CVector(1, 0, 0), 1.5, 3e-9, 1e-14, d, 0.02, 1.3, 0.0, 0.7)
+        a.setReferenceLayer(m.Reference.bottom)
+        b.setReferenceLayer(m.Reference.top)
+        j = m.Junction([a, b], 100, 200)
+        j.setLayerAnisotropyDriver("free", m.ScalarDriver.getConstantDriver(4e5))
+        j.setLayerAnisotropyDriver("bottom", m.ScalarDriver.getConstantDriver(1e5))
+        j.setLayerCurrentDriver("all", m.ScalarDriver.getSineDriver(2e10, 1e10, 4e9, 0))
+        j.setLayerAlternativeSTT("bottom", True)
+        j.setIECDriver("free", "bottom", m.ScalarDriver.getConstantDriver(2e-5))
+        return j
+
+    for mode in MODES:
+        (g, _), (w, _) = _both(build, 1e-9, 1e-13, 1e-12, mode)
+        _check(g, w)
+
+
+def test_dormand_prince():
+    (g, _), (w, _) = _both(helpers.single_layer_mtj, 3e-9, 1e-12, 1e-11, "DormandPrince")
+    # adaptive: the accepted-step sequence must be identical, values within 1e-9
+    assert np.allclose(g["time"], w["time"], rtol=1e-9, atol=0)
+    for k in w:
+        if k != "time":
+            assert helpers.max_rel_err(g[k], w[k]) <= 1e-8, k
+
+
+def test_carried_state_and_default_write_frequency():
+    res = []
+    for backend in (None, helpers.oracle_backend()):
+        _abi._active = backend
+        try:
+            j = helpers.two_layer_mtj(cmtj_b200, mag=(0.3, -0.2, 1.0))
+            for H in (0.0, 50e3, 100e3):
+                j.setLayerExternalFieldDriver("all", cmtj_b200.AxialDriver(H, 10e3, 0.0))
+                j.runSimulation(0.5e-9)
+            res.append(helpers.log_arrays(j.getLog()))
+        finally:
+            _abi._active = None
+    assert len(res[0]["time"]) == 3 * 51
+    _check(res[0], res[1])
+
+
+def test_batch_matches_oracle_per_instance():
+    rng = np.random.default_rng(1)
+    B = 300  # not a multiple of the block size
+    H = np.stack([np.linspace(-500e3, 500e3, B), rng.normal(0, 1e4, B), rng.normal(0, 1e4, B)], axis=1)
+    m_free = rng.normal(0, 1e-3, (B, 3)) + np.array([0, 0, 1.0])
+    m_bot = rng.normal(0, 1e-3, (B, 3)) + np.array([0, 0, 1.0])
+    logs = []
+    for backend in (None, helpers.oracle_backend()):
+        _abi._active = backend
+        try:
+            j = helpers.two_layer_mtj(cmtj_b200)
+            oe = cmtj_b200.ScalarDriver.getStepDriver(0, 50, 0, 3e-13)
+            j.setLayerOerstedFieldDriver("all", cmtj_b200.AxialDriver(cmtj_b200.NullDriver(), cmtj_b200.NullDriver(), oe))
+            b = cmtj_b200.JunctionBatch(j, B)
+            b.set_external_field("all", H)
+            b.set_magnetisation("free", m_free)
+            b.set_magnetisation("bottom", m_bot)
+            logs.append((b.run(1e-9, 1e-13, 1e-12), b.get_magnetisation("free")))
+        finally:
+            _abi._active = None
+    (g, mg), (w, mw) = logs
+    for k in w:
+        if k == "time":
+            continue
+        # per-instance relative error
+        scale = np.maximum(np.max(np.abs(w[k]), axis=0), 1e-300)
+        err = np.max(np.abs(g[k] - w[k]), axis=0) / scale
+        assert err.max() <= TOL, (k, err.max(), int(err.argmax()))
+    assert np.abs(mg - mw).max() <= 1e-9
+
+
+def test_batch_overrides_scalar_slots_and_device_path():
+    """F_OVR path: per-instance K1 constant, current amplitude, sine frequency; plus the
+    torch device-resident entry (cmtjb_run_device)."""
+    import torch
+
+    rng = np.random.default_rng(2)
+    B = 130
+    K = rng.uniform(300e3, 400e3, B)
+    I = rng.uniform(-2e10, 2e10, B)
+    fr = rng.uniform(1e9, 9e9, B)
+    outs = []
+    for which in ("cuda-host", "cuda-device", "oracle"):
+        _abi._active = helpers.oracle_backend() if which == "oracle" else None
+        try:
+            j = helpers.stt_layer_mtj(cmtj_b200)
+            j.setLayerCurrentDriver("free", cmtj_b200.ScalarDriver.getSineDriver(-1e10, 1e10, 3e9, 0.0))
+            b = cmtj_b200.JunctionBatch(j, B)
+            b.set_override("free", "K1", "constantValue", K)
+            b.set_override("free", "current", "amplitude", I)
+            b.set_override("free", "current", "frequency", fr)
+            if which == "cuda-device":
+                r = b.run_device(1e-9, 1e-13, 1e-12, solverMode=cmtj_b200.SolverMode.Heun)
+                torch.cuda.synchronize()
+                outs.append({k: v.cpu().numpy() for k, v in r.items() if k != "_log"})
+            else:
+                outs.append(dict(b.run(1e-9, 1e-13, 1e-12, solverMode=cmtj_b200.SolverMode.Heun)))
+        finally:
+            _abi._active = None
+    host, dev, want = outs
+    for k in want:
+        assert np.array_equal(host[k], dev[k]), k  # same kernel, same inputs
+        if k != "time":
+            assert helpers.max_rel_err(host[k], want[k]) <= TOL, k
+
+
+def test_nan_is_reported_as_runtime_error():
+    j = helpers.single_layer_mtj(cmtj_b200)
+    j.setLayerExternalFieldDriver("all", cmtj_b200.AxialDriver(float("nan"), 0.0, 0.0))
+    with pytest.raises(RuntimeError, match="NAN magnetisation"):
+        j.runSimulation(1e-10, 1e-13, 1e-13)
+
+
+def test_fp64_peak_probe_runs():
+    lib = _abi.load_library()
+    flops, ms = C.c_double(), C.c_double()
+    assert lib.cmtjb_fp64_peak(0, C.c_int64(20000), C.byref(flops), C.byref(ms)) == 0
+    assert flops.value > 5e12  # a B200 sustains tens of TFLOP/s FP64
