@@ -6,8 +6,12 @@
 // Python, no C++ types across the boundary.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <mutex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,6 +29,7 @@ int variants_dopri(const Variant **out);
 namespace {
 
 thread_local std::string g_err;
+std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
 
 int fail(int code, const std::string &msg) {
   g_err = msg;
@@ -96,6 +101,18 @@ bool any_nonzero(const double *p, int n) {
   return false;
 }
 
+// K1 anisotropy + demag fold into one DIAGONAL operator when K1 is constant and uniform, the
+// easy axis is axis-aligned and the demag tensor is diagonal (DevLayer::lin).
+bool layer_foldable(const cmtjb_layer_t &L, int l, const cmtjb_override_t *ovr, int n_ovr) {
+  if (slot_dynamic(L.drivers[CMTJB_SLOT_K1])) return false;
+  for (int k = 0; k < n_ovr; k++)
+    if ((ovr[k].layer < 0 || ovr[k].layer == l) && ovr[k].slot == CMTJB_SLOT_K1) return false;
+  const int nz = (L.anis[0] != 0) + (L.anis[1] != 0) + (L.anis[2] != 0);
+  if (nz > 1) return false;
+  const double *T = L.demagTensor;
+  return T[1] == 0 && T[2] == 0 && T[3] == 0 && T[5] == 0 && T[6] == 0 && T[7] == 0;
+}
+
 // which terms does this model need compiled in?
 uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
                          const cmtjb_run_args_t *a, int solver) {
@@ -126,10 +143,21 @@ uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
       if (L.noiseScale != 0 && a->onef_buffer) F |= F_ONEF;
     }
     for (int s = 0; s < CMTJB_NSLOTS; s++)
-      if (slot_dynamic(L.drivers[s])) F |= F_DYN;
+      if (slot_dynamic(L.drivers[s])) F |= (s < CMTJB_SLOT_K1) ? F_DYN : F_DYNS;
+    if (!layer_foldable(L, l, ovr, n_ovr)) F |= F_NOFOLD;
   }
-  for (int k = 0; k < n_ovr; k++)
+  for (int k = 0; k < n_ovr; k++) {
     if (!(ovr[k].field == CMTJB_FIELD_CONSTANT && ovr[k].slot < CMTJB_SLOT_K1)) F |= F_OVR;
+    if (ovr[k].field == CMTJB_FIELD_CONSTANT) continue;
+    // a per-instance waveform parameter makes the driver non-uniform across the batch: the shared
+    // stage table cannot hold it.  Scalar slots keep the table for per-instance AMPLITUDE only.
+    const bool field_slot = ovr[k].slot < CMTJB_SLOT_K1;
+    if (!field_slot && ovr[k].field == CMTJB_FIELD_AMPLITUDE) continue;
+    for (int l = 0; l < n; l++)
+      if ((ovr[k].layer < 0 || ovr[k].layer == l) && slot_dynamic(layers[l].drivers[ovr[k].slot])) F |= F_DYNI;
+  }
+  if ((F & (F_DYN | F_DYNS)) && solver == CMTJB_DORMAND_PRINCE) F |= F_DYNI;  // adaptive time: no stage table
+  if (F & F_DYNI) F &= ~(F_DYN | F_DYNS);
   return F;
 }
 
@@ -156,8 +184,9 @@ const Variant *pick_variant(int nl, int solver, uint32_t need) {
   return best;
 }
 
-template <int NL> struct ModelBox {
-  DevModel<NL> M;
+// sub-range of a run executed by one launch (time-chunked pipelining in cmtjb_run_host)
+struct Span {
+  long long it_begin, it_end, first_sample;
 };
 
 void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D) {
@@ -178,6 +207,7 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
     o.edgeTime = d.edgeTime;
     o.steadyTime = d.steadyTime;
     if (slot_dynamic(d)) D.dynmask |= (1u << s);
+    D.dyncol[s] = -1;
     for (int f = 0; f < 10; f++) D.ovidx[s][f] = -1;
   }
   for (int c = 0; c < 3; c++) {
@@ -194,6 +224,8 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
     D.dipB[k] = L.dipoleBottom[k] * Msmu;
     D.dipT[k] = L.dipoleTop[k] * Msmu;
   }
+  for (int c = 0; c < 3; c++)
+    D.lin[c] = D.cK1 * L.drivers[CMTJB_SLOT_K1].constantValue * L.anis[c] * L.anis[c] - D.demag[4 * c];
   D.alpha = L.damping;
   D.llg = -gyro / (1.0 + L.damping * L.damping);
   D.aJ_c = J.HBAR / (J.ELECTRON_CHARGE * L.Ms * L.thickness);
@@ -235,7 +267,7 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
 template <int NL>
 int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
               const cmtjb_run_args_t *a, const cmtjb_plan_t &plan, const Variant *v, double *m_state, double *log,
-              int32_t *status, int32_t *n_samples_out, double *time_log, cudaStream_t stream) {
+              int32_t *status, int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span) {
   static_assert(sizeof(DevModel<NL>) + sizeof(RunParams) < 32000, "kernel parameters exceed the 32 KB limit");
   DevModel<NL> M;
   std::memset(&M, 0, sizeof(M));
@@ -263,18 +295,45 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   R.B = a->n_instances;
   R.inst_offset = a->instance_offset;
   R.n_samples = plan.n_samples;
-  R.it_begin = a->start_iteration;
-  R.it_end = plan.total_iterations;
+  R.it_begin = span ? span->it_begin : a->start_iteration;
+  R.it_end = span ? span->it_end : plan.total_iterations;
   R.total_iterations = plan.total_iterations;
   R.write_every = plan.write_every > 0 ? plan.write_every : 1;
-  R.first_sample = 0;
+  R.first_sample = span ? span->first_sample : 0;
   R.dt = a->timeStep;
   R.sqrt_dt = std::sqrt(a->timeStep);
   R.total_time = a->totalTime;
   R.write_frequency = a->writeFrequency;
   R.seed = a->seed;
   if (R.B <= 0) return CMTJB_OK;
+  // table of the time-dependent drivers at this launch's stage times (F_DYN / F_DYNS variants)
+  double *tab = nullptr;
+  if ((v->features & (F_DYN | F_DYNS)) && !(v->features & F_DYNI) && R.it_end > R.it_begin) {
+    int ncols = 3 * NL;
+    bool any = false;
+    for (int l = 0; l < NL; l++) {
+      M.L[l].dynH = (M.L[l].dynmask & 0xFFFu) ? 1 : 0;
+      any = any || M.L[l].dynmask != 0;
+      for (int s = CMTJB_SLOT_K1; s < CMTJB_NSLOTS; s++)
+        if ((M.L[l].dynmask >> s) & 1u) M.L[l].dyncol[s] = (int8_t)ncols++;
+    }
+    R.dyn_ncols = ncols;
+    if (any) {
+      const size_t bytes = (size_t)ncols * (size_t)(R.it_end - R.it_begin) * 3 * sizeof(double);
+      cudaError_t e = cudaMallocAsync((void **)&tab, bytes, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(driver table)");
+      R.dyn_tab = tab;
+      e = launch_build_dyn_table<NL>(M, R, tab, stream);
+      g_launches++;
+      if (e != cudaSuccess) {
+        cudaFreeAsync(tab, stream);
+        return cuda_fail(e, "build_dyn_table_kernel");
+      }
+    }
+  }
   cudaError_t e = v->launch(&M, &R, stream);
+  g_launches++;
+  if (tab) cudaFreeAsync(tab, stream);
   if (e != cudaSuccess) return cuda_fail(e, v->name);
   return CMTJB_OK;
 }
@@ -292,14 +351,24 @@ int check_overrides(const cmtjb_junction_t *jn, const cmtjb_override_t *ovr, int
 
 int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
                     const cmtjb_run_args_t *a, double *m_state, double *log, int32_t *status, int32_t *n_samples_out,
-                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out) {
+                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span = nullptr) {
   cmtjb_plan_t plan;
   int rc = make_plan(jn, layers, a, &plan);
   if (rc) return rc;
   rc = check_overrides(jn, ovr, n_ovr);
   if (rc) return rc;
   if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
-  const uint32_t need = needed_features(jn, layers, ovr, n_ovr, a, plan.effective_solver);
+  uint32_t need = needed_features(jn, layers, ovr, n_ovr, a, plan.effective_solver);
+  if (need & (F_DYN | F_DYNS)) {
+    // the stage table costs 24 B per column per step; beyond 2 GiB evaluate inline instead
+    size_t n_cols = 3 * (size_t)jn->n_layers;
+    for (int l = 0; l < jn->n_layers; l++)
+      for (int s = CMTJB_SLOT_K1; s < CMTJB_NSLOTS; s++) n_cols += slot_dynamic(layers[l].drivers[s]) ? 1 : 0;
+    if (n_cols * (size_t)(plan.total_iterations - a->start_iteration) * 24 > ((size_t)2 << 30))
+      need = (need & ~(F_DYN | F_DYNS)) | F_DYNI;
+  }
+  const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel (testing)
+  if (force && std::strcmp(force, "full") == 0) need = F_ALL;
   const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need);
   if (!v) {
     char buf[160];
@@ -311,19 +380,44 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
   std::snprintf(plan.variant, sizeof(plan.variant), "%s", v->name);
   if (plan_out) *plan_out = plan;
   switch (jn->n_layers) {
-  case 1: return run_typed<1>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream);
-  case 2: return run_typed<2>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream);
-  case 3: return run_typed<3>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream);
-  case 4: return run_typed<4>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream);
+  case 1: return run_typed<1>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
+  case 2: return run_typed<2>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
+  case 3: return run_typed<3>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
+  case 4: return run_typed<4>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
   default: return fail(CMTJB_ENOTSUP, "junctions with more than 4 layers need the warp-per-instance kernel (not built yet)");
   }
+}
+
+// Device scratch reused across cmtjb_run_host calls (one slab per device, grown on demand):
+// a sweep loop calling run_host repeatedly should not pay cudaMalloc + first-touch page
+// mapping of a multi-GB log buffer on every call.
+struct Slab {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+std::mutex g_slab_mu;
+Slab g_slab[64];
+
+int slab_reserve(int device, size_t bytes, void **out) {
+  if (device < 0 || device >= 64) return fail(CMTJB_EINVAL, "device index out of range");
+  Slab &s = g_slab[device];
+  if (s.bytes < bytes) {
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr;
+    s.bytes = 0;
+    cudaError_t e = cudaMalloc(&s.p, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(run_host scratch)");
+    s.bytes = bytes;
+  }
+  *out = s.p;
+  return CMTJB_OK;
 }
 
 // ---- small utility kernels ---------------------------------------------------------------------
 __global__ void eval_driver_kernel(const __grid_constant__ DevLayer Lr, const __grid_constant__ RunParams R,
                                    const double *times, long long n, double *out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = slot_value<F_DYN>(Lr, R, 0, times[i], 0);
+  if (i < n) out[i] = slot_value<F_DYNI>(Lr, R, CMTJB_SLOT_K1, StageTime{times[i], nullptr}, 0);
 }
 
 // 8 independent DFMA chains per thread; 2 flop per DFMA
@@ -355,6 +449,19 @@ extern "C" {
 
 int cmtjb_abi_version(void) { return CMTJB_ABI_VERSION; }
 const char *cmtjb_last_error(void) { return g_err.c_str(); }
+
+long long cmtjb_launch_count(void) { return g_launches.load(); }
+
+int cmtjb_release_cache(void) {
+  std::lock_guard<std::mutex> lock(g_slab_mu);
+  for (int d = 0; d < 64; d++)
+    if (g_slab[d].p) {
+      cudaSetDevice(d);
+      cudaFree(g_slab[d].p);
+      g_slab[d] = Slab();
+    }
+  return CMTJB_OK;
+}
 
 int cmtjb_device_count(void) {
   int n = 0;
@@ -400,49 +507,85 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   const size_t nm = (size_t)jn->n_layers * 3 * B * sizeof(double);
   const bool want_log = (args->log_mode == CMTJB_LOG_FULL) && log && plan.n_samples > 0;
   const size_t nlog = want_log ? (size_t)plan.n_channels * plan.n_samples * B * sizeof(double) : 0;
-  std::vector<void *> to_free;
-  auto dalloc = [&](size_t bytes, void **p) -> cudaError_t {
-    cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
-    if (e == cudaSuccess) to_free.push_back(*p);
-    return e;
+  // carve every device buffer of this call out of the per-device slab (256-byte aligned)
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t n_tlog = (plan.variable_samples && want_log && time_log) ? (size_t)plan.n_samples * B * sizeof(double) : 0;
+  const size_t n_onef = args->onef_buffer ? (size_t)jn->n_layers * 3 * plan.total_iterations * B * sizeof(double) : 0;
+  const size_t total = al(nm) + al(nlog) + 2 * al(B * sizeof(int32_t)) + al(n_tlog) + al(n_onef) +
+                       (size_t)n_overrides * al(B * sizeof(double)) + 256;
+  std::lock_guard<std::mutex> lock(g_slab_mu);
+  void *base = nullptr;
+  rc = slab_reserve(device, total, &base);
+  if (rc) return rc;
+  char *cur = (char *)base;
+  auto take = [&](size_t bytes) {
+    void *p = cur;
+    cur += al(bytes);
+    return p;
   };
-  struct Cleanup {
-    std::vector<void *> &v;
-    ~Cleanup() {
-      for (void *p : v) cudaFree(p);
-    }
-  } cleanup{to_free};
-
-  double *d_m = nullptr, *d_log = nullptr, *d_tlog = nullptr, *d_onef = nullptr;
-  int32_t *d_status = nullptr, *d_ns = nullptr;
-  CUDA_TRY(dalloc(nm, (void **)&d_m));
+  double *d_m = (double *)take(nm);
+  double *d_log = want_log ? (double *)take(nlog) : nullptr;
+  int32_t *d_status = (int32_t *)take(B * sizeof(int32_t));
+  int32_t *d_ns = plan.variable_samples ? (int32_t *)take(B * sizeof(int32_t)) : nullptr;
+  double *d_tlog = n_tlog ? (double *)take(n_tlog) : nullptr;
+  double *d_onef = n_onef ? (double *)take(n_onef) : nullptr;
   CUDA_TRY(cudaMemcpy(d_m, m_state, nm, cudaMemcpyHostToDevice));
-  if (want_log) CUDA_TRY(dalloc(nlog, (void **)&d_log));
-  CUDA_TRY(dalloc(B * sizeof(int32_t), (void **)&d_status));
   CUDA_TRY(cudaMemset(d_status, 0, B * sizeof(int32_t)));
-  if (plan.variable_samples) {
-    CUDA_TRY(dalloc(B * sizeof(int32_t), (void **)&d_ns));
-    if (want_log && time_log) CUDA_TRY(dalloc((size_t)plan.n_samples * B * sizeof(double), (void **)&d_tlog));
-  }
   std::vector<cmtjb_override_t> d_ovr(overrides, overrides + n_overrides);
   for (int k = 0; k < n_overrides; k++) {
-    double *p = nullptr;
-    CUDA_TRY(dalloc(B * sizeof(double), (void **)&p));
+    double *p = (double *)take(B * sizeof(double));
     CUDA_TRY(cudaMemcpy(p, overrides[k].values, B * sizeof(double), cudaMemcpyHostToDevice));
     d_ovr[k].values = p;
   }
   cmtjb_run_args_t a = *args;
-  if (args->onef_buffer) {
-    const size_t nb = (size_t)jn->n_layers * 3 * plan.total_iterations * B * sizeof(double);
-    CUDA_TRY(dalloc(nb, (void **)&d_onef));
-    CUDA_TRY(cudaMemcpy(d_onef, args->onef_buffer, nb, cudaMemcpyHostToDevice));
+  if (d_onef) {
+    CUDA_TRY(cudaMemcpy(d_onef, args->onef_buffer, n_onef, cudaMemcpyHostToDevice));
     a.onef_buffer = d_onef;
   }
-  rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, d_log, d_status, d_ns, d_tlog, nullptr, nullptr);
-  if (rc) return rc;
-  CUDA_TRY(cudaDeviceSynchronize());
+  // Large fixed-step logs: run in time chunks and copy chunk k to the host while chunk k+1
+  // integrates (the copy engine overlaps the FP64 pipe; effective when `log` is pinned memory).
+  int n_chunks = 1;
+  if (want_log && !plan.variable_samples && nlog > ((size_t)64 << 20) && plan.n_samples >= 16)
+    n_chunks = (int)std::min<long long>(16, plan.n_samples / 4);
+  if (n_chunks == 1) {
+    rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, d_log, d_status, d_ns, d_tlog, nullptr, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (want_log) CUDA_TRY(cudaMemcpy(log, d_log, nlog, cudaMemcpyDeviceToHost));
+  } else {
+    cudaStream_t sc = nullptr, sd = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+    const long long we = plan.write_every, S0 = a.start_iteration;
+    const long long i0 = ((S0 + we - 1) / we) * we;  // iteration of this run's sample 0
+    std::vector<cudaEvent_t> evs;
+    for (int c = 0; c < n_chunks && rc == CMTJB_OK; c++) {
+      const long long s0 = plan.n_samples * c / n_chunks, s1 = plan.n_samples * (c + 1) / n_chunks;
+      Span sp;
+      sp.it_begin = (c == 0) ? S0 : i0 + s0 * we;
+      sp.it_end = (c == n_chunks - 1) ? plan.total_iterations : i0 + s1 * we;
+      sp.first_sample = s0;
+      rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, d_log, d_status, d_ns, d_tlog, sc, nullptr, &sp);
+      if (rc) break;
+      cudaEvent_t ev;
+      cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      evs.push_back(ev);
+      cudaEventRecord(ev, sc);
+      cudaStreamWaitEvent(sd, ev, 0);
+      for (int ch = 0; ch < plan.n_channels; ch++) {
+        const size_t off = ((size_t)ch * plan.n_samples + s0) * B;
+        cudaMemcpyAsync(log + off, d_log + off, (size_t)(s1 - s0) * B * sizeof(double), cudaMemcpyDeviceToHost, sd);
+      }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sd);
+    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+    cudaStreamDestroy(sc);
+    cudaStreamDestroy(sd);
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "chunked run (compute stream)");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "chunked run (copy stream)");
+  }
   CUDA_TRY(cudaMemcpy(m_state, d_m, nm, cudaMemcpyDeviceToHost));
-  if (want_log) CUDA_TRY(cudaMemcpy(log, d_log, nlog, cudaMemcpyDeviceToHost));
   if (d_tlog) CUDA_TRY(cudaMemcpy(time_log, d_tlog, (size_t)plan.n_samples * B * sizeof(double), cudaMemcpyDeviceToHost));
   if (d_ns && n_samples_out) CUDA_TRY(cudaMemcpy(n_samples_out, d_ns, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
   std::vector<int32_t> st_local;
@@ -469,7 +612,7 @@ int cmtjb_eval_driver_host(const cmtjb_driver_t *driver, const double *times, in
   std::memset(&L, 0, sizeof(L));
   L.Ms = 1;
   L.thickness = 1;
-  L.drivers[0] = *driver;
+  L.drivers[CMTJB_SLOT_K1] = *driver;
   static DevLayer D;  // large; keep off the stack
   derive_layer(J, L, D);
   RunParams R;

@@ -25,9 +25,16 @@ enum : uint32_t {
   F_SOT = 1u << 6,        // SOT primary + secondary          (junction.hpp:770-812)
   F_THERMAL = 1u << 7,    // Langevin field                   (junction.hpp:1111-1128)
   F_ONEF = 1u << 8,       // pre-generated 1/f^alpha vector   (junction.hpp:1130-1136)
-  F_DYN = 1u << 9,        // at least one time-dependent driver
+  F_DYN = 1u << 9,        // time-dependent FIELD drivers (Hext/Hoe/Hdmi/Hres): per-layer sum read from a
+                          // per-launch table (uniform in the batch)
   F_OVR = 1u << 10,       // per-instance overrides other than constant field components
-  F_ALL = (1u << 11) - 1
+  F_DYNI = 1u << 11,      // time-dependent drivers evaluated inline per thread (per-instance
+                          // frequency/phase/timing overrides, adaptive time); wins over F_DYN
+  F_NOFOLD = 1u << 12,    // K1 anisotropy and demag kept as separate terms; without this bit the
+                          // kernel applies the host-folded DIAGONAL operator lin = (2K1/Ms) a a^T - N Ms/mu0
+  F_DYNS = 1u << 13,      // time-dependent SCALAR drivers (K, J, I, torques, T) read from the same table
+  F_ALL = (1u << 14) - 1,
+  F_ALL_TAB = F_ALL & ~F_DYNI
 };
 
 struct DevDriver {
@@ -56,7 +63,10 @@ struct DevLayer {
       integral_error;
   int32_t refType;           // cmtjb_reference
   int32_t stt, sot, dynamicSOT, altSTT, thermal, onef, pid;
+  double lin[3];             // folded diagonal linear operator (valid when the variant lacks F_NOFOLD)
   uint32_t dynmask;          // bit s: slot s is time dependent
+  int8_t dyncol[CMTJB_NSLOTS];     // column of scalar slot s in the per-launch driver table, or -1
+  int32_t dynH;              // 1: the layer has time-dependent field drivers (table columns 3l..3l+2)
   uint32_t ovmask;           // bit s: slot s has a per-instance override of some field
   int8_t ovidx[CMTJB_NSLOTS][10];  // override table row of (slot, field) or -1
   DevDriver drv[CMTJB_NSLOTS];
@@ -80,6 +90,11 @@ struct RunParams {
   double *time_log;          // [n_samples][B] (DP)
   const double *ovr[kMaxOverrides];  // row k: [B] values of override k
   const double *onef;        // [NL*3][total_iterations][B] or null
+  // [it_end-it_begin][3][dyn_ncols]: time-dependent driver values at the three stage times
+  // t, t+dt/2, t+dt of every step.  Columns 3l..3l+2: summed dynamic field of layer l (A/m);
+  // further columns: unit-amplitude waveform of each dynamic scalar slot (DevLayer::dyncol).
+  const double *dyn_tab;
+  long long dyn_ncols;
   long long B;
   long long inst_offset;
   long long n_samples;       // row count of the log

@@ -74,70 +74,97 @@ __device__ __forceinline__ double ovr_or(const DevLayer &Lr, const RunParams &R,
 // drivers: the time-dependent part of ScalarDriver::getCurrentScalarValue
 // (drivers.hpp:262-305, helpers :73-108); constantValue is added by the caller.
 // ---------------------------------------------------------------------------------------
+// unit-amplitude waveform s(t) with  dynamic part = post(A * s(t));  post = |.| for posine,
+// min(.,0) for halfsine, identity otherwise.
 template <uint32_t F>
-__device__ __noinline__ double driver_dynamic(const DevLayer &Lr, const RunParams &R, int s, double t, long long i) {
+__device__ __forceinline__ double driver_shape(const DevLayer &Lr, const RunParams &R, int s, double t, long long i) {
   const DevDriver &d = Lr.drv[s];
-  const double A = ovr_or<F>(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, d.amplitude);
   switch (d.type) {
   case CMTJB_UPD_PULSE: {
     const double period = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PERIOD, i, d.period);
     const double cycle = ovr_or<F>(Lr, R, s, CMTJB_FIELD_CYCLE, i, d.cycle);
     const int n = (int)(t / period);
     const double nT = n * period;
-    return (nT <= t && t <= (nT + cycle * period)) ? A : 0.0;
+    return (nT <= t && t <= (nT + cycle * period)) ? 1.0 : 0.0;
   }
   case CMTJB_UPD_SINE:
   case CMTJB_UPD_POSINE:
   case CMTJB_UPD_HALFSINE: {
     const double f = ovr_or<F>(Lr, R, s, CMTJB_FIELD_FREQUENCY, i, d.frequency);
     const double ph = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PHASE, i, d.phase);
-    const double v = A * sin(2 * M_PI * t * f + ph);
-    if (d.type == CMTJB_UPD_SINE) return v;
-    if (d.type == CMTJB_UPD_POSINE) return fabs(v);
-    return v <= 0 ? v : 0.0;
+    return sin(2 * M_PI * t * f + ph);
   }
   case CMTJB_UPD_STEP: {
     const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
     const double t1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTOP, i, d.timeStop);
-    return (t >= t0 && t <= t1) ? A : 0.0;
+    return (t >= t0 && t <= t1) ? 1.0 : 0.0;
   }
   case CMTJB_UPD_TRAPEZOID: {
     const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
     const double e = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
     const double st = ovr_or<F>(Lr, R, s, CMTJB_FIELD_STEADYTIME, i, d.steadyTime);
     if (t < t0) return 0.0;
-    if (t <= t0 + e) return (A / e) * (t - t0);
-    if (t <= t0 + e + st) return A;
-    if (t <= t0 + 2 * e + st) return A - (A / e) * (t - (t0 + e + st));
+    if (t <= t0 + e) return (t - t0) / e;
+    if (t <= t0 + e + st) return 1.0;
+    if (t <= t0 + 2 * e + st) return 1.0 - (t - (t0 + e + st)) / e;
     return 0.0;
   }
   case CMTJB_UPD_GAUSSIMPULSE: {
     const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
     const double e = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
     const double x = t - t0;
-    return A * exp(-(x * x) / (2 * (e * e)));
+    return exp(-(x * x) / (2 * (e * e)));
   }
   case CMTJB_UPD_GAUSSSTEP: {
     const double t0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
     const double e = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
-    return 0.5 * A * (1 + erf((t - t0) / (sqrt(2.0) * e)));
+    return 0.5 * (1 + erf((t - t0) / (sqrt(2.0) * e)));
   }
   default:
     return 0.0;
   }
 }
+__device__ __forceinline__ double driver_post(int type, double v) {
+  if (type == CMTJB_UPD_POSINE) return fabs(v);
+  if (type == CMTJB_UPD_HALFSINE) return v <= 0 ? v : 0.0;
+  return v;
+}
+template <uint32_t F>
+__device__ __noinline__ double driver_dynamic_inline(const DevLayer &Lr, const RunParams &R, int s, double t, long long i) {
+  const double A = ovr_or<F>(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, Lr.drv[s].amplitude);
+  return driver_post(Lr.drv[s].type, A * driver_shape<F>(Lr, R, s, t, i));
+}
+
+// Where in time a right-hand-side evaluation sits: the step index and which of the three
+// stage times of that step (0: t, 1: t+dt/2, 2: t+dt).  Fixed-step solvers only ever
+// evaluate drivers at these times, which are the same for every instance of a batch, so
+// F_DYN variants read the waveform from a table built once per launch.
+struct StageTime {
+  double t;
+  const double *row;  // this stage time's row of RunParams::dyn_tab (F_DYN / F_DYNS variants)
+};
+
+template <uint32_t F>
+__device__ __forceinline__ double driver_dynamic(const DevLayer &Lr, const RunParams &R, int s, StageTime st, long long i) {
+  if constexpr ((F & F_DYNI) != 0) {
+    return driver_dynamic_inline<F>(Lr, R, s, st.t, i);
+  } else {
+    const double A = ovr_or<F>(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, Lr.drv[s].amplitude);
+    return driver_post(Lr.drv[s].type, A * __ldg(st.row + Lr.dyncol[s]));
+  }
+}
 
 // value of a scalar slot at time t
 template <uint32_t F>
-__device__ __forceinline__ double slot_value(const DevLayer &Lr, const RunParams &R, int s, double t, long long i) {
+__device__ __forceinline__ double slot_value(const DevLayer &Lr, const RunParams &R, int s, StageTime t, long long i) {
   double v = ovr_or<F>(Lr, R, s, CMTJB_FIELD_CONSTANT, i, Lr.cst[s]);
-  if constexpr ((F & F_DYN) != 0) {
+  if constexpr ((F & (F_DYNS | F_DYNI)) != 0) {
     if ((Lr.dynmask >> s) & 1u) v += driver_dynamic<F>(Lr, R, s, t, i);
   }
   return v;
 }
 template <uint32_t F>
-__device__ __forceinline__ d3 slot_vec(const DevLayer &Lr, const RunParams &R, int s0, double t, long long i) {
+__device__ __forceinline__ d3 slot_vec(const DevLayer &Lr, const RunParams &R, int s0, StageTime t, long long i) {
   return mk(slot_value<F>(Lr, R, s0, t, i), slot_value<F>(Lr, R, s0 + 1, t, i), slot_value<F>(Lr, R, s0 + 2, t, i));
 }
 
@@ -155,18 +182,23 @@ __device__ __forceinline__ d3 constant_field(const DevLayer &Lr, const RunParams
   return mk(h[0], h[1], h[2]);
 }
 
-// time-dependent parts of the same four drivers
+// time-dependent parts of the same four drivers.  l is the layer index (table columns 3l..3l+2).
 template <uint32_t F>
-__device__ __forceinline__ d3 dynamic_field(const DevLayer &Lr, const RunParams &R, double t, long long i, d3 H) {
-  if constexpr ((F & F_DYN) != 0) {
+__device__ __forceinline__ d3 dynamic_field(const DevLayer &Lr, const RunParams &R, int l, StageTime t, long long i, d3 H) {
+  if constexpr ((F & F_DYNI) != 0) {
     if (Lr.dynmask & 0xFFFu) {
       double h[3] = {H.x, H.y, H.z};
 #pragma unroll
       for (int g = 0; g < 4; g++)
 #pragma unroll
         for (int c = 0; c < 3; c++)
-          if ((Lr.dynmask >> (g * 3 + c)) & 1u) h[c] += driver_dynamic<F>(Lr, R, g * 3 + c, t, i);
+          if ((Lr.dynmask >> (g * 3 + c)) & 1u) h[c] += driver_dynamic_inline<F>(Lr, R, g * 3 + c, t.t, i);
       return mk(h[0], h[1], h[2]);
+    }
+  } else if constexpr ((F & F_DYN) != 0) {
+    if (Lr.dynH) {
+      const double *p = t.row + 3 * l;
+      return mk(H.x + __ldg(p), H.y + __ldg(p + 1), H.z + __ldg(p + 2));
     }
   }
   return H;
@@ -178,29 +210,34 @@ __device__ __forceinline__ d3 dynamic_field(const DevLayer &Lr, const RunParams 
 //   HAS_BOT / HAS_TOP: the layer has a neighbour on that side (else the reference passes 0).
 // ---------------------------------------------------------------------------------------
 template <uint32_t F, bool HAS_BOT, bool HAS_TOP>
-__device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, long long i, double t, d3 m, d3 bot, d3 top,
-                                    d3 Hc) {
-  d3 H = dynamic_field<F>(Lr, R, t, i, Hc);
+__device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, int l, long long i, StageTime t, d3 m, d3 bot,
+                                    d3 top, d3 Hc) {
+  static_assert((F & F_DEMAG_FULL) == 0 || (F & F_NOFOLD) != 0, "a full demag tensor cannot be folded into the diagonal operator");
+  d3 H = dynamic_field<F>(Lr, R, l, t, i, Hc);
   const d3 a = ld3(Lr.anis);
-  const double am = dot(a, m);
-  {  // K1 (junction.hpp:638-643)
+  if constexpr ((F & F_NOFOLD) != 0) {  // K1 (junction.hpp:638-643)
     const double K = slot_value<F>(Lr, R, CMTJB_SLOT_K1, t, i);
-    H = axpy(a, (Lr.cK1 * K) * am, H);
+    H = axpy(a, (Lr.cK1 * K) * dot(a, m), H);
+  } else {
+    // K1 anisotropy and demag folded on the host into one diagonal operator (constant K1,
+    // axis-aligned easy axis, diagonal demag tensor): three FMAs instead of ten.
+    H = mk(fma(Lr.lin[0], m.x, H.x), fma(Lr.lin[1], m.y, H.y), fma(Lr.lin[2], m.z, H.z));
   }
   if constexpr ((F & F_K2) != 0) {  // (junction.hpp:645-652)
     const double K2 = slot_value<F>(Lr, R, CMTJB_SLOT_K2, t, i);
+    const double am = dot(a, m);
     H = axpy(a, (Lr.cK2 * K2) * (am * am * am), H);
   }
   if constexpr ((F & F_IEC) != 0) {  // (junction.hpp:654-675)
     if constexpr (HAS_BOT) {
       const double J = slot_value<F>(Lr, R, CMTJB_SLOT_IEC_BOTTOM, t, i);
       const double J2 = slot_value<F>(Lr, R, CMTJB_SLOT_IECQ_BOTTOM, t, i);
-      H = axpy(bot, fma(2 * J2, dot(bot, m), J) * Lr.inv_Mst, H);
+      H = axpy(bot, fma(2 * J2 * Lr.inv_Mst, dot(bot, m), J * Lr.inv_Mst), H);
     }
     if constexpr (HAS_TOP) {
       const double J = slot_value<F>(Lr, R, CMTJB_SLOT_IEC_TOP, t, i);
       const double J2 = slot_value<F>(Lr, R, CMTJB_SLOT_IECQ_TOP, t, i);
-      H = axpy(top, fma(2 * J2, dot(top, m), J) * Lr.inv_Mst, H);
+      H = axpy(top, fma(2 * J2 * Lr.inv_Mst, dot(top, m), J * Lr.inv_Mst), H);
     }
   }
   if constexpr ((F & F_IDMI) != 0) {  // (junction.hpp:677-701)
@@ -216,7 +253,7 @@ __device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, long
   // demag (junction.hpp:598-599); off-diagonal entries only in F_DEMAG_FULL variants
   if constexpr ((F & F_DEMAG_FULL) != 0) {
     H = sub_matvec(Lr.demag, m, H);
-  } else {
+  } else if constexpr ((F & F_NOFOLD) != 0) {
     H = mk(fma(-Lr.demag[0], m.x, H.x), fma(-Lr.demag[4], m.y, H.y), fma(-Lr.demag[8], m.z, H.z));
   }
   if constexpr ((F & F_DIPOLE) != 0) {  // (junction.hpp:583-585)
@@ -321,7 +358,7 @@ __device__ __forceinline__ d3 normal3(unsigned long long seed, unsigned long lon
 
 // the step's noise vector dW (junction.hpp:1121-1136): Langevin + 1/f^alpha buffer
 template <uint32_t F, int NL>
-__device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, int l, long long i, long long it, double t) {
+__device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, int l, long long i, long long it, StageTime t) {
   d3 dW = mk(0, 0, 0);
   if constexpr ((F & F_THERMAL) != 0) {
     if (Lr.thermal) {

@@ -4,11 +4,16 @@ namespace cmtjb {
 static const Variant kTable[] = {
     CMTJB_FIXED(1, CMTJB_EULER_HEUN, 0),
     CMTJB_FIXED(1, CMTJB_EULER_HEUN, F_STT | F_THERMAL),
+    CMTJB_FIXED(1, CMTJB_EULER_HEUN, F_STT | F_THERMAL | F_OVR),
+    CMTJB_FIXED(1, CMTJB_EULER_HEUN, F_ALL_TAB),
     CMTJB_FIXED(1, CMTJB_EULER_HEUN, F_ALL),
     CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_IEC),
+    CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_ALL_TAB),
     CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_ALL),
     CMTJB_FIXED(3, CMTJB_EULER_HEUN, F_IEC),
+    CMTJB_FIXED(3, CMTJB_EULER_HEUN, F_ALL_TAB),
     CMTJB_FIXED(3, CMTJB_EULER_HEUN, F_ALL),
+    CMTJB_FIXED(4, CMTJB_EULER_HEUN, F_ALL_TAB),
     CMTJB_FIXED(4, CMTJB_EULER_HEUN, F_ALL),
 };
 int variants_euler_heun(const Variant **out) {

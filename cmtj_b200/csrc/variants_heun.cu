@@ -4,12 +4,18 @@ namespace cmtjb {
 static const Variant kTable[] = {
     CMTJB_FIXED(1, CMTJB_HEUN, 0),
     CMTJB_FIXED(1, CMTJB_HEUN, F_STT | F_THERMAL),
+    CMTJB_FIXED(1, CMTJB_HEUN, F_STT | F_THERMAL | F_OVR),
+    CMTJB_FIXED(1, CMTJB_HEUN, F_SOT | F_K2 | F_OVR | F_DYN | F_DYNS),
+    CMTJB_FIXED(1, CMTJB_HEUN, F_ALL_TAB),
     CMTJB_FIXED(1, CMTJB_HEUN, F_ALL),
     CMTJB_FIXED(2, CMTJB_HEUN, F_IEC),
+    CMTJB_FIXED(2, CMTJB_HEUN, F_ALL_TAB),
     CMTJB_FIXED(2, CMTJB_HEUN, F_ALL),
     CMTJB_FIXED(3, CMTJB_HEUN, F_IEC),
-    CMTJB_FIXED(3, CMTJB_HEUN, F_IEC | F_SOT | F_K2 | F_OVR | F_DYN),
+    CMTJB_FIXED(3, CMTJB_HEUN, F_IEC | F_SOT | F_K2 | F_OVR | F_DYN | F_DYNS),
+    CMTJB_FIXED(3, CMTJB_HEUN, F_ALL_TAB),
     CMTJB_FIXED(3, CMTJB_HEUN, F_ALL),
+    CMTJB_FIXED(4, CMTJB_HEUN, F_ALL_TAB),
     CMTJB_FIXED(4, CMTJB_HEUN, F_ALL),
 };
 int variants_heun(const Variant **out) {

@@ -2,17 +2,23 @@
 #include "variants.h"
 namespace cmtjb {
 static const Variant kTable[] = {
-    // lean: K1 + diagonal demag + constant fields
+    // lean: folded K1+demag diagonal operator + constant fields
     CMTJB_FIXED(1, CMTJB_RK4, 0),
     CMTJB_FIXED(1, CMTJB_RK4, F_DYN),
     CMTJB_FIXED(1, CMTJB_RK4, F_STT),
+    CMTJB_FIXED(1, CMTJB_RK4, F_NOFOLD | F_DYN | F_DYNS | F_K2 | F_SOT | F_STT | F_DEMAG_FULL),
+    CMTJB_FIXED(1, CMTJB_RK4, F_ALL_TAB),
     CMTJB_FIXED(1, CMTJB_RK4, F_ALL),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN),
+    CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN | F_DYNS | F_NOFOLD),
+    CMTJB_FIXED(2, CMTJB_RK4, F_ALL_TAB),
     CMTJB_FIXED(2, CMTJB_RK4, F_ALL),
     CMTJB_FIXED(3, CMTJB_RK4, F_IEC),
     CMTJB_FIXED(3, CMTJB_RK4, F_IEC | F_DYN),
+    CMTJB_FIXED(3, CMTJB_RK4, F_ALL_TAB),
     CMTJB_FIXED(3, CMTJB_RK4, F_ALL),
+    CMTJB_FIXED(4, CMTJB_RK4, F_ALL_TAB),
     CMTJB_FIXED(4, CMTJB_RK4, F_ALL),
 };
 int variants_rk4(const Variant **out) {

@@ -225,6 +225,11 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
                    const cmtjb_run_args_t *args, double *m_state, double *log,
                    int32_t *status, int32_t *n_samples_out, double *time_log, int device);
 
+/* Number of kernels this library has launched in this process (monotonic). */
+long long cmtjb_launch_count(void);
+/* cmtjb_run_host keeps one device scratch slab per device between calls; this frees them. */
+int cmtjb_release_cache(void);
+
 /* ScalarDriver::getCurrentScalarValue (core/drivers.hpp:262-305) evaluated on the device
  * for n times (host pointers); used by the parity tests of the inline driver code. */
 int cmtjb_eval_driver_host(const cmtjb_driver_t *driver, const double *times, int64_t n,
