@@ -375,24 +375,20 @@ def main():
         import helpers
 
         # parity gate: 64 random instances, first 2000 steps, CUDA vs the oracle restatement
-        try:
-            sel = np.sort(np.random.default_rng(123).choice(B, size=64, replace=False))
-            logs = []
-            for be in (None, helpers.oracle_backend()):
-                _abi._active = be
+        sel = np.sort(np.random.default_rng(123).choice(B, size=64, replace=False))
+        logs = []
+        for be in (None, helpers.oracle_backend()):
+            with helpers.facade_on(be):
                 bb = cmtj_b200.JunctionBatch(j, 64)
                 bb.set_external_field("all", H[sel])
                 bb.set_magnetisation("free", m_free[sel])
                 bb.set_magnetisation("bottom", m_bot[sel])
                 logs.append(bb.run(2000 * DT * (1 + 1e-9), DT, 10 * DT * (1 + 1e-9)))
-                _abi._active = None
-            worst = 0.0
-            for k in logs[1]:
-                if k != "time":
-                    worst = max(worst, helpers.max_rel_err(logs[0][k], logs[1][k]))
-            parity = {"instances": 64, "steps": 2000, "max_rel_err_vs_oracle": worst, "bound": 1e-9}
-        finally:
-            _abi._active = None
+        worst = 0.0
+        for k in logs[1]:
+            if k != "time":
+                worst = max(worst, helpers.max_rel_err(logs[0][k], logs[1][k]))
+        parity = {"instances": 64, "steps": 2000, "max_rel_err_vs_oracle": worst, "bound": 1e-9}
         if helpers.reference_module() is not None:
             cores = os.cpu_count() or 1
             ctx = mp.get_context("fork")

@@ -185,8 +185,8 @@ class Backend:
     """Uniform view over a shared library exporting the run/plan entry points.
 
     The product uses exactly one instance of this class, bound to ``libcmtj_b200.so``
-    (`cuda_backend()`).  The parity tests build a second one over ``oracle/liboracle.so``
-    to drive the *same facade* with the CPU restatement as the checker.
+    (`cuda_backend()`).  (tests/helpers.py binds a second instance to the CPU oracle and
+    monkeypatches it in as the checker; nothing in this package knows about the oracle.)
     """
 
     def __init__(self, lib: C.CDLL, prefix: str, has_device_arg: bool):
@@ -266,9 +266,6 @@ class Backend:
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcmtj_b200.so")
 _cuda: Optional[Backend] = None
 _cuda_lib: Optional[C.CDLL] = None
-# The ONE indirection point of the facade.  Product code never assigns it; tests may
-# install an oracle-backed Backend here to check the host logic without a GPU.
-_active: Optional[Backend] = None
 
 
 def load_library() -> C.CDLL:
@@ -302,4 +299,5 @@ def cuda_backend() -> Backend:
 
 
 def backend() -> Backend:
-    return _active if _active is not None else cuda_backend()
+    """The backend every compute call of the facade goes through: always the CUDA library."""
+    return cuda_backend()

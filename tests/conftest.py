@@ -37,19 +37,15 @@ def ref():
 def on_oracle(oracle):
     """Route the facade through the oracle for host-logic tests on a CPU-only machine.
     Only tests may do this; the product has no such fallback."""
-    from cmtj_b200 import _abi
+    import helpers
 
-    prev = _abi._active
-    _abi._active = oracle
-    yield oracle
-    _abi._active = prev
+    with helpers.facade_on(oracle):
+        yield oracle
 
 
 @pytest.fixture
 def on_cuda():
-    from cmtj_b200 import _abi
+    import helpers
 
-    prev = _abi._active
-    _abi._active = None
-    yield _abi.cuda_backend()
-    _abi._active = prev
+    with helpers.facade_on(None) as be:
+        yield be

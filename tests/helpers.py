@@ -1,5 +1,6 @@
 """Shared test helpers: oracle loader, reference-module loader, and model builders that
 construct the SAME system against either API (the reference `_cmtj` or `cmtj_b200`)."""
+import contextlib
 import ctypes
 import glob
 import importlib.util
@@ -28,6 +29,24 @@ def oracle_backend():
         lib = ctypes.CDLL(so)
         _oracle = _abi.Backend(lib, "oracle_", has_device_arg=False)
     return _oracle
+
+
+@contextlib.contextmanager
+def facade_on(backend):
+    """Run the cmtj_b200 facade against `backend` for the duration of the block: None = the
+    product's own CUDA library (no patching), otherwise e.g. oracle_backend().  Test
+    infrastructure only: this monkeypatches cmtj_b200._abi.backend; the product has no switch."""
+    from cmtj_b200 import _abi
+
+    if backend is None:
+        yield _abi.cuda_backend()
+        return
+    prev = _abi.backend
+    _abi.backend = lambda: backend
+    try:
+        yield backend
+    finally:
+        _abi.backend = prev
 
 
 def reference_module():

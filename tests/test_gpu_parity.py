@@ -40,11 +40,8 @@ def _three(fn):
     change of the initial state does to the reference."""
     out = []
     for backend, eps in ((None, 0.0), (helpers.oracle_backend(), 0.0), (helpers.oracle_backend(), EPS)):
-        _abi._active = backend
-        try:
+        with helpers.facade_on(backend):
             out.append(fn(eps))
-        finally:
-            _abi._active = None
     g, w, p = out
     sens = {}
     for k in w:
@@ -246,11 +243,8 @@ def test_batch_matches_oracle_per_instance():
     g, w, _ = _three(fn)
     assert "F_DYN" in variants[0] and "F_NOFOLD" not in variants[0], variants[0]
     # per-instance bound: sensitivity measured per instance
-    _abi._active = helpers.oracle_backend()
-    try:
+    with helpers.facade_on(helpers.oracle_backend()):
         pert = fn(EPS)
-    finally:
-        _abi._active = None
     worst_sens = np.zeros(B)
     for k in w:
         if k in ("time", "m_final"):
@@ -277,8 +271,7 @@ def test_batch_overrides_scalar_slots_and_device_path():
     fr = rng.uniform(1e9, 9e9, B)
     outs = []
     for which in ("cuda-host", "cuda-device", "oracle"):
-        _abi._active = helpers.oracle_backend() if which == "oracle" else None
-        try:
+        with helpers.facade_on(helpers.oracle_backend() if which == "oracle" else None):
             j = helpers.stt_layer_mtj(cmtj_b200)
             j.setLayerCurrentDriver("free", cmtj_b200.ScalarDriver.getSineDriver(-1e10, 1e10, 3e9, 0.0))
             b = cmtj_b200.JunctionBatch(j, B)
@@ -291,8 +284,6 @@ def test_batch_overrides_scalar_slots_and_device_path():
                 outs.append({k: v.cpu().numpy() for k, v in r.items() if k != "_log"})
             else:
                 outs.append(dict(b.run(1e-9, 1e-13, 1e-12, solverMode=cmtj_b200.SolverMode.Heun)))
-        finally:
-            _abi._active = None
     host, dev, want = outs
     for k in want:
         assert np.array_equal(host[k], dev[k]), k  # same kernel, same inputs

@@ -173,11 +173,14 @@ def test_dormand_prince_single_layer(ref, on_oracle):
     assert len(jo.getLog()["time"]) > 10
 
 
-def test_dormand_prince_pid(ref, on_oracle):
+def test_dormand_prince_custom_tolerances(ref, on_oracle):
+    # use_pid_control=True is not pinned: the unmodified reference segfaults on it in this
+    # toolchain (NaN step -> "Invalid timestep detected" -> crash), so there is nothing to compare.
     def tweak(m, j):
         p = m.AdaptiveIntegrationParams()
-        p.use_pid_control = True
         p.abs_tol = 1e-7
+        p.rel_tol = 1e-4
+        p.max_factor = 3.0
         j.getLayer("free").setAdaptiveParams(p)
 
     jr, jo = _run_both(ref, helpers.single_layer_mtj, T=2e-9, dt=1e-12, wf=2e-11, mode="DormandPrince", tweak=tweak)

@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box session: parity tests, the bench line, the ncu launch list of the same command and a
+# full ncu capture of the dominant kernel.  Outputs land in gpurun_out/ (scratch); summaries are
+# copied into profiles/ by tools/summarise_profiles.py afterwards.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+echo "== probe"; timeout 600 python tools/probe.py > gpurun_out/probe.log 2>&1; echo "probe rc=$?"; tail -30 gpurun_out/probe.log
+echo "== bench"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+echo "== ncu launch list (same bench command, reduced steps)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
+echo "== ncu full (S1 kernel, 100000 instances x 2000 steps, log every 100)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:llgs_fixed -s 1 -c 1 -o gpurun_out/prof_s1 -f \
+    python tools/s1_run.py 100000 2000 100 2 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out
