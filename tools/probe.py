@@ -1,7 +1,10 @@
 """Quick GPU probe: FP64 peak + a first throughput number for the S1 sweep shape."""
 import ctypes as C, time, sys, json
 import numpy as np
-sys.path.insert(0, "tests")
+import os
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cmtj_b200, helpers
 from cmtj_b200 import _abi
 import torch
