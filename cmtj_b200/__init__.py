@@ -5,7 +5,7 @@ cmtj/__init__.py:11-14) so scripts can switch with ``import cmtj_b200 as cmtj`` 
 ``cmtj_b200.install_as_cmtj()``.  Compute runs only on the GPU through the C-ABI library
 ``libcmtj_b200.so`` (see include/cmtj_b200.h); there is no CPU fallback.
 """
-from . import constants, noise  # noqa: F401
+from . import constants, noise, reservoir, stack  # noqa: F401
 from .constants import PhysicalConstants  # noqa: F401
 from .batch import BatchLog, JunctionBatch  # noqa: F401
 from .core import (  # noqa: F401
@@ -50,3 +50,17 @@ constant, pulse, sine, step, posine, halfsine, trapezoid, gaussimpulse, gaussste
 )
 
 __version__ = "0.1.0"
+
+
+def install_as_cmtj() -> None:
+    """Make ``import cmtj`` (and ``cmtj.stack``, ``cmtj.reservoir``, ``cmtj.noise``,
+    ``cmtj.constants``, ``_cmtj``) resolve to this package, so scripts written against the
+    reference run unchanged (cmtj/__init__.py:11-14 re-exports ``_cmtj`` the same way)."""
+    import sys
+
+    me = sys.modules[__name__]
+    sys.modules["cmtj"] = me
+    sys.modules["_cmtj"] = me
+    for sub in ("stack", "reservoir", "noise", "constants"):
+        sys.modules["cmtj." + sub] = getattr(me, sub)
+        sys.modules["_cmtj." + sub] = getattr(me, sub)

@@ -166,6 +166,52 @@ class Plan(C.Structure):
     ]
 
 
+LAYER_SYSTEM = -2
+STACK_SERIES, STACK_PARALLEL = 0, 1
+INT_NULL, INT_DIPOLE, INT_DIPOLE_NOMURA = 0, 1, 2
+
+
+class Stack(C.Structure):
+    _fields_ = [
+        ("n_junctions", C.c_int32),
+        ("kind", C.c_int32),
+        ("use_kcl", C.c_int32),
+        ("delayed", C.c_int32),
+        ("top_layer", C.c_int32),
+        ("bottom_layer", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("reserved1", C.c_int32),
+        ("phaseOffset", C.c_double),
+        ("polarisation", C.c_double * 3),
+        ("coupling", C.c_void_p),
+        ("currentDriver", Driver),
+    ]
+
+
+class Group(C.Structure):
+    _fields_ = [
+        ("n_junctions", C.c_int32),
+        ("interaction", C.c_int32),
+        ("top_layer", C.c_int32),
+        ("reserved", C.c_int32),
+        ("coordinates", C.c_void_p),
+    ]
+
+
+class CoupledPlan(C.Structure):
+    _fields_ = [
+        ("effective_solver", C.c_int32),
+        ("solver_overridden", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("n_junction_channels", C.c_int32),
+        ("n_system_channels", C.c_int32),
+        ("cooperative", C.c_int32),
+        ("total_iterations", C.c_int64),
+        ("write_every", C.c_int64),
+        ("n_samples", C.c_int64),
+    ]
+
+
 _P = C.POINTER
 
 
@@ -216,6 +262,53 @@ class Backend:
         f.restype = C.c_char_p
         f.argtypes = []
         self._last_error = f
+
+    # ---- coupled systems (Stack / GroupInteraction) ------------------------------------------
+    def _fn(self, name, argtypes):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = C.c_int
+        f.argtypes = argtypes
+        return f
+
+    def stack_plan(self, st: "Stack", jns, layers, args: RunArgs) -> "CoupledPlan":
+        p = CoupledPlan()
+        f = self._fn("stack_plan", [_P(Stack), C.c_void_p, C.c_void_p, _P(RunArgs), _P(CoupledPlan)])
+        self.check(f(C.byref(st), C.cast(jns, C.c_void_p), C.cast(layers, C.c_void_p), C.byref(args), C.byref(p)))
+        return p
+
+    def group_plan(self, g: "Group", jns, layers, args: RunArgs) -> "CoupledPlan":
+        p = CoupledPlan()
+        f = self._fn("group_plan", [_P(Group), C.c_void_p, C.c_void_p, _P(RunArgs), _P(CoupledPlan)])
+        self.check(f(C.byref(g), C.cast(jns, C.c_void_p), C.cast(layers, C.c_void_p), C.byref(args), C.byref(p)))
+        return p
+
+    @staticmethod
+    def _ptr(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def stack_run_host(self, st, jns, layers, overrides, n_overrides, args, m_state, jlog, slog, status, device=0) -> int:
+        f = self._fn(
+            "stack_run_host",
+            [_P(Stack), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _P(RunArgs)] + [C.c_void_p] * 4
+            + ([C.c_int] if self.has_device_arg else []),
+        )  # fmt: skip
+        extra = (device,) if self.has_device_arg else ()
+        return f(
+            C.byref(st), C.cast(jns, C.c_void_p), C.cast(layers, C.c_void_p), C.cast(overrides, C.c_void_p), n_overrides,
+            C.byref(args), self._ptr(m_state), self._ptr(jlog), self._ptr(slog), self._ptr(status), *extra,
+        )  # fmt: skip
+
+    def group_run_host(self, g, jns, layers, overrides, n_overrides, args, m_state, jlog, status, device=0) -> int:
+        f = self._fn(
+            "group_run_host",
+            [_P(Group), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _P(RunArgs)] + [C.c_void_p] * 3
+            + ([C.c_int] if self.has_device_arg else []),
+        )  # fmt: skip
+        extra = (device,) if self.has_device_arg else ()
+        return f(
+            C.byref(g), C.cast(jns, C.c_void_p), C.cast(layers, C.c_void_p), C.cast(overrides, C.c_void_p), n_overrides,
+            C.byref(args), self._ptr(m_state), self._ptr(jlog), self._ptr(status), *extra,
+        )  # fmt: skip
 
     def last_error(self) -> str:
         s = self._last_error()

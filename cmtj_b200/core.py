@@ -988,6 +988,22 @@ class Junction:
             self._strip = dict(zip(names3, strip))
             self.MR_mode = MR_STRIP
 
+    def _clone(self) -> "Junction":
+        """Value semantics of ``std::vector<Junction>`` arguments (Stack / GroupInteraction copy
+        their junctions, log included)."""
+        j = copy.copy(self)
+        j._layers = [l._clone() for l in self._layers]
+        j._log = {k: list(v) for k, v in self._log.items()}
+        j._strip = None if self._strip is None else {k: list(v) for k, v in self._strip.items()}
+        return j
+
+    def _append_samples(self, channels: np.ndarray, times: np.ndarray) -> None:
+        """logLayerParams for a block of samples: channels [n_channels, n_samples]."""
+        for name, row in zip(self._channel_names(), channels):
+            self._log.setdefault(name, []).extend(row.tolist())
+        self._log.setdefault("time", []).extend(np.asarray(times).tolist())
+        self._logLength += len(times)
+
     # -- introspection -----------------------------------------------------------------------
     @property
     def layers(self) -> List[Layer]:

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "dev_model.h"
+#include "host_common.h"
 #include "llgs_kernels.cuh"
 
 namespace cmtjb {
@@ -25,8 +26,6 @@ int variants_rk4(const Variant **out);
 int variants_heun(const Variant **out);
 int variants_euler_heun(const Variant **out);
 int variants_dopri(const Variant **out);
-
-namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
@@ -38,13 +37,12 @@ int fail(int code, const std::string &msg) {
 int cuda_fail(cudaError_t e, const char *what) {
   return fail(CMTJB_ECUDA, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
 }
-#define CUDA_TRY(expr)                                   \
-  do {                                                   \
-    cudaError_t _e = (expr);                             \
-    if (_e != cudaSuccess) return cuda_fail(_e, #expr);  \
-  } while (0)
+
+namespace {
 
 bool slot_dynamic(const cmtjb_driver_t &d) { return d.update != CMTJB_UPD_CONSTANT; }
+
+}  // namespace
 
 // Mirrors Junction::runSimulation's guards (junction.hpp:1952-1959), getSolver's solver
 // override (:1891-1931) and the run-time throws reachable from the hot loop.
@@ -94,6 +92,8 @@ int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   }
   return CMTJB_OK;
 }
+
+namespace {
 
 bool any_nonzero(const double *p, int n) {
   for (int i = 0; i < n; i++)
@@ -189,6 +189,8 @@ struct Span {
   long long it_begin, it_end, first_sample;
 };
 
+}  // namespace
+
 void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D) {
   std::memset(&D, 0, sizeof(D));
   const double mu0 = J.MAGNETIC_PERMEABILITY, gyro = J.GYRO;
@@ -263,6 +265,8 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
   D.onef = (L.noiseScale != 0) ? 1 : 0;
   D.pid = L.use_pid_control ? 1 : 0;
 }
+
+namespace {
 
 template <int NL>
 int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,

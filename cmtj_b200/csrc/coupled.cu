@@ -1,0 +1,540 @@
+// coupled.cu -- extern "C" entry points for Stack and GroupInteraction batches
+// (include/cmtj_b200.h, "coupled systems"); kernels in coupled_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "coupled_kernels.cuh"
+#include "host_common.h"
+
+namespace cmtjb {
+namespace {
+
+struct Common {
+  int nl = 0;
+  int solver = CMTJB_RK4;
+  int overridden = 0;
+  int n_jch = 0;
+  cmtjb_plan_t plan0;
+};
+
+// Shared validation: same layer count everywhere, per-junction runSimulation guards, one solver
+// mode for the whole system (stack.hpp:36-64, reservoir.hpp:196-213).
+int validate_system(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a, Common *c) {
+  if (!jns || !layers || !a) return fail(CMTJB_EINVAL, "null argument");
+  if (a->timeStep > a->writeFrequency) return fail(CMTJB_ERUNTIME, "The time step cannot be larger than write frequency!");
+  c->nl = jns[0].n_layers;
+  cmtjb_run_args_t aj = *a;
+  aj.solverMode = CMTJB_RK4;
+  aj.onef_buffer = nullptr;
+  for (int j = 0; j < n; j++) {
+    if (jns[j].n_layers != c->nl)
+      return fail(CMTJB_ENOTSUP, "junctions of a coupled system must all have the same number of layers in this build");
+    cmtjb_plan_t p;
+    int rc = make_plan(&jns[j], layers + (size_t)j * c->nl, &aj, &p);
+    if (rc) return rc;
+    for (int l = 0; l < c->nl; l++)
+      if (layers[(size_t)j * c->nl + l].noiseScale != 0)
+        return fail(CMTJB_ENOTSUP, "1/f^alpha noise inside a coupled system is not supported");
+    if (j == 0) {
+      c->plan0 = p;
+      c->solver = p.effective_solver;
+      c->overridden = p.solver_overridden;
+    } else if (p.effective_solver != c->solver) {
+      return fail(CMTJB_ERUNTIME,
+                  "Junctions have different solver modes! Set the same solver mode for all junctions explicitly. Do not "
+                  "mix stochastic and deterministic solvers!");
+    }
+  }
+  c->n_jch = c->plan0.n_channels;
+  return CMTJB_OK;
+}
+
+void fill_plan(const Common &c, int n_sys_ch, cmtjb_coupled_plan_t *p) {
+  std::memset(p, 0, sizeof(*p));
+  p->effective_solver = c.solver;
+  p->solver_overridden = c.overridden;
+  p->n_layers = c.nl;
+  p->n_junction_channels = c.n_jch;
+  p->n_system_channels = n_sys_ch;
+  p->total_iterations = c.plan0.total_iterations;
+  p->write_every = c.plan0.write_every;
+  p->n_samples = c.plan0.n_samples;
+}
+
+template <int NL>
+void build_models(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                  int clear_hres_layer, std::vector<DevModel<NL>> &out, RunParams &R) {
+  out.resize(n);
+  for (int j = 0; j < n; j++) {
+    DevModel<NL> &M = out[j];
+    std::memset(&M, 0, sizeof(M));
+    for (int l = 0; l < NL; l++) {
+      cmtjb_layer_t L = layers[(size_t)j * NL + l];
+      if (l == clear_hres_layer) {
+        // GroupInteraction replaces the reserved-field driver of the top layer every step
+        for (int s = CMTJB_SLOT_HRES_X; s <= CMTJB_SLOT_HRES_Z; s++) {
+          std::memset(&L.drivers[s], 0, sizeof(L.drivers[s]));
+          L.drivers[s].update = CMTJB_UPD_CONSTANT;
+        }
+      }
+      derive_layer(jns[j], L, M.L[l]);
+    }
+    M.Rp = jns[j].Rp;
+    M.Rhalf = (jns[j].Rap - jns[j].Rp) / 2.0;
+    M.mr_mode = jns[j].mr_mode;
+    M.n_layers = NL;
+    int k_row = 0;
+    for (int k = 0; k < n_ovr; k++) {
+      if (ovr[k].layer == CMTJB_LAYER_SYSTEM) continue;
+      for (int l = 0; l < NL; l++) {
+        if (ovr[k].layer >= 0 && ovr[k].layer != l) continue;
+        M.L[l].ovmask |= (1u << ovr[k].slot);
+        M.L[l].ovidx[ovr[k].slot][ovr[k].field] = (int8_t)k_row;
+      }
+      k_row++;
+    }
+  }
+  int k_row = 0;
+  for (int k = 0; k < n_ovr; k++) {
+    if (ovr[k].layer == CMTJB_LAYER_SYSTEM) continue;
+    R.ovr[k_row++] = ovr[k].values;
+  }
+}
+
+int check_coupled_overrides(int nl, const cmtjb_override_t *ovr, int n_ovr) {
+  if (n_ovr < 0 || n_ovr > kMaxOverrides) return fail(CMTJB_EINVAL, "too many per-instance overrides (max 24)");
+  if (n_ovr > 0 && !ovr) return fail(CMTJB_EINVAL, "null override table");
+  for (int k = 0; k < n_ovr; k++) {
+    if (ovr[k].field < 0 || ovr[k].field > CMTJB_FIELD_STEADYTIME || !ovr[k].values) return fail(CMTJB_EINVAL, "override out of range");
+    if (ovr[k].layer == CMTJB_LAYER_SYSTEM) continue;
+    if (ovr[k].layer >= nl || ovr[k].layer < -1 || ovr[k].slot < 0 || ovr[k].slot >= CMTJB_NSLOTS)
+      return fail(CMTJB_EINVAL, "override out of range");
+  }
+  return CMTJB_OK;
+}
+
+void fill_run_params(RunParams &R, const Common &c, const cmtjb_run_args_t *a, long long n_elements, double *m_state, double *jlog,
+                     int32_t *status) {
+  R.m_state = m_state;
+  R.log = (a->log_mode == CMTJB_LOG_FULL) ? jlog : nullptr;
+  R.status = status;
+  R.B = n_elements;
+  R.inst_offset = a->instance_offset;
+  R.n_samples = c.plan0.n_samples;
+  R.it_begin = a->start_iteration;
+  R.it_end = c.plan0.total_iterations;
+  R.total_iterations = c.plan0.total_iterations;
+  R.write_every = c.plan0.write_every > 0 ? c.plan0.write_every : 1;
+  R.first_sample = 0;
+  R.dt = a->timeStep;
+  R.sqrt_dt = std::sqrt(a->timeStep);
+  R.total_time = a->totalTime;
+  R.write_frequency = a->writeFrequency;
+  R.seed = a->seed;
+}
+
+// stream-ordered upload of a small host array
+template <class T> cudaError_t upload(const T *src, size_t n, T **dst, cudaStream_t st) {
+  cudaError_t e = cudaMallocAsync((void **)dst, std::max<size_t>(n, 1) * sizeof(T), st);
+  if (e != cudaSuccess) return e;
+  if (n) e = cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stack
+// ---------------------------------------------------------------------------------------------------
+int validate_stack(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a,
+                   Common *c) {
+  if (!st) return fail(CMTJB_EINVAL, "null argument");
+  const int n = st->n_junctions;
+  if (n < 2) return fail(CMTJB_ERUNTIME, "Stack must have at least 2 junctions!");
+  for (int j = 0; j < n; j++)
+    if (jns[j].mr_mode != CMTJB_MR_CLASSIC)
+      return fail(CMTJB_ERUNTIME,
+                  "Junction has a non-classic magnetoresitance mode! Define the junction with Rp and Rap resistance values.");
+  for (int j = 0; j < n; j++)
+    if (jns[j].n_layers >= 3) return fail(CMTJB_ERUNTIME, "At least one junction has more than 2 layers! It's not supported now.");
+  int rc = validate_system(n, jns, layers, a, c);
+  if (rc) return rc;
+  if (!st->coupling) return fail(CMTJB_ERUNTIME, "Coupling strength is not set!");
+  if (st->top_layer < 0 || st->top_layer >= c->nl || st->bottom_layer >= c->nl) return fail(CMTJB_EINVAL, "layer index out of range");
+  if (c->nl == 2 && st->bottom_layer < 0) return fail(CMTJB_EINVAL, "two-layer stack needs the bottom layer index");
+  if (!st->delayed && c->nl != 2) return fail(CMTJB_ERUNTIME, "Non delayed coupling is only supported for 2 layer stacks!");
+  if (c->nl == 1) {
+    // getPolarisationVector (stack.hpp:285-296)
+    const double *p0 = layers[st->top_layer].referenceLayer;
+    for (int j = 1; j < n; j++) {
+      const double *pj = layers[(size_t)j * c->nl + st->top_layer].referenceLayer;
+      if (pj[0] != p0[0] || pj[1] != p0[1] || pj[2] != p0[2]) return fail(CMTJB_ERUNTIME, "Polarisation vectors are not equal in stack");
+    }
+    if (std::sqrt(p0[0] * p0[0] + p0[1] * p0[1] + p0[2] * p0[2]) == 0) return fail(CMTJB_ERUNTIME, "Polarisation is not set!");
+  }
+  if (st->currentDriver.update == CMTJB_UPD_CUSTOM) return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are not supported on the device path");
+  if (n > kCoupledBlockMax) return fail(CMTJB_ENOTSUP, "stacks of more than 512 junctions are not supported by this build");
+  return CMTJB_OK;
+}
+
+template <int NL>
+int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr,
+                 int n_ovr, const cmtjb_run_args_t *a, const Common &c, double *m_state, double *jlog, double *slog,
+                 int32_t *status, cudaStream_t stream) {
+  const int N = st->n_junctions;
+  const long long n_inst = a->n_instances;
+  if (n_inst <= 0) return CMTJB_OK;
+  RunParams R;
+  std::memset(&R, 0, sizeof(R));
+  fill_run_params(R, c, a, n_inst * N, m_state, jlog, status);
+  std::vector<DevModel<NL>> models;
+  build_models<NL>(N, jns, layers, ovr, n_ovr, -1, models, R);
+  StackParams SP;
+  std::memset(&SP, 0, sizeof(SP));
+  SP.N = N;
+  SP.spb = std::max(1, 128 / N);
+  SP.kind = st->kind;
+  SP.use_kcl = st->use_kcl;
+  SP.delayed = st->delayed;
+  SP.top = st->top_layer;
+  SP.bottom = (NL == 2) ? st->bottom_layer : -1;
+  SP.n_inst = n_inst;
+  SP.phaseOffset = st->phaseOffset;
+  if (NL == 1)
+    for (int k = 0; k < 3; k++) SP.pol[k] = layers[st->top_layer].referenceLayer[k];
+  {
+    cmtjb_junction_t J0 = jns[0];
+    cmtjb_layer_t L;
+    std::memset(&L, 0, sizeof(L));
+    L.Ms = 1;
+    L.thickness = 1;
+    for (int s = 0; s < CMTJB_NSLOTS; s++) L.drivers[s].update = CMTJB_UPD_CONSTANT;
+    L.drivers[CMTJB_SLOT_CURRENT] = st->currentDriver;
+    static thread_local DevLayer D;
+    derive_layer(J0, L, D);
+    SP.cur = D.drv[CMTJB_SLOT_CURRENT];
+    SP.cur_cst = D.cst[CMTJB_SLOT_CURRENT];
+    if (st->currentDriver.update == CMTJB_UPD_CONSTANT) SP.cur.amplitude = 0.0;
+  }
+  for (int k = 0; k < n_ovr; k++)
+    if (ovr[k].layer == CMTJB_LAYER_SYSTEM) SP.cur_ovr[ovr[k].field] = ovr[k].values;
+  SP.slog = (a->log_mode == CMTJB_LOG_FULL) ? slog : nullptr;
+  DevModel<NL> *d_models = nullptr;
+  double *d_coupling = nullptr;
+  cudaError_t e = upload(models.data(), models.size(), &d_models, stream);
+  if (e == cudaSuccess) e = upload(st->coupling, (size_t)(N - 1), &d_coupling, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "stack parameter upload");
+  SP.coupling = d_coupling;
+  const int threads = SP.spb * N;
+  const long long blocks = (n_inst + SP.spb - 1) / SP.spb;
+  const size_t smem = 2 * (size_t)threads * sizeof(double);
+  if (c.solver == CMTJB_RK4)
+    stack_kernel<NL, CMTJB_RK4><<<(unsigned)blocks, threads, smem, stream>>>(d_models, SP, R);
+  else
+    stack_kernel<NL, CMTJB_EULER_HEUN><<<(unsigned)blocks, threads, smem, stream>>>(d_models, SP, R);
+  e = cudaGetLastError();
+  g_launches++;
+  cudaFreeAsync(d_models, stream);
+  cudaFreeAsync(d_coupling, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "stack_kernel");
+  return CMTJB_OK;
+}
+
+int stack_run(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr,
+              int n_ovr, const cmtjb_run_args_t *a, double *m_state, double *jlog, double *slog, int32_t *status,
+              cudaStream_t stream) {
+  Common c;
+  int rc = validate_stack(st, jns, layers, a, &c);
+  if (rc) return rc;
+  rc = check_coupled_overrides(c.nl, ovr, n_ovr);
+  if (rc) return rc;
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  if (c.nl == 1) return stack_launch<1>(st, jns, layers, ovr, n_ovr, a, c, m_state, jlog, slog, status, stream);
+  return stack_launch<2>(st, jns, layers, ovr, n_ovr, a, c, m_state, jlog, slog, status, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupInteraction
+// ---------------------------------------------------------------------------------------------------
+int validate_group(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a,
+                   Common *c) {
+  if (!g) return fail(CMTJB_EINVAL, "null argument");
+  const int n = g->n_junctions;
+  if (n <= 0 || !g->coordinates) return fail(CMTJB_ERUNTIME, "Coordinate matrix and junction list cannot be empty!");
+  int rc = validate_system(n, jns, layers, a, c);
+  if (rc) return rc;
+  if (c->nl > 4) return fail(CMTJB_ENOTSUP, "coupled junctions with more than 4 layers are not supported by this build");
+  if (g->top_layer < 0 || g->top_layer >= c->nl) return fail(CMTJB_EINVAL, "layer index out of range");
+  if (g->interaction < CMTJB_INT_NULL || g->interaction > CMTJB_INT_DIPOLE_NOMURA) return fail(CMTJB_EINVAL, "unknown interaction function");
+  // reservoir.hpp:171-177 (unique coordinates) and the per-pair distance guards (:84-87, :39-42)
+  const double lim = (g->interaction == CMTJB_INT_DIPOLE_NOMURA) ? 1e-14 : 1e-10;
+  const double *r = g->coordinates;
+  for (int i = 0; i < n; i++)
+    for (int j = i + 1; j < n; j++) {
+      const double dx = r[3 * i] - r[3 * j], dy = r[3 * i + 1] - r[3 * j + 1], dz = r[3 * i + 2] - r[3 * j + 2];
+      if (dx == 0 && dy == 0 && dz == 0) return fail(CMTJB_ERUNTIME, "Coordinate vectors must be unique!");
+      if (g->interaction != CMTJB_INT_NULL && std::sqrt(dx * dx + dy * dy + dz * dz) < lim)
+        return fail(CMTJB_ERUNTIME, "Points are too close for stable dipole calculation");
+    }
+  return CMTJB_OK;
+}
+
+int pow2_floor(long long v) {
+  int p = 1;
+  while ((long long)p * 2 <= v) p *= 2;
+  return p;
+}
+
+template <int NL> bool group_uses_grid(int N) { return N * 1 > kCoupledBlockMax / 2; }
+
+template <int NL>
+int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr,
+                 int n_ovr, const cmtjb_run_args_t *a, const Common &c, double *m_state, double *jlog, int32_t *status,
+                 int device, cudaStream_t stream) {
+  const int N = g->n_junctions;
+  const long long n_inst = a->n_instances;
+  if (n_inst <= 0) return CMTJB_OK;
+  RunParams R;
+  std::memset(&R, 0, sizeof(R));
+  fill_run_params(R, c, a, n_inst * N, m_state, jlog, status);
+  std::vector<DevModel<NL>> models;
+  build_models<NL>(N, jns, layers, ovr, n_ovr, g->top_layer, models, R);
+  std::vector<double> pos(3 * (size_t)N), pref(N);
+  for (int k = 0; k < N; k++) {
+    for (int d = 0; d < 3; d++) pos[(size_t)d * N + k] = g->coordinates[3 * k + d];
+    const cmtjb_layer_t &L = layers[(size_t)k * NL + g->top_layer];
+    pref[k] = (L.Ms / jns[k].MAGNETIC_PERMEABILITY) * (L.thickness * L.cellSurface);
+  }
+  GroupParams GP;
+  std::memset(&GP, 0, sizeof(GP));
+  GP.N = N;
+  GP.interaction = g->interaction;
+  GP.top = g->top_layer;
+  GP.n_inst = n_inst;
+  DevModel<NL> *d_models = nullptr;
+  double *d_pos = nullptr, *d_pref = nullptr, *d_mbuf = nullptr;
+  cudaError_t e = upload(models.data(), models.size(), &d_models, stream);
+  if (e == cudaSuccess) e = upload(pos.data(), pos.size(), &d_pos, stream);
+  if (e == cudaSuccess) e = upload(pref.data(), pref.size(), &d_pref, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "group parameter upload");
+  GP.pos = d_pos;
+  GP.pref = d_pref;
+  int rc = CMTJB_OK;
+  const bool rk4 = (c.solver == CMTJB_RK4);
+  if (!group_uses_grid<NL>(N)) {
+    GP.P = std::min(32, pow2_floor(kCoupledBlockMax / N));
+    const int threads = ((N * GP.P + 31) / 32) * 32;
+    const size_t smem = 10 * (size_t)N * sizeof(double);
+    if (rk4)
+      group_block_kernel<NL, CMTJB_RK4><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, GP, R);
+    else
+      group_block_kernel<NL, CMTJB_EULER_HEUN><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, GP, R);
+    e = cudaGetLastError();
+    g_launches++;
+    if (e != cudaSuccess) rc = cuda_fail(e, "group_block_kernel");
+  } else {
+    // one array across the grid: cooperative launch, as many co-resident CTAs as the pair sum can use
+    const void *fn = rk4 ? (const void *)group_grid_kernel<NL, CMTJB_RK4> : (const void *)group_grid_kernel<NL, CMTJB_EULER_HEUN>;
+    int per_sm = 0, sms = 0, coop = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
+    if (e != cudaSuccess || per_sm <= 0 || !coop) {
+      rc = fail(CMTJB_ECUDA, "cooperative launch is not available for the group kernel on this device");
+    } else {
+      const long long max_threads = (long long)per_sm * sms * 256;
+      if (N > max_threads) {
+        rc = fail(CMTJB_ENOTSUP, "dipole-coupled array exceeds one GPU's co-resident thread capacity");
+      } else {
+        GP.P = std::min(32, pow2_floor(max_threads / N));
+        const long long blocks = ((long long)N * GP.P + 255) / 256;
+        e = cudaMallocAsync((void **)&d_mbuf, 6 * (size_t)N * sizeof(double), stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync(group exchange buffer)");
+        GP.mbuf = d_mbuf;
+        for (long long inst = 0; inst < n_inst && rc == CMTJB_OK; inst++) {
+          GP.inst = inst;
+          void *args[] = {(void *)&d_models, (void *)&GP, (void *)&R};
+          e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(256), args, 0, stream);
+          g_launches++;
+          if (e != cudaSuccess) rc = cuda_fail(e, "group_grid_kernel");
+        }
+      }
+    }
+  }
+  cudaFreeAsync(d_models, stream);
+  cudaFreeAsync(d_pos, stream);
+  cudaFreeAsync(d_pref, stream);
+  if (d_mbuf) cudaFreeAsync(d_mbuf, stream);
+  return rc;
+}
+
+int group_run(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr,
+              int n_ovr, const cmtjb_run_args_t *a, double *m_state, double *jlog, int32_t *status, int device,
+              cudaStream_t stream) {
+  Common c;
+  int rc = validate_group(g, jns, layers, a, &c);
+  if (rc) return rc;
+  rc = check_coupled_overrides(c.nl, ovr, n_ovr);
+  if (rc) return rc;
+  for (int k = 0; k < n_ovr; k++)
+    if (ovr[k].layer == CMTJB_LAYER_SYSTEM) return fail(CMTJB_EINVAL, "a group has no system-level driver to override");
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  switch (c.nl) {
+  case 1: return group_launch<1>(g, jns, layers, ovr, n_ovr, a, c, m_state, jlog, status, device, stream);
+  case 2: return group_launch<2>(g, jns, layers, ovr, n_ovr, a, c, m_state, jlog, status, device, stream);
+  default: return fail(CMTJB_ENOTSUP, "dipole-coupled junctions with more than 2 layers are not supported by this build");
+  }
+}
+
+// host-pointer wrapper shared by both systems: stage, run, copy back
+struct HostStage {
+  std::vector<void *> allocs;
+  ~HostStage() {
+    for (void *p : allocs) cudaFree(p);
+  }
+  template <class T> int in(const T *h, size_t n, T **d) {
+    *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)d, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(coupled host staging)");
+    allocs.push_back(*d);
+    if (h && n) {
+      e = cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy H2D");
+    }
+    return CMTJB_OK;
+  }
+};
+
+int finish_status(const int32_t *d_status, int32_t *status, long long n) {
+  std::vector<int32_t> st(n);
+  cudaError_t e = cudaMemcpy(st.data(), d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy D2H(status)");
+  if (status) std::memcpy(status, st.data(), n * sizeof(int32_t));
+  for (long long i = 0; i < n; i++)
+    if (st[i]) return fail(CMTJB_ENAN, "NAN magnetisation");
+  return CMTJB_OK;
+}
+
+}  // namespace
+}  // namespace cmtjb
+
+using namespace cmtjb;
+
+extern "C" {
+
+int cmtjb_stack_plan(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                     const cmtjb_run_args_t *args, cmtjb_coupled_plan_t *plan) {
+  if (!plan) return fail(CMTJB_EINVAL, "null argument");
+  Common c;
+  int rc = validate_stack(st, jns, layers, args, &c);
+  if (rc) return rc;
+  fill_plan(c, 1 + st->n_junctions + (st->n_junctions - 1), plan);
+  return CMTJB_OK;
+}
+
+int cmtjb_stack_run_device(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                           const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                           double *m_state, double *junction_log, double *stack_log, int32_t *status, int device,
+                           void *stream) {
+  CUDA_TRY(cudaSetDevice(device));
+  return stack_run(st, jns, layers, overrides, n_overrides, args, m_state, junction_log, stack_log, status, (cudaStream_t)stream);
+}
+
+int cmtjb_stack_run_host(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                         const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                         double *m_state, double *junction_log, double *stack_log, int32_t *status, int device) {
+  cmtjb_coupled_plan_t plan;
+  int rc = cmtjb_stack_plan(st, jns, layers, args, &plan);
+  if (rc) return rc;
+  rc = check_coupled_overrides(plan.n_layers, overrides, n_overrides);
+  if (rc) return rc;
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  CUDA_TRY(cudaSetDevice(device));
+  const long long n_inst = args->n_instances, N = st->n_junctions, E = n_inst * N;
+  if (E <= 0) return CMTJB_OK;
+  const bool want_log = args->log_mode == CMTJB_LOG_FULL && plan.n_samples > 0;
+  const size_t nm = (size_t)plan.n_layers * 3 * E;
+  const size_t njl = (want_log && junction_log) ? (size_t)plan.n_junction_channels * plan.n_samples * E : 0;
+  const size_t nsl = (want_log && stack_log) ? (size_t)plan.n_system_channels * plan.n_samples * n_inst : 0;
+  HostStage hs;
+  double *d_m, *d_jl, *d_sl;
+  int32_t *d_st;
+  if ((rc = hs.in(m_state, nm, &d_m))) return rc;
+  if ((rc = hs.in((const double *)nullptr, njl, &d_jl))) return rc;
+  if ((rc = hs.in((const double *)nullptr, nsl, &d_sl))) return rc;
+  if ((rc = hs.in((const int32_t *)nullptr, (size_t)E, &d_st))) return rc;
+  CUDA_TRY(cudaMemset(d_st, 0, E * sizeof(int32_t)));
+  std::vector<cmtjb_override_t> d_ovr(overrides, overrides + n_overrides);
+  for (int k = 0; k < n_overrides; k++) {
+    double *p;
+    const size_t n = (overrides[k].layer == CMTJB_LAYER_SYSTEM) ? (size_t)n_inst : (size_t)E;
+    if ((rc = hs.in(overrides[k].values, n, &p))) return rc;
+    d_ovr[k].values = p;
+  }
+  rc = stack_run(st, jns, layers, d_ovr.data(), n_overrides, args, d_m, njl ? d_jl : nullptr, nsl ? d_sl : nullptr, d_st, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(m_state, d_m, nm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (njl) CUDA_TRY(cudaMemcpy(junction_log, d_jl, njl * sizeof(double), cudaMemcpyDeviceToHost));
+  if (nsl) CUDA_TRY(cudaMemcpy(stack_log, d_sl, nsl * sizeof(double), cudaMemcpyDeviceToHost));
+  return finish_status(d_st, status, E);
+}
+
+int cmtjb_group_plan(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                     const cmtjb_run_args_t *args, cmtjb_coupled_plan_t *plan) {
+  if (!plan) return fail(CMTJB_EINVAL, "null argument");
+  Common c;
+  int rc = validate_group(g, jns, layers, args, &c);
+  if (rc) return rc;
+  fill_plan(c, 0, plan);
+  plan->cooperative = (g->n_junctions > kCoupledBlockMax / 2) ? 1 : 0;
+  return CMTJB_OK;
+}
+
+int cmtjb_group_run_device(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                           const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                           double *m_state, double *junction_log, int32_t *status, int device, void *stream) {
+  CUDA_TRY(cudaSetDevice(device));
+  return group_run(g, jns, layers, overrides, n_overrides, args, m_state, junction_log, status, device, (cudaStream_t)stream);
+}
+
+int cmtjb_group_run_host(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                         const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                         double *m_state, double *junction_log, int32_t *status, int device) {
+  cmtjb_coupled_plan_t plan;
+  int rc = cmtjb_group_plan(g, jns, layers, args, &plan);
+  if (rc) return rc;
+  rc = check_coupled_overrides(plan.n_layers, overrides, n_overrides);
+  if (rc) return rc;
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  CUDA_TRY(cudaSetDevice(device));
+  const long long n_inst = args->n_instances, N = g->n_junctions, E = n_inst * N;
+  if (E <= 0) return CMTJB_OK;
+  const bool want_log = args->log_mode == CMTJB_LOG_FULL && plan.n_samples > 0;
+  const size_t nm = (size_t)plan.n_layers * 3 * E;
+  const size_t njl = (want_log && junction_log) ? (size_t)plan.n_junction_channels * plan.n_samples * E : 0;
+  HostStage hs;
+  double *d_m, *d_jl;
+  int32_t *d_st;
+  if ((rc = hs.in(m_state, nm, &d_m))) return rc;
+  if ((rc = hs.in((const double *)nullptr, njl, &d_jl))) return rc;
+  if ((rc = hs.in((const int32_t *)nullptr, (size_t)E, &d_st))) return rc;
+  CUDA_TRY(cudaMemset(d_st, 0, E * sizeof(int32_t)));
+  std::vector<cmtjb_override_t> d_ovr(overrides, overrides + n_overrides);
+  for (int k = 0; k < n_overrides; k++) {
+    double *p;
+    if ((rc = hs.in(overrides[k].values, (size_t)E, &p))) return rc;
+    d_ovr[k].values = p;
+  }
+  rc = group_run(g, jns, layers, d_ovr.data(), n_overrides, args, d_m, njl ? d_jl : nullptr, d_st, device, nullptr);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(m_state, d_m, nm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (njl) CUDA_TRY(cudaMemcpy(junction_log, d_jl, njl * sizeof(double), cudaMemcpyDeviceToHost));
+  return finish_status(d_st, status, E);
+}
+
+} /* extern "C" */

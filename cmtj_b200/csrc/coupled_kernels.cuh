@@ -1,0 +1,459 @@
+// coupled_kernels.cuh -- junctions that exchange information every time step:
+//
+//   stack_kernel   Stack<T>::runSimulation{KCL,NonKCL}   (core/stack.hpp:317-423)
+//   group_kernel   GroupInteraction::runSimulation       (core/reservoir.hpp:129-226)
+//
+// One thread owns one junction (element) of one system instance for the whole time loop; its
+// magnetisation stays in registers.  Junction models may differ inside a system, so they are read
+// from a device array (L1/L2-cached) instead of the constant bank, and the fully general term set
+// (F_ALL: every field/torque term, inline drivers, per-element overrides) is compiled in.  The
+// per-step exchange is a block-level scan (stack) or an all-pairs field sum with m staged in
+// shared memory (group); arrays larger than one block use a cooperative launch with one
+// grid-wide barrier per step.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "llgs_kernels.cuh"
+
+namespace cmtjb {
+
+namespace cg = cooperative_groups;
+
+constexpr uint32_t F_COUPLED = F_ALL;
+constexpr int kCoupledBlockMax = 512;  // 128 registers per thread for the general term set
+
+// waveform of an explicit driver record (same expressions as driver_shape, drivers.hpp:262-305)
+__device__ __forceinline__ double shape_of(const DevDriver &d, double phase, double t) {
+  switch (d.type) {
+  case CMTJB_UPD_PULSE: {
+    const int n = (int)(t / d.period);
+    const double nT = n * d.period;
+    return (nT <= t && t <= (nT + d.cycle * d.period)) ? 1.0 : 0.0;
+  }
+  case CMTJB_UPD_SINE:
+  case CMTJB_UPD_POSINE:
+  case CMTJB_UPD_HALFSINE: return sin(2 * M_PI * t * d.frequency + phase);
+  case CMTJB_UPD_STEP: return (t >= d.timeStart && t <= d.timeStop) ? 1.0 : 0.0;
+  case CMTJB_UPD_TRAPEZOID: {
+    const double t0 = d.timeStart, e = d.edgeTime, st = d.steadyTime;
+    if (t < t0) return 0.0;
+    if (t <= t0 + e) return (t - t0) / e;
+    if (t <= t0 + e + st) return 1.0;
+    if (t <= t0 + 2 * e + st) return 1.0 - (t - (t0 + e + st)) / e;
+    return 0.0;
+  }
+  case CMTJB_UPD_GAUSSIMPULSE: {
+    const double x = t - d.timeStart;
+    return exp(-(x * x) / (2 * (d.edgeTime * d.edgeTime)));
+  }
+  case CMTJB_UPD_GAUSSSTEP: return 0.5 * (1 + erf((t - d.timeStart) / (sqrt(2.0) * d.edgeTime)));
+  default: return 0.0;
+  }
+}
+
+// the current a Stack pushes into every layer of a junction for one step (stack.hpp:370-371,
+// :413-415): constant + post(amplitude * waveform(t; phase))
+struct StackCurrent {
+  static constexpr bool kCurrent = true;
+  const DevDriver *d;
+  double cst, amp, phase;
+  __device__ __forceinline__ double current(double t) const {
+    if (amp == 0.0) return cst;
+    return cst + driver_post(d->type, amp * shape_of(*d, phase, t));
+  }
+};
+
+template <int NL, int SOLVER, class Ext>
+__device__ __forceinline__ void coupled_step(const DevModel<NL> &M, const RunParams &R, long long i, long long it, double t,
+                                             State<NL> &S, const d3 *Hc, const Ext &ext) {
+  State<NL> S1;
+  if constexpr (SOLVER == CMTJB_RK4) rk4_all<NL, F_COUPLED, 0, Ext>(M, R, i, nullptr, t, S, S1, Hc, ext);
+  else euler_heun_all<NL, F_COUPLED, 0, Ext>(M, R, i, it, nullptr, t, S, S1, Hc, ext);
+  S = S1;
+}
+
+template <int NL> __device__ __forceinline__ void load_state(const RunParams &R, long long i, State<NL> &S) {
+#pragma unroll
+  for (int l = 0; l < NL; l++)
+    S.m[l] = mk(R.m_state[(3 * l + 0) * R.B + i], R.m_state[(3 * l + 1) * R.B + i], R.m_state[(3 * l + 2) * R.B + i]);
+}
+template <int NL> __device__ __forceinline__ void store_state(const RunParams &R, long long i, const State<NL> &S) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    R.m_state[(3 * l + 0) * R.B + i] = S.m[l].x;
+    R.m_state[(3 * l + 1) * R.B + i] = S.m[l].y;
+    R.m_state[(3 * l + 2) * R.B + i] = S.m[l].z;
+  }
+}
+template <int NL, int SOLVER> __device__ __forceinline__ int nan_status(const State<NL> &S) {
+  int st = 0;
+  if constexpr (SOLVER == CMTJB_RK4) {
+#pragma unroll
+    for (int l = 0; l < NL; l++) st |= isnan(S.m[l].x) ? 1 : 0;
+  }
+  return st;
+}
+
+// ====================================================================================================
+// Stack
+// ====================================================================================================
+struct StackParams {
+  int N;              // junctions per stack
+  int spb;            // stacks per block (blockDim.x = spb * N)
+  int kind, use_kcl, delayed;
+  int top, bottom;    // layer indices of topId / bottomId (bottom = -1: single-layer junctions)
+  long long n_inst;
+  double phaseOffset;
+  double pol[3];
+  const double *coupling;      // device [N-1]
+  DevDriver cur;               // coupled current driver
+  double cur_cst;
+  const double *cur_ovr[10];   // per-instance override of a current-driver field, or null
+  double *slog;                // [1 + N + (N-1)][n_samples][n_inst]
+};
+
+// inclusive segmented Hillis-Steele scan over the N threads of one stack (sum or product)
+template <bool MUL> __device__ __forceinline__ double seg_scan(double v, double *a, int tid, int j, int N) {
+  a[tid] = v;
+  __syncthreads();
+  for (int off = 1; off < N; off <<= 1) {
+    const double o = (j >= off) ? a[tid - off] : (MUL ? 1.0 : 0.0);
+    __syncthreads();
+    v = MUL ? v * o : v + o;
+    a[tid] = v;
+    __syncthreads();
+  }
+  return v;
+}
+
+template <int NL, int SOLVER>
+__global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<NL> *__restrict__ models, const __grid_constant__ StackParams SP,
+                                                     const __grid_constant__ RunParams R) {
+  extern __shared__ double sm[];
+  const int N = SP.N;
+  const int tid = threadIdx.x;
+  const int sl = tid / N, j = tid - sl * N;
+  const long long s = (long long)blockIdx.x * SP.spb + sl;
+  const bool active = s < SP.n_inst;  // idle threads of the last block still take part in the barriers
+  const long long i = active ? s * N + j : 0;
+  const DevModel<NL> &M = models[j];
+  double *dots = sm;               // [blockDim]  m_top . p of every junction
+  double *scan = sm + blockDim.x;  // [blockDim]  scan workspace
+
+  State<NL> S;
+  d3 Hc[NL];
+  load_state<NL>(R, i, S);
+#pragma unroll
+  for (int l = 0; l < NL; l++) Hc[l] = constant_field(M.L[l], R, i);
+
+  // this instance's coupled current driver (per-instance overrides of its fields)
+  auto cur_field = [&](int f, double dflt) { return (SP.cur_ovr[f] && active) ? __ldg(SP.cur_ovr[f] + s) : dflt; };
+  DevDriver cd = SP.cur;
+  const double cur_cst = cur_field(CMTJB_FIELD_CONSTANT, SP.cur_cst);
+  cd.amplitude = cur_field(CMTJB_FIELD_AMPLITUDE, cd.amplitude);
+  cd.frequency = cur_field(CMTJB_FIELD_FREQUENCY, cd.frequency);
+  cd.phase = cur_field(CMTJB_FIELD_PHASE, cd.phase);
+  cd.period = cur_field(CMTJB_FIELD_PERIOD, cd.period);
+  cd.cycle = cur_field(CMTJB_FIELD_CYCLE, cd.cycle);
+  cd.timeStart = cur_field(CMTJB_FIELD_TIMESTART, cd.timeStart);
+  cd.timeStop = cur_field(CMTJB_FIELD_TIMESTOP, cd.timeStop);
+  cd.edgeTime = cur_field(CMTJB_FIELD_EDGETIME, cd.edgeTime);
+  cd.steadyTime = cur_field(CMTJB_FIELD_STEADYTIME, cd.steadyTime);
+  // getPhaseOffset: series phaseOffset * order, parallel phaseOffset (stack.hpp:441-443, :470-472)
+  const double my_phase = cd.phase + (SP.kind == CMTJB_STACK_SERIES ? SP.phaseOffset * j : SP.phaseOffset);
+  const double sign = (SP.kind == CMTJB_STACK_SERIES) ? 1.0 : -1.0;
+  const double c_here = (j < N - 1) ? __ldg(SP.coupling + j) : 0.0;      // coupling(j)   : pair (j, j+1)
+  const double c_prev = (j > 0) ? __ldg(SP.coupling + j - 1) : 0.0;      // coupling(j-1) : pair (j-1, j)
+  const d3 pol = mk(SP.pol[0], SP.pol[1], SP.pol[2]);
+
+  auto my_dot = [&]() {
+    const d3 mt = S.m[SP.top < NL ? SP.top : 0];
+    if (NL >= 2 && SP.bottom >= 0) return dot(mt, S.m[SP.bottom < NL ? SP.bottom : 0]);
+    return dot(mt, pol);
+  };
+  auto resistance = [&]() {  // getMagnetoresistance()[0], classic (junction.hpp:1865-1889)
+    double c;
+    if constexpr (NL == 1) c = dot(S.m[0], ld3(M.L[0].ref));
+    else c = dot(S.m[0], S.m[1]);
+    return fma(M.Rhalf, 1.0 - c, M.Rp);
+  };
+
+  long long until_write = (R.write_every - (R.it_begin % R.write_every)) % R.write_every;
+  long long sample = R.first_sample;
+  const long long scs = R.n_samples * SP.n_inst;  // stack-log channel stride
+  for (long long it = R.it_begin; it < R.it_end; ++it) {
+    const double t = (double)it * R.dt;
+    StackCurrent ext{&cd, 0.0, 0.0, my_phase};
+    double c_log = 0.0;  // what the reference logs as C_(j-1)_j (non-KCL) or C_j_(j+1) (KCL)
+    if (SP.use_kcl) {
+      // stack.hpp:397-408: I_total = I0(t) (1 + sum_j C_j), C_j = c_j (m_j.p_j +- m_(j+1).p_(j+1))
+      dots[tid] = my_dot();
+      __syncthreads();
+      const double C = (j < N - 1) ? c_here * (dots[tid] + sign * dots[tid + 1]) : 0.0;
+      seg_scan<false>(C, scan, tid, j, N);
+      const double sumC = scan[sl * N + N - 1];
+      const double I0 = cur_cst + (cd.amplitude == 0.0 ? 0.0 : driver_post(cd.type, cd.amplitude * shape_of(cd, cd.phase, t)));
+      ext.cst = fma(sumC, I0, I0);
+      c_log = C;
+      __syncthreads();  // dots/scan are rewritten next step
+      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hc, ext);
+    } else if (SP.delayed) {
+      // stack.hpp:335-354: eff_j = prod_{k<=j, k>0} (1 + C_(k-1)) from the frozen magnetisations
+      dots[tid] = my_dot();
+      __syncthreads();
+      const double f = (j > 0) ? 1.0 + c_prev * (dots[tid - 1] + sign * dots[tid]) : 1.0;
+      const double eff = seg_scan<true>(f, scan, tid, j, N);
+      ext.cst = cur_cst * eff;
+      ext.amp = cd.amplitude * eff;
+      c_log = eff;
+      __syncthreads();
+      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hc, ext);
+    } else {
+      // stack.hpp:356-365: Gauss-Seidel chain -- junction j sees the ALREADY STEPPED j-1
+      for (int jj = 0; jj < N; jj++) {
+        if (j == jj) {
+          double eff = 1.0;
+          if (jj > 0) eff = scan[tid - 1] * (1.0 + c_prev * (dots[tid - 1] + sign * my_dot()));
+          ext.cst = cur_cst * eff;
+          ext.amp = cd.amplitude * eff;
+          c_log = eff;
+          coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hc, ext);
+          dots[tid] = my_dot();
+          scan[tid] = eff;
+        }
+        __syncthreads();
+      }
+    }
+    if (until_write == 0) {
+      // logSimulationStep (stack.hpp:93-103): stack resistance, per-junction current and coupling
+      const double Rj = resistance();
+      const double tot = seg_scan<false>(SP.kind == CMTJB_STACK_SERIES ? Rj : 1.0 / Rj, scan, tid, j, N);
+      if (active && R.log) write_sample<NL>(M, R, S, sample, i);
+      if (active && SP.slog) {
+        double *p = SP.slog + sample * SP.n_inst + s;
+        if (j == N - 1) __stcs(p, SP.kind == CMTJB_STACK_SERIES ? tot : 1.0 / tot);
+        __stcs(p + (1 + j) * scs, ext.current(t));
+        if (SP.use_kcl) {
+          if (j < N - 1) __stcs(p + (1 + N + j) * scs, c_log);
+        } else if (j > 0) {
+          __stcs(p + (1 + N + j - 1) * scs, c_log);
+        }
+      }
+      __syncthreads();
+      sample++;
+      until_write = R.write_every;
+    }
+    until_write--;
+  }
+  if (active) {
+    store_state<NL>(R, i, S);
+    if (R.status) R.status[i] = nan_status<NL, SOLVER>(S);
+  }
+}
+
+// ====================================================================================================
+// GroupInteraction
+// ====================================================================================================
+struct GroupParams {
+  int N;             // elements per group
+  int P;             // threads cooperating on one element's pair sum (power of two <= 32)
+  int interaction;   // cmtjb_interaction
+  int top;           // layer index of topId
+  long long n_inst;
+  const double *pos;   // device [3][N]
+  const double *pref;  // device [N]: (Ms_b / mu0) * thickness_b * cellSurface_b  (reservoir.hpp:91-94)
+  double *mbuf;        // cooperative kernel: [2][3][N] top-layer magnetisation exchange
+  long long inst;      // cooperative kernel: which instance of the batch this launch integrates
+};
+
+// field at a from the dipole at b (reservoir.hpp:79-97); r = r_a - r_b
+__device__ __forceinline__ void pair_accumulate(d3 &H, d3 r, d3 mb, double pref) {
+  const double r2 = dot(r, r);
+  const double inv = rsqrt(r2);
+  const double inv2 = inv * inv;
+  const double inv3 = inv2 * inv;
+  const double a = 3.0 * dot(mb, r) * (inv3 * inv2);
+  H = mk(fma(pref, fma(a, r.x, -inv3 * mb.x), H.x), fma(pref, fma(a, r.y, -inv3 * mb.y), H.y),
+         fma(pref, fma(a, r.z, -inv3 * mb.z), H.z));
+}
+
+// GroupInteraction, one group per block: blockDim.x = N * P rounded up to a warp multiple.  Thread
+// (a = tid / P, p = tid % P) sums the pair field of element a over b = p, p+P, ...; lane p == 0
+// owns junction a.
+template <int NL, int SOLVER>
+__global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const DevModel<NL> *__restrict__ models,
+                                                           const __grid_constant__ GroupParams GP,
+                                                           const __grid_constant__ RunParams R) {
+  extern __shared__ double sm[];
+  const int N = GP.N, P = GP.P;
+  const int tid = threadIdx.x;
+  const int a_raw = tid / P, p = tid - a_raw * P;
+  const int a = a_raw < N ? a_raw : N - 1;  // padding lanes of the last warp shadow element N-1
+  const long long g = blockIdx.x;
+  const long long i = g * N + a;
+  const bool owner = (p == 0) && a_raw < N;
+  const DevModel<NL> &M = models[a];
+  double *px = sm, *py = px + N, *pz = py + N, *pf = pz + N;  // static geometry + prefactors
+  double *mb0 = pf + N;                                      // [2][3][N] double-buffered m_top
+  for (int k = tid; k < N; k += blockDim.x) {
+    px[k] = GP.pos[k];
+    py[k] = GP.pos[N + k];
+    pz[k] = GP.pos[2 * N + k];
+    pf[k] = GP.pref[k];
+  }
+  State<NL> S;
+  d3 Hc[NL];
+  if (owner) {
+    load_state<NL>(R, i, S);
+#pragma unroll
+    for (int l = 0; l < NL; l++) Hc[l] = constant_field(M.L[l], R, i);
+    const d3 mt = S.m[GP.top < NL ? GP.top : 0];
+    mb0[a] = mt.x;
+    mb0[N + a] = mt.y;
+    mb0[2 * N + a] = mt.z;
+  }
+  __syncthreads();
+  const d3 ra = mk(px[a], py[a], pz[a]);
+  const double scale = (GP.interaction == CMTJB_INT_DIPOLE_NOMURA) ? 1.0 / (4.0 * M_PI) : 1.0;
+  long long until_write = (R.write_every - (R.it_begin % R.write_every)) % R.write_every;
+  long long sample = R.first_sample;
+  int cur = 0;
+  for (long long it = R.it_begin; it < R.it_end; ++it) {
+    const double t = (double)it * R.dt;
+    const double *mx = mb0 + cur * 3 * N, *my = mx + N, *mz = my + N;
+    d3 H = mk(0, 0, 0);
+    if (GP.interaction != CMTJB_INT_NULL) {
+      for (int b = p; b < N; b += P) {
+        if (b == a) continue;
+        pair_accumulate(H, mk(ra.x - px[b], ra.y - py[b], ra.z - pz[b]), mk(mx[b], my[b], mz[b]), pf[b]);
+      }
+      for (int off = P >> 1; off > 0; off >>= 1) {
+        H.x += __shfl_xor_sync(0xffffffffu, H.x, off);
+        H.y += __shfl_xor_sync(0xffffffffu, H.y, off);
+        H.z += __shfl_xor_sync(0xffffffffu, H.z, off);
+      }
+    }
+    if (owner) {
+      // setLayerReservedInteractionField(topId, AxialDriver(H_extra)) (reservoir.hpp:145-146)
+      d3 Hs[NL];
+#pragma unroll
+      for (int l = 0; l < NL; l++) Hs[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
+      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hs, NoExt());
+      double *nx = mb0 + (cur ^ 1) * 3 * N;
+      const d3 mt = S.m[GP.top < NL ? GP.top : 0];
+      nx[a] = mt.x;
+      nx[N + a] = mt.y;
+      nx[2 * N + a] = mt.z;
+      if (until_write == 0) {
+        if (R.log) write_sample<NL>(M, R, S, sample, i);
+      }
+    }
+    if (until_write == 0) {
+      sample++;
+      until_write = R.write_every;
+    }
+    until_write--;
+    cur ^= 1;
+    __syncthreads();
+  }
+  if (owner) {
+    store_state<NL>(R, i, S);
+    if (R.status) R.status[i] = nan_status<NL, SOLVER>(S);
+  }
+}
+
+// GroupInteraction, one large group across the whole grid (cooperative launch).  Thread
+// (a, p) as above with a = global_thread / P; the j-loop walks shared-memory tiles of kTile
+// partners; the top-layer magnetisation is exchanged through a double-buffered global array with
+// ONE grid-wide barrier per time step.
+constexpr int kGroupTile = 256;
+
+template <int NL, int SOLVER>
+__global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__restrict__ models,
+                                                         const __grid_constant__ GroupParams GP,
+                                                         const __grid_constant__ RunParams R) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double tx[kGroupTile], ty[kGroupTile], tz[kGroupTile], tf[kGroupTile];
+  __shared__ double tmx[kGroupTile], tmy[kGroupTile], tmz[kGroupTile];
+  const int N = GP.N, P = GP.P;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long a_raw = gt / P;
+  const int p = (int)(gt - a_raw * P);
+  const bool valid = a_raw < N;
+  const int a = valid ? (int)a_raw : N - 1;
+  const bool owner = valid && p == 0;
+  const long long i = GP.inst * N + a;
+  const DevModel<NL> &M = models[a];
+  State<NL> S;
+  d3 Hc[NL];
+  if (owner) {
+    load_state<NL>(R, i, S);
+#pragma unroll
+    for (int l = 0; l < NL; l++) Hc[l] = constant_field(M.L[l], R, i);
+    const d3 mt = S.m[GP.top < NL ? GP.top : 0];
+    GP.mbuf[a] = mt.x;
+    GP.mbuf[N + a] = mt.y;
+    GP.mbuf[2 * N + a] = mt.z;
+  }
+  const d3 ra = mk(__ldg(GP.pos + a), __ldg(GP.pos + N + a), __ldg(GP.pos + 2 * N + a));
+  const double scale = (GP.interaction == CMTJB_INT_DIPOLE_NOMURA) ? 1.0 / (4.0 * M_PI) : 1.0;
+  long long until_write = (R.write_every - (R.it_begin % R.write_every)) % R.write_every;
+  long long sample = R.first_sample;
+  int cur = 0;
+  grid.sync();
+  for (long long it = R.it_begin; it < R.it_end; ++it) {
+    const double t = (double)it * R.dt;
+    const double *mcur = GP.mbuf + (size_t)cur * 3 * N;
+    d3 H = mk(0, 0, 0);
+    if (GP.interaction != CMTJB_INT_NULL) {
+      for (int b0 = 0; b0 < N; b0 += kGroupTile) {
+        const int nb = min(kGroupTile, N - b0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+          tx[k] = __ldg(GP.pos + b0 + k);
+          ty[k] = __ldg(GP.pos + N + b0 + k);
+          tz[k] = __ldg(GP.pos + 2 * N + b0 + k);
+          tf[k] = __ldg(GP.pref + b0 + k);
+          tmx[k] = __ldcg(mcur + b0 + k);  // written by other SMs last step: read through L2
+          tmy[k] = __ldcg(mcur + N + b0 + k);
+          tmz[k] = __ldcg(mcur + 2 * N + b0 + k);
+        }
+        __syncthreads();
+        for (int k = p; k < nb; k += P) {
+          if (b0 + k == a) continue;
+          pair_accumulate(H, mk(ra.x - tx[k], ra.y - ty[k], ra.z - tz[k]), mk(tmx[k], tmy[k], tmz[k]), tf[k]);
+        }
+      }
+      for (int off = P >> 1; off > 0; off >>= 1) {
+        H.x += __shfl_xor_sync(0xffffffffu, H.x, off);
+        H.y += __shfl_xor_sync(0xffffffffu, H.y, off);
+        H.z += __shfl_xor_sync(0xffffffffu, H.z, off);
+      }
+    }
+    if (owner) {
+      d3 Hs[NL];
+#pragma unroll
+      for (int l = 0; l < NL; l++) Hs[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
+      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hs, NoExt());
+      double *nx = GP.mbuf + (size_t)(cur ^ 1) * 3 * N;
+      const d3 mt = S.m[GP.top < NL ? GP.top : 0];
+      __stcg(nx + a, mt.x);
+      __stcg(nx + N + a, mt.y);
+      __stcg(nx + 2 * N + a, mt.z);
+      if (until_write == 0 && R.log) write_sample<NL>(M, R, S, sample, i);
+    }
+    if (until_write == 0) {
+      sample++;
+      until_write = R.write_every;
+    }
+    until_write--;
+    cur ^= 1;
+    grid.sync();
+  }
+  if (owner) {
+    store_state<NL>(R, i, S);
+    if (R.status) R.status[i] = nan_status<NL, SOLVER>(S);
+  }
+}
+
+}  // namespace cmtjb

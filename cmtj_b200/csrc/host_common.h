@@ -1,0 +1,27 @@
+// host_common.h -- host-side helpers shared by the translation units of libcmtj_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+
+#include "dev_model.h"
+
+namespace cmtjb {
+
+extern thread_local std::string g_err;
+extern std::atomic<long long> g_launches;
+
+int fail(int code, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define CUDA_TRY(expr)                                          \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) return ::cmtjb::cuda_fail(_e, #expr); \
+  } while (0)
+
+// validation + derived quantities (cabi.cu)
+int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a, cmtjb_plan_t *p);
+void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D);
+
+}  // namespace cmtjb

@@ -205,13 +205,22 @@ __device__ __forceinline__ d3 dynamic_field(const DevLayer &Lr, const RunParams 
 }
 
 // ---------------------------------------------------------------------------------------
+// External per-thread inputs of the coupled-system kernels (coupled_kernels.cuh): a Stack
+// replaces every layer's current driver each step (stack.hpp:79-91).  NoExt = plain junction.
+// ---------------------------------------------------------------------------------------
+struct NoExt {
+  static constexpr bool kCurrent = false;
+  __device__ __forceinline__ double current(double) const { return 0.0; }
+};
+
+// ---------------------------------------------------------------------------------------
 // u(t, m) with dm/dt = Lr.llg * u : field assembly (calculateHeff, junction.hpp:579-622)
 // fused with solveLLG (junction.hpp:716-815).
 //   HAS_BOT / HAS_TOP: the layer has a neighbour on that side (else the reference passes 0).
 // ---------------------------------------------------------------------------------------
-template <uint32_t F, bool HAS_BOT, bool HAS_TOP>
+template <uint32_t F, bool HAS_BOT, bool HAS_TOP, class Ext = NoExt>
 __device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, int l, long long i, StageTime t, d3 m, d3 bot,
-                                    d3 top, d3 Hc) {
+                                    d3 top, d3 Hc, const Ext &ext = Ext()) {
   static_assert((F & F_DEMAG_FULL) == 0 || (F & F_NOFOLD) != 0, "a full demag tensor cannot be folded into the diagonal operator");
   d3 H = dynamic_field<F>(Lr, R, l, t, i, Hc);
   const d3 a = ld3(Lr.anis);
@@ -273,7 +282,7 @@ __device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, int 
     else if (Lr.refType == CMTJB_REF_BOTTOM) ref = bot;
     if constexpr ((F & F_STT) != 0) {
       if (Lr.stt) {
-        const double I = slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
+        const double I = Ext::kCurrent ? ext.current(t.t) : slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
         const double mp = dot(m, ref);
         double eta;
         if (Lr.altSTT) eta = Lr.P / fma(Lr.lam, mp, 1.0);
@@ -295,7 +304,7 @@ __device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, int 
           Hdl2 = slot_value<F>(Lr, R, CMTJB_SLOT_DL2, t, i);
           Hfl2 = slot_value<F>(Lr, R, CMTJB_SLOT_FL2, t, i);
         } else {
-          const double I = slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
+          const double I = Ext::kCurrent ? ext.current(t.t) : slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
           Hdl = Lr.dlT * I;
           Hfl = Lr.flT * I;
         }

@@ -53,47 +53,48 @@ __device__ __forceinline__ void write_sample(const DevModel<NL> &M, const RunPar
 // Each stepper is written per layer with compile-time layer index so that every DevLayer
 // access is a constant-bank operand.
 
-template <int NL, uint32_t F, int l>
+template <int NL, uint32_t F, int l, class Ext = NoExt>
 __device__ __forceinline__ d3 layer_u(const DevModel<NL> &M, const RunParams &R, long long i, StageTime t, d3 m,
-                                      const State<NL> &nb, const d3 *Hc) {
+                                      const State<NL> &nb, const d3 *Hc, const Ext &ext = Ext()) {
   const d3 zero = mk(0, 0, 0);
   const d3 bot = (l > 0) ? nb.m[l > 0 ? l - 1 : 0] : zero;
   const d3 top = (l < NL - 1) ? nb.m[l < NL - 1 ? l + 1 : 0] : zero;
-  return llg_u<F, (l > 0), (l < NL - 1)>(M.L[l], R, l, i, t, m, bot, top, Hc[l]);
+  return llg_u<F, (l > 0), (l < NL - 1), Ext>(M.L[l], R, l, i, t, m, bot, top, Hc[l], ext);
 }
 
 // RK4: Layer::rk4_step (junction.hpp:1017-1041) under runMultiLayerSolver (:1682-1696):
 // neighbours frozen at their pre-step values for all four stages (Jacobi).
-template <int NL, uint32_t F, int l>
+template <int NL, uint32_t F, int l, class Ext = NoExt>
 __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &R, long long i, const double *row, double t,
-                                        const State<NL> &S0, const d3 *Hc) {
+                                        const State<NL> &S0, const d3 *Hc, const Ext &ext = Ext()) {
   const DevLayer &Lr = M.L[l];
   const double h = Lr.llg * R.dt;  // dm = h * u
   const d3 m0 = S0.m[l];
   const StageTime t0{t, row}, t1{t + 0.5 * R.dt, row + R.dyn_ncols}, t2{t + R.dt, row + 2 * R.dyn_ncols};
-  const d3 u1 = layer_u<NL, F, l>(M, R, i, t0, m0, S0, Hc);
-  const d3 u2 = layer_u<NL, F, l>(M, R, i, t1, axpy(u1, 0.5 * h, m0), S0, Hc);
-  const d3 u3 = layer_u<NL, F, l>(M, R, i, t1, axpy(u2, 0.5 * h, m0), S0, Hc);
-  const d3 u4 = layer_u<NL, F, l>(M, R, i, t2, axpy(u3, h, m0), S0, Hc);
+  const d3 u1 = layer_u<NL, F, l, Ext>(M, R, i, t0, m0, S0, Hc, ext);
+  const d3 u2 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u1, 0.5 * h, m0), S0, Hc, ext);
+  const d3 u3 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u2, 0.5 * h, m0), S0, Hc, ext);
+  const d3 u4 = layer_u<NL, F, l, Ext>(M, R, i, t2, axpy(u3, h, m0), S0, Hc, ext);
   const d3 acc = mk(fma(2.0, u2.x + u3.x, u1.x + u4.x), fma(2.0, u2.y + u3.y, u1.y + u4.y), fma(2.0, u2.z + u3.z, u1.z + u4.z));
   return normalize3(axpy(acc, h * (1.0 / 6.0), m0));
 }
 
-template <int NL, uint32_t F, int l = 0>
+template <int NL, uint32_t F, int l = 0, class Ext = NoExt>
 __device__ __forceinline__ void rk4_all(const DevModel<NL> &M, const RunParams &R, long long i, const double *row, double t,
-                                        const State<NL> &S0, State<NL> &S1, const d3 *Hc) {
-  S1.m[l] = rk4_layer<NL, F, l>(M, R, i, row, t, S0, Hc);
-  if constexpr (l + 1 < NL) rk4_all<NL, F, l + 1>(M, R, i, row, t, S0, S1, Hc);
+                                        const State<NL> &S0, State<NL> &S1, const d3 *Hc, const Ext &ext = Ext()) {
+  S1.m[l] = rk4_layer<NL, F, l, Ext>(M, R, i, row, t, S0, Hc, ext);
+  if constexpr (l + 1 < NL) rk4_all<NL, F, l + 1, Ext>(M, R, i, row, t, S0, S1, Hc, ext);
 }
 
 // Euler-Heun: Junction::eulerHeunSolverStep (junction.hpp:1709-1754)
-template <int NL, uint32_t F, int l = 0>
+template <int NL, uint32_t F, int l = 0, class Ext = NoExt>
 __device__ __forceinline__ void euler_heun_all(const DevModel<NL> &M, const RunParams &R, long long i, long long it,
-                                               const double *row, double t, const State<NL> &S0, State<NL> &S1, const d3 *Hc) {
+                                               const double *row, double t, const State<NL> &S0, State<NL> &S1, const d3 *Hc,
+                                               const Ext &ext = Ext()) {
   const DevLayer &Lr = M.L[l];
   const d3 m0 = S0.m[l];
   const StageTime t0{t, row};
-  const d3 f = layer_u<NL, F, l>(M, R, i, t0, m0, S0, Hc);
+  const d3 f = layer_u<NL, F, l, Ext>(M, R, i, t0, m0, S0, Hc, ext);
   d3 mn = axpy(f, Lr.llg * R.dt, m0);
   if constexpr ((F & (F_THERMAL | F_ONEF)) != 0) {
     const d3 dW = noise_dW<F, NL>(Lr, R, l, i, it, t0);
@@ -103,7 +104,7 @@ __device__ __forceinline__ void euler_heun_all(const DevModel<NL> &M, const RunP
     mn = axpy(g + gp, 0.5 * gs, mn);
   }
   S1.m[l] = normalize3(mn);
-  if constexpr (l + 1 < NL) euler_heun_all<NL, F, l + 1>(M, R, i, it, row, t, S0, S1, Hc);
+  if constexpr (l + 1 < NL) euler_heun_all<NL, F, l + 1, Ext>(M, R, i, it, row, t, S0, S1, Hc, ext);
 }
 
 // Heun: Junction::heunSolverStep (junction.hpp:1756-1815); predictor for every layer first,

@@ -235,6 +235,83 @@ int cmtjb_release_cache(void);
 int cmtjb_eval_driver_host(const cmtjb_driver_t *driver, const double *times, int64_t n,
                            double *out, int device);
 
+/* ---- coupled systems: Stack (core/stack.hpp) and GroupInteraction (core/reservoir.hpp) ---------
+ *
+ * A coupled system is `n_junctions` junction models that all have the same number of layers,
+ * stepped together with a per-step exchange.  A batch is `args->n_instances` copies of the whole
+ * system; an *element* is one junction of one copy, index e = instance * n_junctions + junction.
+ *   jns     [n_junctions]               junction headers (all MR_CLASSIC for a stack)
+ *   layers  [n_junctions * n_layers]    layer records, junction-major
+ *   m_state [n_layers*3][n_elements]    in/out
+ *   junction_log [3*n_layers+1|+3|+0][n_samples][n_elements]   per-junction logLayerParams channels
+ * Overrides: `values` has one entry per ELEMENT; layer = CMTJB_LAYER_SYSTEM targets the stack's
+ * coupled current driver instead, with one entry per INSTANCE (slot is ignored).
+ * Solver: the reference always requests RK4 here (stack.hpp:50, reservoir.hpp:200), which
+ * getSolver turns into Euler-Heun when any layer has a temperature; mixing is an error. */
+#define CMTJB_LAYER_SYSTEM (-2)
+
+enum cmtjb_stack_kind { CMTJB_STACK_SERIES = 0, CMTJB_STACK_PARALLEL = 1 };
+
+/* Stack<T> members (core/stack.hpp:20-22, :106-110) */
+typedef struct cmtjb_stack {
+  int32_t n_junctions;
+  int32_t kind;          /* cmtjb_stack_kind */
+  int32_t use_kcl;       /* ctor argument useKCL (stack.hpp:131-139) */
+  int32_t delayed;       /* setDelayed (stack.hpp:166-172) */
+  int32_t top_layer;     /* index of the layer called topId inside each junction */
+  int32_t bottom_layer;  /* index of bottomId, or -1 for single-layer junctions */
+  int32_t reserved0, reserved1;
+  double phaseOffset;
+  double polarisation[3]; /* getPolarisationVector() (stack.hpp:285-296); used when junctions have one layer */
+  const double *coupling; /* HOST pointer, [n_junctions-1] */
+  cmtjb_driver_t currentDriver; /* setCoupledCurrentDriver (stack.hpp:214-220) */
+} cmtjb_stack_t;
+
+/* reservoir.hpp:63-120 */
+enum cmtjb_interaction { CMTJB_INT_NULL = 0, CMTJB_INT_DIPOLE = 1, CMTJB_INT_DIPOLE_NOMURA = 2 };
+
+typedef struct cmtjb_group {
+  int32_t n_junctions;
+  int32_t interaction;   /* cmtjb_interaction */
+  int32_t top_layer;     /* index of the layer called topId inside each junction */
+  int32_t reserved;
+  const double *coordinates; /* HOST pointer, [n_junctions][3] */
+} cmtjb_group_t;
+
+typedef struct cmtjb_coupled_plan {
+  int32_t effective_solver;
+  int32_t solver_overridden;
+  int32_t n_layers;
+  int32_t n_junction_channels; /* rows of junction_log */
+  int32_t n_system_channels;   /* stack: 1 + n_junctions + (n_junctions-1); group: 0 */
+  int32_t cooperative;         /* group: 1 when the array spans the grid (one launch, grid-wide barrier per step) */
+  int64_t total_iterations, write_every, n_samples;
+} cmtjb_coupled_plan_t;
+
+int cmtjb_stack_plan(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                     const cmtjb_run_args_t *args, cmtjb_coupled_plan_t *plan);
+/* Stack::runSimulation (core/stack.hpp:311-423).  stack_log: [n_system_channels][n_samples][n_instances]
+ * with channel 0 = "Resistance", 1+j = "I_j", 1+n_junctions+j = "C_j_(j+1)" (stack.hpp:255-266).
+ * Host pointers; synchronous. */
+int cmtjb_stack_run_host(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                         const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                         double *m_state, double *junction_log, double *stack_log, int32_t *status, int device);
+/* Same with DEVICE pointers for m_state / logs / status / override values; asynchronous on stream. */
+int cmtjb_stack_run_device(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                           const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                           double *m_state, double *junction_log, double *stack_log, int32_t *status, int device,
+                           void *stream);
+
+int cmtjb_group_plan(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                     const cmtjb_run_args_t *args, cmtjb_coupled_plan_t *plan);
+/* GroupInteraction::runSimulation (core/reservoir.hpp:185-226). */
+int cmtjb_group_run_host(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                         const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                         double *m_state, double *junction_log, int32_t *status, int device);
+int cmtjb_group_run_device(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                           const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
+                           double *m_state, double *junction_log, int32_t *status, int device, void *stream);
+
 /* FP64 FMA-pipe microbenchmark used for the roofline denominator: runs `iters` dependent
  * DFMA chains on every SM and returns achieved FLOP/s in *flops (2 flop per DFMA). */
 int cmtjb_fp64_peak(int device, int64_t iters, double *flops, double *ms);

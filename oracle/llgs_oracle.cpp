@@ -592,3 +592,351 @@ int oracle_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
 }
 
 } /* extern "C" */
+
+/* ------------------------------------------------------------------------------------------------
+ * Coupled systems (include/cmtj_b200.h "coupled systems"): Stack and GroupInteraction.
+ * ---------------------------------------------------------------------------------------------- */
+namespace {
+
+struct SystemSim {
+  std::vector<JunctionSim> j;
+  int nl = 0;
+  int solver = CMTJB_RK4;
+  cmtjb_plan_t plan;
+};
+
+int build_system(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                 const cmtjb_run_args_t *a, const double *m_state, int64_t E, int64_t inst, SystemSim &S) {
+  S.nl = jns[0].n_layers;
+  S.j.resize(n);
+  cmtjb_run_args_t aj = *a;
+  aj.solverMode = CMTJB_RK4; /* stack.hpp:50, reservoir.hpp:200 */
+  aj.onef_buffer = nullptr;
+  for (int k = 0; k < n; k++) {
+    if (jns[k].n_layers != S.nl) return fail(CMTJB_ENOTSUP, "junctions of a coupled system must all have the same number of layers in this build");
+    cmtjb_plan_t p;
+    int rc = validate(&jns[k], layers + (size_t)k * S.nl, &aj, &p);
+    if (rc) return rc;
+    if (k == 0) {
+      S.plan = p;
+      S.solver = p.effective_solver;
+    } else if (p.effective_solver != S.solver) {
+      return fail(CMTJB_ERUNTIME, "Junctions have different solver modes! Set the same solver mode for all junctions explicitly. Do not mix stochastic and deterministic solvers!");
+    }
+    JunctionSim &J = S.j[k];
+    J.J = &jns[k];
+    J.n = S.nl;
+    J.layers.resize(S.nl);
+    const int64_t e = inst * n + k;
+    for (int l = 0; l < S.nl; l++) {
+      LayerSim &s = J.layers[l];
+      s.L = &layers[(size_t)k * S.nl + l];
+      s.J = &jns[k];
+      std::memcpy(s.drv, s.L->drivers, sizeof(s.drv));
+      s.mag = v3(m_state[(l * 3 + 0) * E + e], m_state[(l * 3 + 1) * E + e], m_state[(l * 3 + 2) * E + e]);
+      std::seed_seq seq{(uint32_t)(a->seed), (uint32_t)(a->seed >> 32), (uint32_t)(a->instance_offset + e), (uint32_t)l, 0x5eedu};
+      s.rng.seed(seq);
+      s.onef = nullptr;
+      s.onef_comp_stride = s.onef_iter_stride = 0;
+      s.integral_error = s.L->integral_error;
+      s.prev_error_ratio = s.L->prev_error_ratio;
+    }
+    for (int q = 0; q < n_ovr; q++) {
+      if (ovr[q].layer == CMTJB_LAYER_SYSTEM) continue;
+      for (int l = 0; l < S.nl; l++) {
+        if (ovr[q].layer >= 0 && ovr[q].layer != l) continue;
+        double *f = &J.layers[l].drv[ovr[q].slot].constantValue;
+        f[ovr[q].field] = ovr[q].values[e];
+      }
+    }
+  }
+  return CMTJB_OK;
+}
+
+bool step_junction(JunctionSim &J, int solver, double t, double dt, int64_t iter) {
+  if (solver == CMTJB_RK4) return step_rk4(J, t, dt);
+  step_euler_heun(J, t, dt, iter);
+  return true;
+}
+
+/* Junction::getMagnetoresistance()[0], CLASSIC (core/junction.hpp:1865-1889) */
+double classic_resistance(const JunctionSim &J) {
+  const cmtjb_junction_t &H = *J.J;
+  const double c = (J.n == 1) ? dot(J.layers[0].mag, arr3(J.layers[0].L->referenceLayer)) : dot(J.layers[0].mag, J.layers[1].mag);
+  return H.Rp + (((H.Rap - H.Rp) / 2.0) * (1.0 - c));
+}
+
+void store_system(const SystemSim &S, double *m_state, int64_t E, int64_t inst) {
+  const int n = (int)S.j.size();
+  for (int k = 0; k < n; k++)
+    for (int l = 0; l < S.nl; l++) {
+      const int64_t e = inst * n + k;
+      m_state[(l * 3 + 0) * E + e] = S.j[k].layers[l].mag.x;
+      m_state[(l * 3 + 1) * E + e] = S.j[k].layers[l].mag.y;
+      m_state[(l * 3 + 2) * E + e] = S.j[k].layers[l].mag.z;
+    }
+}
+
+int stack_checks(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers) {
+  if (!st || !jns || !layers) return fail(CMTJB_EINVAL, "null argument");
+  const int n = st->n_junctions;
+  if (n < 2) return fail(CMTJB_ERUNTIME, "Stack must have at least 2 junctions!");
+  for (int k = 0; k < n; k++)
+    if (jns[k].mr_mode != CMTJB_MR_CLASSIC)
+      return fail(CMTJB_ERUNTIME, "Junction has a non-classic magnetoresitance mode! Define the junction with Rp and Rap resistance values.");
+  for (int k = 0; k < n; k++)
+    if (jns[k].n_layers >= 3) return fail(CMTJB_ERUNTIME, "At least one junction has more than 2 layers! It's not supported now.");
+  if (!st->coupling) return fail(CMTJB_ERUNTIME, "Coupling strength is not set!");
+  const int nl = jns[0].n_layers;
+  if (!st->delayed && nl != 2) return fail(CMTJB_ERUNTIME, "Non delayed coupling is only supported for 2 layer stacks!");
+  if (nl == 1) {
+    const double *p0 = layers[st->top_layer].referenceLayer;
+    for (int k = 1; k < n; k++) {
+      const double *pk = layers[(size_t)k * nl + st->top_layer].referenceLayer;
+      if (pk[0] != p0[0] || pk[1] != p0[1] || pk[2] != p0[2]) return fail(CMTJB_ERUNTIME, "Polarisation vectors are not equal in stack");
+    }
+    if (vlen(arr3(p0)) == 0) return fail(CMTJB_ERUNTIME, "Polarisation is not set!");
+  }
+  return CMTJB_OK;
+}
+
+/* reservoir.hpp:79-97 */
+V3 dipole_kanao(V3 r1, V3 r2, const LayerSim &l2) {
+  const V3 rij = r1 - r2;
+  const double len = vlen(rij);
+  const double r3 = std::pow(len, 3), r5 = std::pow(len, 5);
+  const V3 m1 = l2.mag;
+  const double V = l2.L->thickness * l2.L->cellSurface;
+  const double prefactor = (l2.L->Ms / l2.J->MAGNETIC_PERMEABILITY) * V;
+  return prefactor * ((3 * dot(m1, rij) * rij) / r5 - m1 / r3);
+}
+/* reservoir.hpp:36-56, :108-120 */
+V3 dipole_nomura(V3 r1, V3 r2, const LayerSim &l2) {
+  const V3 rij = r1 - r2;
+  const double len = vlen(rij);
+  const double r_mag = std::pow(len, 2);
+  const double mult = 3 / (4 * M_PI * std::pow(len, 5));
+  const V3 row0 = v3(std::pow(rij.x, 2) - (r_mag / 3), rij.x * rij.y, rij.x * rij.z) * mult;
+  const V3 row1 = v3(rij.x * rij.y, std::pow(rij.y, 2) - (r_mag / 3), rij.y * rij.z) * mult;
+  const V3 row2 = v3(rij.x * rij.z, rij.y * rij.z, std::pow(rij.z, 2) - (r_mag / 3)) * mult;
+  const double T[9] = {row0.x, row0.y, row0.z, row1.x, row1.y, row1.z, row2.x, row2.y, row2.z};
+  const double V = l2.L->thickness * l2.L->cellSurface;
+  return tensor_interaction(l2.mag, T, l2.L->Ms * V, l2.J->MAGNETIC_PERMEABILITY);
+}
+
+} // namespace
+
+extern "C" {
+
+int oracle_stack_plan(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                      const cmtjb_run_args_t *args, cmtjb_coupled_plan_t *plan) {
+  int rc = stack_checks(st, jns, layers);
+  if (rc) return rc;
+  if (args->timeStep > args->writeFrequency) return fail(CMTJB_ERUNTIME, "The time step cannot be larger than write frequency!");
+  SystemSim S;
+  std::vector<double> m0((size_t)jns[0].n_layers * 3 * st->n_junctions, 0.0);
+  rc = build_system(st->n_junctions, jns, layers, nullptr, 0, args, m0.data(), st->n_junctions, 0, S);
+  if (rc) return rc;
+  std::memset(plan, 0, sizeof(*plan));
+  plan->effective_solver = S.solver;
+  plan->solver_overridden = S.plan.solver_overridden;
+  plan->n_layers = S.nl;
+  plan->n_junction_channels = S.plan.n_channels;
+  plan->n_system_channels = 1 + st->n_junctions + (st->n_junctions - 1);
+  plan->total_iterations = S.plan.total_iterations;
+  plan->write_every = S.plan.write_every;
+  plan->n_samples = S.plan.n_samples;
+  return CMTJB_OK;
+}
+
+/* Stack::runSimulationKCL / NonKCL (core/stack.hpp:317-423) */
+int oracle_stack_run_host(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                          const cmtjb_override_t *ovr, int32_t n_ovr, const cmtjb_run_args_t *args, double *m_state,
+                          double *jlog, double *slog, int32_t *status) {
+  cmtjb_coupled_plan_t plan;
+  int rc = oracle_stack_plan(st, jns, layers, args, &plan);
+  if (rc) return rc;
+  const int N = st->n_junctions;
+  const int64_t n_inst = args->n_instances, E = n_inst * N, NS = plan.n_samples;
+  const double dt = args->timeStep;
+  const bool do_log = args->log_mode == CMTJB_LOG_FULL;
+  const bool two = plan.n_layers == 2;
+  int worst = CMTJB_OK;
+  for (int64_t inst = 0; inst < n_inst; inst++) {
+    SystemSim S;
+    rc = build_system(N, jns, layers, ovr, n_ovr, args, m_state, E, inst, S);
+    if (rc) return rc;
+    cmtjb_driver_t cur = st->currentDriver;
+    for (int q = 0; q < n_ovr; q++)
+      if (ovr[q].layer == CMTJB_LAYER_SYSTEM) (&cur.constantValue)[ovr[q].field] = ovr[q].values[inst];
+    std::vector<double> Rt(N), It(N), Ct(N - 1);
+    std::vector<V3> fm(N), fp(N);
+    const V3 pol = arr3(layers[st->top_layer].referenceLayer);
+    auto coupling = [&](int order, V3 m1, V3 m2, V3 p1, V3 p2) {
+      const double a = dot(m1, p1), b = dot(m2, p2);
+      return st->coupling[order] * (st->kind == CMTJB_STACK_SERIES ? (a + b) : (a - b));
+    };
+    auto phase_offset = [&](int order) { return st->kind == CMTJB_STACK_SERIES ? st->phaseOffset * order : st->phaseOffset; };
+    auto top = [&](int k) { return S.j[k].layers[st->top_layer].mag; };
+    auto bot = [&](int k) { return S.j[k].layers[st->bottom_layer].mag; };
+    int64_t sample = 0;
+    bool nan = false;
+    for (int64_t i = args->start_iteration; i < plan.total_iterations && !nan; i++) {
+      const double t = i * dt;
+      for (int k = 0; k < N; k++) {
+        fm[k] = top(k);
+        fp[k] = two ? bot(k) : pol;
+      }
+      auto exec = [&](int k, const cmtjb_driver_t &local) {
+        for (int l = 0; l < S.nl; l++) S.j[k].layers[l].drv[CMTJB_SLOT_CURRENT] = local;
+        if (!step_junction(S.j[k], S.solver, t, dt, i)) nan = true;
+        Rt[k] = classic_resistance(S.j[k]);
+        It[k] = driver_value(local, t);
+      };
+      if (st->use_kcl) {
+        const double I0 = driver_value(cur, t);
+        double total = I0;
+        for (int k = 0; k < N - 1; k++) {
+          Ct[k] = coupling(k, fm[k], fm[k + 1], fp[k], fp[k + 1]);
+          total += Ct[k] * I0;
+        }
+        for (int k = 0; k < N && !nan; k++) {
+          cmtjb_driver_t local;
+          std::memset(&local, 0, sizeof(local));
+          local.update = CMTJB_UPD_CONSTANT;
+          local.constantValue = total;
+          local.frequency = local.period = local.cycle = local.timeStart = local.timeStop = local.edgeTime = local.steadyTime = -1;
+          local.phase += phase_offset(k);
+          exec(k, local);
+        }
+      } else {
+        double eff = 1;
+        for (int k = 0; k < N && !nan; k++) {
+          if (k > 0) {
+            if (st->delayed) eff *= (1 + coupling(k - 1, fm[k - 1], fm[k], fp[k - 1], fp[k]));
+            else eff *= (1 + coupling(k - 1, top(k - 1), top(k), bot(k - 1), bot(k)));
+            Ct[k - 1] = eff;
+          }
+          cmtjb_driver_t local = cur;
+          local.constantValue = cur.constantValue * eff;
+          local.amplitude = cur.amplitude * eff;
+          local.phase += phase_offset(k);
+          exec(k, local);
+        }
+      }
+      if (nan) break;
+      if (!(i % plan.write_every)) {
+        if (do_log && slog) {
+          double res;
+          if (st->kind == CMTJB_STACK_SERIES) {
+            res = 0.0;
+            for (int k = 0; k < N; k++) res += Rt[k];
+          } else {
+            double inv = 0.0;
+            for (int k = 0; k < N; k++) inv += 1.0 / Rt[k];
+            res = 1. / inv;
+          }
+          auto put = [&](int ch, double v) { slog[((int64_t)ch * NS + sample) * n_inst + inst] = v; };
+          put(0, res);
+          for (int k = 0; k < N; k++) put(1 + k, It[k]);
+          for (int k = 0; k < N - 1; k++) put(1 + N + k, Ct[k]);
+        }
+        if (do_log && jlog)
+          for (int k = 0; k < N; k++) write_sample(S.j[k], jlog, NS, E, sample, inst * N + k);
+        sample++;
+      }
+    }
+    store_system(S, m_state, E, inst);
+    for (int k = 0; k < N; k++)
+      if (status) status[inst * N + k] = nan ? 1 : 0;
+    if (nan) worst = CMTJB_ENAN;
+  }
+  if (worst) return fail(CMTJB_ENAN, "NAN magnetisation");
+  return CMTJB_OK;
+}
+
+int oracle_group_plan(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                      const cmtjb_run_args_t *args, cmtjb_coupled_plan_t *plan) {
+  if (!g || !jns || !layers || !args || !plan) return fail(CMTJB_EINVAL, "null argument");
+  const int n = g->n_junctions;
+  if (n <= 0 || !g->coordinates) return fail(CMTJB_ERUNTIME, "Coordinate matrix and junction list cannot be empty!");
+  if (args->timeStep > args->writeFrequency) return fail(CMTJB_ERUNTIME, "The time step cannot be larger than write frequency!");
+  const double lim = (g->interaction == CMTJB_INT_DIPOLE_NOMURA) ? 1e-14 : 1e-10;
+  for (int i = 0; i < n; i++)
+    for (int j = i + 1; j < n; j++) {
+      const V3 d = arr3(g->coordinates + 3 * i) - arr3(g->coordinates + 3 * j);
+      if (d.x == 0 && d.y == 0 && d.z == 0) return fail(CMTJB_ERUNTIME, "Coordinate vectors must be unique!");
+      if (g->interaction != CMTJB_INT_NULL && vlen(d) < lim) return fail(CMTJB_ERUNTIME, "Points are too close for stable dipole calculation");
+    }
+  SystemSim S;
+  std::vector<double> m0((size_t)jns[0].n_layers * 3 * n, 0.0);
+  int rc = build_system(n, jns, layers, nullptr, 0, args, m0.data(), n, 0, S);
+  if (rc) return rc;
+  std::memset(plan, 0, sizeof(*plan));
+  plan->effective_solver = S.solver;
+  plan->solver_overridden = S.plan.solver_overridden;
+  plan->n_layers = S.nl;
+  plan->n_junction_channels = S.plan.n_channels;
+  plan->total_iterations = S.plan.total_iterations;
+  plan->write_every = S.plan.write_every;
+  plan->n_samples = S.plan.n_samples;
+  return CMTJB_OK;
+}
+
+/* GroupInteraction::runSimulation + stepFunctionalSolver (core/reservoir.hpp:129-152, :185-226) */
+int oracle_group_run_host(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                          const cmtjb_override_t *ovr, int32_t n_ovr, const cmtjb_run_args_t *args, double *m_state,
+                          double *jlog, int32_t *status) {
+  cmtjb_coupled_plan_t plan;
+  int rc = oracle_group_plan(g, jns, layers, args, &plan);
+  if (rc) return rc;
+  const int N = g->n_junctions;
+  const int64_t n_inst = args->n_instances, E = n_inst * N, NS = plan.n_samples;
+  const double dt = args->timeStep;
+  const bool do_log = args->log_mode == CMTJB_LOG_FULL && jlog;
+  int worst = CMTJB_OK;
+  for (int64_t inst = 0; inst < n_inst; inst++) {
+    SystemSim S;
+    rc = build_system(N, jns, layers, ovr, n_ovr, args, m_state, E, inst, S);
+    if (rc) return rc;
+    int64_t sample = 0;
+    bool nan = false;
+    for (int64_t i = args->start_iteration; i < plan.total_iterations && !nan; i++) {
+      const double t = i * dt;
+      for (int a = 0; a < N; a++) {
+        V3 H = v3(0, 0, 0);
+        for (int b = 0; b < N; b++) {
+          if (a == b) continue;
+          const V3 ra = arr3(g->coordinates + 3 * a), rb = arr3(g->coordinates + 3 * b);
+          const LayerSim &lb = S.j[b].layers[g->top_layer];
+          if (g->interaction == CMTJB_INT_DIPOLE) H = H + dipole_kanao(ra, rb, lb);
+          else if (g->interaction == CMTJB_INT_DIPOLE_NOMURA) H = H + dipole_nomura(ra, rb, lb);
+        }
+        LayerSim &la = S.j[a].layers[g->top_layer];
+        const double h[3] = {H.x, H.y, H.z};
+        for (int c = 0; c < 3; c++) {
+          cmtjb_driver_t &d = la.drv[CMTJB_SLOT_HRES_X + c];
+          std::memset(&d, 0, sizeof(d));
+          d.update = CMTJB_UPD_CONSTANT;
+          d.constantValue = h[c];
+        }
+      }
+      for (int a = 0; a < N && !nan; a++)
+        if (!step_junction(S.j[a], S.solver, t, dt, i)) nan = true;
+      if (nan) break;
+      if (!(i % plan.write_every)) {
+        if (do_log)
+          for (int a = 0; a < N; a++) write_sample(S.j[a], jlog, NS, E, sample, inst * N + a);
+        sample++;
+      }
+    }
+    store_system(S, m_state, E, inst);
+    for (int a = 0; a < N; a++)
+      if (status) status[inst * N + a] = nan ? 1 : 0;
+    if (nan) worst = CMTJB_ENAN;
+  }
+  if (worst) return fail(CMTJB_ENAN, "NAN magnetisation");
+  return CMTJB_OK;
+}
+
+} /* extern "C" */
