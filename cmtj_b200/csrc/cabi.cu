@@ -424,6 +424,26 @@ __global__ void eval_driver_kernel(const __grid_constant__ DevLayer Lr, const __
   if (i < n) out[i] = slot_value<F_DYNI>(Lr, R, CMTJB_SLOT_K1, StageTime{times[i], nullptr}, 0);
 }
 
+// RNG test hooks: the raw Philox block for a given counter/key, and the normal3 stream the
+// steppers draw from
+__global__ void philox_kernel(uint4 ctr, uint2 key, uint32_t *out) {
+  const uint4 r = philox4x32_10(ctr, key);
+  out[0] = r.x;
+  out[1] = r.y;
+  out[2] = r.z;
+  out[3] = r.w;
+}
+__global__ void normals_kernel(unsigned long long seed, long long inst0, long long n_inst, unsigned layer, long long step0,
+                               long long n_steps, double *out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_inst * n_steps) return;
+  const long long st = q / n_inst, i = q - st * n_inst;
+  const d3 v = normal3(seed, (unsigned long long)(inst0 + i), layer, (unsigned long long)(step0 + st));
+  out[3 * q + 0] = v.x;
+  out[3 * q + 1] = v.y;
+  out[3 * q + 2] = v.z;
+}
+
 // 8 independent DFMA chains per thread; 2 flop per DFMA
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, long long iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -632,6 +652,32 @@ int cmtjb_eval_driver_host(const cmtjb_driver_t *driver, const double *times, in
   cudaFree(d_t);
   cudaFree(d_o);
   if (e != cudaSuccess) return cuda_fail(e, "eval_driver_kernel");
+  return CMTJB_OK;
+}
+
+int cmtjb_philox_host(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int device) {
+  if (!ctr || !key || !out) return fail(CMTJB_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  uint32_t *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 16));
+  philox_kernel<<<1, 1>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
+  cudaError_t e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "philox_kernel");
+  return CMTJB_OK;
+}
+
+int cmtjb_normals_host(uint64_t seed, int64_t inst0, int64_t n_inst, int32_t layer, int64_t step0, int64_t n_steps,
+                       double *out, int device) {
+  if (!out || n_inst <= 0 || n_steps <= 0) return fail(CMTJB_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  const long long n = n_inst * n_steps;
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(double)));
+  normals_kernel<<<(unsigned)((n + 255) / 256), 256>>>(seed, inst0, n_inst, (unsigned)layer, step0, n_steps, d);
+  cudaError_t e = cudaMemcpy(out, d, 3 * n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "normals_kernel");
   return CMTJB_OK;
 }
 

@@ -312,6 +312,15 @@ int cmtjb_group_run_device(const cmtjb_group_t *g, const cmtjb_junction_t *jns, 
                            const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
                            double *m_state, double *junction_log, int32_t *status, int device, void *stream);
 
+/* RNG test hooks.  cmtjb_philox_host: one Philox4x32-10 block for counter ctr[4] / key key[2]
+ * (known-answer tests).  cmtjb_normals_host: the N(0,1) triples the stochastic steppers draw for
+ * instances inst0..inst0+n_inst-1, layer `layer`, steps step0..step0+n_steps-1 under `seed`
+ * (replaces std::normal_distribution + mt19937, core/junction.hpp:174-175);
+ * out is [n_steps][n_inst][3]. */
+int cmtjb_philox_host(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int device);
+int cmtjb_normals_host(uint64_t seed, int64_t inst0, int64_t n_inst, int32_t layer, int64_t step0, int64_t n_steps,
+                       double *out, int device);
+
 /* FP64 FMA-pipe microbenchmark used for the roofline denominator: runs `iters` dependent
  * DFMA chains on every SM and returns achieved FLOP/s in *flops (2 flop per DFMA). */
 int cmtjb_fp64_peak(int device, int64_t iters, double *flops, double *ms);
