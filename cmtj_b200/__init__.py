@@ -8,6 +8,7 @@ cmtj/__init__.py:11-14) so scripts can switch with ``import cmtj_b200 as cmtj`` 
 from . import constants, noise, reservoir, stack  # noqa: F401
 from .constants import PhysicalConstants  # noqa: F401
 from .batch import BatchLog, JunctionBatch  # noqa: F401
+from .sweep import ShardedSweep, shard_range  # noqa: F401
 from .core import (  # noqa: F401
     AdaptiveIntegrationParams,
     AxialDriver,
