@@ -264,6 +264,16 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
   D.thermal = L.temperatureSet ? 1 : 0;
   D.onef = (L.noiseScale != 0) ? 1 : 0;
   D.pid = L.use_pid_control ? 1 : 0;
+  D.iecB_a = L.drivers[CMTJB_SLOT_IEC_BOTTOM].constantValue * D.inv_Mst;
+  D.iecB_b = 2 * L.drivers[CMTJB_SLOT_IECQ_BOTTOM].constantValue * D.inv_Mst;
+  D.iecT_a = L.drivers[CMTJB_SLOT_IEC_TOP].constantValue * D.inv_Mst;
+  D.iecT_b = 2 * L.drivers[CMTJB_SLOT_IECQ_TOP].constantValue * D.inv_Mst;
+}
+
+void set_step_products(DevLayer &D, double dt) {
+  D.h = D.llg * dt;
+  D.h_half = 0.5 * D.h;
+  D.h_sixth = D.h * (1.0 / 6.0);
 }
 
 namespace {
@@ -275,7 +285,10 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   static_assert(sizeof(DevModel<NL>) + sizeof(RunParams) < 32000, "kernel parameters exceed the 32 KB limit");
   DevModel<NL> M;
   std::memset(&M, 0, sizeof(M));
-  for (int l = 0; l < NL; l++) derive_layer(*jn, layers[l], M.L[l]);
+  for (int l = 0; l < NL; l++) {
+    derive_layer(*jn, layers[l], M.L[l]);
+    set_step_products(M.L[l], a->timeStep);
+  }
   M.Rp = jn->Rp;
   M.Rhalf = (jn->Rap - jn->Rp) / 2.0;
   M.mr_mode = jn->mr_mode;
@@ -353,23 +366,18 @@ int check_overrides(const cmtjb_junction_t *jn, const cmtjb_override_t *ovr, int
   return CMTJB_OK;
 }
 
-int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
-                    const cmtjb_run_args_t *a, double *m_state, double *log, int32_t *status, int32_t *n_samples_out,
-                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span = nullptr) {
-  cmtjb_plan_t plan;
-  int rc = make_plan(jn, layers, a, &plan);
-  if (rc) return rc;
-  rc = check_overrides(jn, ovr, n_ovr);
-  if (rc) return rc;
-  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+// One launch over the step range `span` (or the whole run) with the leanest variant covering `layers`.
+int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                const cmtjb_run_args_t *a, cmtjb_plan_t &plan, double *m_state, double *log, int32_t *status,
+                int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span) {
   uint32_t need = needed_features(jn, layers, ovr, n_ovr, a, plan.effective_solver);
   if (need & (F_DYN | F_DYNS)) {
     // the stage table costs 24 B per column per step; beyond 2 GiB evaluate inline instead
     size_t n_cols = 3 * (size_t)jn->n_layers;
     for (int l = 0; l < jn->n_layers; l++)
       for (int s = CMTJB_SLOT_K1; s < CMTJB_NSLOTS; s++) n_cols += slot_dynamic(layers[l].drivers[s]) ? 1 : 0;
-    if (n_cols * (size_t)(plan.total_iterations - a->start_iteration) * 24 > ((size_t)2 << 30))
-      need = (need & ~(F_DYN | F_DYNS)) | F_DYNI;
+    const long long steps = span ? span->it_end - span->it_begin : plan.total_iterations - a->start_iteration;
+    if (n_cols * (size_t)std::max<long long>(steps, 0) * 24 > ((size_t)2 << 30)) need = (need & ~(F_DYN | F_DYNS)) | F_DYNI;
   }
   const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel (testing)
   if (force && std::strcmp(force, "full") == 0) need = F_ALL;
@@ -380,9 +388,11 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
                   plan.effective_solver, need);
     return fail(CMTJB_ENOTSUP, buf);
   }
-  plan.feature_mask = (int32_t)v->features;
-  std::snprintf(plan.variant, sizeof(plan.variant), "%s", v->name);
-  if (plan_out) *plan_out = plan;
+  // the plan reports the variant of the (last) segment that still evaluates time-dependent drivers
+  if (plan.variant[0] == 0 || (v->features & (F_DYN | F_DYNS | F_DYNI))) {
+    plan.feature_mask = (int32_t)v->features;
+    std::snprintf(plan.variant, sizeof(plan.variant), "%s", v->name);
+  }
   switch (jn->n_layers) {
   case 1: return run_typed<1>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
   case 2: return run_typed<2>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
@@ -390,6 +400,91 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
   case 4: return run_typed<4>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
   default: return fail(CMTJB_ENOTSUP, "junctions with more than 4 layers need the warp-per-instance kernel (not built yet)");
   }
+}
+
+// Support of a driver's time-dependent part: step and trapezoid drivers add their amplitude only
+// inside a finite window (drivers.hpp:73-108, :262-305); everything else is treated as unbounded.
+bool driver_window(const cmtjb_driver_t &d, double *t0, double *t1) {
+  switch (d.update) {
+  case CMTJB_UPD_STEP:
+    *t0 = d.timeStart;
+    *t1 = d.timeStop;
+    return true;
+  case CMTJB_UPD_TRAPEZOID:
+    *t0 = d.timeStart;
+    *t1 = d.timeStart + 2 * d.edgeTime + d.steadyTime;
+    return true;
+  default: return false;
+  }
+}
+
+int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                    const cmtjb_run_args_t *a, double *m_state, double *log, int32_t *status, int32_t *n_samples_out,
+                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span = nullptr) {
+  cmtjb_plan_t plan;
+  int rc = make_plan(jn, layers, a, &plan);
+  if (rc) return rc;
+  rc = check_overrides(jn, ovr, n_ovr);
+  if (rc) return rc;
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  plan.variant[0] = 0;
+  // Time-window specialisation: when every time-dependent driver has finite support and none of its
+  // timing fields varies per instance, only the steps inside the union of the windows run the
+  // driver-evaluating variant; the steps before and after run the lean constant-driver variant
+  // (a PIMM sweep excites for 3 of its 2e5 steps).  State chains through m_state between launches.
+  const int n = jn->n_layers;
+  bool windowed = plan.effective_solver != CMTJB_DORMAND_PRINCE;
+  bool any_dynamic = false;
+  double w0 = 0, w1 = 0;
+  for (int l = 0; l < n && windowed; l++)
+    for (int s = 0; s < CMTJB_NSLOTS && windowed; s++) {
+      const cmtjb_driver_t &d = layers[l].drivers[s];
+      if (!slot_dynamic(d)) continue;
+      double t0, t1;
+      if (!driver_window(d, &t0, &t1) || !(t1 >= t0)) {
+        windowed = false;
+        break;
+      }
+      for (int k = 0; k < n_ovr; k++)
+        if ((ovr[k].layer < 0 || ovr[k].layer == l) && ovr[k].slot == s && ovr[k].field >= CMTJB_FIELD_TIMESTART) windowed = false;
+      w0 = any_dynamic ? std::min(w0, t0) : t0;
+      w1 = any_dynamic ? std::max(w1, t1) : t1;
+      any_dynamic = true;
+    }
+  const long long it0 = span ? span->it_begin : a->start_iteration;
+  const long long it1 = span ? span->it_end : plan.total_iterations;
+  const long long fs0 = span ? span->first_sample : 0;
+  if (!windowed || !any_dynamic || it1 <= it0) {
+    rc = launch_span(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log, stream, span);
+    if (plan_out) *plan_out = plan;
+    return rc;
+  }
+  // step `it` touches times [it*dt, it*dt + dt]; two steps of margin absorb rounding at the edges
+  const double dt = a->timeStep;
+  long long a_on = (long long)std::floor(w0 / dt) - 2, a_off = (long long)std::ceil(w1 / dt) + 2;
+  a_on = std::min(std::max(a_on, it0), it1);
+  a_off = std::min(std::max(a_off + 1, a_on), it1);
+  std::vector<cmtjb_layer_t> frozen(layers, layers + n);  // drivers reduced to their constant part
+  for (int l = 0; l < n; l++)
+    for (int s = 0; s < CMTJB_NSLOTS; s++)
+      if (slot_dynamic(frozen[l].drivers[s])) {
+        frozen[l].drivers[s].update = CMTJB_UPD_CONSTANT;
+        frozen[l].drivers[s].amplitude = 0.0;
+      }
+  const long long we = plan.write_every > 0 ? plan.write_every : 1;
+  auto count_upto = [&](long long m) { return m <= 0 ? 0LL : (m - 1) / we + 1; };
+  const long long cuts[4] = {it0, a_on, a_off, it1};
+  for (int seg = 0; seg < 3 && rc == CMTJB_OK; seg++) {
+    Span sp;
+    sp.it_begin = cuts[seg];
+    sp.it_end = cuts[seg + 1];
+    if (sp.it_end <= sp.it_begin) continue;
+    sp.first_sample = fs0 + count_upto(sp.it_begin) - count_upto(it0);
+    rc = launch_span(jn, seg == 1 ? layers : frozen.data(), ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log,
+                     stream, &sp);
+  }
+  if (plan_out) *plan_out = plan;
+  return rc;
 }
 
 // Device scratch reused across cmtjb_run_host calls (one slab per device, grown on demand):

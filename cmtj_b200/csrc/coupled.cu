@@ -68,7 +68,7 @@ void fill_plan(const Common &c, int n_sys_ch, cmtjb_coupled_plan_t *p) {
 
 template <int NL>
 void build_models(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
-                  int clear_hres_layer, std::vector<DevModel<NL>> &out, RunParams &R) {
+                  int clear_hres_layer, double dt, std::vector<DevModel<NL>> &out, RunParams &R) {
   out.resize(n);
   for (int j = 0; j < n; j++) {
     DevModel<NL> &M = out[j];
@@ -83,6 +83,7 @@ void build_models(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layer
         }
       }
       derive_layer(jns[j], L, M.L[l]);
+      set_step_products(M.L[l], dt);
     }
     M.Rp = jns[j].Rp;
     M.Rhalf = (jns[j].Rap - jns[j].Rp) / 2.0;
@@ -191,7 +192,7 @@ int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmt
   std::memset(&R, 0, sizeof(R));
   fill_run_params(R, c, a, n_inst * N, m_state, jlog, status);
   std::vector<DevModel<NL>> models;
-  build_models<NL>(N, jns, layers, ovr, n_ovr, -1, models, R);
+  build_models<NL>(N, jns, layers, ovr, n_ovr, -1, a->timeStep, models, R);
   StackParams SP;
   std::memset(&SP, 0, sizeof(SP));
   SP.N = N;
@@ -301,7 +302,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   std::memset(&R, 0, sizeof(R));
   fill_run_params(R, c, a, n_inst * N, m_state, jlog, status);
   std::vector<DevModel<NL>> models;
-  build_models<NL>(N, jns, layers, ovr, n_ovr, g->top_layer, models, R);
+  build_models<NL>(N, jns, layers, ovr, n_ovr, g->top_layer, a->timeStep, models, R);
   std::vector<double> pos(3 * (size_t)N), pref(N);
   for (int k = 0; k < N; k++) {
     for (int d = 0; d < 3; d++) pos[(size_t)d * N + k] = g->coordinates[3 * k + d];

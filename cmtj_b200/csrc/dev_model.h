@@ -64,6 +64,10 @@ struct DevLayer {
   int32_t refType;           // cmtjb_reference
   int32_t stt, sot, dynamicSOT, altSTT, thermal, onef, pid;
   double lin[3];             // folded diagonal linear operator (valid when the variant lacks F_NOFOLD)
+  // per-launch products (run_typed): h = llg*dt and the IEC coefficients J/(Ms t), 2 J2/(Ms t) of
+  // constant, batch-uniform couplings (used by variants without F_DYNS / F_DYNI / F_OVR)
+  double h, h_half, h_sixth;
+  double iecB_a, iecB_b, iecT_a, iecT_b;
   uint32_t dynmask;          // bit s: slot s is time dependent
   int8_t dyncol[CMTJB_NSLOTS];     // column of scalar slot s in the per-launch driver table, or -1
   int32_t dynH;              // 1: the layer has time-dependent field drivers (table columns 3l..3l+2)

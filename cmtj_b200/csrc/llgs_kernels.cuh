@@ -68,15 +68,15 @@ template <int NL, uint32_t F, int l, class Ext = NoExt>
 __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &R, long long i, const double *row, double t,
                                         const State<NL> &S0, const d3 *Hc, const Ext &ext = Ext()) {
   const DevLayer &Lr = M.L[l];
-  const double h = Lr.llg * R.dt;  // dm = h * u
+  const double h = Lr.h;  // llg * dt: dm = h * u
   const d3 m0 = S0.m[l];
   const StageTime t0{t, row}, t1{t + 0.5 * R.dt, row + R.dyn_ncols}, t2{t + R.dt, row + 2 * R.dyn_ncols};
   const d3 u1 = layer_u<NL, F, l, Ext>(M, R, i, t0, m0, S0, Hc, ext);
-  const d3 u2 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u1, 0.5 * h, m0), S0, Hc, ext);
-  const d3 u3 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u2, 0.5 * h, m0), S0, Hc, ext);
+  const d3 u2 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u1, Lr.h_half, m0), S0, Hc, ext);
+  const d3 u3 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u2, Lr.h_half, m0), S0, Hc, ext);
   const d3 u4 = layer_u<NL, F, l, Ext>(M, R, i, t2, axpy(u3, h, m0), S0, Hc, ext);
   const d3 acc = mk(fma(2.0, u2.x + u3.x, u1.x + u4.x), fma(2.0, u2.y + u3.y, u1.y + u4.y), fma(2.0, u2.z + u3.z, u1.z + u4.z));
-  return normalize3(axpy(acc, h * (1.0 / 6.0), m0));
+  return normalize3(axpy(acc, Lr.h_sixth, m0));
 }
 
 template <int NL, uint32_t F, int l = 0, class Ext = NoExt>
