@@ -53,7 +53,7 @@ FIELD_NAMES = (
     "steadyTime",
 )
 
-LOG_FULL, LOG_NONE = 0, 1
+LOG_FULL, LOG_NONE, LOG_ENERGY = 0, 1, 2
 
 
 class Driver(C.Structure):

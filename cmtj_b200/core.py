@@ -1183,6 +1183,17 @@ class Junction:
             names += ["Rx", "Ry", "Rz"]
         return names
 
+    def _energy_channel_names(self) -> List[str]:
+        """Keys added by calculateEnergies=True, in the order of the CMTJB_LOG_ENERGY channels
+        (logLayerParams, junction.hpp:1584-1613)."""
+        names = []
+        for l in self._layers:
+            names += [f"{l.id}_{k}" for k in ("K", "K2", "Jbottom", "Jtop", "I")]
+            groups = ["Hext", "Hiec", "Hanis", "Hdemag", "Hth"] + (["Hfl", "Hdl"] if l.includeSOT else [])
+            for g in groups:
+                names += [f"{l.id}_{g}{v}" for v in _VEC]
+        return names
+
     def _pack(self):
         if self.layerNo > _abi.MAX_LAYERS:
             raise NotImplementedError(f"junctions with more than {_abi.MAX_LAYERS} layers are not supported")
@@ -1233,8 +1244,6 @@ class Junction:
         """``Junction::runSimulation`` (core/junction.hpp:1948-2056) on the GPU."""
         import time as _time
 
-        if calculateEnergies:
-            raise NotImplementedError("calculateEnergies=True is not supported by the device log writer yet")
         be = _abi.backend()
         t0 = _time.perf_counter()
         jn, layers = self._pack()
@@ -1243,7 +1252,7 @@ class Junction:
         args.timeStep = float(timeStep)
         args.writeFrequency = float(writeFrequency)
         args.solverMode = int(solverMode)
-        args.log_mode = _abi.LOG_FULL
+        args.log_mode = _abi.LOG_ENERGY if calculateEnergies else _abi.LOG_FULL
         args.seed = _next_seed()
         args.n_instances = 1
         args.instance_offset = 0
@@ -1272,8 +1281,12 @@ class Junction:
             we = int(plan.write_every)
             times = np.arange(0, int(plan.total_iterations), we, dtype=np.float64) * float(timeStep)
         if rc == _abi.OK or rc == _abi.ENAN:
-            for name, ch in zip(self._channel_names(), range(n_ch)):
-                self._log.setdefault(name, []).extend(log[ch, :n_s, 0].tolist())
+            names = self._channel_names() + (self._energy_channel_names() if calculateEnergies else [])
+            # the reference pushes "<id>_I" twice per sample for STT / SOT layers (junction.hpp:1593, :1611-1612)
+            twice = {f"{l.id}_I" for l in self._layers if l.includeSTT or l.includeSOT} if calculateEnergies else set()
+            for name, ch in zip(names, range(n_ch)):
+                vals = log[ch, :n_s, 0]
+                self._log.setdefault(name, []).extend((np.repeat(vals, 2) if name in twice else vals).tolist())
             self._log.setdefault("time", []).extend(times[:n_s].tolist())
             self._logLength += n_s
         be.check(rc)

@@ -79,6 +79,8 @@ int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   }
   p->effective_solver = mode;
   p->n_channels = 3 * jn->n_layers + (jn->mr_mode == CMTJB_MR_CLASSIC ? 1 : jn->mr_mode == CMTJB_MR_STRIP ? 3 : 0);
+  if (a->log_mode == CMTJB_LOG_ENERGY)
+    for (int i = 0; i < jn->n_layers; i++) p->n_channels += layers[i].includeSOT ? CMTJB_ENERGY_CHANNELS_SOT : CMTJB_ENERGY_CHANNELS;
   if (mode == CMTJB_DORMAND_PRINCE) {
     if (jn->n_layers > 1)
       return fail(CMTJB_ENOTSUP,
@@ -264,6 +266,7 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
   D.thermal = L.temperatureSet ? 1 : 0;
   D.onef = (L.noiseScale != 0) ? 1 : 0;
   D.pid = L.use_pid_control ? 1 : 0;
+  D.includeSOT = L.includeSOT ? 1 : 0;
   D.iecB_a = L.drivers[CMTJB_SLOT_IEC_BOTTOM].constantValue * D.inv_Mst;
   D.iecB_b = 2 * L.drivers[CMTJB_SLOT_IECQ_BOTTOM].constantValue * D.inv_Mst;
   D.iecT_a = L.drivers[CMTJB_SLOT_IEC_TOP].constantValue * D.inv_Mst;
@@ -304,7 +307,10 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
     }
   }
   R.m_state = m_state;
-  R.log = (a->log_mode == CMTJB_LOG_FULL) ? log : nullptr;
+  R.log = (a->log_mode == CMTJB_LOG_FULL || a->log_mode == CMTJB_LOG_ENERGY) ? log : nullptr;
+  R.elog_ch0 = -1;
+  if (a->log_mode == CMTJB_LOG_ENERGY)
+    R.elog_ch0 = 3 * NL + (jn->mr_mode == CMTJB_MR_CLASSIC ? 1 : jn->mr_mode == CMTJB_MR_STRIP ? 3 : 0);
   R.status = status;
   R.n_samples_out = n_samples_out;
   R.time_log = time_log;
@@ -381,6 +387,7 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
   }
   const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel (testing)
   if (force && std::strcmp(force, "full") == 0) need = F_ALL;
+  if (a->log_mode == CMTJB_LOG_ENERGY) need = F_ALL;  // the energy log lives in the general variants only
   const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need);
   if (!v) {
     char buf[160];
@@ -433,7 +440,7 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
   // driver-evaluating variant; the steps before and after run the lean constant-driver variant
   // (a PIMM sweep excites for 3 of its 2e5 steps).  State chains through m_state between launches.
   const int n = jn->n_layers;
-  bool windowed = plan.effective_solver != CMTJB_DORMAND_PRINCE;
+  bool windowed = plan.effective_solver != CMTJB_DORMAND_PRINCE && a->log_mode != CMTJB_LOG_ENERGY;
   bool any_dynamic = false;
   double w0 = 0, w1 = 0;
   for (int l = 0; l < n && windowed; l++)
@@ -624,7 +631,7 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   const long long B = args->n_instances;
   if (B <= 0) return CMTJB_OK;
   const size_t nm = (size_t)jn->n_layers * 3 * B * sizeof(double);
-  const bool want_log = (args->log_mode == CMTJB_LOG_FULL) && log && plan.n_samples > 0;
+  const bool want_log = (args->log_mode == CMTJB_LOG_FULL || args->log_mode == CMTJB_LOG_ENERGY) && log && plan.n_samples > 0;
   const size_t nlog = want_log ? (size_t)plan.n_channels * plan.n_samples * B * sizeof(double) : 0;
   // carve every device buffer of this call out of the per-device slab (256-byte aligned)
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };

@@ -132,6 +132,7 @@ void fill_run_params(RunParams &R, const Common &c, const cmtjb_run_args_t *a, l
   R.total_iterations = c.plan0.total_iterations;
   R.write_every = c.plan0.write_every > 0 ? c.plan0.write_every : 1;
   R.first_sample = 0;
+  R.elog_ch0 = -1;
   R.dt = a->timeStep;
   R.sqrt_dt = std::sqrt(a->timeStep);
   R.total_time = a->totalTime;

@@ -66,8 +66,8 @@ struct StackCurrent {
 template <int NL, int SOLVER, class Ext>
 __device__ __forceinline__ void coupled_step(const DevModel<NL> &M, const RunParams &R, long long i, long long it, double t,
                                              State<NL> &S, const d3 *Hc, const Ext &ext) {
-  State<NL> S1;
-  if constexpr (SOLVER == CMTJB_RK4) rk4_all<NL, F_COUPLED, 0, Ext>(M, R, i, nullptr, t, S, S1, Hc, ext);
+  State<NL> S1, M4;
+  if constexpr (SOLVER == CMTJB_RK4) rk4_all<NL, F_COUPLED, 0, Ext>(M, R, i, nullptr, t, S, S1, Hc, M4, ext);
   else euler_heun_all<NL, F_COUPLED, 0, Ext>(M, R, i, it, nullptr, t, S, S1, Hc, ext);
   S = S1;
 }

@@ -63,6 +63,7 @@ struct DevLayer {
       integral_error;
   int32_t refType;           // cmtjb_reference
   int32_t stt, sot, dynamicSOT, altSTT, thermal, onef, pid;
+  int32_t includeSOT;        // raw flag: the energy log writes Hfl/Hdl for these layers (junction.hpp:1604-1609)
   double lin[3];             // folded diagonal linear operator (valid when the variant lacks F_NOFOLD)
   // per-launch products (run_typed): h = llg*dt and the IEC coefficients J/(Ms t), 2 J2/(Ms t) of
   // constant, batch-uniform couplings (used by variants without F_DYNS / F_DYNI / F_OVR)
@@ -106,6 +107,7 @@ struct RunParams {
   long long total_iterations;
   long long write_every;
   long long first_sample;    // sample index of the first write of this launch
+  long long elog_ch0;        // first CMTJB_LOG_ENERGY channel, or -1 (general variants only)
   double dt, sqrt_dt, total_time, write_frequency;
   unsigned long long seed;
 };

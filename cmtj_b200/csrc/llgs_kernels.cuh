@@ -49,6 +49,69 @@ __device__ __forceinline__ void write_sample(const DevModel<NL> &M, const RunPar
   }
 }
 
+// ---- calculateEnergies = true (junction.hpp:1584-1613): the field terms of the LAST right-hand-side
+// evaluation of the step, recomputed at the point (t_eval, Sm, Snb) where the reference cached them.
+// General (F_ALL) variants only; off the hot path (__noinline__, runs on written samples).
+template <int NL, uint32_t F>
+__device__ __noinline__ void write_energy(const DevModel<NL> &M, const RunParams &R, const State<NL> &Sm, const State<NL> &Snb,
+                                          double t_eval, long long sample, long long i) {
+  const long long cs = R.n_samples * R.B;
+  double *p = R.log + R.elog_ch0 * cs + sample * R.B + i;
+  auto put = [&](double v) {
+    __stcs(p, v);
+    p += cs;
+  };
+  auto put3 = [&](d3 v) {
+    put(v.x);
+    put(v.y);
+    put(v.z);
+  };
+  const StageTime t{t_eval, nullptr};
+  const d3 zero = mk(0, 0, 0);
+  for (int l = 0; l < NL; l++) {
+    const DevLayer &Lr = M.L[l];
+    const d3 m = Sm.m[l];
+    const d3 bot = l > 0 ? Snb.m[l - 1] : zero;
+    const d3 top = l < NL - 1 ? Snb.m[l + 1] : zero;
+    const double K = slot_value<F>(Lr, R, CMTJB_SLOT_K1, t, i);
+    const double Jb = slot_value<F>(Lr, R, CMTJB_SLOT_IEC_BOTTOM, t, i), Jt = slot_value<F>(Lr, R, CMTJB_SLOT_IEC_TOP, t, i);
+    put(K);
+    put(slot_value<F>(Lr, R, CMTJB_SLOT_K2, t, i));
+    put(Jb);
+    put(Jt);
+    put((Lr.stt || (Lr.sot && !Lr.dynamicSOT)) ? slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i) : 0.0);
+    put3(slot_vec<F>(Lr, R, CMTJB_SLOT_HEXT_X, t, i));
+    const double J2b = slot_value<F>(Lr, R, CMTJB_SLOT_IECQ_BOTTOM, t, i), J2t = slot_value<F>(Lr, R, CMTJB_SLOT_IECQ_TOP, t, i);
+    put3(bot * ((Jb + 2 * J2b * dot(bot, m)) * Lr.inv_Mst) + top * ((Jt + 2 * J2t * dot(top, m)) * Lr.inv_Mst));
+    const d3 a = ld3(Lr.anis);
+    put3(a * ((Lr.cK1 * K) * dot(a, m)));
+    put3(mk(0, 0, 0) - sub_matvec(Lr.demag, m, zero));
+    put3(zero);  // Hfluctuation: never passed non-default in the reference
+    if (Lr.includeSOT) {
+      d3 fl = zero, dl = zero;
+      if (Lr.sot) {
+        d3 ref = zero;
+        if (Lr.refType == CMTJB_REF_FIXED) ref = ld3(Lr.ref);
+        else if (Lr.refType == CMTJB_REF_TOP) ref = top;
+        else if (Lr.refType == CMTJB_REF_BOTTOM) ref = bot;
+        double Hdl, Hfl;
+        if (Lr.dynamicSOT) {
+          Hdl = slot_value<F>(Lr, R, CMTJB_SLOT_DL, t, i);
+          Hfl = slot_value<F>(Lr, R, CMTJB_SLOT_FL, t, i);
+        } else {
+          const double I = slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
+          Hdl = Lr.dlT * I;
+          Hfl = Lr.flT * I;
+        }
+        fl = ref * (Hfl - Lr.alpha * Hdl);
+        dl = ref * (Hdl + Lr.alpha * Hfl);
+      }
+      put3(fl);
+      put3(dl);
+    }
+  }
+}
+
 // ---- steppers -------------------------------------------------------------------------------------
 // Each stepper is written per layer with compile-time layer index so that every DevLayer
 // access is a constant-bank operand.
@@ -66,7 +129,7 @@ __device__ __forceinline__ d3 layer_u(const DevModel<NL> &M, const RunParams &R,
 // neighbours frozen at their pre-step values for all four stages (Jacobi).
 template <int NL, uint32_t F, int l, class Ext = NoExt>
 __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &R, long long i, const double *row, double t,
-                                        const State<NL> &S0, const d3 *Hc, const Ext &ext = Ext()) {
+                                        const State<NL> &S0, const d3 *Hc, d3 &m4, const Ext &ext = Ext()) {
   const DevLayer &Lr = M.L[l];
   const double h = Lr.h;  // llg * dt: dm = h * u
   const d3 m0 = S0.m[l];
@@ -74,16 +137,17 @@ __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &
   const d3 u1 = layer_u<NL, F, l, Ext>(M, R, i, t0, m0, S0, Hc, ext);
   const d3 u2 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u1, Lr.h_half, m0), S0, Hc, ext);
   const d3 u3 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u2, Lr.h_half, m0), S0, Hc, ext);
-  const d3 u4 = layer_u<NL, F, l, Ext>(M, R, i, t2, axpy(u3, h, m0), S0, Hc, ext);
+  m4 = axpy(u3, h, m0);  // where the reference's cached log values come from (energy log)
+  const d3 u4 = layer_u<NL, F, l, Ext>(M, R, i, t2, m4, S0, Hc, ext);
   const d3 acc = mk(fma(2.0, u2.x + u3.x, u1.x + u4.x), fma(2.0, u2.y + u3.y, u1.y + u4.y), fma(2.0, u2.z + u3.z, u1.z + u4.z));
   return normalize3(axpy(acc, Lr.h_sixth, m0));
 }
 
 template <int NL, uint32_t F, int l = 0, class Ext = NoExt>
 __device__ __forceinline__ void rk4_all(const DevModel<NL> &M, const RunParams &R, long long i, const double *row, double t,
-                                        const State<NL> &S0, State<NL> &S1, const d3 *Hc, const Ext &ext = Ext()) {
-  S1.m[l] = rk4_layer<NL, F, l, Ext>(M, R, i, row, t, S0, Hc, ext);
-  if constexpr (l + 1 < NL) rk4_all<NL, F, l + 1, Ext>(M, R, i, row, t, S0, S1, Hc, ext);
+                                        const State<NL> &S0, State<NL> &S1, const d3 *Hc, State<NL> &M4, const Ext &ext = Ext()) {
+  S1.m[l] = rk4_layer<NL, F, l, Ext>(M, R, i, row, t, S0, Hc, M4.m[l], ext);
+  if constexpr (l + 1 < NL) rk4_all<NL, F, l + 1, Ext>(M, R, i, row, t, S0, S1, Hc, M4, ext);
 }
 
 // Euler-Heun: Junction::eulerHeunSolverStep (junction.hpp:1709-1754)
@@ -145,18 +209,26 @@ __device__ __forceinline__ void heun_correct(const DevModel<NL> &M, const RunPar
   if constexpr (l + 1 < NL) heun_correct<NL, F, l + 1>(M, R, i, row, t, S0, P, Fn, Gn, dWs, S1, Hc);
 }
 
+// One step.  Em / Enb receive the point of the step's LAST right-hand-side evaluation (stage
+// magnetisations and the neighbour set it used); only the energy log of the general variants reads
+// them, everywhere else they are dead code.
 template <int NL, int SOLVER, uint32_t F>
 __device__ __forceinline__ void do_step(const DevModel<NL> &M, const RunParams &R, long long i, long long it,
-                                        const double *row, double t, State<NL> &S, const d3 *Hc) {
+                                        const double *row, double t, State<NL> &S, const d3 *Hc, State<NL> &Em, State<NL> &Enb) {
   State<NL> S1;
   if constexpr (SOLVER == CMTJB_RK4) {
-    rk4_all<NL, F>(M, R, i, row, t, S, S1, Hc);
+    rk4_all<NL, F>(M, R, i, row, t, S, S1, Hc, Em);
+    Enb = S;
   } else if constexpr (SOLVER == CMTJB_EULER_HEUN) {
     euler_heun_all<NL, F>(M, R, i, it, row, t, S, S1, Hc);
+    Em = S;
+    Enb = S;
   } else {
     State<NL> P, Fn, Gn, dWs;
     heun_predict<NL, F>(M, R, i, it, row, t, S, P, Fn, Gn, dWs, Hc);
     heun_correct<NL, F>(M, R, i, row, t, S, P, Fn, Gn, dWs, S1, Hc);
+    Em = P;
+    Enb = P;
   }
   S = S1;
 }
@@ -181,10 +253,14 @@ __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constan
   const double *row = R.dyn_tab;  // advances by one step (3 stage rows) per iteration
   for (long long it = R.it_begin; it < R.it_end; ++it) {
     const double t = (double)it * R.dt;
-    do_step<NL, SOLVER, F>(M, R, i, it, row, t, S, Hc);
+    State<NL> Em, Enb;
+    do_step<NL, SOLVER, F>(M, R, i, it, row, t, S, Hc, Em, Enb);
     if constexpr ((F & (F_DYN | F_DYNS)) != 0 && (F & F_DYNI) == 0) row += 3 * R.dyn_ncols;
     if (until_write == 0) {
       if (logging) write_sample<NL>(M, R, S, sample, i);
+      if constexpr (F == F_ALL) {
+        if (logging && R.elog_ch0 >= 0) write_energy<NL, F>(M, R, Em, Enb, SOLVER == CMTJB_EULER_HEUN ? t : t + R.dt, sample, i);
+      }
       sample++;
       until_write = R.write_every;
     }
@@ -246,6 +322,7 @@ __global__ void __launch_bounds__(kBlock) llgs_dopri_kernel(const __grid_constan
     const d3 m5 = axpy(k6, 11.0 / 84.0,
                        axpy(k5, -2187.0 / 6784.0, axpy(k4, 125.0 / 192.0, axpy(k3, 500.0 / 1113.0, axpy(k1, 35.0 / 384.0, m)))));
     const d3 k7 = f(t + h, m5) * h;
+    const double t_last = t + h;  // last right-hand-side evaluation of this attempt (energy log)
     const d3 m4 = axpy(k7, 1.0 / 40.0,
                        axpy(k6, 187.0 / 2100.0,
                             axpy(k5, -92097.0 / 339200.0,
@@ -285,6 +362,14 @@ __global__ void __launch_bounds__(kBlock) llgs_dopri_kernel(const __grid_constan
       if (t >= next_write) {
         if (logging && sample < R.n_samples) {
           write_sample<1>(M, R, S, sample, i);
+          if constexpr (F == F_ALL) {
+            if (R.elog_ch0 >= 0) {
+              State<1> Em, Enb;
+              Em.m[0] = m5;
+              Enb.m[0] = m5;
+              write_energy<1, F>(M, R, Em, Enb, t_last, sample, i);
+            }
+          }
           if (R.time_log) R.time_log[sample * R.B + i] = t;
         }
         sample++;

@@ -172,8 +172,15 @@ typedef struct cmtjb_run_args {
 
 enum cmtjb_log_mode {
   CMTJB_LOG_FULL = 0,   /* every channel at every written sample */
-  CMTJB_LOG_NONE = 1    /* final state only: m_state is updated, no samples written */
+  CMTJB_LOG_NONE = 1,   /* final state only: m_state is updated, no samples written */
+  /* calculateEnergies = true (core/junction.hpp:1584-1613): after the LOG_FULL channels, per layer
+   * K, K2, Jbottom, Jtop, I, Hext[3], Hiec[3], Hanis[3], Hdemag[3], Hth[3] and, for layers with
+   * includeSOT, Hfl[3], Hdl[3] -- the values the reference caches in its LAST right-hand-side
+   * evaluation of the step (RK4: stage 4 at t+dt; Heun: corrector; Euler-Heun: the evaluation at t). */
+  CMTJB_LOG_ENERGY = 2
 };
+#define CMTJB_ENERGY_CHANNELS 20      /* per layer */
+#define CMTJB_ENERGY_CHANNELS_SOT 26  /* per layer with includeSOT */
 
 /* What a run will do; filled by cmtjb_plan() so the caller can size buffers. */
 typedef struct cmtjb_plan {

@@ -121,6 +121,9 @@ struct LayerSim {
   int64_t onef_comp_stride, onef_iter_stride;
   /* adaptive controller state (core/junction.hpp:136-138) */
   double integral_error, prev_error_ratio;
+  /* values cached by the last RHS evaluation, logged when calculateEnergies (core/junction.hpp:226-236) */
+  mutable double K_log = 0, K2_log = 0, Jbottom_log = 0, Jtop_log = 0, I_log = 0;
+  mutable V3 cHext{0, 0, 0}, cHIEC{0, 0, 0}, cHAnis{0, 0, 0}, cHdemag{0, 0, 0}, cHfl{0, 0, 0}, cHdl{0, 0, 0};
 
   double slot(int s, double t) const { return driver_value(drv[s], t); }
   V3 axial(int s0, double t) const { return v3(slot(s0, t), slot(s0 + 1, t), slot(s0 + 2, t)); }
@@ -164,6 +167,14 @@ V3 heff(const LayerSim &s, double t, V3 m, V3 bottom, V3 top) {
   const double K2 = s.slot(CMTJB_SLOT_K2, t);
   const V3 HAnis2 = anis * ((4 * K2) * std::pow(dot(anis, m), 3) / L.Ms);
   const V3 zero = v3(0, 0, 0);
+  s.cHext = Hext;
+  s.cHdemag = Hdemag;
+  s.cHIEC = HIEC;
+  s.cHAnis = HAnis;
+  s.K_log = K;
+  s.K2_log = K2;
+  s.Jbottom_log = s.slot(CMTJB_SLOT_IEC_BOTTOM, t);
+  s.Jtop_log = s.slot(CMTJB_SLOT_IEC_TOP, t);
   return Hext + HAnis + HAnis2 + HIEC + Hidmi + Hoe + Hdmi + zero - Hdemag - Hdipole + Hres;
 }
 
@@ -184,6 +195,7 @@ V3 solve_llg(const LayerSim &s, double t, V3 m, V3 bottom, V3 top, V3 H) {
   }
   if (L.includeSTT) {
     const double I = s.slot(CMTJB_SLOT_CURRENT, t);
+    s.I_log = I;
     const double aJ = s.J->HBAR * I / (s.J->ELECTRON_CHARGE * L.Ms * L.thickness);
     double eta;
     if (L.alternativeSTT) {
@@ -205,9 +217,12 @@ V3 solve_llg(const LayerSim &s, double t, V3 m, V3 bottom, V3 top, V3 H) {
       Hfl2 = s.slot(CMTJB_SLOT_FL2, t);
     } else {
       const double I = s.slot(CMTJB_SLOT_CURRENT, t);
+      s.I_log = I;
       Hdl = L.dampingLikeTorque * I;
       Hfl = L.fieldLikeTorque * I;
     }
+    s.cHfl = ref * (Hfl - L.damping * Hdl); /* core/junction.hpp:786-787 */
+    s.cHdl = ref * (Hdl + L.damping * Hfl);
     const V3 ref2 = arr3(L.secondaryReferenceLayer);
     const V3 cm1 = cross(m, ref);
     const V3 ccm1 = cross(m, cm1);
@@ -408,6 +423,39 @@ void write_sample(const JunctionSim &j, double *log, int64_t n_samples, int64_t 
   }
 }
 
+/* core/junction.hpp:1584-1613 (calculateEnergies); channels follow the LOG_FULL ones */
+void write_energy_sample(const JunctionSim &j, double *log, int64_t n_samples, int64_t B, int64_t sample, int64_t inst, int ch) {
+  auto put = [&](double v) { log[((int64_t)ch++ * n_samples + sample) * B + inst] = v; };
+  auto put3 = [&](V3 v) {
+    put(v.x);
+    put(v.y);
+    put(v.z);
+  };
+  for (int i = 0; i < j.n; i++) {
+    const LayerSim &s = j.layers[i];
+    put(s.K_log);
+    put(s.K2_log);
+    put(s.Jbottom_log);
+    put(s.Jtop_log);
+    put(s.I_log);
+    put3(s.cHext);
+    put3(s.cHIEC);
+    put3(s.cHAnis);
+    put3(s.cHdemag);
+    put3(v3(0, 0, 0)); /* Hfluctuation is never passed non-default (SURVEY 8a note 6) */
+    if (s.L->includeSOT) {
+      put3(s.cHfl);
+      put3(s.cHdl);
+    }
+  }
+}
+
+int energy_channels(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers) {
+  int n = 0;
+  for (int i = 0; i < jn->n_layers; i++) n += layers[i].includeSOT ? CMTJB_ENERGY_CHANNELS_SOT : CMTJB_ENERGY_CHANNELS;
+  return n;
+}
+
 int validate(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a, cmtjb_plan_t *p) {
   if (!jn || !layers || !a || !p) return fail(CMTJB_EINVAL, "null argument");
   if (jn->n_layers <= 0) return fail(CMTJB_EINVAL, "Passed a zero length Layer vector!");
@@ -437,6 +485,7 @@ int validate(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtj
   }
   p->effective_solver = mode;
   p->n_channels = 3 * jn->n_layers + (jn->mr_mode == CMTJB_MR_CLASSIC ? 1 : jn->mr_mode == CMTJB_MR_STRIP ? 3 : 0);
+  if (a->log_mode == CMTJB_LOG_ENERGY) p->n_channels += energy_channels(jn, layers);
   if (mode == CMTJB_DORMAND_PRINCE) {
     if (jn->n_layers > 1)
       return fail(CMTJB_ENOTSUP,
@@ -483,7 +532,9 @@ int oracle_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
   const int n = jn->n_layers;
   const double dt = args->timeStep;
   const int64_t NS = plan.n_samples;
-  const bool do_log = (args->log_mode == CMTJB_LOG_FULL) && log;
+  const bool do_log = (args->log_mode == CMTJB_LOG_FULL || args->log_mode == CMTJB_LOG_ENERGY) && log;
+  const bool do_energy = args->log_mode == CMTJB_LOG_ENERGY;
+  const int base_ch = plan.n_channels - (do_energy ? energy_channels(jn, layers) : 0);
   for (int k = 0; k < n_ovr; k++) {
     if (ovr[k].layer >= n || ovr[k].slot < 0 || ovr[k].slot >= CMTJB_NSLOTS || ovr[k].field < 0 ||
         ovr[k].field > CMTJB_FIELD_STEADYTIME)
@@ -534,6 +585,7 @@ int oracle_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
         }
         if (!(i % plan.write_every)) {
           if (do_log) write_sample(j, log, NS, B, sample, inst);
+          if (do_log && do_energy) write_energy_sample(j, log, NS, B, sample, inst, base_ch);
           sample++;
         }
       }
@@ -568,6 +620,7 @@ int oracle_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
           if (t >= next_write) {
             if (do_log && sample < NS) {
               write_sample(j, log, NS, B, sample, inst);
+              if (do_energy) write_energy_sample(j, log, NS, B, sample, inst, base_ch);
               if (time_log) time_log[sample * B + inst] = t;
             }
             sample++;

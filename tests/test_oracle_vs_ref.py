@@ -241,3 +241,33 @@ def test_reference_is_ill_conditioned_for_euler_heun(ref):
     d_rk = np.abs(run("RK4", 0.0) - run("RK4", 1e-15)).max()
     assert d_eh > 1e-6
     assert d_rk < 1e-10
+
+
+@pytest.mark.parametrize("mode", MODES + ["DormandPrince"])
+@pytest.mark.parametrize("build", ["two_layer_mtj", "stt_layer_mtj", "sot_dynamic", "sot_static"])
+def test_calculate_energies_bit_exact(ref, on_oracle, build, mode):
+    """calculateEnergies=True (junction.hpp:1584-1613): the cached values of the LAST right-hand-side
+    evaluation of each step, incl. the doubled "<id>_I" key for STT / SOT layers."""
+    if mode == "DormandPrince" and build == "two_layer_mtj":
+        pytest.skip("multi-layer Dormand-Prince diverges in the reference")
+    logs = []
+    for m in (ref, cmtj_b200):
+        if build.startswith("sot"):
+            j = helpers.sot_layer(m, dynamic=build == "sot_dynamic")
+        else:
+            j = getattr(helpers, build)(m)
+        if build == "two_layer_mtj":
+            j.setLayerAnisotropyDriver("free", m.ScalarDriver.getSineDriver(1e3, 300.0, 5e9, 0.1))
+            j.setIECDriver("free", "bottom", m.ScalarDriver.getStepDriver(-1.78e-3, 1e-4, 1e-10, 3e-10))
+            j.setLayerExternalFieldDriver("all", m.AxialDriver(m.ScalarDriver.getSineDriver(1e4, 2e3, 7e9, 0), m.NullDriver(), m.NullDriver()))
+        dt = 1e-12 if mode == "DormandPrince" else 1e-13
+        j.runSimulation(0.5e-9, dt, 10 * dt, False, True, getattr(m.SolverMode, mode))
+        logs.append(j.getLog())
+    lr, lo = helpers.log_arrays(logs[0]), helpers.log_arrays(logs[1])
+    assert set(lr) == set(lo), sorted(set(lr) ^ set(lo))
+    for k in lr:
+        assert lr[k].shape == lo[k].shape, (k, lr[k].shape, lo[k].shape)
+        assert np.array_equal(lr[k], lo[k]), (k, helpers.max_rel_err(lo[k], lr[k]))
+    assert any(k.endswith("_Hanisx") for k in lo)
+    if build != "two_layer_mtj":
+        assert len(lo["free_I"]) == 2 * len(lo["time"])
