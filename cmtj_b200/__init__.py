@@ -5,7 +5,7 @@ cmtj/__init__.py:11-14) so scripts can switch with ``import cmtj_b200 as cmtj`` 
 ``cmtj_b200.install_as_cmtj()``.  Compute runs only on the GPU through the C-ABI library
 ``libcmtj_b200.so`` (see include/cmtj_b200.h); there is no CPU fallback.
 """
-from . import constants, noise, reservoir, stack  # noqa: F401
+from . import constants, noise, reservoir, stack, utils  # noqa: F401
 from .constants import PhysicalConstants  # noqa: F401
 from .batch import BatchLog, JunctionBatch  # noqa: F401
 from .sweep import ShardedSweep, shard_range  # noqa: F401
@@ -62,6 +62,8 @@ def install_as_cmtj() -> None:
     me = sys.modules[__name__]
     sys.modules["cmtj"] = me
     sys.modules["_cmtj"] = me
-    for sub in ("stack", "reservoir", "noise", "constants"):
+    for sub in ("stack", "reservoir", "noise", "constants", "utils"):
         sys.modules["cmtj." + sub] = getattr(me, sub)
         sys.modules["_cmtj." + sub] = getattr(me, sub)
+    for sub in ("procedures", "resistance", "linear", "filters", "parallel", "constants"):
+        sys.modules["cmtj.utils." + sub] = getattr(me.utils, sub)

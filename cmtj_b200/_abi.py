@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 8
 NSLOTS = 30
 
@@ -209,6 +209,28 @@ class CoupledPlan(C.Structure):
         ("total_iterations", C.c_int64),
         ("write_every", C.c_int64),
         ("n_samples", C.c_int64),
+    ]
+
+
+MAX_PROJ, POST_MAX_LAYERS, RES_NFIELDS = 4, 4, 6
+SD_NONE, SD_RZ, SD_RX_SERIES, SD_RY_SERIES, SD_RX_PARALLEL, SD_RY_PARALLEL = range(6)
+
+
+class Post(C.Structure):
+    """cmtjb_post_t: fused reductions of the sweep procedures (projection log, spin-diode IIR)."""
+
+    _fields_ = [
+        ("n_proj", C.c_int32),
+        ("sd_mode", C.c_int32),
+        ("proj", (C.c_double * (3 * POST_MAX_LAYERS)) * MAX_PROJ),
+        ("res", (C.c_double * RES_NFIELDS) * POST_MAX_LAYERS),
+        ("sd_b", C.c_double * 4),
+        ("sd_a", C.c_double * 4),
+        ("sd_omega", C.c_void_p),
+        ("proj_log", C.c_void_p),
+        ("proj_n_samples", C.c_int64),
+        ("proj_sample0", C.c_int64),
+        ("sd_state", C.c_void_p),
     ]
 
 

@@ -125,7 +125,7 @@ class JunctionBatch:
             self.m_state = self._m_dev.cpu().numpy()
 
     # ---- shared plumbing -------------------------------------------------------------------------------
-    def _args(self, totalTime, timeStep, writeFrequency, solverMode, log, seed, onef) -> _abi.RunArgs:
+    def _args(self, totalTime, timeStep, writeFrequency, solverMode, log, seed, onef, start_iteration=0) -> _abi.RunArgs:
         a = _abi.RunArgs()
         a.totalTime = float(totalTime)
         a.timeStep = float(timeStep)
@@ -135,7 +135,7 @@ class JunctionBatch:
         a.seed = _next_seed() if seed is None else int(seed)
         a.n_instances = self.B
         a.instance_offset = self.instance_offset
-        a.start_iteration = 0
+        a.start_iteration = int(start_iteration)
         a.onef_buffer = onef
         return a
 
@@ -214,9 +214,15 @@ class JunctionBatch:
         log: bool = True,
         seed: Optional[int] = None,
         out=None,
+        post: Optional["PostSpec"] = None,
+        start_iteration: int = 0,
     ):
         """Same run with everything resident on the GPU.  Returns a dict of ``torch`` tensors
-        (views of one [n_channels, n_samples, B] tensor); asynchronous on the current stream."""
+        (views of one [n_channels, n_samples, B] tensor); asynchronous on the current stream.
+
+        ``post`` fuses the reductions of the sweep procedures into the time loop
+        (``cmtjb_run_device_post``: projection log, spin-diode IIR); ``start_iteration`` continues a
+        run whose first steps were integrated by an earlier call (state carried on the device)."""
         import torch
 
         self._check_onef()
@@ -224,7 +230,7 @@ class JunctionBatch:
         lib = be.lib
         dev = torch.device("cuda", self.device)
         jn, layers = self.junction._pack()
-        a = self._args(totalTime, timeStep, writeFrequency, solverMode, log, seed, None)
+        a = self._args(totalTime, timeStep, writeFrequency, solverMode, log, seed, None, start_iteration)
         plan = be.plan(jn, layers, a)
         self.last_plan = plan
         n_ch, n_s = int(plan.n_channels), int(plan.n_samples)
@@ -241,18 +247,28 @@ class JunctionBatch:
         status = torch.zeros(self.B, dtype=torch.int32, device=dev)
         nsamp = torch.zeros(self.B, dtype=torch.int32, device=dev) if plan.variable_samples else None
         tlog = torch.zeros((n_s, self.B), dtype=torch.float64, device=dev) if plan.variable_samples and log else None
-        f = lib.cmtjb_run_device
-        f.restype = C.c_int
-        f.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
 
         def p(t):
             return None if t is None else C.c_void_p(t.data_ptr())
 
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = f(
-            C.byref(jn), layers, tab, n, C.byref(a), p(self._m_dev), p(buf), p(status), p(nsamp), p(tlog),
-            self.device, C.c_void_p(stream),
-        )  # fmt: skip
+        if post is None:
+            f = lib.cmtjb_run_device
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+            rc = f(
+                C.byref(jn), layers, tab, n, C.byref(a), p(self._m_dev), p(buf), p(status), p(nsamp), p(tlog),
+                self.device, C.c_void_p(stream),
+            )  # fmt: skip
+        else:
+            f = lib.cmtjb_run_device_post
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+            pc = post._pack(self.B, L=self.junction.layerNo)
+            rc = f(
+                C.byref(jn), layers, tab, n, C.byref(a), C.byref(pc), p(self._m_dev), p(buf), p(status),
+                self.device, C.c_void_p(stream),
+            )  # fmt: skip
         be.check(rc)
         self.status_dev = status
         res = {}
@@ -263,9 +279,63 @@ class JunctionBatch:
                 res["time"] = tlog
                 res["n_samples"] = nsamp
             else:
-                res["time"] = (
-                    torch.arange(0, int(plan.total_iterations), int(plan.write_every), dtype=torch.float64, device=dev)
-                    * float(timeStep)
+                we = int(plan.write_every)
+                first = -(-int(start_iteration) // we) * we  # first logged step index of this call
+                res["time"] = torch.arange(first, int(plan.total_iterations), we, dtype=torch.float64, device=dev) * float(
+                    timeStep
                 )
         res["_log"] = buf
         return res
+
+
+class PostSpec:
+    """Python view of ``cmtjb_post_t`` (include/cmtj_b200.h): what to reduce inside the time loop.
+
+    proj        [n_proj, 3*L] projection rows (row k: weights on mx,my,mz of every layer)
+    proj_log    torch float64 [n_proj, proj_n_samples, B] on the device
+    sd_mode     _abi.SD_*; res [L, 6] ResistanceParameters rows (Rxx0, Rxy0, Ramr, Rahe, Rsmr, w/l)
+    sd_b, sd_a  order-3 IIR; sd_omega torch [B]; sd_state torch [4, B]
+    """
+
+    def __init__(self, proj=None, proj_log=None, proj_sample0=0, sd_mode=_abi.SD_NONE, res=None, sd_b=None, sd_a=None,
+                 sd_omega=None, sd_state=None):
+        self.proj = None if proj is None else np.atleast_2d(np.asarray(proj, dtype=np.float64))
+        self.proj_log = proj_log
+        self.proj_sample0 = int(proj_sample0)
+        self.sd_mode = int(sd_mode)
+        self.res = None if res is None else np.atleast_2d(np.asarray(res, dtype=np.float64))
+        self.sd_b, self.sd_a = sd_b, sd_a
+        self.sd_omega, self.sd_state = sd_omega, sd_state
+
+    def _pack(self, B: int, L: int) -> _abi.Post:
+        c = _abi.Post()
+        if self.proj is not None:
+            k, w = self.proj.shape
+            if k > _abi.MAX_PROJ or w != 3 * L:
+                raise ValueError(f"proj must be [<= {_abi.MAX_PROJ}, {3 * L}]")
+            t = self.proj_log
+            if t is None or t.dim() != 3 or t.shape[0] != k or t.shape[2] != B or not t.is_contiguous():
+                raise ValueError("proj_log must be a contiguous float64 device tensor [n_proj, n_samples, B]")
+            c.n_proj = k
+            for r in range(k):
+                for q in range(w):
+                    c.proj[r][q] = float(self.proj[r, q])
+            c.proj_log = t.data_ptr()
+            c.proj_n_samples = int(t.shape[1])
+            c.proj_sample0 = self.proj_sample0
+        c.sd_mode = self.sd_mode
+        if self.res is not None:
+            if self.res.shape != (L, _abi.RES_NFIELDS):
+                raise ValueError(f"res must be [{L}, {_abi.RES_NFIELDS}]")
+            for l in range(L):
+                for q in range(_abi.RES_NFIELDS):
+                    c.res[l][q] = float(self.res[l, q])
+        if self.sd_mode != _abi.SD_NONE:
+            for q in range(4):
+                c.sd_b[q] = float(self.sd_b[q])
+                c.sd_a[q] = float(self.sd_a[q])
+            if tuple(self.sd_omega.shape) != (B,) or tuple(self.sd_state.shape) != (4, B):
+                raise ValueError("sd_omega must be [B] and sd_state [4, B]")
+            c.sd_omega = self.sd_omega.data_ptr()
+            c.sd_state = self.sd_state.data_ptr()
+        return c

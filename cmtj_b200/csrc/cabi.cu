@@ -26,6 +26,7 @@ int variants_rk4(const Variant **out);
 int variants_heun(const Variant **out);
 int variants_euler_heun(const Variant **out);
 int variants_dopri(const Variant **out);
+int variants_post(const Variant **out);
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
@@ -167,7 +168,7 @@ const Variant *pick_variant(int nl, int solver, uint32_t need) {
   const Variant *tab = nullptr;
   int n = 0;
   switch (solver) {
-  case CMTJB_RK4: n = variants_rk4(&tab); break;
+  case CMTJB_RK4: n = (need & F_POST) ? variants_post(&tab) : variants_rk4(&tab); break;
   case CMTJB_HEUN: n = variants_heun(&tab); break;
   case CMTJB_EULER_HEUN: n = variants_euler_heun(&tab); break;
   case CMTJB_DORMAND_PRINCE: n = variants_dopri(&tab); break;
@@ -284,7 +285,8 @@ namespace {
 template <int NL>
 int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
               const cmtjb_run_args_t *a, const cmtjb_plan_t &plan, const Variant *v, double *m_state, double *log,
-              int32_t *status, int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span) {
+              int32_t *status, int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span,
+              const cmtjb_post_t *post) {
   static_assert(sizeof(DevModel<NL>) + sizeof(RunParams) < 32000, "kernel parameters exceed the 32 KB limit");
   DevModel<NL> M;
   std::memset(&M, 0, sizeof(M));
@@ -328,6 +330,20 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   R.total_time = a->totalTime;
   R.write_frequency = a->writeFrequency;
   R.seed = a->seed;
+  if (post) {
+    PostParams &P = R.post;
+    P.proj_log = post->proj_log;
+    P.proj_n_samples = post->proj_n_samples > 0 ? post->proj_n_samples : plan.n_samples;
+    P.proj_sample0 = post->proj_sample0;
+    P.sd_omega = post->sd_omega;
+    P.sd_state = post->sd_state;
+    P.n_proj = post->n_proj;
+    P.sd_mode = post->sd_mode;
+    std::memcpy(P.proj, post->proj, sizeof(P.proj));
+    std::memcpy(P.res, post->res, sizeof(P.res));
+    std::memcpy(P.sd_b, post->sd_b, sizeof(P.sd_b));
+    std::memcpy(P.sd_a, post->sd_a, sizeof(P.sd_a));
+  }
   if (R.B <= 0) return CMTJB_OK;
   // table of the time-dependent drivers at this launch's stage times (F_DYN / F_DYNS variants)
   double *tab = nullptr;
@@ -375,7 +391,8 @@ int check_overrides(const cmtjb_junction_t *jn, const cmtjb_override_t *ovr, int
 // One launch over the step range `span` (or the whole run) with the leanest variant covering `layers`.
 int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
                 const cmtjb_run_args_t *a, cmtjb_plan_t &plan, double *m_state, double *log, int32_t *status,
-                int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span) {
+                int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span,
+                const cmtjb_post_t *post = nullptr) {
   uint32_t need = needed_features(jn, layers, ovr, n_ovr, a, plan.effective_solver);
   if (need & (F_DYN | F_DYNS)) {
     // the stage table costs 24 B per column per step; beyond 2 GiB evaluate inline instead
@@ -388,6 +405,7 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
   const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel (testing)
   if (force && std::strcmp(force, "full") == 0) need = F_ALL;
   if (a->log_mode == CMTJB_LOG_ENERGY) need = F_ALL;  // the energy log lives in the general variants only
+  if (post) need |= F_POST;
   const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need);
   if (!v) {
     char buf[160];
@@ -401,10 +419,10 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
     std::snprintf(plan.variant, sizeof(plan.variant), "%s", v->name);
   }
   switch (jn->n_layers) {
-  case 1: return run_typed<1>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
-  case 2: return run_typed<2>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
-  case 3: return run_typed<3>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
-  case 4: return run_typed<4>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span);
+  case 1: return run_typed<1>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span, post);
+  case 2: return run_typed<2>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span, post);
+  case 3: return run_typed<3>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span, post);
+  case 4: return run_typed<4>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span, post);
   default: return fail(CMTJB_ENOTSUP, "junctions with more than 4 layers need the warp-per-instance kernel (not built yet)");
   }
 }
@@ -427,7 +445,8 @@ bool driver_window(const cmtjb_driver_t &d, double *t0, double *t1) {
 
 int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
                     const cmtjb_run_args_t *a, double *m_state, double *log, int32_t *status, int32_t *n_samples_out,
-                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span = nullptr) {
+                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span = nullptr,
+                    const cmtjb_post_t *post = nullptr) {
   cmtjb_plan_t plan;
   int rc = make_plan(jn, layers, a, &plan);
   if (rc) return rc;
@@ -462,7 +481,7 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
   const long long it1 = span ? span->it_end : plan.total_iterations;
   const long long fs0 = span ? span->first_sample : 0;
   if (!windowed || !any_dynamic || it1 <= it0) {
-    rc = launch_span(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log, stream, span);
+    rc = launch_span(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log, stream, span, post);
     if (plan_out) *plan_out = plan;
     return rc;
   }
@@ -488,7 +507,7 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
     if (sp.it_end <= sp.it_begin) continue;
     sp.first_sample = fs0 + count_upto(sp.it_begin) - count_upto(it0);
     rc = launch_span(jn, seg == 1 ? layers : frozen.data(), ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log,
-                     stream, &sp);
+                     stream, &sp, post);
   }
   if (plan_out) *plan_out = plan;
   return rc;
@@ -616,6 +635,32 @@ int cmtjb_run_device(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, co
   CUDA_TRY(cudaSetDevice(device));
   return run_device_impl(jn, layers, overrides, n_overrides, args, m_state, log, status, n_samples_out, time_log,
                          (cudaStream_t)stream, nullptr);
+}
+
+int cmtjb_run_device_post(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *overrides,
+                          int32_t n_overrides, const cmtjb_run_args_t *args, const cmtjb_post_t *post, double *m_state,
+                          double *log, int32_t *status, int device, void *stream) {
+  if (!post || !jn || !args) return fail(CMTJB_EINVAL, "null argument");
+  if (post->n_proj < 0 || post->n_proj > CMTJB_MAX_PROJ) return fail(CMTJB_EINVAL, "n_proj out of range");
+  if (post->sd_mode < CMTJB_SD_NONE || post->sd_mode > CMTJB_SD_RY_PARALLEL) return fail(CMTJB_EINVAL, "unknown sd_mode");
+  if (post->n_proj > 0 && !post->proj_log) return fail(CMTJB_EINVAL, "proj_log is null");
+  if (post->proj_sample0 < 0 || post->proj_n_samples < 0) return fail(CMTJB_EINVAL, "negative projection log extent");
+  if (post->sd_mode != CMTJB_SD_NONE && (!post->sd_state || !post->sd_omega))
+    return fail(CMTJB_EINVAL, "sd_state / sd_omega is null");
+  if (jn->n_layers > CMTJB_POST_MAX_LAYERS) return fail(CMTJB_ENOTSUP, "post-processing supports at most 4 layers");
+  if (post->sd_mode == CMTJB_SD_RZ && (jn->mr_mode != CMTJB_MR_CLASSIC || jn->n_layers > 2))
+    return fail(CMTJB_EINVAL, "Rz can only be used for 2 layer junctions. Use Rx or Ry instead.");
+  if (args->log_mode == CMTJB_LOG_ENERGY) return fail(CMTJB_ENOTSUP, "the energy log cannot be combined with post-processing");
+  cmtjb_plan_t plan;
+  int rc = make_plan(jn, layers, args, &plan);
+  if (rc) return rc;
+  if (post->n_proj > 0 && post->proj_n_samples > 0 && post->proj_sample0 + plan.n_samples > post->proj_n_samples)
+    return fail(CMTJB_EINVAL, "projection log too small for this call");
+  if (plan.effective_solver != CMTJB_RK4)
+    return fail(CMTJB_ENOTSUP, "post-processing is fused into the RK4 kernels only (the procedures run the default solver)");
+  CUDA_TRY(cudaSetDevice(device));
+  return run_device_impl(jn, layers, overrides, n_overrides, args, m_state, log, status, nullptr, nullptr,
+                         (cudaStream_t)stream, nullptr, nullptr, post);
 }
 
 int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *overrides,

@@ -34,7 +34,10 @@ enum : uint32_t {
                           // kernel applies the host-folded DIAGONAL operator lin = (2K1/Ms) a a^T - N Ms/mu0
   F_DYNS = 1u << 13,      // time-dependent SCALAR drivers (K, J, I, torques, T) read from the same table
   F_ALL = (1u << 14) - 1,
-  F_ALL_TAB = F_ALL & ~F_DYNI
+  F_ALL_TAB = F_ALL & ~F_DYNI,
+  // fused post-processing of the sweep procedures (projection log, spin-diode IIR; cmtjb_post_t).
+  // Not part of F_ALL: only the variants of variants_post.cu carry it.
+  F_POST = 1u << 14
 };
 
 struct DevDriver {
@@ -86,6 +89,18 @@ template <int NL> struct DevModel {
 
 constexpr int kMaxOverrides = 24;
 
+// device form of cmtjb_post_t (zeroed = no post-processing)
+struct PostParams {
+  double *proj_log;         // [n_proj][proj_n_samples][B], this launch's sample s lands in row proj_sample0 + s
+  long long proj_n_samples, proj_sample0;
+  const double *sd_omega;   // [B]
+  double *sd_state;         // [4][B]: z0, z1, z2, sum(y)
+  int32_t n_proj, sd_mode;
+  double proj[CMTJB_MAX_PROJ][3 * CMTJB_POST_MAX_LAYERS];
+  double res[CMTJB_POST_MAX_LAYERS][CMTJB_RES_NFIELDS];
+  double sd_b[4], sd_a[4];
+};
+
 // run parameters (also constant bank)
 struct RunParams {
   double *m_state;           // [NL*3][B]
@@ -110,6 +125,7 @@ struct RunParams {
   long long elog_ch0;        // first CMTJB_LOG_ENERGY channel, or -1 (general variants only)
   double dt, sqrt_dt, total_time, write_frequency;
   unsigned long long seed;
+  PostParams post;
 };
 
 }  // namespace cmtjb

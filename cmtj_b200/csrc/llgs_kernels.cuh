@@ -49,6 +49,65 @@ __device__ __forceinline__ void write_sample(const DevModel<NL> &M, const RunPar
   }
 }
 
+// ---- fused post-processing of the sweep procedures (cmtjb_post_t, include/cmtj_b200.h) -----------
+// Per-thread carry of the spin-diode reduction: the three delays of scipy's transposed direct
+// form II order-3 IIR, the running sum of its output and the instance's angular frequency.
+struct PostState {
+  double z0, z1, z2, sum, omega;
+};
+
+// R[n] of compute_sd: the junction's own MR channel (junction.hpp:1865-1867) or Rx / Ry of
+// calculate_resistance_series / _parallel (cmtj/utils/resistance.py:25-66, :96-149).
+template <int NL>
+__device__ __forceinline__ double sd_resistance(const DevModel<NL> &M, const PostParams &P, const State<NL> &S) {
+  if (P.sd_mode == CMTJB_SD_RZ) {
+    double c;
+    if constexpr (NL == 1) c = dot(S.m[0], ld3(M.L[0].ref));
+    else c = dot(S.m[0], S.m[1]);
+    return fma(M.Rhalf, 1.0 - c, M.Rp);
+  }
+  const bool want_x = P.sd_mode == CMTJB_SD_RX_SERIES || P.sd_mode == CMTJB_SD_RX_PARALLEL;
+  const bool parallel = P.sd_mode == CMTJB_SD_RX_PARALLEL || P.sd_mode == CMTJB_SD_RY_PARALLEL;
+  double acc = 0.0;
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const double *r = P.res[l < CMTJB_POST_MAX_LAYERS ? l : 0];
+    const d3 m = S.m[l];
+    const double s = want_x ? r[CMTJB_RES_RXX0] + (r[CMTJB_RES_AMR] * (m.x * m.x) + r[CMTJB_RES_SMR] * (m.y * m.y))
+                            : r[CMTJB_RES_RXY0] + 0.5 * r[CMTJB_RES_AHE] * m.z +
+                                  r[CMTJB_RES_W_OVER_L] * (r[CMTJB_RES_SMR] + r[CMTJB_RES_AMR]) * m.x * m.y;
+    acc += parallel ? 1.0 / s : s;
+  }
+  return parallel ? 1.0 / acc : acc;
+}
+
+template <int NL>
+__device__ __forceinline__ void post_sample(const DevModel<NL> &M, const RunParams &R, const State<NL> &S, PostState &ps,
+                                            double t, long long sample, long long i) {
+  const PostParams &P = R.post;
+  // projection channels (PIMM: sum_l w_l m_l,c ; procedures.py:171-181)
+  for (int k = 0; k < P.n_proj; k++) {
+    double v = 0.0;
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const double *w = P.proj[k] + 3 * (l < CMTJB_POST_MAX_LAYERS ? l : 0);
+      v = fma(w[2], S.m[l].z, fma(w[1], S.m[l].y, fma(w[0], S.m[l].x, v)));
+    }
+    __stcs(P.proj_log + ((long long)k * P.proj_n_samples + P.proj_sample0 + sample) * R.B + i, v);
+  }
+  // spin-diode mixing + low-pass (compute_sd, resistance.py:12-22): scipy's lfilter recurrence
+  // in its own operation order, without FMA contraction (the filter is ill-conditioned: its poles
+  // sit 6e-6 from the unit circle, so the operation order is visible in the fifth digit).
+  if (P.sd_mode != CMTJB_SD_NONE) {
+    const double x = -sin(ps.omega * t) * sd_resistance<NL>(M, P, S);
+    const double y = __dadd_rn(ps.z0, __dmul_rn(P.sd_b[0], x));
+    ps.z0 = __dsub_rn(__dadd_rn(ps.z1, __dmul_rn(x, P.sd_b[1])), __dmul_rn(y, P.sd_a[1]));
+    ps.z1 = __dsub_rn(__dadd_rn(ps.z2, __dmul_rn(x, P.sd_b[2])), __dmul_rn(y, P.sd_a[2]));
+    ps.z2 = __dsub_rn(__dmul_rn(x, P.sd_b[3]), __dmul_rn(y, P.sd_a[3]));
+    ps.sum += y;
+  }
+}
+
 // ---- calculateEnergies = true (junction.hpp:1584-1613): the field terms of the LAST right-hand-side
 // evaluation of the step, recomputed at the point (t_eval, Sm, Snb) where the reference cached them.
 // General (F_ALL) variants only; off the hot path (__noinline__, runs on written samples).
@@ -251,6 +310,16 @@ __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constan
   long long sample = R.first_sample;
   const bool logging = R.log != nullptr;
   const double *row = R.dyn_tab;  // advances by one step (3 stage rows) per iteration
+  PostState ps{0.0, 0.0, 0.0, 0.0, 0.0};
+  if constexpr ((F & F_POST) != 0) {
+    if (R.post.sd_mode != CMTJB_SD_NONE) {
+      ps.z0 = R.post.sd_state[i];
+      ps.z1 = R.post.sd_state[R.B + i];
+      ps.z2 = R.post.sd_state[2 * R.B + i];
+      ps.sum = R.post.sd_state[3 * R.B + i];
+      ps.omega = R.post.sd_omega[i];
+    }
+  }
   for (long long it = R.it_begin; it < R.it_end; ++it) {
     const double t = (double)it * R.dt;
     State<NL> Em, Enb;
@@ -258,6 +327,7 @@ __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constan
     if constexpr ((F & (F_DYN | F_DYNS)) != 0 && (F & F_DYNI) == 0) row += 3 * R.dyn_ncols;
     if (until_write == 0) {
       if (logging) write_sample<NL>(M, R, S, sample, i);
+      if constexpr ((F & F_POST) != 0) post_sample<NL>(M, R, S, ps, t, sample, i);
       if constexpr (F == F_ALL) {
         if (logging && R.elog_ch0 >= 0) write_energy<NL, F>(M, R, Em, Enb, SOLVER == CMTJB_EULER_HEUN ? t : t + R.dt, sample, i);
       }
@@ -271,6 +341,14 @@ __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constan
     R.m_state[(3 * l + 0) * R.B + i] = S.m[l].x;
     R.m_state[(3 * l + 1) * R.B + i] = S.m[l].y;
     R.m_state[(3 * l + 2) * R.B + i] = S.m[l].z;
+  }
+  if constexpr ((F & F_POST) != 0) {
+    if (R.post.sd_mode != CMTJB_SD_NONE) {
+      R.post.sd_state[i] = ps.z0;
+      R.post.sd_state[R.B + i] = ps.z1;
+      R.post.sd_state[2 * R.B + i] = ps.z2;
+      R.post.sd_state[3 * R.B + i] = ps.sum;
+    }
   }
   // RK4 throws "NAN magnetisation" on isnan(mag.x) (junction.hpp:1037-1039); NaN is absorbing,
   // so testing the final state is equivalent.

@@ -1,0 +1,411 @@
+"""Batched, device-resident versions of the reference's sweep procedures
+(cmtj/utils/procedures.py: ``PIMM_procedure`` :42-204, ``VSD_procedure`` :207-331).
+
+The reference loops ``runSimulation`` over field (and frequency) points, logs every layer at every
+step, pulls the log through pybind11 and reduces it with numpy/scipy.  Here the sweep points are the
+instance axis of ONE fused launch and the reductions happen on the GPU:
+
+* PIMM: the kernel writes only the projected signal ``sum_l w_l m_l,c`` per step
+  (``cmtjb_post_t.proj``), the spectrum is a batched FFT over that buffer, and the static
+  resistances come from a ``take_last_n``-sample log evaluated by ``strip_resistance_kernel``.
+* VSD: the mixing ``-I(t) R(t)``, the 10 MHz Butterworth low-pass and the mean run inside the time
+  loop (``cmtjb_post_t.sd_*``); nothing is logged at all.
+
+Semantics.  The reference carries the magnetisation from one sweep point to the next (hysteresis).
+``carry_state=True`` reproduces exactly that (sweep points run one after another, each a batch of
+one); the default ``carry_state=False`` starts every point from the junction's current
+magnetisation (plus the same ``disturbance`` draws), which is what makes the sweep a batch.
+Everything else -- arguments, validation, return shapes -- follows the reference.
+"""
+from __future__ import annotations
+
+import math
+from collections import defaultdict
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .. import _abi
+from ..batch import JunctionBatch, PostSpec
+from ..core import AxialDriver, Axis, CVector, Junction, NullDriver, ScalarDriver
+from . import resistance as _res
+from .filters import butter_lowpass_coefficients
+from .resistance import calculate_resistance_series
+
+
+@dataclass
+class ResistanceParameters:
+    """procedures.py:15-26"""
+
+    Rxx0: float = 0
+    Rxy0: float = 0
+    Rahe: float = 0
+    Rsmr: float = 0
+    Ramr: float = 0
+    w: float = 0  # width
+    l: float = 0  # length
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _spectrum_bins(n: int, int_step: float, max_frequency: float):
+    """The bins compute_spectrum_strip keeps (procedures.py:29-40): first n//2 of fftfreq(n, dt),
+    then those <= max_frequency.  Returns (findx [K,1], freqs[findx] [K,1])."""
+    freqs = np.fft.fftfreq(n, int_step)[: n // 2]
+    findx = np.argwhere(freqs <= max_frequency)
+    return findx, freqs[findx]
+
+
+def spectrum_device(signal, int_step: float, max_frequency: float):
+    """|FFT| of B real series stored [n, B] on the device, restricted like compute_spectrum_strip.
+    Returns (CUDA tensor [K, B], freqs [K,1])."""
+    torch = _torch()
+    n = int(signal.shape[0])
+    findx, freqs = _spectrum_bins(n, int_step, max_frequency)
+    half = torch.fft.rfft(signal, dim=0)[: n // 2]
+    idx = torch.from_numpy(findx.ravel()).to(signal.device)
+    return half.index_select(0, idx).abs(), freqs
+
+
+def compute_spectrum_strip(input_m, int_step: float, max_frequency: float):
+    """procedures.py:29-40 for one host series (runs on the device)."""
+    torch = _torch()
+    x = torch.from_numpy(np.ascontiguousarray(np.asarray(input_m, dtype=np.float64))).cuda().reshape(-1, 1)
+    yf, freqs = spectrum_device(x, int_step, max_frequency)
+    return yf.cpu().numpy(), freqs
+
+
+def _steps(total: float, dt: float) -> int:
+    """(unsigned)(totalTime / timeStep) of Junction::runSimulation (junction.hpp:1956)."""
+    return int(total / dt)
+
+
+def _time_for_steps(n: int, dt: float) -> float:
+    """A totalTime whose (unsigned)(totalTime/dt) is exactly n (used to stop a run after n steps)."""
+    t = n * dt
+    for _ in range(8):
+        k = int(t / dt)
+        if k == n:
+            return t
+        t = math.nextafter(t, math.inf if k < n else -math.inf)
+    raise RuntimeError("could not represent the requested step count")
+
+
+def _res_rows(resistance_params: List[ResistanceParameters]) -> np.ndarray:
+    return _res._res_rows(
+        [r.Rxx0 for r in resistance_params],
+        [r.Rxy0 for r in resistance_params],
+        [r.Ramr for r in resistance_params],
+        [r.Rahe for r in resistance_params],
+        [r.Rsmr for r in resistance_params],
+        [r.l for r in resistance_params],
+        [r.w for r in resistance_params],
+    )
+
+
+def _resistance_kind(fn: Callable) -> Optional[bool]:
+    """True = parallel, False = series, None = an unknown callable (evaluated on host arrays)."""
+    name = getattr(fn, "__name__", "")
+    if name == "calculate_resistance_parallel":
+        return True
+    if name == "calculate_resistance_series":
+        return False
+    return None
+
+
+def _oersted_driver(direction: Axis, driver: ScalarDriver) -> Tuple[str, int, AxialDriver]:
+    if direction == Axis.zaxis:
+        return "z", 2, AxialDriver(NullDriver(), NullDriver(), driver)
+    if direction == Axis.yaxis:
+        return "y", 1, AxialDriver(NullDriver(), driver, NullDriver())
+    return "x", 0, AxialDriver(driver, NullDriver(), NullDriver())
+
+
+def _disturbed(junction: Junction, layer_ids: List[str], n: int, disturbance: float) -> Dict[str, np.ndarray]:
+    """Initial magnetisation of n instances: the junction's current m plus the reference's
+    np.random.normal(0, disturbance) per component (same draw order: point, layer, x/y/z),
+    normalised (procedures.py:131-140)."""
+    base = np.array([junction.getLayerMagnetisation(lid).tolist() for lid in layer_ids])  # [L,3]
+    m = np.repeat(base[None], n, axis=0)
+    if disturbance:
+        m = m + np.random.normal(0, disturbance, size=m.shape)
+        m = m / np.sqrt((m * m).sum(axis=2, keepdims=True))
+    return {lid: m[:, i, :] for i, lid in enumerate(layer_ids)}
+
+
+def _instance_chunks(n: int, bytes_per_instance: float, budget: float) -> List[Tuple[int, int]]:
+    per = max(1, int(budget // max(bytes_per_instance, 1.0)))
+    return [(lo, min(n, lo + per)) for lo in range(0, n, per)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# PIMM
+# ---------------------------------------------------------------------------------------------------
+def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resistance_params, comp, weights, simulation_duration,
+                wait_time, max_frequency, take_last_n, full_output, static_only, device):
+    """One batch of field points (all start from m0).  Returns a dict of host arrays."""
+    torch = _torch()
+    B = Hc.shape[0]
+    L = junction.layerNo
+    layer_ids = junction.getLayerIds()
+    dev = torch.device("cuda", device)
+    n_total = _steps(simulation_duration, int_step)
+    n_last = min(int(take_last_n), n_total)
+    batch = JunctionBatch(junction, B, device=device)
+    batch.set_external_field("all", Hc)
+    for lid in layer_ids:
+        batch.set_magnetisation(lid, m0[lid])
+    out: Dict[str, Any] = {}
+    n_proj = 0 if static_only else (1 + L if full_output else 1)
+    if n_proj > _abi.MAX_PROJ:
+        raise NotImplementedError("full_output supports junctions of up to 3 layers")
+    proj = np.zeros((max(n_proj, 1), 3 * L))
+    for l in range(L):
+        proj[0, 3 * l + comp] = weights[l]
+        if full_output and not static_only:
+            proj[1 + l, 3 * l + comp] = weights[l]
+    proj_log = torch.empty((n_proj, n_total, B), dtype=torch.float64, device=dev) if n_proj else None
+
+    def spec(sample0):
+        return PostSpec(proj=proj[:n_proj], proj_log=proj_log, proj_sample0=sample0) if n_proj else None
+
+    if full_output and not static_only:
+        res = batch.run_device(simulation_duration, int_step, int_step, post=spec(0))
+        log_all = res["_log"]
+        log_last = log_all[:, n_total - n_last :, :]
+        out["m_traj_dev"] = log_all[: 3 * L]
+    else:
+        n_a = n_total - n_last
+        if n_a > 0:
+            batch.run_device(_time_for_steps(n_a, int_step), int_step, int_step, log=False, post=spec(0))
+        res = batch.run_device(simulation_duration, int_step, int_step, post=spec(n_a), start_iteration=n_a)
+        log_last = res["_log"]
+    m_last = log_last[: 3 * L].contiguous()  # [3L, n_last, B]
+    w_dev = torch.tensor(weights, dtype=torch.float64, device=dev)
+    # static resistance over the last samples, from the thickness*Ms-weighted m (procedures.py:152-162)
+    if kind is not None:
+        Rx, Ry = _res.strip_resistance_device(res_rows, m_last, kind, weights=weights, device=device)
+        out["Rx"], out["Ry"] = Rx.cpu().numpy().T, Ry.cpu().numpy().T  # [B, n_last]
+    else:
+        mh = (m_last.reshape(L, 3, n_last, B) * w_dev[:, None, None, None]).cpu().numpy()
+        rx, ry = [], []
+        for i in range(B):
+            a, b = resistance_fn(
+                [r.Rxx0 for r in resistance_params], [r.Rxy0 for r in resistance_params], [r.Ramr for r in resistance_params],
+                [r.Rahe for r in resistance_params], [r.Rsmr for r in resistance_params], mh[:, :, :, i],
+                l=[r.l for r in resistance_params], w=[r.w for r in resistance_params],
+            )  # fmt: skip
+            rx.append(a)
+            ry.append(b)
+        out["Rx"], out["Ry"] = np.asarray(rx), np.asarray(ry)
+    final = m_last[:, -1, :].reshape(L, 3, B)
+    out["m_avg"] = (final * w_dev[:, None, None]).sum(0).cpu().numpy().T  # [B,3]
+    out["m_final"] = final.cpu().numpy()  # [L,3,B]
+    if not static_only:
+        time = np.arange(n_total, dtype=np.float64) * float(int_step)
+        n0 = int(np.argwhere(time >= wait_time).ravel()[0]) if np.any(time >= wait_time) else n_total
+        yf, freqs = spectrum_device(proj_log[0, n0:, :], int_step, max_frequency)
+        out["spectrum"] = yf.cpu().numpy().T  # [B,K]
+        out["freqs"] = freqs
+        if full_output:
+            out["layer_spectra"] = [spectrum_device(proj_log[1 + l, n0:, :], int_step, max_frequency)[0].cpu().numpy().T
+                                    for l in range(L)]
+            mt = out.pop("m_traj_dev").reshape(L, 3, n_total, B) * w_dev[:, None, None, None]
+            out["m_traj"] = mt.permute(3, 0, 1, 2).cpu().numpy()  # [B,L,3,T]
+    return out
+
+
+def PIMM_procedure(
+    junction: Junction,
+    Hvecs: np.ndarray,
+    int_step: float,
+    resistance_params: List[ResistanceParameters],
+    Hoe_direction: Axis = Axis.zaxis,
+    Hoe_excitation: float = 50,
+    Hoe_duration: int = 3,
+    simulation_duration: float = 5e-9,
+    wait_time: float = 0e-9,
+    max_frequency: float = 80e9,
+    resistance_fn: Callable = calculate_resistance_series,
+    disturbance: float = 1e-3,
+    take_last_n: int = 100,
+    full_output: bool = False,
+    disable_tqdm: bool = False,
+    static_only: bool = False,
+    carry_state: bool = False,
+    device: int = 0,
+    memory_budget: float = 24e9,
+) -> Tuple[np.ndarray, np.ndarray, Dict[str, Any]]:
+    """Pulse-induced microwave magnetometry over a field sweep (procedures.py:42-204): returns
+    ``(spectrum [n_H, n_f], frequencies [n_f, 1], other_data)`` with other_data keys ``H``, ``Rx``,
+    ``Ry``, ``m_avg`` (+ ``m_traj`` and per-layer spectra when ``full_output``).
+
+    ``carry_state`` / ``device`` / ``memory_budget`` are additions: see the module docstring."""
+    if wait_time > simulation_duration:
+        raise ValueError("wait_time must be smaller than simulation_duration!")
+    comp_name, comp, oedriver = _oersted_driver(
+        Hoe_direction, ScalarDriver.getStepDriver(0, Hoe_excitation, 0, int_step * Hoe_duration)
+    )
+    layer_ids = junction.getLayerIds()
+    if len(layer_ids) != len(resistance_params):
+        raise ValueError("The number of layers in the junction must match the number of resistance parameters!")
+    Hvecs = np.asarray(Hvecs, dtype=np.float64).reshape(-1, 3)
+    layers = junction.layers
+    normalising_factor = np.sum([layer.thickness * layer.Ms for layer in layers])
+    weights = np.array([layer.thickness * layer.Ms / normalising_factor for layer in layers])
+    kind = _resistance_kind(resistance_fn)
+    rows = _res_rows(resistance_params)
+    junction.clearLog()
+    junction.setLayerOerstedFieldDriver("all", oedriver)
+    n_total = _steps(simulation_duration, int_step)
+    L = len(layer_ids)
+
+    def run(Hc, m0):
+        return _pimm_batch(junction, Hc, m0, int_step, rows, kind, resistance_fn, resistance_params, comp, weights,
+                           simulation_duration, wait_time, max_frequency, take_last_n, full_output, static_only, device)
+
+    parts: List[Dict[str, Any]] = []
+    if carry_state:
+        for H in Hvecs:
+            r = run(H[None], _disturbed(junction, layer_ids, 1, disturbance))
+            for i, lid in enumerate(layer_ids):
+                junction.setLayerMagnetisation(lid, CVector(*r["m_final"][i, :, 0]))
+            parts.append(r)
+    else:
+        m0 = _disturbed(junction, layer_ids, Hvecs.shape[0], disturbance)
+        n_series = 0 if static_only else (1 + L if full_output else 1)
+        per_inst = 8.0 * n_total * (3.0 * n_series + (2.0 * (3 * L + 3) if full_output else 0.0)) + 8.0 * 200 * (3 * L + 3)
+        for lo, hi in _instance_chunks(Hvecs.shape[0], per_inst, memory_budget):
+            parts.append(run(Hvecs[lo:hi], {k: v[lo:hi] for k, v in m0.items()}))
+        if parts:
+            last = parts[-1]["m_final"]
+            for i, lid in enumerate(layer_ids):
+                junction.setLayerMagnetisation(lid, CVector(*last[i, :, -1]))
+    if len(Hvecs):
+        junction.setLayerExternalFieldDriver("all", AxialDriver(*[ScalarDriver.getConstantDriver(float(h)) for h in Hvecs[-1]]))
+
+    output: Dict[str, Any] = defaultdict(list)
+    spectrum: List[np.ndarray] = []
+    freqs = None
+    k = 0
+    for r in parts:
+        for i in range(r["Rx"].shape[0]):
+            output["H"].append(Hvecs[k])
+            output["Rx"].append(r["Rx"][i])
+            output["Ry"].append(r["Ry"][i])
+            output["m_avg"].append(r["m_avg"][i])
+            if not static_only:
+                spectrum.append(r["spectrum"][i][:, None])
+                freqs = r["freqs"]
+                if full_output:
+                    output["m_traj"].append(r["m_traj"][i])
+                    for li, lid in enumerate(layer_ids):
+                        output[lid].append(r["layer_spectra"][li][i][:, None])
+            k += 1
+    spectrum_arr = np.squeeze(np.asarray(spectrum))
+    if full_output:
+        for lid in layer_ids:
+            output[lid] = np.asarray(output[lid]).squeeze()
+    return spectrum_arr, freqs, output
+
+
+# ---------------------------------------------------------------------------------------------------
+# VSD
+# ---------------------------------------------------------------------------------------------------
+def _vsd_batch(junction, Hc, fc, m0, int_step, sd_mode, rows, comp, simulation_duration, device):
+    torch = _torch()
+    B = Hc.shape[0]
+    dev = torch.device("cuda", device)
+    layer_ids = junction.getLayerIds()
+    L = len(layer_ids)
+    n_total = _steps(simulation_duration, int_step)
+    batch = JunctionBatch(junction, B, device=device)
+    batch.set_external_field("all", Hc)
+    batch.set_override("all", _abi.SLOT_HOE + comp, "frequency", fc)
+    for lid in layer_ids:
+        batch.set_magnetisation(lid, m0[lid])
+    b, a = butter_lowpass_coefficients(10e6, 1.0 / int_step, order=3)  # compute_sd, resistance.py:19-21
+    omega = torch.from_numpy(np.ascontiguousarray(2 * math.pi * fc)).to(dev)  # procedures.py:327
+    state = torch.zeros((4, B), dtype=torch.float64, device=dev)
+    post = PostSpec(sd_mode=sd_mode, res=rows if rows is not None else np.zeros((L, _abi.RES_NFIELDS)), sd_b=b, sd_a=a / a[0],
+                    sd_omega=omega, sd_state=state)
+    batch.run_device(simulation_duration, int_step, int_step, log=False, post=post)
+    vmix = (state[3] / float(n_total)).cpu().numpy()
+    return vmix, batch.get_magnetisation
+
+
+def VSD_procedure(
+    junction: Junction,
+    Hvecs: np.ndarray,
+    frequencies: np.ndarray,
+    int_step: float,
+    resistance_params: Optional[List[ResistanceParameters]] = None,
+    Hoe_direction: Axis = Axis.yaxis,
+    Hoe_excitation: float = 50,
+    simulation_duration: float = 30e-9,
+    disturbance: float = 1e-3,
+    Rtype: str = "Rz",
+    resistance_fn: Callable = calculate_resistance_series,
+    disable_tqdm: bool = False,
+    carry_state: bool = False,
+    device: int = 0,
+    max_batch: int = 1 << 22,
+) -> np.ndarray:
+    """Voltage spin-diode map over (field, frequency) (procedures.py:207-331): every (H, f) pair is one
+    instance; the Oersted sine excitation, the mixing with sin(2 pi f t), the low-pass and the mean
+    are evaluated inside the time loop.  Returns ``spectrum [len(Hvecs), len(frequencies)]``."""
+    if resistance_params is None:
+        resistance_params = []
+    layer_ids = junction.getLayerIds()
+    if Rtype == "Rz" and len(layer_ids) > 2:
+        raise ValueError("Rz can only be used for 2 layer junctions. Use Rx or Ry instead.")
+    elif len(resistance_params) != len(layer_ids):  # also for Rz, as in the reference (procedures.py:247-250)
+        raise ValueError("The number of layers in the junction must match the number of resistance parameters!")
+    Hvecs = np.asarray(Hvecs, dtype=np.float64).reshape(-1, 3)
+    frequencies = np.asarray(frequencies, dtype=np.float64).reshape(-1)
+    rows = None
+    if Rtype == "Rz":
+        if len(layer_ids) == 1:
+            raise KeyError("Resistance")  # the reference asks a 1-layer log for a key it never writes (procedures.py:301)
+        sd_mode = _abi.SD_RZ
+    elif Rtype in ("Rx", "Ry"):
+        kind = _resistance_kind(resistance_fn)
+        if kind is None:
+            raise NotImplementedError("VSD_procedure fuses calculate_resistance_series / calculate_resistance_parallel only")
+        rows = _res_rows(resistance_params)
+        sd_mode = {("Rx", False): _abi.SD_RX_SERIES, ("Ry", False): _abi.SD_RY_SERIES, ("Rx", True): _abi.SD_RX_PARALLEL,
+                   ("Ry", True): _abi.SD_RY_PARALLEL}[(Rtype, kind)]
+    else:
+        raise ValueError("Rtype must be either Rx or Ry or Rz")
+    _, comp, oedriver = _oersted_driver(
+        Hoe_direction, ScalarDriver.getSineDriver(0, Hoe_excitation, float(frequencies[0]) if len(frequencies) else 0.0, 0)
+    )
+    junction.clearLog()
+    junction.setLayerOerstedFieldDriver("all", oedriver)
+    nH, nF = Hvecs.shape[0], frequencies.shape[0]
+    Hall = np.repeat(Hvecs, nF, axis=0)  # instance = h * nF + f (the reference's loop order)
+    fall = np.tile(frequencies, nH)
+    spectrum = np.zeros(nH * nF)
+    if carry_state:
+        for i in range(nH * nF):
+            v, getm = _vsd_batch(junction, Hall[i : i + 1], fall[i : i + 1], _disturbed(junction, layer_ids, 1, disturbance),
+                                 int_step, sd_mode, rows, comp, simulation_duration, device)
+            spectrum[i] = v[0]
+            for lid in layer_ids:
+                junction.setLayerMagnetisation(lid, CVector(*getm(lid)[0]))
+    else:
+        m0 = _disturbed(junction, layer_ids, nH * nF, disturbance)
+        getm = None
+        for lo in range(0, nH * nF, max_batch):
+            hi = min(nH * nF, lo + max_batch)
+            spectrum[lo:hi], getm = _vsd_batch(junction, Hall[lo:hi], fall[lo:hi], {k: v[lo:hi] for k, v in m0.items()},
+                                               int_step, sd_mode, rows, comp, simulation_duration, device)
+        if getm is not None:
+            for lid in layer_ids:
+                junction.setLayerMagnetisation(lid, CVector(*getm(lid)[-1]))
+    return spectrum.reshape(nH, nF)

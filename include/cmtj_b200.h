@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CMTJB_ABI_VERSION 1
+#define CMTJB_ABI_VERSION 2
 #define CMTJB_MAX_LAYERS 8
 
 /* ---- error codes --------------------------------------------------------------- */
@@ -231,6 +231,82 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
                    const cmtjb_override_t *overrides, int32_t n_overrides,
                    const cmtjb_run_args_t *args, double *m_state, double *log,
                    int32_t *status, int32_t *n_samples_out, double *time_log, int device);
+
+/* ---- fused post-processing of the callers of runSimulation ------------------
+ *
+ * The reference's sweep procedures (cmtj/utils/procedures.py: PIMM_procedure :42-204,
+ * VSD_procedure :207-331) log every layer's m at every step, pull the log through pybind11 as
+ * Python lists and reduce it with numpy/scipy.  cmtjb_run_device_post runs the same integration
+ * and performs those reductions inside the time loop, so the full-rate log never exists:
+ *
+ *  - projection channels (PIMM, procedures.py:142-150, :171-181): at every logged sample
+ *        proj_log[k][proj_sample0 + sample][inst] = sum_{l,c} proj[k][3*l + c] * m_{l,c}
+ *    e.g. one row holding thickness_l*Ms_l/sum(thickness*Ms) on the extraction component gives the
+ *    `mixed_sum` signal whose FFT is the PIMM spectrum; one row per layer gives the per-layer spectra.
+ *
+ *  - spin-diode voltage (VSD, procedures.py:327-329 + cmtj/utils/resistance.py:12-22):
+ *        SD[n] = -sin(sd_omega[inst] * t_n) * R[n],   t_n = n*timeStep (the sample's time label)
+ *        y = lfilter(sd_b, sd_a, SD)   order-3 IIR, transposed direct form II in scipy's operation
+ *                                      order (scipy/signal/_lfilter.c.in)
+ *        sd_state[3][inst] += sum_n y[n]    (the caller divides by the sample count: np.mean)
+ *    R[n] is the junction's own magnetoresistance channel (CMTJB_SD_RZ, junction.hpp:1865-1867) or
+ *    Rx / Ry of calculate_resistance_series / _parallel (resistance.py:25-66, :96-149) from the
+ *    per-layer parameters `res`.
+ *
+ * Requires a fixed-step RK4 run (the procedures always request the default solver) and at most
+ * CMTJB_POST_MAX_LAYERS layers.  A LOG_FULL `log` may be requested in the same call. */
+#define CMTJB_MAX_PROJ 4
+#define CMTJB_POST_MAX_LAYERS 4
+
+enum cmtjb_sd_mode {
+  CMTJB_SD_NONE = 0,
+  CMTJB_SD_RZ = 1,          /* R / R_<id0>_<id1> channel of the junction (MR_CLASSIC) */
+  CMTJB_SD_RX_SERIES = 2,   /* calculate_resistance_series(...)[0] */
+  CMTJB_SD_RY_SERIES = 3,   /* calculate_resistance_series(...)[1] */
+  CMTJB_SD_RX_PARALLEL = 4, /* calculate_resistance_parallel(...)[0] */
+  CMTJB_SD_RY_PARALLEL = 5  /* calculate_resistance_parallel(...)[1] */
+};
+
+/* per-layer ResistanceParameters (procedures.py:16-26): Rxx0, Rxy0, Ramr, Rahe, Rsmr, w/l */
+enum cmtjb_res_field { CMTJB_RES_RXX0 = 0, CMTJB_RES_RXY0, CMTJB_RES_AMR, CMTJB_RES_AHE, CMTJB_RES_SMR, CMTJB_RES_W_OVER_L, CMTJB_RES_NFIELDS };
+
+typedef struct cmtjb_post {
+  int32_t n_proj;   /* 0..CMTJB_MAX_PROJ projection channels */
+  int32_t sd_mode;  /* cmtjb_sd_mode */
+  double proj[CMTJB_MAX_PROJ][3 * CMTJB_POST_MAX_LAYERS];
+  double res[CMTJB_POST_MAX_LAYERS][CMTJB_RES_NFIELDS];
+  double sd_b[4], sd_a[4];  /* scipy.signal.butter(3, ...) coefficients, a[0] == 1 */
+  const double *sd_omega;   /* DEVICE [n_instances]: 2*pi*frequency of the mixing current */
+  double *proj_log;         /* DEVICE out [n_proj][proj_n_samples][n_instances]; this call writes rows
+                               proj_sample0 .. proj_sample0 + (samples of this call) - 1 */
+  int64_t proj_n_samples;   /* row count of proj_log per channel; 0 = the samples of this call */
+  int64_t proj_sample0;     /* first row this call writes (lets chained calls fill one buffer) */
+  double *sd_state;         /* DEVICE in/out [4][n_instances]: filter delays z0,z1,z2 and sum(y); zero it before
+                               the first call, chain it through calls that continue a run (start_iteration) */
+} cmtjb_post_t;
+
+/* cmtjb_run_device plus the fused reductions above.  All pointers are DEVICE pointers. */
+int cmtjb_run_device_post(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
+                          const cmtjb_override_t *overrides, int32_t n_overrides,
+                          const cmtjb_run_args_t *args, const cmtjb_post_t *post, double *m_state,
+                          double *log, int32_t *status, int device, void *stream);
+
+/* calculate_resistance_series / _parallel (cmtj/utils/resistance.py:96-149) over a device log:
+ * m is [n_layers*3][n] (n = samples x instances, any flattening), weights[l] scales layer l's m
+ * first (PIMM passes thickness*Ms/normalising_factor, procedures.py:152-162; VSD passes 1);
+ * Rx, Ry are [n].  parallel = 0 -> series. */
+int cmtjb_strip_resistance_device(int32_t n_layers, const double *res /* [n_layers][6] host */,
+                                  const double *weights /* [n_layers] host */, int32_t parallel,
+                                  const double *m, int64_t n, double *Rx, double *Ry, int device, void *stream);
+
+/* compute_sd (cmtj/utils/resistance.py:12-22) for B series at once: R is DEVICE [n][B]; I is DEVICE [n]
+ * (shared by all series) or [n][B] when current_per_series != 0; b, a are the HOST order-3 IIR
+ * coefficients of Filters.butter_lowpass_filter (filters.py:33-44); out is DEVICE [B] = mean(lfilter(b, a, -I*R)). */
+int cmtjb_compute_sd_device(const double *R, const double *I, int32_t current_per_series, int64_t n, int64_t B,
+                            const double *b, const double *a, double *out, int device, void *stream);
+/* compute_gmr (resistance.py:68-74): m1, m2 DEVICE [3][n], out DEVICE [n]. */
+int cmtjb_compute_gmr_device(double Rp, double Rap, const double *m1, const double *m2, int64_t n, double *out,
+                             int device, void *stream);
 
 /* Number of kernels this library has launched in this process (monotonic). */
 long long cmtjb_launch_count(void);

@@ -22,7 +22,7 @@ def declared_functions():
 def test_header_declares_the_expected_surface():
     names = declared_functions()
     for must in ("cmtjb_plan", "cmtjb_run_host", "cmtjb_run_device", "cmtjb_stack_run_host", "cmtjb_group_run_host",
-                 "cmtjb_last_error", "cmtjb_abi_version"):
+                 "cmtjb_last_error", "cmtjb_abi_version", "cmtjb_run_device_post", "cmtjb_strip_resistance_device"):
         assert must in names
 
 
@@ -36,15 +36,15 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_header(tmp_path):
     prog = tmp_path / "sizes.c"
     prog.write_text(
-        '#include <stdio.h>\n#include "cmtj_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+        '#include <stdio.h>\n#include "cmtj_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
         "sizeof(cmtjb_driver_t),sizeof(cmtjb_layer_t),sizeof(cmtjb_junction_t),sizeof(cmtjb_override_t),"
-        "sizeof(cmtjb_run_args_t),sizeof(cmtjb_plan_t),sizeof(cmtjb_stack_t),sizeof(cmtjb_group_t),sizeof(cmtjb_coupled_plan_t));return 0;}\n"
+        "sizeof(cmtjb_run_args_t),sizeof(cmtjb_plan_t),sizeof(cmtjb_stack_t),sizeof(cmtjb_group_t),sizeof(cmtjb_coupled_plan_t),sizeof(cmtjb_post_t));return 0;}\n"
     )
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(t) for t in (_abi.Driver, _abi.Layer, _abi.Junction, _abi.Override, _abi.RunArgs, _abi.Plan,
-                                  _abi.Stack, _abi.Group, _abi.CoupledPlan)]
+                                  _abi.Stack, _abi.Group, _abi.CoupledPlan, _abi.Post)]
     assert got == want
 
 

@@ -25,7 +25,16 @@ def load_reference_tests():
     cmtj_b200.install_as_cmtj()
     ref_pkg = os.path.join(REF, "cmtj")
     if ref_pkg not in cmtj_b200.__path__:
-        cmtj_b200.__path__.append(ref_pkg)  # cmtj.utils, cmtj.models: the reference's pure-Python helpers
+        cmtj_b200.__path__.append(ref_pkg)  # cmtj.models etc.: the reference's pure-Python helpers
+    # `cmtj.utils` must be the REFERENCE's numpy/scipy helpers here (ours reduce on the GPU and this is
+    # the CPU-side pin of the facade + oracle); install_as_cmtj pointed it at cmtj_b200.utils.
+    for k in [k for k in sys.modules if k == "cmtj.utils" or k.startswith("cmtj.utils.")]:
+        del sys.modules[k]
+    uspec = importlib.util.spec_from_file_location("cmtj.utils", os.path.join(ref_pkg, "utils", "__init__.py"),
+                                                   submodule_search_locations=[os.path.join(ref_pkg, "utils")])
+    umod = importlib.util.module_from_spec(uspec)
+    sys.modules["cmtj.utils"] = umod
+    uspec.loader.exec_module(umod)
     name = "_ref_curated_examples"
     if name in sys.modules:
         return sys.modules[name]
