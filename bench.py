@@ -336,7 +336,27 @@ def main():
     e2e = None
     if not args.no_e2e:
         del res
-        host_log = torch.empty((7, n_samples, B), dtype=torch.float64, pin_memory=True).numpy()
+        # pinned pages land on the NUMA node of the allocating thread: allocate from the GPU-local CPUs
+        from cmtj_b200 import _numa
+
+        prev_aff = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+        bound = _numa.bind_host_to_gpu(local_rank)
+        host_log_t = torch.empty((7, n_samples, B), dtype=torch.float64, pin_memory=True)
+        host_log_t.zero_()  # first touch while bound
+        host_log = host_log_t.numpy()
+        if bound is not None:
+            os.sched_setaffinity(0, prev_aff)
+        # raw D2H rate of this box's PCIe path into that buffer (diagnostic: e2e is copy-bound when
+        # d2h_bytes / this rate exceeds the kernel time)
+        probe = logbuf[0]
+        ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host_log_t[0].copy_(probe, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        ec0.record(stream)
+        host_log_t[0].copy_(probe, non_blocking=True)
+        ec1.record(stream)
+        torch.cuda.synchronize(dev)
+        d2h_gbs = probe.numel() * 8 / (ec0.elapsed_time(ec1) * 1e-3) / 1e9
         bh = fresh_batch()
         h2d = (3 + 6) * B * 8
         d2h = host_log.nbytes + 6 * B * 8 + B * 4
@@ -366,6 +386,8 @@ def main():
             "ms_per_step": 1e3 * float(t.item()) / args.steps,
             "api": "JunctionBatch.run -> cmtjb_run_host (pinned host log buffer, time-chunked D2H overlap)",
             "checksum_free_mz_last": checksum,
+            "pcie_d2h_gbs_measured": d2h_gbs,
+            "host_numa_binding": f"{len(bound)} GPU-local CPUs during pinned allocation" if bound else "none (single node or unknown)",
         }
         lib.cmtjb_release_cache()
 

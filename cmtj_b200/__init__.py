@@ -27,6 +27,7 @@ from .core import (  # noqa: F401
     gaussianStepDriver,
     posSineDriver,
     pulseDriver,
+    seed,
     sineDriver,
     stepDriver,
     trapezoidDriver,

@@ -54,6 +54,40 @@ class BatchLog(dict):
             out[k] = np.asarray(a[:n])
         return out
 
+    # ---- on-disk formats ---------------------------------------------------------------
+    def save_csv(self, filename: str, instance: int) -> None:
+        """One instance in the reference's ``saveLog`` format (Junction::saveLogs, junction.hpp:1638-1656):
+        ';'-terminated fields, a header row of keys, one row per sample, values in the C++ stream
+        default (``%g``).  Columns follow this log's key order (the reference's is its hash order)."""
+        if filename == "":
+            raise RuntimeError("The filename may not be empty!")
+        cols = self.instance(instance)
+        keys = list(cols.keys())
+        n = min((len(v) for v in cols.values()), default=0)
+        with open(filename, "w") as f:
+            f.write("".join(k + ";" for k in keys) + "\n")
+            for i in range(n):
+                f.write("".join(f"{cols[k][i]:g};" for k in keys) + "\n")
+
+    def save_npz(self, filename: str, compressed: bool = False) -> None:
+        """The whole sweep in one ``.npz``: every channel as float64 [n_samples, B] (lossless, unlike the
+        6-digit CSV), plus ``__n_samples_per_instance`` for adaptive-step runs."""
+        arrays = {k: np.asarray(v) for k, v in self.items()}
+        if self.n_samples_per_instance is not None:
+            arrays["__n_samples_per_instance"] = np.asarray(self.n_samples_per_instance)
+        (np.savez_compressed if compressed else np.savez)(filename, **arrays)
+
+    @classmethod
+    def load_npz(cls, filename: str) -> "BatchLog":
+        out = cls()
+        with np.load(filename) as z:
+            for k in z.files:
+                if k == "__n_samples_per_instance":
+                    out.n_samples_per_instance = z[k]
+                else:
+                    out[k] = z[k]
+        return out
+
 
 class JunctionBatch:
     def __init__(self, junction: Junction, n_instances: int, device: int = 0, instance_offset: int = 0):
@@ -103,13 +137,17 @@ class JunctionBatch:
         for c in range(3):
             self.set_override(layer_id, _abi.SLOT_HEXT + c, 0, H[:, c])
 
-    def set_magnetisation(self, layer_id: str, m) -> None:
-        """Per-instance magnetisation, m: [B,3]; normalised like ``Layer::setMagnetisation``."""
+    def set_magnetisation(self, layer_id: str, m, normalise: bool = True) -> None:
+        """Per-instance magnetisation, m: [B,3]; normalised like ``Layer::setMagnetisation``
+        (junction.hpp:491-498).  ``normalise=False`` stores m as given: the state of a layer whose
+        magnetisation was only ever set by the ``Layer`` constructor, which keeps the un-normalised
+        input until the first step (junction.hpp:178-195)."""
         m = np.asarray(m, dtype=np.float64).reshape(self.B, 3)
         n = np.sqrt((m * m).sum(axis=1))
         if np.any(n == 0):
             raise RuntimeError("Initial magnetisation was set to a zero vector!")
-        m = m / n[:, None]
+        if normalise:
+            m = m / n[:, None]
         self.sync_state_to_host()
         for l in range(self.junction.layerNo) if layer_id == "all" else [self._layer_index(layer_id)]:
             self.m_state[3 * l : 3 * l + 3, :] = m.T

@@ -1296,11 +1296,20 @@ class Junction:
             print(f"Simulation time = {int(_time.perf_counter() - t0)}[s]")
 
 
-_seed_counter = [0x243F6A8885A308D3]
+_seed_rng = np.random.default_rng()  # OS entropy, like std::random_device
+
+
+def seed(value: Optional[int] = None) -> None:
+    """Re-seed the private generator the Philox keys of stochastic runs are drawn from
+    (``None`` = OS entropy).  An addition: the reference cannot repeat a stochastic run."""
+    global _seed_rng
+    _seed_rng = np.random.default_rng(value)
 
 
 def _next_seed() -> int:
     """Philox key for the next stochastic run.  The reference seeds every Layer from
-    ``std::random_device`` (junction.hpp:174-175), i.e. runs are unrepeatable; we draw from
-    ``numpy.random`` so that ``np.random.seed`` makes runs reproducible."""
-    return int(np.random.randint(0, 2**63 - 1, dtype=np.int64))
+    ``std::random_device`` (junction.hpp:174-175), i.e. runs are unrepeatable and never touch
+    numpy's global generator: scripts that ``np.random.seed`` and then draw their own disturbances
+    between runs (cmtj/utils/procedures.py:131-140) must see the same stream with us, so the keys
+    come from a private generator (``cmtj_b200.seed`` makes runs reproducible)."""
+    return int(_seed_rng.integers(0, 2**63 - 1, dtype=np.int64))

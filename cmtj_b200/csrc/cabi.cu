@@ -194,6 +194,49 @@ struct Span {
 
 }  // namespace
 
+// When does the SMSP-balanced persistent form (llgs_balanced_kernel) pay?  With W = ceil(B / 32) warps
+// over S = 4 * numSMs sub-partitions, the plain form lasts as long as its fullest sub-partition:
+//   * the whole sweep co-resident (W / S <= resident warps per sub-partition): each sub-partition holds
+//     floor or ceil of W / S warps for the whole run  ->  efficiency (W/S) / ceil(W/S);
+//   * several waves of blocks: every block runs the same number of steps, so waves end together and the
+//     last, partly filled one costs a full wave  ->  efficiency waves / ceil(waves).
+// Balance when that model loses more than 3 % and the launch is long enough to be cut into >= 8 rounds.
+BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const void *plain_kernel) {
+  BalancePlan bp{false, 0, 0, 0, 0};
+  const char *force = std::getenv("CMTJB_BALANCE");
+  if (force && force[0] == '0') return bp;
+  const bool forced = force && force[0] == '1';
+  const long long steps = R.it_end - R.it_begin;
+  if (steps <= 0 || R.B <= 0) return bp;
+  static int n_sm[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return bp;
+  if (n_sm[dev] == 0 && cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return bp;
+  int bal_blocks = 0, plain_blocks = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bal_blocks, balanced_kernel, kBalBlock, 0) != cudaSuccess || bal_blocks <= 0 ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plain_blocks, plain_kernel, kBlock, 0) != cudaSuccess || plain_blocks <= 0) {
+    cudaGetLastError();
+    return bp;
+  }
+  bal_blocks = std::min(bal_blocks, 8);  // kBalBlock = 4 warps: at most 8 resident warps per sub-partition
+  const long long W = (R.B + 31) / 32;
+  const double mean = (double)W / (4.0 * n_sm[dev]);
+  const double cap = plain_blocks * (kBlock / 32) / 4.0;  // resident warps per sub-partition, plain form
+  const double waves = mean / cap;
+  const double eff = mean <= cap ? mean / std::ceil(mean) : waves / std::ceil(waves);
+  // a task is a whole number of log periods and at least 128 steps long
+  const long long we = R.write_every > 0 ? R.write_every : 1;
+  const long long chunk = we * ((128 + we - 1) / we);
+  const long long rounds = (steps + chunk - 1) / chunk;
+  if (!forced && (eff > 0.97 || rounds < 8)) return bp;
+  bp.use = true;
+  bp.chunk = forced ? std::max<long long>(1, std::min(chunk, (steps + 2) / 3)) : chunk;  // forced runs (tests) always see >= 3 rounds
+  bp.n_rounds = (steps + bp.chunk - 1) / bp.chunk;
+  bp.n_wtasks = W;
+  bp.blocks = (int)std::min<long long>((long long)bal_blocks * n_sm[dev], (W + 3) / 4);
+  return bp;
+}
+
 void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D) {
   std::memset(&D, 0, sizeof(D));
   const double mu0 = J.MAGNETIC_PERMEABILITY, gyro = J.GYRO;

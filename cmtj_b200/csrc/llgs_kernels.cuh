@@ -292,35 +292,40 @@ __device__ __forceinline__ void do_step(const DevModel<NL> &M, const RunParams &
   S = S1;
 }
 
-// ---- fixed-step kernel (RK4 / Heun / Euler-Heun) ------------------------------------------------
+// ---- fixed-step time loop (RK4 / Heun / Euler-Heun) ----------------------------------------------
+// Steps [it0, it1) of instance i, a sub-range of the launch's [R.it_begin, R.it_end).  State is
+// read from and written back to m_state (and sd_state), so consecutive sub-ranges of one instance
+// may be integrated by different warps (llgs_balanced_kernel); loads go through L2 (__ldcg) because
+// an earlier sub-range may have been written from another SM.
 template <int NL, int SOLVER, uint32_t F>
-__global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constant__ DevModel<NL> M,
-                                                            const __grid_constant__ RunParams R) {
-  const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= R.B) return;
+__device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams &R, long long i, long long it0, long long it1) {
   State<NL> S;
   d3 Hc[NL];
 #pragma unroll
   for (int l = 0; l < NL; l++) {
-    S.m[l] = mk(R.m_state[(3 * l + 0) * R.B + i], R.m_state[(3 * l + 1) * R.B + i], R.m_state[(3 * l + 2) * R.B + i]);
+    S.m[l] = mk(__ldcg(R.m_state + (3 * l + 0) * R.B + i), __ldcg(R.m_state + (3 * l + 1) * R.B + i),
+                __ldcg(R.m_state + (3 * l + 2) * R.B + i));
     Hc[l] = constant_field(M.L[l], R, i);
   }
-  // sample k is written after step k*write_every (junction.hpp:1973-1980)
-  long long until_write = (R.write_every - (R.it_begin % R.write_every)) % R.write_every;
-  long long sample = R.first_sample;
+  // sample k is written after step k*write_every (junction.hpp:1973-1980): step `it` writes when
+  // it % write_every == 0, so ceil(x / write_every) samples precede step x
+  const long long we = R.write_every;
+  long long until_write = (we - (it0 % we)) % we;
+  long long sample = R.first_sample + ((it0 + we - 1) / we - (R.it_begin + we - 1) / we);
   const bool logging = R.log != nullptr;
-  const double *row = R.dyn_tab;  // advances by one step (3 stage rows) per iteration
+  // advances by one step (3 stage rows) per iteration
+  const double *row = R.dyn_tab ? R.dyn_tab + (it0 - R.it_begin) * 3 * R.dyn_ncols : nullptr;
   PostState ps{0.0, 0.0, 0.0, 0.0, 0.0};
   if constexpr ((F & F_POST) != 0) {
     if (R.post.sd_mode != CMTJB_SD_NONE) {
-      ps.z0 = R.post.sd_state[i];
-      ps.z1 = R.post.sd_state[R.B + i];
-      ps.z2 = R.post.sd_state[2 * R.B + i];
-      ps.sum = R.post.sd_state[3 * R.B + i];
+      ps.z0 = __ldcg(R.post.sd_state + i);
+      ps.z1 = __ldcg(R.post.sd_state + R.B + i);
+      ps.z2 = __ldcg(R.post.sd_state + 2 * R.B + i);
+      ps.sum = __ldcg(R.post.sd_state + 3 * R.B + i);
       ps.omega = R.post.sd_omega[i];
     }
   }
-  for (long long it = R.it_begin; it < R.it_end; ++it) {
+  for (long long it = it0; it < it1; ++it) {
     const double t = (double)it * R.dt;
     State<NL> Em, Enb;
     do_step<NL, SOLVER, F>(M, R, i, it, row, t, S, Hc, Em, Enb);
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constan
         if (logging && R.elog_ch0 >= 0) write_energy<NL, F>(M, R, Em, Enb, SOLVER == CMTJB_EULER_HEUN ? t : t + R.dt, sample, i);
       }
       sample++;
-      until_write = R.write_every;
+      until_write = we;
     }
     until_write--;
   }
@@ -351,14 +356,78 @@ __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constan
     }
   }
   // RK4 throws "NAN magnetisation" on isnan(mag.x) (junction.hpp:1037-1039); NaN is absorbing,
-  // so testing the final state is equivalent.
+  // so testing the state at the end of a sub-range is equivalent.
   if (R.status) {
     int st = 0;
     if constexpr (SOLVER == CMTJB_RK4) {
 #pragma unroll
       for (int l = 0; l < NL; l++) st |= isnan(S.m[l].x) ? 1 : 0;
     }
-    if (R.it_begin == 0 || st) R.status[i] = st;
+    if (it0 == 0 || st) R.status[i] = st;
+  }
+}
+
+// One thread per instance, whole step range of the launch.
+template <int NL, int SOLVER, uint32_t F>
+__global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constant__ DevModel<NL> M,
+                                                            const __grid_constant__ RunParams R) {
+  const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= R.B) return;
+  run_span<NL, SOLVER, F>(M, R, i, R.it_begin, R.it_end);
+}
+
+// ---- SMSP-balanced persistent form ---------------------------------------------------------------------
+// The FP64 pipe is per SM sub-partition (4 x 148 = 592 on B200) and a warp is bound to one sub-
+// partition for its lifetime.  A sweep of W = ceil(B/32) warps that is not a multiple of 592 leaves
+// the run time set by the sub-partitions carrying ceil(W/592) warps while the others idle at the
+// end: W = 3125 (the 1e5-point PIMM sweep) is 5.28 per sub-partition, i.e. 12 % lost to the ones
+// that carry 6.  Here the run is cut into (round, instance-warp) tasks of `chunk` steps; resident
+// warps draw tasks from a ticket counter in (round-major) order, so every sub-partition stays busy
+// until the queue drains.  Task (r, w) may start once (r-1, w) has published the state of its 32
+// instances: a per-instance-warp round counter, release/acquire at gpu scope.  Tickets are handed
+// out in dependency order, so a waiting warp only ever waits on a warp that is already running.
+struct Balance {
+  unsigned long long *ticket;  // zeroed before the launch
+  int *done;                   // [n_wtasks] rounds completed per instance-warp, zeroed before the launch
+  long long chunk;             // steps per task
+  long long n_rounds, n_wtasks;
+};
+constexpr int kBalBlock = 128;  // one warp per sub-partition per block
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int NL, int SOLVER, uint32_t F>
+__global__ void __launch_bounds__(kBalBlock) llgs_balanced_kernel(const __grid_constant__ DevModel<NL> M,
+                                                                  const __grid_constant__ RunParams R,
+                                                                  const __grid_constant__ Balance Q) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long total = (unsigned long long)Q.n_wtasks * (unsigned long long)Q.n_rounds;
+  for (;;) {
+    unsigned long long id = 0;
+    if (lane == 0) id = atomicAdd(Q.ticket, 1ULL);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= total) break;
+    const long long round = (long long)(id / (unsigned long long)Q.n_wtasks);
+    const long long w = (long long)(id - (unsigned long long)round * (unsigned long long)Q.n_wtasks);
+    if (round > 0) {
+      if (lane == 0)
+        while (ld_acquire_gpu(Q.done + w) < (int)round) __nanosleep(256);
+      __syncwarp();
+    }
+    const long long i = w * 32 + lane;
+    const long long it0 = R.it_begin + round * Q.chunk;
+    const long long it1 = (it0 + Q.chunk < R.it_end) ? it0 + Q.chunk : R.it_end;
+    if (i < R.B) run_span<NL, SOLVER, F>(M, R, i, it0, it1);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_gpu(Q.done + w, (int)round + 1);
   }
 }
 
@@ -500,9 +569,36 @@ template <int NL> cudaError_t launch_build_dyn_table(const DevModel<NL> &M, cons
 // ---- host-side launch shims ---------------------------------------------------------------------
 typedef cudaError_t (*LaunchFn)(const void *model, const RunParams *R, cudaStream_t stream);
 
+// Decide between the plain and the SMSP-balanced form (see llgs_balanced_kernel).  CMTJB_BALANCE=0/1
+// forces the choice (tests run both and compare bit-for-bit).
+struct BalancePlan {
+  bool use;
+  long long chunk, n_rounds, n_wtasks;
+  int blocks;
+};
+BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const void *plain_kernel);
+
 template <int NL, int SOLVER, uint32_t F>
 cudaError_t launch_fixed(const void *model, const RunParams *R, cudaStream_t stream) {
   const DevModel<NL> *M = static_cast<const DevModel<NL> *>(model);
+  const BalancePlan bp = plan_balance(*R, (const void *)&llgs_balanced_kernel<NL, SOLVER, F>, (const void *)&llgs_fixed_kernel<NL, SOLVER, F>);
+  if (bp.use) {
+    const size_t bytes = 256 + (size_t)bp.n_wtasks * sizeof(int);
+    char *scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&scratch, bytes, stream);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(scratch, 0, bytes, stream);
+    Balance Q;
+    Q.ticket = (unsigned long long *)scratch;
+    Q.done = (int *)(scratch + 256);
+    Q.chunk = bp.chunk;
+    Q.n_rounds = bp.n_rounds;
+    Q.n_wtasks = bp.n_wtasks;
+    llgs_balanced_kernel<NL, SOLVER, F><<<(unsigned)bp.blocks, kBalBlock, 0, stream>>>(*M, *R, Q);
+    e = cudaGetLastError();
+    cudaFreeAsync(scratch, stream);
+    return e;
+  }
   const long long blocks = (R->B + kBlock - 1) / kBlock;
   llgs_fixed_kernel<NL, SOLVER, F><<<(unsigned)blocks, kBlock, 0, stream>>>(*M, *R);
   return cudaGetLastError();

@@ -129,7 +129,9 @@ def _oersted_driver(direction: Axis, driver: ScalarDriver) -> Tuple[str, int, Ax
 def _disturbed(junction: Junction, layer_ids: List[str], n: int, disturbance: float) -> Dict[str, np.ndarray]:
     """Initial magnetisation of n instances: the junction's current m plus the reference's
     np.random.normal(0, disturbance) per component (same draw order: point, layer, x/y/z),
-    normalised (procedures.py:131-140)."""
+    normalised (procedures.py:131-140).  With disturbance == 0 the reference never touches the
+    magnetisation, so a freshly constructed layer starts its first step from the un-normalised
+    constructor input; callers store the result with ``set_magnetisation(..., normalise=bool(disturbance))``."""
     base = np.array([junction.getLayerMagnetisation(lid).tolist() for lid in layer_ids])  # [L,3]
     m = np.repeat(base[None], n, axis=0)
     if disturbance:
@@ -147,7 +149,7 @@ def _instance_chunks(n: int, bytes_per_instance: float, budget: float) -> List[T
 # PIMM
 # ---------------------------------------------------------------------------------------------------
 def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resistance_params, comp, weights, simulation_duration,
-                wait_time, max_frequency, take_last_n, full_output, static_only, device):
+                wait_time, max_frequency, take_last_n, full_output, static_only, device, normalise):
     """One batch of field points (all start from m0).  Returns a dict of host arrays."""
     torch = _torch()
     B = Hc.shape[0]
@@ -159,7 +161,7 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
     batch = JunctionBatch(junction, B, device=device)
     batch.set_external_field("all", Hc)
     for lid in layer_ids:
-        batch.set_magnetisation(lid, m0[lid])
+        batch.set_magnetisation(lid, m0[lid], normalise=normalise)
     out: Dict[str, Any] = {}
     n_proj = 0 if static_only else (1 + L if full_output else 1)
     if n_proj > _abi.MAX_PROJ:
@@ -267,7 +269,7 @@ def PIMM_procedure(
 
     def run(Hc, m0):
         return _pimm_batch(junction, Hc, m0, int_step, rows, kind, resistance_fn, resistance_params, comp, weights,
-                           simulation_duration, wait_time, max_frequency, take_last_n, full_output, static_only, device)
+                           simulation_duration, wait_time, max_frequency, take_last_n, full_output, static_only, device, bool(disturbance))
 
     parts: List[Dict[str, Any]] = []
     if carry_state:
@@ -317,7 +319,7 @@ def PIMM_procedure(
 # ---------------------------------------------------------------------------------------------------
 # VSD
 # ---------------------------------------------------------------------------------------------------
-def _vsd_batch(junction, Hc, fc, m0, int_step, sd_mode, rows, comp, simulation_duration, device):
+def _vsd_batch(junction, Hc, fc, m0, int_step, sd_mode, rows, comp, simulation_duration, device, normalise):
     torch = _torch()
     B = Hc.shape[0]
     dev = torch.device("cuda", device)
@@ -328,7 +330,7 @@ def _vsd_batch(junction, Hc, fc, m0, int_step, sd_mode, rows, comp, simulation_d
     batch.set_external_field("all", Hc)
     batch.set_override("all", _abi.SLOT_HOE + comp, "frequency", fc)
     for lid in layer_ids:
-        batch.set_magnetisation(lid, m0[lid])
+        batch.set_magnetisation(lid, m0[lid], normalise=normalise)
     b, a = butter_lowpass_coefficients(10e6, 1.0 / int_step, order=3)  # compute_sd, resistance.py:19-21
     omega = torch.from_numpy(np.ascontiguousarray(2 * math.pi * fc)).to(dev)  # procedures.py:327
     state = torch.zeros((4, B), dtype=torch.float64, device=dev)
@@ -394,7 +396,7 @@ def VSD_procedure(
     if carry_state:
         for i in range(nH * nF):
             v, getm = _vsd_batch(junction, Hall[i : i + 1], fall[i : i + 1], _disturbed(junction, layer_ids, 1, disturbance),
-                                 int_step, sd_mode, rows, comp, simulation_duration, device)
+                                 int_step, sd_mode, rows, comp, simulation_duration, device, bool(disturbance))
             spectrum[i] = v[0]
             for lid in layer_ids:
                 junction.setLayerMagnetisation(lid, CVector(*getm(lid)[0]))
@@ -404,7 +406,7 @@ def VSD_procedure(
         for lo in range(0, nH * nF, max_batch):
             hi = min(nH * nF, lo + max_batch)
             spectrum[lo:hi], getm = _vsd_batch(junction, Hall[lo:hi], fall[lo:hi], {k: v[lo:hi] for k, v in m0.items()},
-                                               int_step, sd_mode, rows, comp, simulation_duration, device)
+                                               int_step, sd_mode, rows, comp, simulation_duration, device, bool(disturbance))
         if getm is not None:
             for lid in layer_ids:
                 junction.setLayerMagnetisation(lid, CVector(*getm(lid)[-1]))

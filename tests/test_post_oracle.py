@@ -105,3 +105,42 @@ def test_field_scan_matches_reference_formulas():
     assert Hb.tolist() == [0.0, 0.5, 1.0, 0.5, 0.0] and vb.shape == (5, 3)
     th, ph_, r = cm.utils.FieldScan.vector2angle(*cm.utils.FieldScan.angle2vector(40, 70, 2.0).tolist())
     np.testing.assert_allclose([th, ph_, r], [40, 70, 2.0], rtol=1e-12)
+
+
+def test_carried_sweep_through_the_facade_reproduces_golden_bit_exact(on_oracle):
+    """The reference's own loop (procedures.py:120-141: field, pulse, seeded disturbance drawn from
+    numpy's GLOBAL generator between runs, state carried) written against the facade.  Pins two
+    host-side behaviours: runSimulation must not consume numpy's global stream (the Philox keys come
+    from a private generator), and the carried magnetisation round-trips through
+    getLayerMagnetisation / setLayerMagnetisation unchanged."""
+    want = ph.golden("pimm_carried")
+    j = helpers.two_layer_mtj(cm)
+    np.random.seed(11)
+    ids = j.getLayerIds()
+    oe = cm.AxialDriver(cm.NullDriver(), cm.NullDriver(), cm.ScalarDriver.getStepDriver(0, 500, 0, ps.DT * 3))
+    params = [(p.Rxx0, p.Rxy0, p.Ramr, p.Rahe, p.Rsmr, p.w, p.l) for p in ps.rparams(_P, 2)]
+    for k, H in enumerate(ps.H_PIMM[:4]):
+        j.clearLog()
+        j.setLayerExternalFieldDriver("all", cm.AxialDriver(*[cm.ScalarDriver.getConstantDriver(float(h)) for h in H]))
+        j.setLayerOerstedFieldDriver("all", oe)
+        for lid in ids:
+            o = j.getLayerMagnetisation(lid)
+            n = cm.CVector(o.x + np.random.normal(0, 1e-3), o.y + np.random.normal(0, 1e-3), o.z + np.random.normal(0, 1e-3))
+            n.normalize()
+            j.setLayerMagnetisation(lid, n)
+        j.runSimulation(ps.PIMM_KW["simulation_duration"], ps.DT, ps.DT)
+        layers = j.layers
+        r = ph.post_oracle.pimm_point(j.getLog(), ids, [l.thickness for l in layers], [l.Ms for l in layers], "z", ps.DT, params,
+                                      False, 0.0, ps.PIMM_KW["max_frequency"], ps.PIMM_KW["take_last_n"])
+        assert np.array_equal(r["spectrum"].ravel(), want["spectrum"][k]), k
+        assert np.array_equal(r["m_avg"], want["m_avg"][k]), k
+
+
+def test_runs_do_not_consume_numpys_global_generator(on_oracle):
+    j = helpers.single_layer_mtj(cm)
+    j.setLayerTemperatureDriver("all", cm.constantDriver(300.0))
+    np.random.seed(3)
+    a = np.random.normal()
+    np.random.seed(3)
+    j.runSimulation(1e-11, 1e-13, 1e-13, solverMode=cm.SolverMode.Heun)
+    assert np.random.normal() == a
