@@ -194,6 +194,12 @@ struct Span {
 
 }  // namespace
 
+// needed_features for the other translation units (coupled.cu picks its kernel variant with it)
+uint32_t model_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                        const cmtjb_run_args_t *a, int solver) {
+  return needed_features(jn, layers, ovr, n_ovr, a, solver);
+}
+
 // When does the SMSP-balanced persistent form (llgs_balanced_kernel) pay?  With W = ceil(B / 32) warps
 // over S = 4 * numSMs sub-partitions, the plain form lasts as long as its fullest sub-partition:
 //   * the whole sweep co-resident (W / S <= resident warps per sub-partition): each sub-partition holds
@@ -224,16 +230,29 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
   const double cap = plain_blocks * (kBlock / 32) / 4.0;  // resident warps per sub-partition, plain form
   const double waves = mean / cap;
   const double eff = mean <= cap ? mean / std::ceil(mean) : waves / std::ceil(waves);
-  // a task is a whole number of log periods and at least 128 steps long
+  // a task is a whole number of log periods ...
   const long long we = R.write_every > 0 ? R.write_every : 1;
-  const long long chunk = we * ((128 + we - 1) / we);
+  // ... and the launch is cut into about 64 rounds (tail <= 1/64 of the quantisation loss), 128 to 400 steps
+  // each (measured on B200, S1: 100..400 steps per task within 0.1 % of each other, 1000+ slower)
+  long long target = std::min<long long>(400, std::max<long long>(128, steps / 64));
+  if (const char *c = std::getenv("CMTJB_BALANCE_CHUNK")) target = std::max<long long>(1, std::atoll(c));  // tuning knob
+  const long long chunk = we * ((target + we - 1) / we);
   const long long rounds = (steps + chunk - 1) / chunk;
-  if (!forced && (eff > 0.97 || rounds < 8)) return bp;
+  // Resident warps per sub-partition of the balanced form: at most 0.9 W / S, so that a warp drawing a
+  // ticket (almost) always finds the predecessor task finished -- tickets are issued round-major, and
+  // the W - S k instance-warps not being integrated at any moment are the slack that keeps the queue
+  // from stalling (measured on B200, S1 with W / S = 5.28: k = 4 -> 1.151e11 layer-steps/s, k = 5 ->
+  // 1.105e11, plain -> 1.044e11).  Below four the FP64 pipe is latency- rather than throughput-bound
+  // and time-slicing would serialise what the plain form overlaps.
+  long long k = std::min<long long>(bal_blocks, (long long)std::floor(0.9 * mean));
+  if (const char *c = std::getenv("CMTJB_BALANCE_WARPS")) k = std::max<long long>(1, std::min<long long>(std::atoll(c), bal_blocks));
+  if (!forced && (eff > 0.97 || rounds < 8 || k < 4)) return bp;
+  k = std::max<long long>(k, 1);
   bp.use = true;
   bp.chunk = forced ? std::max<long long>(1, std::min(chunk, (steps + 2) / 3)) : chunk;  // forced runs (tests) always see >= 3 rounds
   bp.n_rounds = (steps + bp.chunk - 1) / bp.chunk;
   bp.n_wtasks = W;
-  bp.blocks = (int)std::min<long long>((long long)bal_blocks * n_sm[dev], (W + 3) / 4);
+  bp.blocks = (int)std::min<long long>(k * n_sm[dev], (W + 3) / 4);
   return bp;
 }
 

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,6 +65,31 @@ void fill_plan(const Common &c, int n_sys_ch, cmtjb_coupled_plan_t *p) {
   p->total_iterations = c.plan0.total_iterations;
   p->write_every = c.plan0.write_every;
   p->n_samples = c.plan0.n_samples;
+}
+
+// Union of the term sets the junctions of a system need (cabi.cu: needed_features).  The coupled
+// kernels have no per-launch driver table, so any time-dependent driver means inline evaluation;
+// system-level overrides (the stack's current driver) are not junction terms.
+uint32_t system_features(int n, int nl, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr,
+                         int n_ovr, const cmtjb_run_args_t *a, int solver) {
+  std::vector<cmtjb_override_t> jo;
+  for (int k = 0; k < n_ovr; k++)
+    if (ovr[k].layer != CMTJB_LAYER_SYSTEM) jo.push_back(ovr[k]);
+  cmtjb_run_args_t aj = *a;
+  aj.onef_buffer = nullptr;
+  uint32_t F = 0;
+  for (int j = 0; j < n; j++) F |= model_features(&jns[j], layers + (size_t)j * nl, jo.data(), (int)jo.size(), &aj, solver);
+  if (F & (F_DYN | F_DYNS)) F = (F & ~(F_DYN | F_DYNS)) | F_DYNI;
+  const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel (testing)
+  if (force && std::strcmp(force, "full") == 0) F = F_ALL;
+  return F;
+}
+inline bool lean_ok(uint32_t need) { return (need & ~F_COUPLED_LEAN) == 0; }
+// every junction carries the same derived model (bytewise): pass it once, by value
+template <int NL> bool models_uniform(const std::vector<DevModel<NL>> &m) {
+  for (size_t j = 1; j < m.size(); j++)
+    if (std::memcmp(&m[0], &m[j], sizeof(DevModel<NL>)) != 0) return false;
+  return true;
 }
 
 template <int NL>
@@ -232,11 +258,26 @@ int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmt
   SP.coupling = d_coupling;
   const int threads = SP.spb * N;
   const long long blocks = (n_inst + SP.spb - 1) / SP.spb;
-  const size_t smem = 2 * (size_t)threads * sizeof(double);
-  if (c.solver == CMTJB_RK4)
-    stack_kernel<NL, CMTJB_RK4><<<(unsigned)blocks, threads, smem, stream>>>(d_models, SP, R);
-  else
-    stack_kernel<NL, CMTJB_EULER_HEUN><<<(unsigned)blocks, threads, smem, stream>>>(d_models, SP, R);
+  const size_t smem = (3 * (size_t)threads + 2 * ((size_t)threads / 32 + 1)) * sizeof(double);
+  const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver));
+  const bool uni = lean && models_uniform<NL>(models);
+  const DevModel<NL> &M0 = models[0];
+#define CMTJB_STACK_LAUNCH2(SOLVER, MODE)                                                                                                \
+  do {                                                                                                                                   \
+    if (uni) stack_kernel<NL, SOLVER, F_COUPLED_LEAN, true, MODE><<<(unsigned)blocks, threads, smem, stream>>>(d_models, M0, SP, R);       \
+    else if (lean) stack_kernel<NL, SOLVER, F_COUPLED_LEAN, false, MODE><<<(unsigned)blocks, threads, smem, stream>>>(d_models, M0, SP, R); \
+    else stack_kernel<NL, SOLVER, F_ALL, false, MODE><<<(unsigned)blocks, threads, smem, stream>>>(d_models, M0, SP, R);                   \
+  } while (0)
+#define CMTJB_STACK_LAUNCH(SOLVER)                                    \
+  do {                                                                \
+    if (SP.use_kcl) CMTJB_STACK_LAUNCH2(SOLVER, STACK_KCL);           \
+    else if (SP.delayed) CMTJB_STACK_LAUNCH2(SOLVER, STACK_DELAYED);  \
+    else CMTJB_STACK_LAUNCH2(SOLVER, STACK_SEQUENTIAL);               \
+  } while (0)
+  if (c.solver == CMTJB_RK4) CMTJB_STACK_LAUNCH(CMTJB_RK4);
+  else CMTJB_STACK_LAUNCH(CMTJB_EULER_HEUN);
+#undef CMTJB_STACK_LAUNCH2
+#undef CMTJB_STACK_LAUNCH
   e = cudaGetLastError();
   g_launches++;
   cudaFreeAsync(d_models, stream);
@@ -326,20 +367,32 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   GP.pref = d_pref;
   int rc = CMTJB_OK;
   const bool rk4 = (c.solver == CMTJB_RK4);
+  const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver));
+  const bool uni = lean && models_uniform<NL>(models);
+  DevModel<NL> M0 = models[0];
   if (!group_uses_grid<NL>(N)) {
     GP.P = std::min(32, pow2_floor(kCoupledBlockMax / N));
     const int threads = ((N * GP.P + 31) / 32) * 32;
     const size_t smem = 10 * (size_t)N * sizeof(double);
-    if (rk4)
-      group_block_kernel<NL, CMTJB_RK4><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, GP, R);
-    else
-      group_block_kernel<NL, CMTJB_EULER_HEUN><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, GP, R);
+#define CMTJB_GROUP_LAUNCH(SOLVER)                                                                                              \
+  do {                                                                                                                          \
+    if (uni) group_block_kernel<NL, SOLVER, F_COUPLED_LEAN, true><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, M0, GP, R); \
+    else if (lean) group_block_kernel<NL, SOLVER, F_COUPLED_LEAN, false><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, M0, GP, R); \
+    else group_block_kernel<NL, SOLVER, F_ALL, false><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, M0, GP, R);         \
+  } while (0)
+    if (rk4) CMTJB_GROUP_LAUNCH(CMTJB_RK4);
+    else CMTJB_GROUP_LAUNCH(CMTJB_EULER_HEUN);
+#undef CMTJB_GROUP_LAUNCH
     e = cudaGetLastError();
     g_launches++;
     if (e != cudaSuccess) rc = cuda_fail(e, "group_block_kernel");
   } else {
     // one array across the grid: cooperative launch, as many co-resident CTAs as the pair sum can use
-    const void *fn = rk4 ? (const void *)group_grid_kernel<NL, CMTJB_RK4> : (const void *)group_grid_kernel<NL, CMTJB_EULER_HEUN>;
+#define CMTJB_GRID_FN(SOLVER)                                                                    \
+  (uni ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, true>                      \
+       : lean ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, false> : (const void *)group_grid_kernel<NL, SOLVER, F_ALL, false>)
+    const void *fn = rk4 ? CMTJB_GRID_FN(CMTJB_RK4) : CMTJB_GRID_FN(CMTJB_EULER_HEUN);
+#undef CMTJB_GRID_FN
     int per_sm = 0, sms = 0, coop = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
@@ -358,7 +411,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
         GP.mbuf = d_mbuf;
         for (long long inst = 0; inst < n_inst && rc == CMTJB_OK; inst++) {
           GP.inst = inst;
-          void *args[] = {(void *)&d_models, (void *)&GP, (void *)&R};
+          void *args[] = {(void *)&d_models, (void *)&M0, (void *)&GP, (void *)&R};
           e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(256), args, 0, stream);
           g_launches++;
           if (e != cudaSuccess) rc = cuda_fail(e, "group_grid_kernel");

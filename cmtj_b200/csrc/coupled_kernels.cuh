@@ -5,8 +5,11 @@
 //
 // One thread owns one junction (element) of one system instance for the whole time loop; its
 // magnetisation stays in registers.  Junction models may differ inside a system, so they are read
-// from a device array (L1/L2-cached) instead of the constant bank, and the fully general term set
-// (F_ALL: every field/torque term, inline drivers, per-element overrides) is compiled in.  The
+// from a device array (L1/L2-cached) instead of the constant bank.  Two term sets are compiled: the
+// lean one (F_COUPLED_LEAN: folded K1 + demag, constant drivers, IEC, STT / static SOT, thermal
+// noise -- what stacks of STT junctions and plain macrospin arrays need) and the fully general one
+// (F_ALL: every field/torque term, inline drivers, per-element overrides); coupled.cu takes the
+// union of the junctions' needs and picks.  The
 // per-step exchange is a block-level scan (stack) or an all-pairs field sum with m staged in
 // shared memory (group); arrays larger than one block use a cooperative launch with one
 // grid-wide barrier per step.
@@ -19,7 +22,7 @@ namespace cmtjb {
 
 namespace cg = cooperative_groups;
 
-constexpr uint32_t F_COUPLED = F_ALL;
+constexpr uint32_t F_COUPLED_LEAN = F_IEC | F_STT | F_SOT | F_THERMAL;
 constexpr int kCoupledBlockMax = 512;  // 128 registers per thread for the general term set
 
 // waveform of an explicit driver record (same expressions as driver_shape, drivers.hpp:262-305)
@@ -51,24 +54,41 @@ __device__ __forceinline__ double shape_of(const DevDriver &d, double phase, dou
   }
 }
 
-// the current a Stack pushes into every layer of a junction for one step (stack.hpp:370-371,
-// :413-415): constant + post(amplitude * waveform(t; phase))
+// The current a Stack pushes into every layer of a junction for one step (stack.hpp:370-371,
+// :413-415): constant + post(amplitude * waveform(t; phase)).  A step only ever asks for it at its
+// three stage times t, t + dt/2, t + dt (Euler-Heun: t), so the values are computed once per step
+// (one call site of the waveform code) and llg_u selects by comparing the stage time it was given.
 struct StackCurrent {
   static constexpr bool kCurrent = true;
-  const DevDriver *d;
-  double cst, amp, phase;
-  __device__ __forceinline__ double current(double t) const {
-    if (amp == 0.0) return cst;
-    return cst + driver_post(d->type, amp * shape_of(*d, phase, t));
-  }
+  double t1, t2;      // thresholds t + dt/4, t + 3dt/4 separating the stage times t, t + dt/2, t + dt
+  double I0, I1, I2;  // current at the three stage times
+  __device__ __forceinline__ double current(double t) const { return t >= t2 ? I2 : (t >= t1 ? I1 : I0); }
 };
+template <int SOLVER>
+__device__ __forceinline__ StackCurrent stack_current(const DevDriver &d, double cst, double amp, double phase, double t, double dt) {
+  StackCurrent c;
+  c.t1 = t + 0.25 * dt;
+  c.t2 = t + 0.75 * dt;
+  if (amp == 0.0) {
+    c.I0 = c.I1 = c.I2 = cst;
+    return c;
+  }
+  double v[3];
+  const double ts[3] = {t, t + 0.5 * dt, t + dt};  // the reference's stage-time expressions (junction.hpp:1020-1033)
+#pragma unroll 1
+  for (int k = 0; k < (SOLVER == CMTJB_RK4 ? 3 : 1); k++) v[k] = cst + driver_post(d.type, amp * shape_of(d, phase, ts[k]));
+  c.I0 = v[0];
+  c.I1 = SOLVER == CMTJB_RK4 ? v[1] : v[0];
+  c.I2 = SOLVER == CMTJB_RK4 ? v[2] : v[0];
+  return c;
+}
 
-template <int NL, int SOLVER, class Ext>
+template <int NL, int SOLVER, uint32_t F, class Ext>
 __device__ __forceinline__ void coupled_step(const DevModel<NL> &M, const RunParams &R, long long i, long long it, double t,
                                              State<NL> &S, const d3 *Hc, const Ext &ext) {
   State<NL> S1, M4;
-  if constexpr (SOLVER == CMTJB_RK4) rk4_all<NL, F_COUPLED, 0, Ext>(M, R, i, nullptr, t, S, S1, Hc, M4, ext);
-  else euler_heun_all<NL, F_COUPLED, 0, Ext>(M, R, i, it, nullptr, t, S, S1, Hc, ext);
+  if constexpr (SOLVER == CMTJB_RK4) rk4_all<NL, F, 0, Ext>(M, R, i, nullptr, t, S, S1, Hc, M4, ext);
+  else euler_heun_all<NL, F, 0, Ext>(M, R, i, it, nullptr, t, S, S1, Hc, ext);
   S = S1;
 }
 
@@ -126,9 +146,45 @@ template <bool MUL> __device__ __forceinline__ double seg_scan(double v, double 
   return v;
 }
 
-template <int NL, int SOLVER>
-__global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<NL> *__restrict__ models, const __grid_constant__ StackParams SP,
-                                                     const __grid_constant__ RunParams R) {
+// Sum of v over the N threads of one stack, returned to all of them.  When stacks are warp-aligned
+// (N a multiple of 32, or a power of two <= 32) it is a shuffle reduction plus, for N > 32, one
+// shared-memory exchange of the per-warp partials: ONE block barrier instead of the scan's
+// 1 + 2 log2 N.  `part` is double-buffered by the caller (step parity), so no trailing barrier is needed.
+__device__ __forceinline__ double stack_sum(double v, double *scan, double *part, int tid, int j, int sl, int N, bool aligned) {
+  if (!aligned) {
+    seg_scan<false>(v, scan, tid, j, N);
+    const double tot = scan[sl * N + N - 1];
+    __syncthreads();  // scan[] is rewritten by the next reduction
+    return tot;
+  }
+  const int width = N < 32 ? N : 32;
+  for (int off = width >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, width);
+  if (N <= 32) return v;
+  const int wps = N >> 5;  // warps per stack
+  if ((tid & 31) == 0) part[tid >> 5] = v;
+  __syncthreads();
+  double tot = 0.0;
+  const int w0 = sl * wps;
+  for (int k = 0; k < wps; k++) tot += part[w0 + k];
+  return tot;
+}
+
+template <int NL> __device__ __forceinline__ d3 layer_m(const State<NL> &S, int idx) {
+  if constexpr (NL == 1) return S.m[0];
+  else return idx == 0 ? S.m[0] : S.m[1];  // stacks hold junctions of at most two layers (stack.hpp:298-308)
+}
+
+// MODE: which of the three coupling schemes of Stack::runSimulation this instantiation integrates
+enum { STACK_KCL = 0, STACK_DELAYED = 1, STACK_SEQUENTIAL = 2 };
+
+// UNIFORM: every junction of the system has the same model (the usual `[junction] * N` construction);
+// it is then passed by value like in the sweep kernels and its parameters are constant-bank operands
+// instead of registers loaded from models[j].
+template <int NL, int SOLVER, uint32_t F, bool UNIFORM, int MODE>
+__global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<NL> *__restrict__ models,
+                                                                 const __grid_constant__ DevModel<NL> Mu,
+                                                                 const __grid_constant__ StackParams SP,
+                                                                 const __grid_constant__ RunParams R) {
   extern __shared__ double sm[];
   const int N = SP.N;
   const int tid = threadIdx.x;
@@ -136,9 +192,12 @@ __global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<
   const long long s = (long long)blockIdx.x * SP.spb + sl;
   const bool active = s < SP.n_inst;  // idle threads of the last block still take part in the barriers
   const long long i = active ? s * N + j : 0;
-  const DevModel<NL> &M = models[j];
-  double *dots = sm;               // [blockDim]  m_top . p of every junction
-  double *scan = sm + blockDim.x;  // [blockDim]  scan workspace
+  const DevModel<NL> &M = UNIFORM ? Mu : models[j];
+  double *dots = sm;                    // [2][blockDim]  m_top . p of every junction (double-buffered)
+  double *scan = sm + 2 * blockDim.x;   // [blockDim]     scan workspace
+  double *part = sm + 3 * blockDim.x;   // [2][blockDim / 32 + 1] per-warp partial sums (double-buffered)
+  const int part_stride = (blockDim.x >> 5) + 1;
+  const bool aligned = (N % 32 == 0) || (N <= 32 && (N & (N - 1)) == 0);
 
   State<NL> S;
   d3 Hc[NL];
@@ -167,8 +226,8 @@ __global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<
   const d3 pol = mk(SP.pol[0], SP.pol[1], SP.pol[2]);
 
   auto my_dot = [&]() {
-    const d3 mt = S.m[SP.top < NL ? SP.top : 0];
-    if (NL >= 2 && SP.bottom >= 0) return dot(mt, S.m[SP.bottom < NL ? SP.bottom : 0]);
+    const d3 mt = layer_m<NL>(S, SP.top);
+    if (NL >= 2 && SP.bottom >= 0) return dot(mt, layer_m<NL>(S, SP.bottom));
     return dot(mt, pol);
   };
   auto resistance = [&]() {  // getMagnetoresistance()[0], classic (junction.hpp:1865-1889)
@@ -181,43 +240,45 @@ __global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<
   long long until_write = (R.write_every - (R.it_begin % R.write_every)) % R.write_every;
   long long sample = R.first_sample;
   const long long scs = R.n_samples * SP.n_inst;  // stack-log channel stride
+  int buf = 0;
   for (long long it = R.it_begin; it < R.it_end; ++it) {
     const double t = (double)it * R.dt;
-    StackCurrent ext{&cd, 0.0, 0.0, my_phase};
+    StackCurrent ext;
     double c_log = 0.0;  // what the reference logs as C_(j-1)_j (non-KCL) or C_j_(j+1) (KCL)
-    if (SP.use_kcl) {
+    if constexpr (MODE == STACK_KCL) {
       // stack.hpp:397-408: I_total = I0(t) (1 + sum_j C_j), C_j = c_j (m_j.p_j +- m_(j+1).p_(j+1))
-      dots[tid] = my_dot();
+      double *db = dots + buf * blockDim.x;
+      db[tid] = my_dot();
       __syncthreads();
-      const double C = (j < N - 1) ? c_here * (dots[tid] + sign * dots[tid + 1]) : 0.0;
-      seg_scan<false>(C, scan, tid, j, N);
-      const double sumC = scan[sl * N + N - 1];
+      const double C = (j < N - 1) ? c_here * (db[tid] + sign * db[tid + 1]) : 0.0;
+      const double sumC = stack_sum(C, scan, part + buf * part_stride, tid, j, sl, N, aligned);
       const double I0 = cur_cst + (cd.amplitude == 0.0 ? 0.0 : driver_post(cd.type, cd.amplitude * shape_of(cd, cd.phase, t)));
-      ext.cst = fma(sumC, I0, I0);
+      const double I = fma(sumC, I0, I0);
+      ext.t1 = ext.t2 = t;
+      ext.I0 = ext.I1 = ext.I2 = I;  // held over the step
       c_log = C;
-      __syncthreads();  // dots/scan are rewritten next step
-      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hc, ext);
-    } else if (SP.delayed) {
+      buf ^= 1;
+      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hc, ext);
+    } else if constexpr (MODE == STACK_DELAYED) {
       // stack.hpp:335-354: eff_j = prod_{k<=j, k>0} (1 + C_(k-1)) from the frozen magnetisations
       dots[tid] = my_dot();
       __syncthreads();
       const double f = (j > 0) ? 1.0 + c_prev * (dots[tid - 1] + sign * dots[tid]) : 1.0;
       const double eff = seg_scan<true>(f, scan, tid, j, N);
-      ext.cst = cur_cst * eff;
-      ext.amp = cd.amplitude * eff;
+      ext = stack_current<SOLVER>(cd, cur_cst * eff, cd.amplitude * eff, my_phase, t, R.dt);
       c_log = eff;
-      __syncthreads();
-      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hc, ext);
+      __syncthreads();  // dots/scan are rewritten next step
+      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hc, ext);
     } else {
-      // stack.hpp:356-365: Gauss-Seidel chain -- junction j sees the ALREADY STEPPED j-1
+      // stack.hpp:356-365: Gauss-Seidel chain -- junction j sees the ALREADY STEPPED j-1.  One call site
+      // of the step: every thread walks the chain, only thread jj commits.
       for (int jj = 0; jj < N; jj++) {
         if (j == jj) {
           double eff = 1.0;
           if (jj > 0) eff = scan[tid - 1] * (1.0 + c_prev * (dots[tid - 1] + sign * my_dot()));
-          ext.cst = cur_cst * eff;
-          ext.amp = cd.amplitude * eff;
+          ext = stack_current<SOLVER>(cd, cur_cst * eff, cd.amplitude * eff, my_phase, t, R.dt);
           c_log = eff;
-          coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hc, ext);
+          coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hc, ext);
           dots[tid] = my_dot();
           scan[tid] = eff;
         }
@@ -227,13 +288,14 @@ __global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<
     if (until_write == 0) {
       // logSimulationStep (stack.hpp:93-103): stack resistance, per-junction current and coupling
       const double Rj = resistance();
+      __syncthreads();
       const double tot = seg_scan<false>(SP.kind == CMTJB_STACK_SERIES ? Rj : 1.0 / Rj, scan, tid, j, N);
       if (active && R.log) write_sample<NL>(M, R, S, sample, i);
       if (active && SP.slog) {
         double *p = SP.slog + sample * SP.n_inst + s;
         if (j == N - 1) __stcs(p, SP.kind == CMTJB_STACK_SERIES ? tot : 1.0 / tot);
         __stcs(p + (1 + j) * scs, ext.current(t));
-        if (SP.use_kcl) {
+        if (MODE == STACK_KCL) {
           if (j < N - 1) __stcs(p + (1 + N + j) * scs, c_log);
         } else if (j > 0) {
           __stcs(p + (1 + N + j - 1) * scs, c_log);
@@ -280,10 +342,11 @@ __device__ __forceinline__ void pair_accumulate(d3 &H, d3 r, d3 mb, double pref)
 // GroupInteraction, one group per block: blockDim.x = N * P rounded up to a warp multiple.  Thread
 // (a = tid / P, p = tid % P) sums the pair field of element a over b = p, p+P, ...; lane p == 0
 // owns junction a.
-template <int NL, int SOLVER>
+template <int NL, int SOLVER, uint32_t F, bool UNIFORM>
 __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const DevModel<NL> *__restrict__ models,
-                                                           const __grid_constant__ GroupParams GP,
-                                                           const __grid_constant__ RunParams R) {
+                                                                       const __grid_constant__ DevModel<NL> Mu,
+                                                                       const __grid_constant__ GroupParams GP,
+                                                                       const __grid_constant__ RunParams R) {
   extern __shared__ double sm[];
   const int N = GP.N, P = GP.P;
   const int tid = threadIdx.x;
@@ -292,7 +355,7 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
   const long long g = blockIdx.x;
   const long long i = g * N + a;
   const bool owner = (p == 0) && a_raw < N;
-  const DevModel<NL> &M = models[a];
+  const DevModel<NL> &M = UNIFORM ? Mu : models[a];
   double *px = sm, *py = px + N, *pz = py + N, *pf = pz + N;  // static geometry + prefactors
   double *mb0 = pf + N;                                      // [2][3][N] double-buffered m_top
   for (int k = tid; k < N; k += blockDim.x) {
@@ -338,7 +401,7 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
       d3 Hs[NL];
 #pragma unroll
       for (int l = 0; l < NL; l++) Hs[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
-      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hs, NoExt());
+      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hs, NoExt());
       double *nx = mb0 + (cur ^ 1) * 3 * N;
       const d3 mt = S.m[GP.top < NL ? GP.top : 0];
       nx[a] = mt.x;
@@ -368,8 +431,9 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
 // ONE grid-wide barrier per time step.
 constexpr int kGroupTile = 256;
 
-template <int NL, int SOLVER>
+template <int NL, int SOLVER, uint32_t F, bool UNIFORM>
 __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__restrict__ models,
+                                                         const __grid_constant__ DevModel<NL> Mu,
                                                          const __grid_constant__ GroupParams GP,
                                                          const __grid_constant__ RunParams R) {
   cg::grid_group grid = cg::this_grid();
@@ -383,7 +447,7 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
   const int a = valid ? (int)a_raw : N - 1;
   const bool owner = valid && p == 0;
   const long long i = GP.inst * N + a;
-  const DevModel<NL> &M = models[a];
+  const DevModel<NL> &M = UNIFORM ? Mu : models[a];
   State<NL> S;
   d3 Hc[NL];
   if (owner) {
@@ -434,7 +498,7 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
       d3 Hs[NL];
 #pragma unroll
       for (int l = 0; l < NL; l++) Hs[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
-      coupled_step<NL, SOLVER>(M, R, i, it, t, S, Hs, NoExt());
+      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hs, NoExt());
       double *nx = GP.mbuf + (size_t)(cur ^ 1) * 3 * N;
       const d3 mt = S.m[GP.top < NL ? GP.top : 0];
       __stcg(nx + a, mt.x);

@@ -24,5 +24,8 @@ int cuda_fail(cudaError_t e, const char *what);
 int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a, cmtjb_plan_t *p);
 void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D);
 void set_step_products(DevLayer &D, double dt);  // h = llg*dt etc. for this launch's time step
+// feature bits (dev_model.h: F_*) a junction model needs compiled into its kernel
+uint32_t model_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                        const cmtjb_run_args_t *a, int solver);
 
 }  // namespace cmtjb

@@ -12,7 +12,15 @@ echo "== bench"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_o
 echo "== ncu launch list (same bench command, reduced steps)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-echo "== ncu full (S1 kernel, 100000 instances x 2000 steps, log every 100)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:llgs_fixed -s 1 -c 1 -o gpurun_out/prof_s1 -f \
-    python tools/s1_run.py 100000 2000 100 2 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+echo "== ncu full (S1 kernel, 100000 instances x 20000 steps, log every 100)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:llgs_balanced -s 1 -c 1 -o gpurun_out/prof_s1 -f \
+    python tools/s1_run.py 100000 20000 100 2 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+if [ "${PROFILE_CONFIGS:-0}" = "1" ]; then
+  # one full capture per other kernel family (reduced sizes: ncu replays each kernel ~40 times)
+  for spec in "s3:regex:llgs_:0.1" "s4:regex:llgs_:0.02" "s5s:regex:stack_kernel:0.25" "s5g:regex:group_:0.25"; do
+    IFS=: read cfg kind pat scale <<< "$spec"
+    timeout 600 ncu --set full --clock-control none --import-source on -k $kind:$pat -s 1 -c 1 -o gpurun_out/prof_$cfg -f \
+        python tools/bench_configs.py $cfg $scale > gpurun_out/ncu_$cfg.log 2>&1; echo "ncu $cfg rc=$?"
+  done
+fi
 ls -la gpurun_out

@@ -48,6 +48,17 @@ KEYS = [
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    # executed FP64 instruction mix, thread instructions per elapsed cycle summed over the GPU
+    # (peak 64 lanes x 148 SMs = 9472): executed flop/cycle = 2*dfma + dmul + dadd
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed",
+    "sm__inst_executed.sum.per_cycle_elapsed",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "sm__cycles_elapsed.max",
 ]
 
 
@@ -118,7 +129,7 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
-    res = ncu_full(tag, "prof_s1.ncu-rep", "dominant kernel (S1: 100000 instances x 2000 RK4 steps, log every 100)")
+    res = ncu_full(tag, "prof_s1.ncu-rep", "dominant kernel (S1: 100000 instances x 20000 RK4 steps, log every 100)")
     bj = os.path.join(OUT, "bench.json")
     if os.path.exists(bj) and os.path.getsize(bj):
         open(os.path.join(PROF, f"{tag}_bench.json"), "w").write(open(bj).read())
@@ -126,12 +137,12 @@ def main():
         d = res[0]
         rd = to_bytes(*d["dram__bytes_read.sum"])
         wr = to_bytes(*d["dram__bytes_write.sum"])
-        # the capture ran 2000 of the bench launch's 200000 steps per instance: DRAM traffic is the log
+        # the capture ran 20000 of the bench launch's 200000 steps per instance: DRAM traffic is the log
         # (proportional to steps) plus a per-launch constant; scale by the step ratio.
-        scale = 100.0
+        scale = 10.0
         json.dump(
             {
-                "source": f"profiles/{tag}_prof_s1.md (ncu --set full, 100000 instances x 2000 steps)",
+                "source": f"profiles/{tag}_prof_s1.md (ncu --set full, 100000 instances x 20000 steps)",
                 "dram_bytes_captured_launch": rd + wr,
                 "scale_to_bench_launch": scale,
                 "dram_bytes_per_launch": (rd + wr) * scale,
@@ -139,8 +150,11 @@ def main():
             open(os.path.join(PROF, "traffic.json"), "w"),
             indent=1,
         )
-    for extra in ("ncu_group.ncu-rep", "ncu_stack.ncu-rep"):
-        ncu_full(tag, extra, extra)
+    for cfg, title in (("s3", "S3 p-bit: 1-layer STT, 300 K, Heun (first captured launch), 1e5 instances x 5000 steps"),
+                       ("s4", "S4 CIMS: 3-layer Heun with SOT step drivers, reduced grid"),
+                       ("s5s", "S5 SeriesStack of 64 MTJs, 1024 stacks x 2000 steps"),
+                       ("s5g", "S5 GroupInteraction lattice (cooperative grid kernel), reduced lattice")):
+        ncu_full(tag, f"prof_{cfg}.ncu-rep", title)
     print("wrote", sorted(os.listdir(PROF)))
 
 
