@@ -442,9 +442,24 @@ def main():
         except Exception:
             hbm_peak = 6650.0
         traffic = None
+        executed = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("fp64_thread_inst_per_layer_step") and clocks.get("sm_mhz"):
+                # physical utilisation of the FP64 pipe: executed FP64 thread instructions (instruction mix of
+                # the committed ncu capture) over 64 lanes x SMs x the SM clock sampled during the timed region
+                n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+                slots = 64.0 * n_sm * clocks["sm_mhz"] * 1e6
+                rate = units_per_step / kern_s
+                executed = {
+                    "fp64_thread_inst_per_layer_step": tj["fp64_thread_inst_per_layer_step"],
+                    "flop_per_layer_step": tj.get("executed_flop_per_layer_step"),
+                    "issue_slot_frac": tj["fp64_thread_inst_per_layer_step"] * rate / slots,
+                    "tflops": (tj.get("executed_flop_per_layer_step") or 0.0) * rate / 1e12,
+                    "source": tj.get("source"),
+                }
         log_bytes = 7 * n_samples * B * 8
         line = {
             "metric": METRIC,
@@ -474,6 +489,7 @@ def main():
                 "MEASURED_PEAKS.json carries no FP64 figure",
                 "algorithmic_flop_per_layer_step": FLOP_PER_LAYER_STEP,
                 "kernel_ms": kern_s * 1e3,
+                "executed": executed,
                 "hbm": {
                     "achieved_gbs": log_bytes / kern_s / 1e9,
                     "peak_gbs": hbm_peak,

@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS = 8
 NSLOTS = 30
 
@@ -57,7 +57,7 @@ LOG_FULL, LOG_NONE, LOG_ENERGY = 0, 1, 2
 
 
 class Driver(C.Structure):
-    _fields_ = [("update", C.c_int32), ("reserved", C.c_int32)] + [(n, C.c_double) for n in FIELD_NAMES]
+    _fields_ = [("update", C.c_int32), ("custom_column", C.c_int32)] + [(n, C.c_double) for n in FIELD_NAMES]
 
 
 class Layer(C.Structure):
@@ -148,6 +148,8 @@ class RunArgs(C.Structure):
         ("instance_offset", C.c_int64),
         ("start_iteration", C.c_int64),
         ("onef_buffer", C.c_void_p),
+        ("custom_table", C.c_void_p),
+        ("n_custom", C.c_int64),
     ]
 
 

@@ -224,6 +224,10 @@ class JunctionBatch:
         a = self._args(totalTime, timeStep, writeFrequency, solverMode, log, seed, None)
         plan = be.plan(jn, layers, a)
         self.last_plan = plan
+        custom = self.junction._custom_table(layers, plan, timeStep)
+        if custom is not None:
+            a.custom_table = custom.ctypes.data
+            a.n_custom = custom.shape[1]
         n_ch, n_s = int(plan.n_channels), int(plan.n_samples)
         buf = None
         if log:
@@ -272,6 +276,11 @@ class JunctionBatch:
         plan = be.plan(jn, layers, a)
         self.last_plan = plan
         n_ch, n_s = int(plan.n_channels), int(plan.n_samples)
+        custom = self.junction._custom_table(layers, plan, timeStep)
+        if custom is not None:
+            custom_dev = torch.from_numpy(custom).to(dev)  # kept alive until the call below has been enqueued
+            a.custom_table = custom_dev.data_ptr()
+            a.n_custom = custom.shape[1]
         if self._m_dev is None:
             self._m_dev = torch.from_numpy(self.m_state).to(dev)
         for key, v in self._overrides.items():

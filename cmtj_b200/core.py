@@ -1216,6 +1216,34 @@ class Junction:
                     setattr(layers[i], n, vals[i])
         return jn, layers
 
+    def _custom_table(self, layers, plan, timeStep: float) -> Optional[np.ndarray]:
+        """``ScalarDriver.getCustomDriver`` callbacks (drivers.hpp:247-260, :294-303) evaluated where a
+        fixed-step solver will ask for them: the three stage times ``i*dt, i*dt + 0.5*dt, i*dt + dt`` of
+        every step (junction.hpp:1974, :1020-1033; Heun reads stages 0 and 2, Euler-Heun stage 0), in the
+        reference's own floating-point expressions.  Assigns each custom driver its column in the packed
+        ``layers`` and returns the ``[3 * total_iterations, n_custom]`` table (``cmtjb_run_args_t::
+        custom_table``), or None when the model has no custom driver.  A raising callback surfaces as the
+        reference's ``RuntimeError("Error in Python callback")``."""
+        cols: List[ScalarDriver] = []
+        for i, l in enumerate(self._layers):
+            for sidx, d in enumerate(l.drivers):
+                if d.update == UpdateType.custom:
+                    layers[i].drivers[sidx].custom_column = len(cols)
+                    cols.append(d)
+        if not cols:
+            return None
+        n, dt = int(plan.total_iterations), float(timeStep)
+        solver = int(plan.effective_solver)
+        stages = (0, 1, 2) if solver == int(SolverMode.RK4) else ((0, 2) if solver == int(SolverMode.Heun) else (0,))
+        tab = np.zeros((3 * max(n, 1), len(cols)), dtype=np.float64)
+        for i in range(n):
+            t0 = i * dt
+            ts = (t0, t0 + 0.5 * dt, t0 + dt)
+            for st in stages:
+                for c, d in enumerate(cols):
+                    tab[3 * i + st, c] = d.getCurrentScalarValue(ts[st])
+        return tab
+
     def _make_onef(self, total_iterations: int) -> Optional[np.ndarray]:
         """getSolver (junction.hpp:1905-1916): a fresh VectorAlphaNoise buffer per run for every
         layer with scaleNoise != 0; generated on the host once (setup, not the hot path)."""
@@ -1264,6 +1292,10 @@ class Junction:
         onef = self._make_onef(int(plan.total_iterations))
         if onef is not None:
             args.onef_buffer = onef.ctypes.data
+        custom = self._custom_table(layers, plan, timeStep)
+        if custom is not None:
+            args.custom_table = custom.ctypes.data
+            args.n_custom = custom.shape[1]
         n_ch, n_s = int(plan.n_channels), int(plan.n_samples)
         m_state = np.array([c for l in self._layers for c in l.mag.tolist()], dtype=np.float64).reshape(-1, 1)
         log = np.zeros((n_ch, max(n_s, 1), 1), dtype=np.float64)

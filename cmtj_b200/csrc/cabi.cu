@@ -60,6 +60,7 @@ int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   int mode = a->solverMode;
   if (mode != CMTJB_RK4 && mode != CMTJB_HEUN && mode != CMTJB_EULER_HEUN && mode != CMTJB_DORMAND_PRINCE)
     return fail(CMTJB_EINVAL, "unknown solver mode");
+  bool any_custom = false;
   for (int i = 0; i < jn->n_layers; i++) {
     const cmtjb_layer_t &L = layers[i];
     if (L.temperatureSet || L.noiseScale != 0) {
@@ -73,12 +74,20 @@ int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
     if (L.Ms * L.thickness == 0) return fail(CMTJB_ERUNTIME, "Failed to divide vector by zero!");
     for (int s = 0; s < CMTJB_NSLOTS; s++) {
       const int u = L.drivers[s].update;
-      if (u == CMTJB_UPD_CUSTOM)
-        return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are not supported on the device path");
+      if (u == CMTJB_UPD_CUSTOM) {
+        // pre-evaluated by the caller at the stage times of a FIXED-step solver (cmtjb_run_args_t::custom_table)
+        any_custom = true;
+        if (L.drivers[s].custom_column < 0) return fail(CMTJB_EINVAL, "custom driver without a table column");
+        continue;
+      }
       if (u < CMTJB_UPD_CONSTANT || u > CMTJB_UPD_GAUSSSTEP) return fail(CMTJB_EINVAL, "unknown driver update type");
     }
   }
   p->effective_solver = mode;
+  if (any_custom && mode == CMTJB_DORMAND_PRINCE)
+    return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers need a fixed-step solver: Dormand-Prince evaluates drivers at adaptive times");
+  if (any_custom && a->log_mode == CMTJB_LOG_ENERGY)
+    return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers cannot be combined with the energy log");
   p->n_channels = 3 * jn->n_layers + (jn->mr_mode == CMTJB_MR_CLASSIC ? 1 : jn->mr_mode == CMTJB_MR_STRIP ? 3 : 0);
   if (a->log_mode == CMTJB_LOG_ENERGY)
     for (int i = 0; i < jn->n_layers; i++) p->n_channels += layers[i].includeSOT ? CMTJB_ENERGY_CHANNELS_SOT : CMTJB_ENERGY_CHANNELS;
@@ -273,6 +282,12 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
     o.timeStop = d.timeStop;
     o.edgeTime = d.edgeTime;
     o.steadyTime = d.steadyTime;
+    if (d.update == CMTJB_UPD_CUSTOM) {
+      // the callback's value IS the driver's value (drivers.hpp:294-303 returns it directly)
+      D.cst[s] = 0.0;
+      o.amplitude = 1.0;
+      o.pad = d.custom_column;
+    }
     if (slot_dynamic(d)) D.dynmask |= (1u << s);
     D.dyncol[s] = -1;
     for (int f = 0; f < 10; f++) D.ovidx[s][f] = -1;
@@ -379,6 +394,8 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   R.n_samples_out = n_samples_out;
   R.time_log = time_log;
   R.onef = a->onef_buffer;
+  R.custom = a->custom_table;
+  R.n_custom = a->n_custom;
   R.B = a->n_instances;
   R.inst_offset = a->instance_offset;
   R.n_samples = plan.n_samples;
@@ -468,6 +485,18 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
   if (force && std::strcmp(force, "full") == 0) need = F_ALL;
   if (a->log_mode == CMTJB_LOG_ENERGY) need = F_ALL;  // the energy log lives in the general variants only
   if (post) need |= F_POST;
+  {
+    int max_col = -1;
+    for (int l = 0; l < jn->n_layers; l++)
+      for (int s = 0; s < CMTJB_NSLOTS; s++)
+        if (layers[l].drivers[s].update == CMTJB_UPD_CUSTOM) max_col = std::max(max_col, layers[l].drivers[s].custom_column);
+    if (max_col >= 0) {
+      if (!a->custom_table || max_col >= a->n_custom) return fail(CMTJB_EINVAL, "custom driver: custom_table is null or has too few columns");
+      if (need & F_DYNI)
+        return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are tabulated at the batch-uniform stage times and cannot be combined "
+                                   "with per-instance timing overrides or a driver table beyond 2 GiB");
+    }
+  }
   const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need);
   if (!v) {
     char buf[160];
@@ -744,7 +773,8 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t n_tlog = (plan.variable_samples && want_log && time_log) ? (size_t)plan.n_samples * B * sizeof(double) : 0;
   const size_t n_onef = args->onef_buffer ? (size_t)jn->n_layers * 3 * plan.total_iterations * B * sizeof(double) : 0;
-  const size_t total = al(nm) + al(nlog) + 2 * al(B * sizeof(int32_t)) + al(n_tlog) + al(n_onef) +
+  const size_t n_cust = (args->custom_table && args->n_custom > 0) ? (size_t)3 * plan.total_iterations * args->n_custom * sizeof(double) : 0;
+  const size_t total = al(nm) + al(nlog) + 2 * al(B * sizeof(int32_t)) + al(n_tlog) + al(n_onef) + al(n_cust) +
                        (size_t)n_overrides * al(B * sizeof(double)) + 256;
   std::lock_guard<std::mutex> lock(g_slab_mu);
   void *base = nullptr;
@@ -762,6 +792,7 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   int32_t *d_ns = plan.variable_samples ? (int32_t *)take(B * sizeof(int32_t)) : nullptr;
   double *d_tlog = n_tlog ? (double *)take(n_tlog) : nullptr;
   double *d_onef = n_onef ? (double *)take(n_onef) : nullptr;
+  double *d_cust = n_cust ? (double *)take(n_cust) : nullptr;
   CUDA_TRY(cudaMemcpy(d_m, m_state, nm, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(d_status, 0, B * sizeof(int32_t)));
   std::vector<cmtjb_override_t> d_ovr(overrides, overrides + n_overrides);
@@ -774,6 +805,10 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   if (d_onef) {
     CUDA_TRY(cudaMemcpy(d_onef, args->onef_buffer, n_onef, cudaMemcpyHostToDevice));
     a.onef_buffer = d_onef;
+  }
+  if (d_cust) {
+    CUDA_TRY(cudaMemcpy(d_cust, args->custom_table, n_cust, cudaMemcpyHostToDevice));
+    a.custom_table = d_cust;
   }
   // Large fixed-step logs: run in time chunks and copy chunk k to the host while chunk k+1
   // integrates (the copy engine overlaps the FP64 pipe; effective when `log` is pinned memory).

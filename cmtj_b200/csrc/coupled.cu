@@ -38,9 +38,13 @@ int validate_system(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *lay
     cmtjb_plan_t p;
     int rc = make_plan(&jns[j], layers + (size_t)j * c->nl, &aj, &p);
     if (rc) return rc;
-    for (int l = 0; l < c->nl; l++)
+    for (int l = 0; l < c->nl; l++) {
       if (layers[(size_t)j * c->nl + l].noiseScale != 0)
         return fail(CMTJB_ENOTSUP, "1/f^alpha noise inside a coupled system is not supported");
+      for (int s = 0; s < CMTJB_NSLOTS; s++)
+        if (layers[(size_t)j * c->nl + l].drivers[s].update == CMTJB_UPD_CUSTOM)
+          return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are not supported inside a coupled system");
+    }
     if (j == 0) {
       c->plan0 = p;
       c->solver = p.effective_solver;
@@ -70,15 +74,27 @@ void fill_plan(const Common &c, int n_sys_ch, cmtjb_coupled_plan_t *p) {
 // Union of the term sets the junctions of a system need (cabi.cu: needed_features).  The coupled
 // kernels have no per-launch driver table, so any time-dependent driver means inline evaluation;
 // system-level overrides (the stack's current driver) are not junction terms.
+// `stack`: the layers' own current drivers are never evaluated -- the stack pushes its coupled current into
+// every layer each step (stack.hpp:79-91) -- so they do not count as time-dependent terms.
 uint32_t system_features(int n, int nl, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr,
-                         int n_ovr, const cmtjb_run_args_t *a, int solver) {
+                         int n_ovr, const cmtjb_run_args_t *a, int solver, bool stack) {
   std::vector<cmtjb_override_t> jo;
   for (int k = 0; k < n_ovr; k++)
     if (ovr[k].layer != CMTJB_LAYER_SYSTEM) jo.push_back(ovr[k]);
   cmtjb_run_args_t aj = *a;
   aj.onef_buffer = nullptr;
   uint32_t F = 0;
-  for (int j = 0; j < n; j++) F |= model_features(&jns[j], layers + (size_t)j * nl, jo.data(), (int)jo.size(), &aj, solver);
+  std::vector<cmtjb_layer_t> tmp(nl);
+  for (int j = 0; j < n; j++) {
+    for (int l = 0; l < nl; l++) {
+      tmp[l] = layers[(size_t)j * nl + l];
+      if (stack) {
+        std::memset(&tmp[l].drivers[CMTJB_SLOT_CURRENT], 0, sizeof(cmtjb_driver_t));
+        tmp[l].drivers[CMTJB_SLOT_CURRENT].update = CMTJB_UPD_CONSTANT;
+      }
+    }
+    F |= model_features(&jns[j], tmp.data(), jo.data(), (int)jo.size(), &aj, solver);
+  }
   if (F & (F_DYN | F_DYNS)) F = (F & ~(F_DYN | F_DYNS)) | F_DYNI;
   const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel (testing)
   if (force && std::strcmp(force, "full") == 0) F = F_ALL;
@@ -259,7 +275,7 @@ int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmt
   const int threads = SP.spb * N;
   const long long blocks = (n_inst + SP.spb - 1) / SP.spb;
   const size_t smem = (3 * (size_t)threads + 2 * ((size_t)threads / 32 + 1)) * sizeof(double);
-  const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver));
+  const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver, true));
   const bool uni = lean && models_uniform<NL>(models);
   const DevModel<NL> &M0 = models[0];
 #define CMTJB_STACK_LAUNCH2(SOLVER, MODE)                                                                                                \
@@ -367,7 +383,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   GP.pref = d_pref;
   int rc = CMTJB_OK;
   const bool rk4 = (c.solver == CMTJB_RK4);
-  const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver));
+  const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver, false));
   const bool uni = lean && models_uniform<NL>(models);
   DevModel<NL> M0 = models[0];
   if (!group_uses_grid<NL>(N)) {

@@ -328,15 +328,15 @@ struct GroupParams {
   long long inst;      // cooperative kernel: which instance of the batch this launch integrates
 };
 
-// field at a from the dipole at b (reservoir.hpp:79-97); r = r_a - r_b
+// field at a from the dipole at b (reservoir.hpp:79-97); r = r_a - r_b:
+//   H += pref (3 (m.r) r / r^5 - m / r^3)
 __device__ __forceinline__ void pair_accumulate(d3 &H, d3 r, d3 mb, double pref) {
   const double r2 = dot(r, r);
-  const double inv = rsqrt(r2);
+  const double inv = rsqrt(r2);  // MUFU.RSQ64H + Newton; an FP32-seeded variant measured 10 % slower (F2F conversions)
   const double inv2 = inv * inv;
-  const double inv3 = inv2 * inv;
-  const double a = 3.0 * dot(mb, r) * (inv3 * inv2);
-  H = mk(fma(pref, fma(a, r.x, -inv3 * mb.x), H.x), fma(pref, fma(a, r.y, -inv3 * mb.y), H.y),
-         fma(pref, fma(a, r.z, -inv3 * mb.z), H.z));
+  const double p3 = pref * (inv2 * inv);          // pref / r^3
+  const double a = (3.0 * inv2) * dot(mb, r) * p3;  // 3 pref (m.r) / r^5
+  H = mk(fma(a, r.x, fma(-p3, mb.x, H.x)), fma(a, r.y, fma(-p3, mb.y, H.y)), fma(a, r.z, fma(-p3, mb.z, H.z)));
 }
 
 // GroupInteraction, one group per block: blockDim.x = N * P rounded up to a warp multiple.  Thread

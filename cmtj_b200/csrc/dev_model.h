@@ -42,7 +42,7 @@ enum : uint32_t {
 
 struct DevDriver {
   int32_t type;  // cmtjb_update
-  int32_t pad;
+  int32_t pad;   // CMTJB_UPD_CUSTOM: column of RunParams::custom
   double amplitude, frequency, phase, period, cycle, timeStart, timeStop, edgeTime, steadyTime;
 };
 
@@ -110,6 +110,8 @@ struct RunParams {
   double *time_log;          // [n_samples][B] (DP)
   const double *ovr[kMaxOverrides];  // row k: [B] values of override k
   const double *onef;        // [NL*3][total_iterations][B] or null
+  const double *custom;      // [3*total_iterations][n_custom] pre-evaluated CMTJB_UPD_CUSTOM drivers or null
+  long long n_custom;
   // [it_end-it_begin][3][dyn_ncols]: time-dependent driver values at the three stage times
   // t, t+dt/2, t+dt of every step.  Columns 3l..3l+2: summed dynamic field of layer l (A/m);
   // further columns: unit-amplitude waveform of each dynamic scalar slot (DevLayer::dyncol).

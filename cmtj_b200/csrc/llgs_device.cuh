@@ -360,19 +360,32 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// Three standard normals from one Philox block.  Everything after the counter hash runs on the FP32 /
+// SFU pipes, which the FP64 time loop leaves idle: uniforms are built from the top 23 bits by exponent
+// splicing (no I2F), Box-Muller uses the SFU approximations (MUFU.LG2 / RSQ / SIN / COS, absolute
+// error ~2^-21: six orders of magnitude below what any statistic of a Langevin run can resolve; the
+// stream is validated distributionally in tests/test_stochastic_gpu.py -- moments, tails, KS, PSD).
+// u = 1 - (r + 0.5) 2^-32 in (0, 1): top 23 bits spliced into [1, 2), the low 9 bits into an integer-
+// valued float; FP32's relative precision keeps all 32 bits where they matter, next to 0 (the tail of
+// the radius reaches 6.7 sigma as with a 32-bit uniform).
+__device__ __forceinline__ float unit_open_low(uint32_t r) {
+  const float hi = 2.0f - __uint_as_float(0x3f800000u | (r >> 9));              // k 2^-23, k = 1 .. 2^23
+  const float lo = __uint_as_float(0x4b000000u | (r & 0x1ffu)) - 8388608.0f;    // 0 .. 511
+  return fmaf(lo, -2.3283064365386963e-10f, hi) - 1.1641532182693481e-10f;      // - lo 2^-32 - 2^-33
+}
 __device__ __forceinline__ d3 normal3(unsigned long long seed, unsigned long long inst, unsigned int layer,
                                       unsigned long long step) {
   const uint4 ctr = make_uint4((uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)step,
                                ((uint32_t)(step >> 32) << 8) | (layer & 0xFFu));
   const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float k = 2.3283064365386963e-10f;  // 2^-32
-  const float u0 = fmaf((float)r.x, k, 0.5f * k), u2 = fmaf((float)r.z, k, 0.5f * k);
-  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
-  float s0, c0, s1, c1;
-  sincospif(2.0f * ((float)r.y * k), &s0, &c0);
-  sincospif(2.0f * ((float)r.w * k), &s1, &c1);
-  (void)s1;
-  return mk((double)(r0 * c0), (double)(r0 * s0), (double)(r1 * c1));
+  // radius sqrt(-2 ln u), u in (0, 1]: t = -2 ln 2 * log2(u) >= 0; sqrt(t) = t * rsqrt(t), 0 at t = 0
+  const float t0 = -1.3862943611198906f * __log2f(unit_open_low(r.x));
+  const float t1 = -1.3862943611198906f * __log2f(unit_open_low(r.z));
+  const float r0 = t0 * rsqrtf(fmaxf(t0, 1e-30f)), r1 = t1 * rsqrtf(fmaxf(t1, 1e-30f));
+  // angle uniform on [-pi, pi): the SFU sine/cosine are most accurate there
+  const float a0 = 6.283185307179586f * (__uint_as_float(0x3f800000u | (r.y >> 9)) - 1.5f);
+  const float a1 = 6.283185307179586f * (__uint_as_float(0x3f800000u | (r.w >> 9)) - 1.5f);
+  return mk((double)(r0 * __cosf(a0)), (double)(r0 * __sinf(a0)), (double)(r1 * __cosf(a1)));
 }
 
 // the step's noise vector dW (junction.hpp:1121-1136): Langevin + 1/f^alpha buffer

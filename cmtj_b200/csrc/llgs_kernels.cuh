@@ -547,16 +547,22 @@ __global__ void build_dyn_table_kernel(const __grid_constant__ DevModel<NL> M, c
   const double t0 = (double)(R.it_begin + k) * R.dt;
   const double t = stage == 0 ? t0 : (stage == 1 ? t0 + 0.5 * R.dt : t0 + R.dt);
   double *o = tab + q * R.dyn_ncols;
+  // a custom driver's waveform is the caller's pre-evaluated value at this (absolute step, stage)
+  const double *crow = R.custom ? R.custom + (3 * (R.it_begin + k) + stage) * R.n_custom : nullptr;
+  auto shape = [&](const DevLayer &Lr, int s) {
+    if (Lr.drv[s].type == CMTJB_UPD_CUSTOM) return crow ? crow[Lr.drv[s].pad] : 0.0;
+    return driver_shape<0>(Lr, R, s, t, 0);
+  };
   for (int l = 0; l < NL; l++) {
     const DevLayer &Lr = M.L[l];
     double h[3] = {0.0, 0.0, 0.0};
     for (int s = 0; s < CMTJB_SLOT_K1; s++)
-      if ((Lr.dynmask >> s) & 1u) h[s % 3] += driver_post(Lr.drv[s].type, Lr.drv[s].amplitude * driver_shape<0>(Lr, R, s, t, 0));
+      if ((Lr.dynmask >> s) & 1u) h[s % 3] += driver_post(Lr.drv[s].type, Lr.drv[s].amplitude * shape(Lr, s));
     o[3 * l + 0] = h[0];
     o[3 * l + 1] = h[1];
     o[3 * l + 2] = h[2];
     for (int s = CMTJB_SLOT_K1; s < CMTJB_NSLOTS; s++)
-      if (Lr.dyncol[s] >= 0) o[Lr.dyncol[s]] = driver_shape<0>(Lr, R, s, t, 0);
+      if (Lr.dyncol[s] >= 0) o[Lr.dyncol[s]] = shape(Lr, s);
   }
 }
 template <int NL> cudaError_t launch_build_dyn_table(const DevModel<NL> &M, const RunParams &R, double *tab, cudaStream_t stream) {

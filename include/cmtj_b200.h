@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CMTJB_ABI_VERSION 2
+#define CMTJB_ABI_VERSION 3
 #define CMTJB_MAX_LAYERS 8
 
 /* ---- error codes --------------------------------------------------------------- */
@@ -60,13 +60,13 @@ enum cmtjb_update {
   CMTJB_UPD_TRAPEZOID = 6,
   CMTJB_UPD_GAUSSIMPULSE = 7,
   CMTJB_UPD_GAUSSSTEP = 8,
-  CMTJB_UPD_CUSTOM = 100 /* python callback: rejected with CMTJB_ENOTSUP */
+  CMTJB_UPD_CUSTOM = 100 /* host callback (drivers.hpp:294-303), pre-evaluated by the caller: see custom_table */
 };
 
 /* core/drivers.hpp:34-36 (Driver fields) + :68-69 (edgeTime, steadyTime) */
 typedef struct cmtjb_driver {
   int32_t update;
-  int32_t reserved;
+  int32_t custom_column; /* CMTJB_UPD_CUSTOM: column of cmtjb_run_args_t::custom_table; else unused */
   double constantValue, amplitude, frequency, phase, period, cycle, timeStart, timeStop,
       edgeTime, steadyTime;
 } cmtjb_driver_t;
@@ -168,6 +168,18 @@ typedef struct cmtjb_run_args {
    * already scaled; [n_layers*3][total_iterations][n_instances] or NULL.  Host or device
    * pointer according to the entry point. */
   const double *onef_buffer;
+  /* CMTJB_UPD_CUSTOM drivers (ScalarDriver::getCustomDriver, drivers.hpp:247-260, :294-303).  A callback
+   * cannot cross this boundary, but a fixed-step solver only ever asks a driver for its value at the
+   * three stage times of each step, which are the same for every instance.  The caller evaluates each
+   * callback there and passes [3 * total_iterations][n_custom] values: row 3*i + s is stage s of step i,
+   * at the reference's own time expressions  i*dt,  i*dt + 0.5*dt,  i*dt + dt  (junction.hpp:1974,
+   * :1020-1033; Heun reads stages 0 and 2, Euler-Heun stage 0).  As in the reference the callback's
+   * value IS the driver's value (constantValue and amplitude are ignored).  Host or device pointer
+   * according to the entry point; NULL when the model has no custom driver.  Not available for
+   * Dormand-Prince, the energy log, per-instance timing overrides, Stack and GroupInteraction
+   * (CMTJB_ENOTSUP). */
+  const double *custom_table;
+  int64_t n_custom;
 } cmtjb_run_args_t;
 
 enum cmtjb_log_mode {

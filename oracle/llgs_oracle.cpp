@@ -58,8 +58,27 @@ inline V3 normalized(V3 a) {
 }
 inline V3 arr3(const double *p) { return v3(p[0], p[1], p[2]); }
 
+/* CMTJB_UPD_CUSTOM (drivers.hpp:294-303: the Python callback's value IS the driver's value).  A callback
+ * cannot cross the C boundary; the caller pre-evaluates it at the stage times of every step
+ * (cmtjb_run_args_t::custom_table) and the time loop publishes which step it is in, so that the stage can
+ * be recognised from the time argument by exact comparison with the reference's own time expressions. */
+struct CustomCtx {
+  const double *table = nullptr; /* [3 * total_iterations][n_custom] */
+  int64_t n_custom = 0, step = 0;
+  double t0 = 0, dt = 0;
+};
+thread_local CustomCtx g_custom;
+
+double custom_value(const cmtjb_driver_t &d, double time) {
+  const CustomCtx &c = g_custom;
+  if (!c.table || d.custom_column < 0 || d.custom_column >= c.n_custom) return 0.0;
+  const int stage = (time == c.t0) ? 0 : (time == c.t0 + 0.5 * c.dt ? 1 : 2);
+  return c.table[(3 * c.step + stage) * c.n_custom + d.custom_column];
+}
+
 /* core/drivers.hpp:262-305 with helpers :73-108 */
 double driver_value(const cmtjb_driver_t &d, double time) {
+  if (d.update == CMTJB_UPD_CUSTOM) return custom_value(d, time);
   double ret = d.constantValue;
   switch (d.update) {
   case CMTJB_UPD_PULSE: {
@@ -468,6 +487,7 @@ int validate(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtj
   p->total_iterations = (int64_t) static_cast<unsigned int>(a->totalTime / a->timeStep);
   p->write_every = (int64_t) static_cast<unsigned int>(a->writeFrequency / a->timeStep);
   int mode = a->solverMode;
+  bool any_custom = false;
   for (int i = 0; i < jn->n_layers; i++) {
     const cmtjb_layer_t &L = layers[i];
     if (L.temperatureSet || L.noiseScale != 0) {
@@ -480,10 +500,13 @@ int validate(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtj
       return fail(CMTJB_ERUNTIME, "Cell surface cannot be 0 during temp. calculations!");
     if (L.Ms * L.thickness == 0) return fail(CMTJB_ERUNTIME, "Failed to divide vector by zero!");
     for (int s = 0; s < CMTJB_NSLOTS; s++)
-      if (L.drivers[s].update == CMTJB_UPD_CUSTOM)
-        return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are not supported on the device path");
+      if (L.drivers[s].update == CMTJB_UPD_CUSTOM) any_custom = true;
   }
   p->effective_solver = mode;
+  if (any_custom && mode == CMTJB_DORMAND_PRINCE)
+    return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers need a fixed-step solver: Dormand-Prince evaluates drivers at adaptive times");
+  if (any_custom && a->log_mode == CMTJB_LOG_ENERGY)
+    return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers cannot be combined with the energy log");
   p->n_channels = 3 * jn->n_layers + (jn->mr_mode == CMTJB_MR_CLASSIC ? 1 : jn->mr_mode == CMTJB_MR_STRIP ? 3 : 0);
   if (a->log_mode == CMTJB_LOG_ENERGY) p->n_channels += energy_channels(jn, layers);
   if (mode == CMTJB_DORMAND_PRINCE) {
@@ -573,6 +596,11 @@ int oracle_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
       int64_t sample = 0;
       for (int64_t i = args->start_iteration; i < plan.total_iterations; i++) {
         const double t = i * dt;
+        g_custom.table = args->custom_table;
+        g_custom.n_custom = args->n_custom;
+        g_custom.step = i;
+        g_custom.t0 = t;
+        g_custom.dt = dt;
         bool ok = true;
         switch (plan.effective_solver) {
         case CMTJB_RK4: ok = step_rk4(j, t, dt); break;
@@ -670,6 +698,10 @@ int build_system(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers
     cmtjb_plan_t p;
     int rc = validate(&jns[k], layers + (size_t)k * S.nl, &aj, &p);
     if (rc) return rc;
+    for (int l = 0; l < S.nl; l++)
+      for (int s = 0; s < CMTJB_NSLOTS; s++)
+        if (layers[(size_t)k * S.nl + l].drivers[s].update == CMTJB_UPD_CUSTOM)
+          return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are not supported inside a coupled system");
     if (k == 0) {
       S.plan = p;
       S.solver = p.effective_solver;

@@ -190,3 +190,71 @@ def test_thermal_stack_and_group_run_euler_heun():
     g.runSimulation(0.1e-9, 1e-13, 1e-12)
     lg = helpers.log_arrays(g.getLog(2))
     assert np.all(np.isfinite(lg["free_mz"])) and len(lg["time"]) == 100
+
+
+@pytest.fixture
+def general_variant(monkeypatch):
+    """CMTJB_FORCE_VARIANT=full: the fully general term set (F_ALL, models read from the device array)
+    instead of the lean / uniform-model variants the systems above select."""
+    monkeypatch.setenv("CMTJB_FORCE_VARIANT", "full")
+
+
+@pytest.mark.parametrize("mode", ["kcl", "delayed", "instant"])
+def test_stack_general_variant(general_variant, mode):
+    def fn(eps):
+        js = [T._stt_two_layer(m), T._stt_two_layer(m, (0.5, 0.1, 0.8)), T._stt_two_layer(m, (-0.3, 0.3, 0.9))]
+        if eps:
+            _perturb(js[0], eps)
+        s = m.stack.SeriesStack(js, "free", "bottom", 0.1, mode == "kcl")
+        s.setCouplingStrength([0.25, -0.1])
+        if mode == "instant":
+            s.setDelayed(False)
+        s.setCoupledCurrentDriver(m.ScalarDriver.getSineDriver(3e10, 2e10, 5e9, 0.0))
+        s.runSimulation(0.3e-9, 1e-13, 5e-13)
+        return _collect(s, 3)
+
+    g, w, p = _three(fn)
+    _check(g, w, p)
+
+
+def test_group_general_variant(general_variant):
+    def fn(eps):
+        g = _lattice_group(20, eps)
+        out = g.run_batch(1, 0.03e-9, 1e-13, 1e-12)
+        out.pop("m_state")
+        return out
+
+    g, w, p = _three(fn)
+    _check(g, w, p)
+
+    def fn2(eps):
+        g = T._group(m, m.reservoir, n=7, inter=None)
+        if eps:
+            _perturb(g.junctionList[0], eps)
+        g.runSimulation(0.2e-9, 1e-13, 3e-13)
+        return _collect(g, 7)
+
+    g, w, p = _three(fn2)
+    _check(g, w, p)
+
+
+@pytest.mark.parametrize("n", [3, 8, 32, 64, 96])
+def test_stack_kcl_reduction_shapes(n):
+    """The KCL sum takes the shuffle path for warp-aligned stacks (power of two <= 32, multiples of 32)
+    and the block scan otherwise; a batch of 3 stacks so that blocks hold several / partial stacks."""
+    rng = np.random.default_rng(n)
+    mags = rng.normal(0, 0.3, (n, 3)) + np.array([0.2, 0.1, 1.0])
+
+    def fn(eps):
+        js = [T._stt_two_layer(m, tuple(v)) for v in mags]
+        if eps:
+            _perturb(js[0], eps)
+        s = m.stack.SeriesStack(js, useKCL=True)
+        s.setCouplingStrength(0.05)
+        s.setCoupledCurrentDriver(m.ScalarDriver.getSineDriver(1e10, 1e10, 6e9, 0.0))
+        out = s.run_batch(3, 0.05e-9, 1e-13, 5e-13, current={"amplitude": np.array([1e10, 2e10, 3e10])})
+        out.pop("m_state")
+        return out
+
+    g, w, p = _three(fn)
+    _check(g, w, p)

@@ -5,6 +5,7 @@ Bar (BASELINE.json north_star): deterministic trajectories agree within 1e-9 rel
 and R in FP64.  Relative = max|a-b| / max|b| per log channel.
 """
 import ctypes as C
+import math
 
 import numpy as np
 import pytest
@@ -336,3 +337,43 @@ def test_calculate_energies(build, mode):
         assert np.allclose(g.pop("time"), w.pop("time"), rtol=1e-9, atol=0)
         sens.pop("time", None)
     _check(g, w, tol=tol, sens=sens)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("build", ["single_layer_mtj", "two_layer_mtj"])
+def test_custom_python_callback_drivers(build, mode):
+    """getCustomDriver in the dynamics: callbacks pre-evaluated at the stage times (custom_table), read by
+    the kernels from the per-launch driver table.  Field slot + scalar slot, all fixed-step solvers."""
+    import test_oracle_vs_ref as t
+
+    (g, _), (w, _) = _both(getattr(helpers, build), 0.3e-9, 1e-13, 5e-13, mode, t._custom_tweak)
+    _check(g, w)
+
+
+def test_custom_driver_in_a_batch_and_on_the_device_path():
+    """A custom Oersted waveform shared by a 200-instance field sweep, host and device entry points."""
+    import torch
+
+    B = 200
+    H = np.stack([np.linspace(-200e3, 200e3, B), np.zeros(B), np.full(B, 5e3)], axis=1)
+
+    def build():
+        j = helpers.two_layer_mtj(cmtj_b200)
+        cb = cmtj_b200.ScalarDriver.getCustomDriver(lambda t: 400.0 * math.exp(-((t - 5e-12) / 2e-12) ** 2))
+        j.setLayerOerstedFieldDriver("all", cmtj_b200.AxialDriver(cmtj_b200.NullDriver(), cmtj_b200.NullDriver(), cb))
+        b = cmtj_b200.JunctionBatch(j, B)
+        b.set_external_field("all", H)
+        return b
+
+    logs = []
+    for be in (None, helpers.oracle_backend()):
+        with helpers.facade_on(be):
+            logs.append(dict(build().run(0.1e-9, 1e-13, 1e-12)))
+    for k in logs[1]:
+        if k != "time":
+            assert helpers.max_rel_err(logs[0][k], logs[1][k]) <= TOL, k
+    dev = build().run_device(0.1e-9, 1e-13, 1e-12)
+    torch.cuda.synchronize()
+    for k in logs[0]:
+        if k != "time":
+            assert np.array_equal(dev[k].cpu().numpy(), logs[0][k]), k

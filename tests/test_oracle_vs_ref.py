@@ -271,3 +271,34 @@ def test_calculate_energies_bit_exact(ref, on_oracle, build, mode):
     assert any(k.endswith("_Hanisx") for k in lo)
     if build != "two_layer_mtj":
         assert len(lo["free_I"]) == 2 * len(lo["time"])
+
+
+def _custom_tweak(mod, j):
+    """Python callbacks on a field component, the anisotropy and (SOT layer) a torque driver."""
+    cb_h = lambda t: 2e3 * math.sin(2 * math.pi * 7e9 * t) + 1e12 * t  # noqa: E731
+    cb_k = lambda t: 0.8e6 * (1 + 0.05 * math.cos(2 * math.pi * 3e9 * t))  # noqa: E731
+    ids = j.getLayerIds()
+    j.setLayerOerstedFieldDriver(ids[0], mod.AxialDriver(mod.ScalarDriver.getCustomDriver(cb_h), mod.NullDriver(),
+                                                        mod.ScalarDriver.getConstantDriver(100.0)))
+    j.setLayerAnisotropyDriver(ids[-1], mod.ScalarDriver.getCustomDriver(cb_k))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("build", ["single_layer_mtj", "two_layer_mtj"])
+def test_custom_python_callback_drivers_bit_exact(ref, on_oracle, build, mode):
+    """ScalarDriver.getCustomDriver in the dynamics (drivers.hpp:294-303): the reference calls the Python
+    function at every stage time; the facade pre-evaluates it there (Junction._custom_table) and the
+    restatement reads the table.  Same doubles in, bit-identical trajectories out."""
+    jr, jo = _run_both(ref, getattr(helpers, build), T=0.3e-9, wf=5e-13, mode=mode, tweak=_custom_tweak)
+    _assert_same_logs(jr, jo)
+
+
+def test_custom_driver_errors(on_oracle):
+    j = helpers.single_layer_mtj(cmtj_b200)
+    j.setLayerCurrentDriver("free", cmtj_b200.ScalarDriver.getCustomDriver(lambda t: 1 / 0))
+    with pytest.raises(RuntimeError, match="Error in Python callback"):
+        j.runSimulation(1e-11, 1e-13, 1e-13)
+    j = helpers.single_layer_mtj(cmtj_b200)
+    j.setLayerAnisotropyDriver("free", cmtj_b200.ScalarDriver.getCustomDriver(lambda t: 1e5))
+    with pytest.raises(NotImplementedError, match="fixed-step"):
+        j.runSimulation(1e-11, 1e-13, 1e-13, solverMode=cmtj_b200.SolverMode.DormandPrince)

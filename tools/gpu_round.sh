@@ -23,4 +23,7 @@ if [ "${PROFILE_CONFIGS:-0}" = "1" ]; then
         python tools/bench_configs.py $cfg $scale > gpurun_out/ncu_$cfg.log 2>&1; echo "ncu $cfg rc=$?"
   done
 fi
-ls -la gpurun_out
+# summarise on the box (the reports together exceed what gpurun copies back) and keep only the S1 report
+SUMMARY_OUT=gpurun_out/summary python tools/summarise_profiles.py ${TAG:-r01} > gpurun_out/summarise.log 2>&1; echo "summarise rc=$?"
+for f in gpurun_out/prof_s3.ncu-rep gpurun_out/prof_s4.ncu-rep gpurun_out/prof_s5s.ncu-rep gpurun_out/prof_s5g.ncu-rep; do rm -f $f; done
+du -sh gpurun_out; ls -la gpurun_out gpurun_out/summary

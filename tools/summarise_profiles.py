@@ -18,7 +18,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
+PROF = os.environ.get("SUMMARY_OUT") or os.path.join(ROOT, "profiles")
 
 KEYS = [
     "gpu__time_duration.sum",
@@ -140,16 +140,34 @@ def main():
         # the capture ran 20000 of the bench launch's 200000 steps per instance: DRAM traffic is the log
         # (proportional to steps) plus a per-launch constant; scale by the step ratio.
         scale = 10.0
-        json.dump(
-            {
-                "source": f"profiles/{tag}_prof_s1.md (ncu --set full, 100000 instances x 20000 steps)",
-                "dram_bytes_captured_launch": rd + wr,
-                "scale_to_bench_launch": scale,
-                "dram_bytes_per_launch": (rd + wr) * scale,
-            },
-            open(os.path.join(PROF, "traffic.json"), "w"),
-            indent=1,
-        )
+        info = {
+            "source": f"profiles/{tag}_prof_s1.md (ncu --set full, 100000 instances x 20000 steps)",
+            "dram_bytes_captured_launch": rd + wr,
+            "scale_to_bench_launch": scale,
+            "dram_bytes_per_launch": (rd + wr) * scale,
+        }
+        try:
+            # executed FP64 instruction mix of the dominant kernel, per layer-timestep
+            f = lambda k: float(d[k][1].replace(",", ""))
+            dfma = f("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed")
+            dmul = f("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed")
+            dadd = f("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed")
+            all_per_cycle = f("sm__inst_executed.sum.per_cycle_elapsed") * f("smsp__thread_inst_executed_per_inst_executed.ratio")
+            total = f("thread_inst_executed")
+            layer_steps = 100000 * 20000 * 2
+            per = total / layer_steps / all_per_cycle
+            info.update({
+                "thread_inst_per_layer_step": total / layer_steps,
+                "dfma_per_layer_step": dfma * per,
+                "dmul_per_layer_step": dmul * per,
+                "dadd_per_layer_step": dadd * per,
+                "fp64_thread_inst_per_layer_step": (dfma + dmul + dadd) * per,
+                "executed_flop_per_layer_step": (2 * dfma + dmul + dadd) * per,
+                "fp64_pipe_active_pct": f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            })
+        except (KeyError, ValueError, ZeroDivisionError) as e:
+            info["instruction_mix_error"] = repr(e)
+        json.dump(info, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     for cfg, title in (("s3", "S3 p-bit: 1-layer STT, 300 K, Heun (first captured launch), 1e5 instances x 5000 steps"),
                        ("s4", "S4 CIMS: 3-layer Heun with SOT step drivers, reduced grid"),
                        ("s5s", "S5 SeriesStack of 64 MTJs, 1024 stacks x 2000 steps"),
