@@ -359,32 +359,10 @@ void set_step_products(DevLayer &D, double dt) {
 
 namespace {
 
-template <int NL>
-int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
-              const cmtjb_run_args_t *a, const cmtjb_plan_t &plan, const Variant *v, double *m_state, double *log,
-              int32_t *status, int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span,
-              const cmtjb_post_t *post) {
-  static_assert(sizeof(DevModel<NL>) + sizeof(RunParams) < 32000, "kernel parameters exceed the 32 KB limit");
-  DevModel<NL> M;
-  std::memset(&M, 0, sizeof(M));
-  for (int l = 0; l < NL; l++) {
-    derive_layer(*jn, layers[l], M.L[l]);
-    set_step_products(M.L[l], a->timeStep);
-  }
-  M.Rp = jn->Rp;
-  M.Rhalf = (jn->Rap - jn->Rp) / 2.0;
-  M.mr_mode = jn->mr_mode;
-  M.n_layers = NL;
-  RunParams R;
-  std::memset(&R, 0, sizeof(R));
-  for (int k = 0; k < n_ovr; k++) {
-    R.ovr[k] = ovr[k].values;
-    for (int l = 0; l < NL; l++) {
-      if (ovr[k].layer >= 0 && ovr[k].layer != l) continue;
-      M.L[l].ovmask |= (1u << ovr[k].slot);
-      M.L[l].ovidx[ovr[k].slot][ovr[k].field] = (int8_t)k;
-    }
-  }
+// RunParams of one launch of a single-junction batch (everything except the override rows)
+void fill_run_params(RunParams &R, const cmtjb_junction_t *jn, int NL, const cmtjb_run_args_t *a, const cmtjb_plan_t &plan,
+                     double *m_state, double *log, int32_t *status, int32_t *n_samples_out, double *time_log, const Span *span,
+                     const cmtjb_post_t *post) {
   R.m_state = m_state;
   R.log = (a->log_mode == CMTJB_LOG_FULL || a->log_mode == CMTJB_LOG_ENERGY) ? log : nullptr;
   R.elog_ch0 = -1;
@@ -423,6 +401,35 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
     std::memcpy(P.sd_b, post->sd_b, sizeof(P.sd_b));
     std::memcpy(P.sd_a, post->sd_a, sizeof(P.sd_a));
   }
+}
+
+template <int NL>
+int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+              const cmtjb_run_args_t *a, const cmtjb_plan_t &plan, const Variant *v, double *m_state, double *log,
+              int32_t *status, int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span,
+              const cmtjb_post_t *post) {
+  static_assert(sizeof(DevModel<NL>) + sizeof(RunParams) < 32000, "kernel parameters exceed the 32 KB limit");
+  DevModel<NL> M;
+  std::memset(&M, 0, sizeof(M));
+  for (int l = 0; l < NL; l++) {
+    derive_layer(*jn, layers[l], M.L[l]);
+    set_step_products(M.L[l], a->timeStep);
+  }
+  M.Rp = jn->Rp;
+  M.Rhalf = (jn->Rap - jn->Rp) / 2.0;
+  M.mr_mode = jn->mr_mode;
+  M.n_layers = NL;
+  RunParams R;
+  std::memset(&R, 0, sizeof(R));
+  for (int k = 0; k < n_ovr; k++) {
+    R.ovr[k] = ovr[k].values;
+    for (int l = 0; l < NL; l++) {
+      if (ovr[k].layer >= 0 && ovr[k].layer != l) continue;
+      M.L[l].ovmask |= (1u << ovr[k].slot);
+      M.L[l].ovidx[ovr[k].slot][ovr[k].field] = (int8_t)k;
+    }
+  }
+  fill_run_params(R, jn, NL, a, plan, m_state, log, status, n_samples_out, time_log, span, post);
   if (R.B <= 0) return CMTJB_OK;
   // table of the time-dependent drivers at this launch's stage times (F_DYN / F_DYNS variants)
   double *tab = nullptr;
@@ -456,6 +463,59 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   return CMTJB_OK;
 }
 
+// Junctions of 5..CMTJB_MAX_LAYERS layers: the lane-per-layer kernel (llgs_wide_kernel), general term set.
+int run_wide(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+             const cmtjb_run_args_t *a, const cmtjb_plan_t &plan, double *m_state, double *log, int32_t *status,
+             cudaStream_t stream, const Span *span, const cmtjb_post_t *post) {
+  const int NL = jn->n_layers;
+  if (NL > kWideGroup || NL > CMTJB_MAX_LAYERS) return fail(CMTJB_ENOTSUP, "junctions with more than 8 layers are not supported by this build");
+  if (post) return fail(CMTJB_ENOTSUP, "post-processing supports at most 4 layers");
+  if (a->log_mode == CMTJB_LOG_ENERGY) return fail(CMTJB_ENOTSUP, "the energy log supports junctions of at most 4 layers");
+  if (plan.effective_solver == CMTJB_DORMAND_PRINCE) return fail(CMTJB_ENOTSUP, "Dormand-Prince is single-layer only");
+  std::vector<DevLayer> L(NL);
+  for (int l = 0; l < NL; l++) {
+    if (layers[l].noiseScale != 0 && !a->onef_buffer) return fail(CMTJB_EINVAL, "1/f noise requested without a buffer");
+    for (int s = 0; s < CMTJB_NSLOTS; s++)
+      if (layers[l].drivers[s].update == CMTJB_UPD_CUSTOM)
+        return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers support junctions of at most 4 layers");
+    derive_layer(*jn, layers[l], L[l]);
+    set_step_products(L[l], a->timeStep);
+  }
+  RunParams R;
+  std::memset(&R, 0, sizeof(R));
+  for (int k = 0; k < n_ovr; k++) {
+    R.ovr[k] = ovr[k].values;
+    for (int l = 0; l < NL; l++) {
+      if (ovr[k].layer >= 0 && ovr[k].layer != l) continue;
+      L[l].ovmask |= (1u << ovr[k].slot);
+      L[l].ovidx[ovr[k].slot][ovr[k].field] = (int8_t)k;
+    }
+  }
+  fill_run_params(R, jn, NL, a, plan, m_state, log, status, nullptr, nullptr, span, nullptr);
+  if (R.B <= 0 || R.it_end <= R.it_begin) return CMTJB_OK;
+  DevLayer *dL = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&dL, sizeof(DevLayer) * NL, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(layer models)");
+  e = cudaMemcpyAsync(dL, L.data(), sizeof(DevLayer) * NL, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) {
+    WideModel W;
+    W.L = dL;
+    W.n_layers = NL;
+    W.mr_mode = jn->mr_mode;
+    W.Rp = jn->Rp;
+    W.Rhalf = (jn->Rap - jn->Rp) / 2.0;
+    switch (plan.effective_solver) {
+    case CMTJB_RK4: e = launch_wide<CMTJB_RK4>(W, R, stream); break;
+    case CMTJB_HEUN: e = launch_wide<CMTJB_HEUN>(W, R, stream); break;
+    default: e = launch_wide<CMTJB_EULER_HEUN>(W, R, stream); break;
+    }
+    g_launches++;
+  }
+  cudaFreeAsync(dL, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "llgs_wide_kernel");
+  return CMTJB_OK;
+}
+
 int check_overrides(const cmtjb_junction_t *jn, const cmtjb_override_t *ovr, int n_ovr) {
   if (n_ovr < 0 || n_ovr > kMaxOverrides) return fail(CMTJB_EINVAL, "too many per-instance overrides (max 24)");
   if (n_ovr > 0 && !ovr) return fail(CMTJB_EINVAL, "null override table");
@@ -472,6 +532,11 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
                 const cmtjb_run_args_t *a, cmtjb_plan_t &plan, double *m_state, double *log, int32_t *status,
                 int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span,
                 const cmtjb_post_t *post = nullptr) {
+  if (jn->n_layers > 4) {
+    std::snprintf(plan.variant, sizeof(plan.variant), "wide/L%d/F_ALL", jn->n_layers);
+    plan.feature_mask = (int32_t)F_ALL;
+    return run_wide(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, stream, span, post);
+  }
   uint32_t need = needed_features(jn, layers, ovr, n_ovr, a, plan.effective_solver);
   if (need & (F_DYN | F_DYNS)) {
     // the stage table costs 24 B per column per step; beyond 2 GiB evaluate inline instead
@@ -514,7 +579,7 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
   case 2: return run_typed<2>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span, post);
   case 3: return run_typed<3>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span, post);
   case 4: return run_typed<4>(jn, layers, ovr, n_ovr, a, plan, v, m_state, log, status, n_samples_out, time_log, stream, span, post);
-  default: return fail(CMTJB_ENOTSUP, "junctions with more than 4 layers need the warp-per-instance kernel (not built yet)");
+  default: return fail(CMTJB_ENOTSUP, "unreachable: junctions with more than 4 layers run the lane-per-layer kernel");
   }
 }
 
@@ -711,6 +776,11 @@ int cmtjb_device_count(void) {
 int cmtjb_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_run_args_t *args, cmtjb_plan_t *plan) {
   int rc = make_plan(jn, layers, args, plan);
   if (rc) return rc;
+  if (jn->n_layers > 4) {  // lane-per-layer kernel (launch_span)
+    plan->feature_mask = (int32_t)F_ALL;
+    std::snprintf(plan->variant, sizeof(plan->variant), "wide/L%d/F_ALL", jn->n_layers);
+    return CMTJB_OK;
+  }
   const uint32_t need = needed_features(jn, layers, nullptr, 0, args, plan->effective_solver);
   const Variant *v = pick_variant(jn->n_layers, plan->effective_solver, need);
   if (v) {

@@ -389,7 +389,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   if (!group_uses_grid<NL>(N)) {
     GP.P = std::min(32, pow2_floor(kCoupledBlockMax / N));
     const int threads = ((N * GP.P + 31) / 32) * 32;
-    const size_t smem = 10 * (size_t)N * sizeof(double);
+    const size_t smem = 13 * (size_t)N * sizeof(double);
 #define CMTJB_GROUP_LAUNCH(SOLVER)                                                                                              \
   do {                                                                                                                          \
     if (uni) group_block_kernel<NL, SOLVER, F_COUPLED_LEAN, true><<<(unsigned)n_inst, threads, smem, stream>>>(d_models, M0, GP, R); \

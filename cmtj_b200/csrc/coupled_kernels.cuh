@@ -174,6 +174,16 @@ template <int NL> __device__ __forceinline__ d3 layer_m(const State<NL> &S, int 
   else return idx == 0 ? S.m[0] : S.m[1];  // stacks hold junctions of at most two layers (stack.hpp:298-308)
 }
 
+// top-layer pick for the group kernels (junctions of 1 or 2 layers in this build), without dynamic
+// indexing of the register-resident state
+template <int NL> __device__ __forceinline__ d3 layer_m2(const State<NL> &S, int idx) {
+  d3 v = S.m[0];
+#pragma unroll
+  for (int l = 1; l < NL; l++)
+    if (idx == l) v = S.m[l];
+  return v;
+}
+
 // MODE: which of the three coupling schemes of Stack::runSimulation this instantiation integrates
 enum { STACK_KCL = 0, STACK_DELAYED = 1, STACK_SEQUENTIAL = 2 };
 
@@ -330,18 +340,35 @@ struct GroupParams {
 
 // field at a from the dipole at b (reservoir.hpp:79-97); r = r_a - r_b:
 //   H += pref (3 (m.r) r / r^5 - m / r^3)
-__device__ __forceinline__ void pair_accumulate(d3 &H, d3 r, d3 mb, double pref) {
-  const double r2 = dot(r, r);
-  const double inv = rsqrt(r2);  // MUFU.RSQ64H + Newton; an FP32-seeded variant measured 10 % slower (F2F conversions)
+// 1/sqrt(x) without the library routine's special-case branches (BSSY/BSYNC + slow path around every
+// call): the SFU seed rsqrt.approx.ftz.f64 (MUFU.RSQ64H, ~2^-22) refined by two Newton steps, each
+// y <- y (1.5 - 0.5 x y^2): 2^-22 -> 2^-43 -> rounding level.  Inputs are squared pair distances,
+// validated on the host to be >= 1e-28 (reservoir.hpp:84-87, :39-42 guards): no zero / inf / NaN.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+
+// `self`: the pair (a, a) contributes nothing; handled without a branch (r2 -> 1, pref -> 0) so that the
+// pair loop unrolls into independent chains.
+__device__ __forceinline__ void pair_accumulate(d3 &H, d3 r, d3 mb, double pref, bool self) {
+  const double r2 = self ? 1.0 : dot(r, r);
+  pref = self ? 0.0 : pref;
+  const double inv = rsqrt_nr(r2);
   const double inv2 = inv * inv;
   const double p3 = pref * (inv2 * inv);          // pref / r^3
   const double a = (3.0 * inv2) * dot(mb, r) * p3;  // 3 pref (m.r) / r^5
   H = mk(fma(a, r.x, fma(-p3, mb.x, H.x)), fma(a, r.y, fma(-p3, mb.y, H.y)), fma(a, r.z, fma(-p3, mb.z, H.z)));
 }
 
-// GroupInteraction, one group per block: blockDim.x = N * P rounded up to a warp multiple.  Thread
-// (a = tid / P, p = tid % P) sums the pair field of element a over b = p, p+P, ...; lane p == 0
-// owns junction a.
+// GroupInteraction, one group per block: blockDim.x = N * P rounded up to a warp multiple.  Two roles per
+// thread: (a = tid / P, p = tid % P) sums the pair field of element a over b = p, p+P, ...; thread
+// e = tid < N owns junction e (state in registers) and steps it.  The reduced fields pass through shared
+// memory, so the steps run on N consecutive, fully populated lanes instead of one lane in P.
 template <int NL, int SOLVER, uint32_t F, bool UNIFORM>
 __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const DevModel<NL> *__restrict__ models,
                                                                        const __grid_constant__ DevModel<NL> Mu,
@@ -353,11 +380,13 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
   const int a_raw = tid / P, p = tid - a_raw * P;
   const int a = a_raw < N ? a_raw : N - 1;  // padding lanes of the last warp shadow element N-1
   const long long g = blockIdx.x;
-  const long long i = g * N + a;
-  const bool owner = (p == 0) && a_raw < N;
-  const DevModel<NL> &M = UNIFORM ? Mu : models[a];
+  const bool stepper = tid < N;
+  const int e = stepper ? tid : N - 1;
+  const long long i = g * N + e;
+  const DevModel<NL> &M = UNIFORM ? Mu : models[e];
   double *px = sm, *py = px + N, *pz = py + N, *pf = pz + N;  // static geometry + prefactors
   double *mb0 = pf + N;                                      // [2][3][N] double-buffered m_top
+  double *Hs = mb0 + 6 * N;                                  // [3][N] reduced pair fields of this step
   for (int k = tid; k < N; k += blockDim.x) {
     px[k] = GP.pos[k];
     py[k] = GP.pos[N + k];
@@ -366,14 +395,14 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
   }
   State<NL> S;
   d3 Hc[NL];
-  if (owner) {
+  if (stepper) {
     load_state<NL>(R, i, S);
 #pragma unroll
     for (int l = 0; l < NL; l++) Hc[l] = constant_field(M.L[l], R, i);
-    const d3 mt = S.m[GP.top < NL ? GP.top : 0];
-    mb0[a] = mt.x;
-    mb0[N + a] = mt.y;
-    mb0[2 * N + a] = mt.z;
+    const d3 mt = layer_m2<NL>(S, GP.top);
+    mb0[e] = mt.x;
+    mb0[N + e] = mt.y;
+    mb0[2 * N + e] = mt.z;
   }
   __syncthreads();
   const d3 ra = mk(px[a], py[a], pz[a]);
@@ -384,32 +413,36 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
   for (long long it = R.it_begin; it < R.it_end; ++it) {
     const double t = (double)it * R.dt;
     const double *mx = mb0 + cur * 3 * N, *my = mx + N, *mz = my + N;
-    d3 H = mk(0, 0, 0);
     if (GP.interaction != CMTJB_INT_NULL) {
-      for (int b = p; b < N; b += P) {
-        if (b == a) continue;
-        pair_accumulate(H, mk(ra.x - px[b], ra.y - py[b], ra.z - pz[b]), mk(mx[b], my[b], mz[b]), pf[b]);
-      }
+      d3 H = mk(0, 0, 0);
+#pragma unroll 4
+      for (int b = p; b < N; b += P)
+        pair_accumulate(H, mk(ra.x - px[b], ra.y - py[b], ra.z - pz[b]), mk(mx[b], my[b], mz[b]), pf[b], b == a);
       for (int off = P >> 1; off > 0; off >>= 1) {
         H.x += __shfl_xor_sync(0xffffffffu, H.x, off);
         H.y += __shfl_xor_sync(0xffffffffu, H.y, off);
         H.z += __shfl_xor_sync(0xffffffffu, H.z, off);
       }
-    }
-    if (owner) {
-      // setLayerReservedInteractionField(topId, AxialDriver(H_extra)) (reservoir.hpp:145-146)
-      d3 Hs[NL];
-#pragma unroll
-      for (int l = 0; l < NL; l++) Hs[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
-      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hs, NoExt());
-      double *nx = mb0 + (cur ^ 1) * 3 * N;
-      const d3 mt = S.m[GP.top < NL ? GP.top : 0];
-      nx[a] = mt.x;
-      nx[N + a] = mt.y;
-      nx[2 * N + a] = mt.z;
-      if (until_write == 0) {
-        if (R.log) write_sample<NL>(M, R, S, sample, i);
+      if (p == 0 && a_raw < N) {
+        Hs[a] = H.x;
+        Hs[N + a] = H.y;
+        Hs[2 * N + a] = H.z;
       }
+      __syncthreads();
+    }
+    if (stepper) {
+      // setLayerReservedInteractionField(topId, AxialDriver(H_extra)) (reservoir.hpp:145-146)
+      const d3 H = (GP.interaction != CMTJB_INT_NULL) ? mk(Hs[e], Hs[N + e], Hs[2 * N + e]) : mk(0, 0, 0);
+      d3 Hl[NL];
+#pragma unroll
+      for (int l = 0; l < NL; l++) Hl[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
+      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hl, NoExt());
+      double *nx = mb0 + (cur ^ 1) * 3 * N;
+      const d3 mt = layer_m2<NL>(S, GP.top);
+      nx[e] = mt.x;
+      nx[N + e] = mt.y;
+      nx[2 * N + e] = mt.z;
+      if (until_write == 0 && R.log) write_sample<NL>(M, R, S, sample, i);
     }
     if (until_write == 0) {
       sample++;
@@ -419,7 +452,7 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
     cur ^= 1;
     __syncthreads();
   }
-  if (owner) {
+  if (stepper) {
     store_state<NL>(R, i, S);
     if (R.status) R.status[i] = nan_status<NL, SOLVER>(S);
   }
@@ -429,7 +462,7 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
 // (a, p) as above with a = global_thread / P; the j-loop walks shared-memory tiles of kTile
 // partners; the top-layer magnetisation is exchanged through a double-buffered global array with
 // ONE grid-wide barrier per time step.
-constexpr int kGroupTile = 256;
+constexpr int kGroupTile = 512;  // 7 arrays x 512 x 8 B = 28 KB of static shared memory
 
 template <int NL, int SOLVER, uint32_t F, bool UNIFORM>
 __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__restrict__ models,
@@ -437,8 +470,8 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
                                                          const __grid_constant__ GroupParams GP,
                                                          const __grid_constant__ RunParams R) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double tx[kGroupTile], ty[kGroupTile], tz[kGroupTile], tf[kGroupTile];
-  __shared__ double tmx[kGroupTile], tmy[kGroupTile], tmz[kGroupTile];
+  // one array, so that the seven loads of a pair share one address register (immediate offsets)
+  __shared__ double tile[7][kGroupTile];  // x, y, z, prefactor, mx, my, mz of the staged partners
   const int N = GP.N, P = GP.P;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long a_raw = gt / P;
@@ -454,7 +487,7 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
     load_state<NL>(R, i, S);
 #pragma unroll
     for (int l = 0; l < NL; l++) Hc[l] = constant_field(M.L[l], R, i);
-    const d3 mt = S.m[GP.top < NL ? GP.top : 0];
+    const d3 mt = layer_m2<NL>(S, GP.top);
     GP.mbuf[a] = mt.x;
     GP.mbuf[N + a] = mt.y;
     GP.mbuf[2 * N + a] = mt.z;
@@ -474,18 +507,20 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
         const int nb = min(kGroupTile, N - b0);
         __syncthreads();
         for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-          tx[k] = __ldg(GP.pos + b0 + k);
-          ty[k] = __ldg(GP.pos + N + b0 + k);
-          tz[k] = __ldg(GP.pos + 2 * N + b0 + k);
-          tf[k] = __ldg(GP.pref + b0 + k);
-          tmx[k] = __ldcg(mcur + b0 + k);  // written by other SMs last step: read through L2
-          tmy[k] = __ldcg(mcur + N + b0 + k);
-          tmz[k] = __ldcg(mcur + 2 * N + b0 + k);
+          tile[0][k] = __ldg(GP.pos + b0 + k);
+          tile[1][k] = __ldg(GP.pos + N + b0 + k);
+          tile[2][k] = __ldg(GP.pos + 2 * N + b0 + k);
+          tile[3][k] = __ldg(GP.pref + b0 + k);
+          tile[4][k] = __ldcg(mcur + b0 + k);  // written by other SMs last step: read through L2
+          tile[5][k] = __ldcg(mcur + N + b0 + k);
+          tile[6][k] = __ldcg(mcur + 2 * N + b0 + k);
         }
         __syncthreads();
+#pragma unroll 4
         for (int k = p; k < nb; k += P) {
-          if (b0 + k == a) continue;
-          pair_accumulate(H, mk(ra.x - tx[k], ra.y - ty[k], ra.z - tz[k]), mk(tmx[k], tmy[k], tmz[k]), tf[k]);
+          const double *q = &tile[0][k];
+          pair_accumulate(H, mk(ra.x - q[0], ra.y - q[kGroupTile], ra.z - q[2 * kGroupTile]),
+                          mk(q[4 * kGroupTile], q[5 * kGroupTile], q[6 * kGroupTile]), q[3 * kGroupTile], b0 + k == a);
         }
       }
       for (int off = P >> 1; off > 0; off >>= 1) {
@@ -500,7 +535,7 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
       for (int l = 0; l < NL; l++) Hs[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
       coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hs, NoExt());
       double *nx = GP.mbuf + (size_t)(cur ^ 1) * 3 * N;
-      const d3 mt = S.m[GP.top < NL ? GP.top : 0];
+      const d3 mt = layer_m2<NL>(S, GP.top);
       __stcg(nx + a, mt.x);
       __stcg(nx + N + a, mt.y);
       __stcg(nx + 2 * N + a, mt.z);

@@ -431,6 +431,136 @@ __global__ void __launch_bounds__(kBalBlock) llgs_balanced_kernel(const __grid_c
   }
 }
 
+// ---- junctions of 5..8 layers: one LANE per layer -------------------------------------------------------
+// The per-thread kernels above keep every layer of an instance in one thread's registers, which stops
+// paying beyond four layers (the general variant of a 4-layer junction is already 14k instructions).
+// Here an instance is a group of kWideGroup = 8 consecutive lanes, lane l integrating layer l; the
+// neighbours' magnetisations (runMultiLayerSolver's snapshot, junction.hpp:1682-1696) arrive by warp
+// shuffle, the layer models are read from a device array indexed by the lane.  General term set with
+// inline drivers (F_ALL); same arithmetic per layer as the per-thread kernels, same Philox keys.
+constexpr int kWideGroup = 8;
+struct WideModel {
+  const DevLayer *L;  // device [n_layers]
+  int32_t n_layers, mr_mode;
+  double Rp, Rhalf;
+};
+
+__device__ __forceinline__ d3 shfl3(d3 v, int src_lane_in_group) {
+  return mk(__shfl_sync(0xffffffffu, v.x, src_lane_in_group, kWideGroup), __shfl_sync(0xffffffffu, v.y, src_lane_in_group, kWideGroup),
+            __shfl_sync(0xffffffffu, v.z, src_lane_in_group, kWideGroup));
+}
+
+template <int SOLVER>
+__global__ void __launch_bounds__(128) llgs_wide_kernel(const __grid_constant__ WideModel W, const __grid_constant__ RunParams R) {
+  constexpr uint32_t F = F_ALL;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i_raw = gt / kWideGroup;
+  const int l_raw = (int)(gt - i_raw * kWideGroup);
+  const int NL = W.n_layers;
+  const bool live = i_raw < R.B && l_raw < NL;  // idle lanes still take part in the shuffles
+  const long long i = i_raw < R.B ? i_raw : R.B - 1;
+  const int l = l_raw < NL ? l_raw : NL - 1;
+  const DevLayer &Lr = W.L[l];
+  const d3 zero = mk(0, 0, 0);
+  d3 m = mk(__ldcg(R.m_state + (3 * l + 0) * R.B + i), __ldcg(R.m_state + (3 * l + 1) * R.B + i), __ldcg(R.m_state + (3 * l + 2) * R.B + i));
+  const d3 Hc = constant_field(Lr, R, i);
+  // neighbours of the lane's layer; the reference passes the zero vector beyond the ends (junction.hpp:1686-1690)
+  auto neighbours = [&](d3 v, d3 &bot, d3 &top) {
+    const d3 b = shfl3(v, l_raw - 1 < 0 ? 0 : l_raw - 1), t = shfl3(v, l_raw + 1 >= kWideGroup ? kWideGroup - 1 : l_raw + 1);
+    bot = l > 0 ? b : zero;
+    top = l < NL - 1 ? t : zero;
+  };
+  auto rhs = [&](double t, d3 mm, d3 bot, d3 top) { return llg_u<F, true, true>(Lr, R, l, i, StageTime{t, nullptr}, mm, bot, top, Hc); };
+  const long long we = R.write_every;
+  long long until_write = (we - (R.it_begin % we)) % we;
+  long long sample = R.first_sample;
+  const long long cs = R.n_samples * R.B;
+  for (long long it = R.it_begin; it < R.it_end; ++it) {
+    const double t = (double)it * R.dt;
+    d3 bot, top;
+    neighbours(m, bot, top);
+    if constexpr (SOLVER == CMTJB_RK4) {
+      const d3 u1 = rhs(t, m, bot, top);
+      const d3 u2 = rhs(t + 0.5 * R.dt, axpy(u1, Lr.h_half, m), bot, top);
+      const d3 u3 = rhs(t + 0.5 * R.dt, axpy(u2, Lr.h_half, m), bot, top);
+      const d3 u4 = rhs(t + R.dt, axpy(u3, Lr.h, m), bot, top);
+      const d3 acc = mk(fma(2.0, u2.x + u3.x, u1.x + u4.x), fma(2.0, u2.y + u3.y, u1.y + u4.y), fma(2.0, u2.z + u3.z, u1.z + u4.z));
+      m = normalize3(axpy(acc, Lr.h_sixth, m));
+    } else if constexpr (SOLVER == CMTJB_EULER_HEUN) {
+      const StageTime t0{t, nullptr};
+      const d3 f = rhs(t, m, bot, top);
+      d3 mn = axpy(f, Lr.llg * R.dt, m);
+      const d3 dW = noise_dW<F, 1>(Lr, R, l, i, it, t0);
+      const double gs = Lr.llg * R.sqrt_dt;
+      const d3 g = stoch_u(Lr, m, dW);
+      const d3 gp = stoch_u(Lr, axpy(g, gs, m), dW);
+      mn = axpy(g + gp, 0.5 * gs, mn);
+      m = normalize3(mn);
+    } else {  // Heun: predictor with the current neighbours, corrector with the PREDICTED ones (junction.hpp:1756-1815)
+      const StageTime t0{t, nullptr};
+      const d3 f = rhs(t, m, bot, top);
+      const d3 dW = noise_dW<F, 1>(Lr, R, l, i, it, t0);
+      const d3 g = stoch_u(Lr, m, dW);
+      const d3 mp = axpy(g, Lr.llg * R.sqrt_dt, axpy(f, Lr.llg * R.dt, m));
+      d3 pb, pt;
+      neighbours(mp, pb, pt);
+      const d3 f2 = rhs(t + R.dt, mp, pb, pt);
+      const d3 g2 = stoch_u(Lr, mp, dW);
+      d3 mn = axpy(f + f2, 0.5 * (Lr.llg * R.dt), m);
+      mn = axpy(g + g2, 0.5 * (Lr.llg * R.sqrt_dt), mn);
+      m = normalize3(mn);
+    }
+    if (until_write == 0) {
+      if (R.log != nullptr) {  // logLayerParams (junction.hpp:1580-1636), MR :1835-1867
+        double *p = R.log + sample * R.B + i;
+        if (live) {
+          __stcs(p + (3 * l + 0) * cs, m.x);
+          __stcs(p + (3 * l + 1) * cs, m.y);
+          __stcs(p + (3 * l + 2) * cs, m.z);
+        }
+        if (W.mr_mode == CMTJB_MR_CLASSIC) {
+          const d3 m1 = shfl3(m, 1);  // layer 1 of this instance (NL >= 5 here)
+          if (live && l == 0) __stcs(p + (3 * NL) * cs, fma(W.Rhalf, 1.0 - dot(m, m1), W.Rp));
+        } else if (W.mr_mode == CMTJB_MR_STRIP) {
+          double rx = 0.0, ry = 0.0;
+          if (l_raw < NL) {
+            rx = 1.0 / fma(Lr.SMR_X, m.y * m.y, fma(Lr.AMR_X, m.x * m.x, Lr.Rx0));
+            ry = 1.0 / fma(Lr.AMRSMR_Y * m.x, m.y, fma(Lr.AHE_half, m.z, Lr.Ry0));
+          }
+          for (int off = kWideGroup >> 1; off > 0; off >>= 1) {
+            rx += __shfl_xor_sync(0xffffffffu, rx, off, kWideGroup);
+            ry += __shfl_xor_sync(0xffffffffu, ry, off, kWideGroup);
+          }
+          if (live && l == 0) {
+            __stcs(p + (3 * NL + 0) * cs, 1.0 / rx);
+            __stcs(p + (3 * NL + 1) * cs, 1.0 / ry);
+            __stcs(p + (3 * NL + 2) * cs, 0.0);
+          }
+        }
+      }
+      sample++;
+      until_write = we;
+    }
+    until_write--;
+  }
+  if (live) {
+    R.m_state[(3 * l + 0) * R.B + i] = m.x;
+    R.m_state[(3 * l + 1) * R.B + i] = m.y;
+    R.m_state[(3 * l + 2) * R.B + i] = m.z;
+  }
+  if (R.status) {  // RK4 throws "NAN magnetisation" on isnan(mag.x) of any layer (junction.hpp:1037-1039)
+    int st = (SOLVER == CMTJB_RK4 && live && isnan(m.x)) ? 1 : 0;
+    for (int off = kWideGroup >> 1; off > 0; off >>= 1) st |= __shfl_xor_sync(0xffffffffu, st, off, kWideGroup);
+    if (live && l == 0 && (R.it_begin == 0 || st)) R.status[i] = st;
+  }
+}
+
+template <int SOLVER> cudaError_t launch_wide(const WideModel &W, const RunParams &R, cudaStream_t stream) {
+  const long long threads = R.B * kWideGroup;
+  llgs_wide_kernel<SOLVER><<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(W, R);
+  return cudaGetLastError();
+}
+
 // ---- Dormand-Prince (single layer): Layer::dormand_prince_step (junction.hpp:866-1002) and the
 // adaptive loop of runSimulation (:1983-2044), including its quirks: time advances by the NEW
 // step size after an accepted step, and consecutive_rejections is reset every iteration.

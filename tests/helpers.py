@@ -114,6 +114,41 @@ def tri_layer_mtj(mod, mag=(0.1, 0.1, 1.0)):
     return j
 
 
+def multi_layer(mod, n, strip=False, mag=(0.1, 0.1, 1.0)):
+    """An n-layer stack (n up to 8): alternating materials and easy axes, IEC + biquadratic coupling between
+    every pair of neighbours, one tilted-demag layer, a sine Oersted drive and a static SOT layer at the bottom
+    (exercises field terms, neighbour hand-off and torque terms for every layer position)."""
+    Ms = [1.65, 1.45, 0.7, 1.2, 1.0, 0.9, 1.3, 1.1]
+    th = [3e-9, 4e-9, 1e-9, 2e-9, 1.5e-9, 2.5e-9, 1e-9, 3e-9]
+    K = [1.05e3, 50e3, 1e4, 3e4, 2e4, 0.8e4, 4e4, 1e3]
+    axes = [(1, 0, 0), (1, 0, 0), (0, 0, 1), (0, 1, 0), (1, 0, 0), (0, 0, 1), (0, 1, 0), (1, 0, 0)]
+    layers = []
+    for i in range(n):
+        d = DEMAG if i != 2 else [(0.05, 0.01, 0), (0.01, 0.1, 0), (0, 0, 0.85)]
+        v = (mag[0] + 0.05 * i, mag[1] - 0.03 * i, mag[2])
+        if i == n - 1:
+            l = mod.Layer.createSOTLayer(f"L{i}", mod.CVector(*v), mod.CVector(*axes[i]), Ms[i], th[i], SURFACE, _demag(mod, d), 0.02,
+                                         120.0, -80.0)
+            l.setReferenceLayer(mod.CVector(0, 1, 0))
+        else:
+            l = mod.Layer(f"L{i}", mod.CVector(*v), mod.CVector(*axes[i]), Ms[i], th[i], SURFACE, _demag(mod, d), ALPHA * (1 + i))
+        layers.append(l)
+    if strip:  # the Rp/Rap constructor is bilayer-only (junction.hpp:1185-1190)
+        r = [10.0 + i for i in range(n)]
+        j = mod.Junction(layers, r, [2.0 * x for x in r], [0.3] * n, [0.2] * n, [0.1] * n, [-0.15] * n, [0.4] * n)
+    else:
+        j = mod.Junction(layers)
+    for i in range(n):
+        j.setLayerAnisotropyDriver(f"L{i}", mod.ScalarDriver.getConstantDriver(K[i]))
+    for i in range(n - 1):
+        j.setIECDriver(f"L{i}", f"L{i + 1}", mod.ScalarDriver.getConstantDriver((-1) ** i * 4e-4 * (1 + 0.3 * i)))
+        j.setQuadIECDriver(f"L{i}", f"L{i + 1}", mod.ScalarDriver.getConstantDriver(-2e-5 * (1 + i)))
+    j.setLayerCurrentDriver(f"L{n - 1}", mod.ScalarDriver.getConstantDriver(3.0))
+    j.setLayerOerstedFieldDriver("all", mod.AxialDriver(mod.NullDriver(), mod.NullDriver(), mod.ScalarDriver.getSineDriver(0, 500, 9e9, 0.3)))
+    j.setLayerExternalFieldDriver("all", mod.AxialDriver(30e3, -5e3, 10e3))
+    return j
+
+
 def stt_layer_mtj(mod, mag=None, temperature=None):
     """p-bit style STT junction (curated-examples/p-bit.py:188-227 parameters)."""
     if mag is None:

@@ -377,3 +377,33 @@ def test_custom_driver_in_a_batch_and_on_the_device_path():
     for k in logs[0]:
         if k != "time":
             assert np.array_equal(dev[k].cpu().numpy(), logs[0][k]), k
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,strip", [(5, True), (6, False), (8, False)])
+def test_many_layer_junctions_lane_per_layer_kernel(n, strip, mode):
+    """Junctions of 5..8 layers run llgs_wide_kernel (one lane per layer, neighbours by warp shuffle)."""
+    (g, jg), (w, _) = _both(helpers.multi_layer, 0.2e-9, 1e-13, 4e-13, mode, None, n=n, strip=strip)
+    _check(g, w)
+
+
+def test_many_layer_batch_with_overrides():
+    """A 7-layer junction swept over per-instance fields and a per-instance anisotropy (ragged last warp:
+    45 instances x 8 lanes)."""
+    B = 45
+    rng = np.random.default_rng(4)
+    H = rng.uniform(-100e3, 100e3, (B, 3))
+    Ks = rng.uniform(1e4, 5e4, B)
+    logs = []
+    for be in (None, helpers.oracle_backend()):
+        with helpers.facade_on(be):
+            b = cmtj_b200.JunctionBatch(helpers.multi_layer(cmtj_b200, 7), B)
+            b.set_external_field("all", H)
+            b.set_override("L3", "K1", "constantValue", Ks)
+            out = dict(b.run(0.1e-9, 1e-13, 5e-13))
+            assert be is not None or b.last_plan.variant.decode().startswith("wide/L7")
+            out["final"] = b.get_magnetisation("L6")
+            logs.append(out)
+    for k in logs[1]:
+        if k != "time":
+            assert helpers.max_rel_err(logs[0][k], logs[1][k]) <= TOL, k

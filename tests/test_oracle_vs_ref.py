@@ -302,3 +302,12 @@ def test_custom_driver_errors(on_oracle):
     j.setLayerAnisotropyDriver("free", cmtj_b200.ScalarDriver.getCustomDriver(lambda t: 1e5))
     with pytest.raises(NotImplementedError, match="fixed-step"):
         j.runSimulation(1e-11, 1e-13, 1e-13, solverMode=cmtj_b200.SolverMode.DormandPrince)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,strip", [(4, False), (5, True), (8, False)])
+def test_many_layer_junctions_bit_exact(ref, on_oracle, n, strip, mode):
+    """runMultiLayerSolver for L = 4, 5, 8 layers (junction.hpp:1682-1707): the restatement is generic in the
+    layer count; on the GPU, L > 4 runs the lane-per-layer kernel (tests/test_gpu_parity.py)."""
+    jr, jo = _run_both(ref, helpers.multi_layer, T=0.2e-9, wf=4e-13, mode=mode, n=n, strip=strip)
+    _assert_same_logs(jr, jo)
