@@ -34,8 +34,14 @@ except Exception:
 
 
 def timed(fn, reps=3):
-    fn()
-    torch.cuda.synchronize()
+    # warm up for at least 0.5 s of wall time: the short configurations (a few ms per call) would
+    # otherwise be timed while the SM clock is still ramping up from idle
+    t0 = time.perf_counter()
+    while True:
+        fn()
+        torch.cuda.synchronize()
+        if time.perf_counter() - t0 > 0.5:
+            break
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -202,8 +208,44 @@ def s5s(scale):
          {"stacks": n_inst, "junctions": N, "steps": steps})
 
 
+def procs(scale):
+    """The sweep procedures end to end through their reference-shaped API: host field
+    list in, host spectra out.  PIMM: the BASELINE configs[1] shape at reduced length (2-layer MTJ, 1e5 field
+    points x 5 ns, FFT of the projected m_z); VSD: 256 fields x 64 frequencies x 10 ns, spin-diode map."""
+    P = m.utils.procedures
+    rp = [P.ResistanceParameters(Rxx0=100, Rxy0=1, Rahe=1, Rsmr=-0.2, Ramr=0.5, w=3e-5, l=2e-5),
+          P.ResistanceParameters(Rxx0=80, Rxy0=2, Rahe=-0.5, Rsmr=0.1, Ramr=-0.3, w=3e-5, l=2e-5)]
+    nH = int(100000 * scale)
+    H = np.zeros((nH, 3))
+    H[:, 0] = np.linspace(-500e3, 500e3, nH)
+    steps = 50000
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        spec, freqs, out = P.PIMM_procedure(helpers.two_layer_mtj(m), H, 1e-13, rp, simulation_duration=steps * 1e-13 * (1 + 1e-9),
+                                            disturbance=1e-3, disable_tqdm=True)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+    emit("PIMM_procedure end to end: 2-layer MTJ, field sweep, 5 ns, spectrum + Rx/Ry on the host", 2 * nH * steps, secs, 337.0, 0,
+         {"field_points": nH, "steps": steps, "spectrum_shape": list(np.asarray(spec).shape)})
+    nH2, nF, steps2 = int(256 * math.sqrt(scale)), int(64 * math.sqrt(scale)), 100000
+    Hv = np.zeros((nH2, 3))
+    Hv[:, 0] = np.linspace(50e3, 400e3, nH2)
+    Hv[:, 2] = 20e3
+    fs = np.linspace(2e9, 20e9, nF)
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        vm = P.VSD_procedure(helpers.two_layer_mtj(m), Hv, fs, 1e-13, rp, simulation_duration=steps2 * 1e-13 * (1 + 1e-9), Rtype="Rz",
+                             disable_tqdm=True)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+    emit("VSD_procedure end to end: 2-layer MTJ, field x frequency map, 10 ns, mixing + low-pass fused", 2 * nH2 * nF * steps2, secs,
+         337.0 + 4 * 10, 0, {"fields": nH2, "frequencies": nF, "steps": steps2, "map_shape": list(vm.shape)})
+
+
 if __name__ == "__main__":
-    which = [a for a in sys.argv[1:] if not a.replace(".", "").isdigit()] or ["s2", "s3", "s4", "s5g", "s5s"]
+    which = [a for a in sys.argv[1:] if not a.replace(".", "").isdigit()] or ["s2", "s3", "s4", "s5g", "s5s", "procs"]
     scale = [float(a) for a in sys.argv[1:] if a.replace(".", "").isdigit()]
     scale = scale[0] if scale else 1.0
     print(json.dumps({"fp64_peak_tflops_measured": PEAK / 1e12, "hbm_gbs": HBM}), flush=True)

@@ -15,6 +15,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "== ncu full (S1 kernel, 100000 instances x 20000 steps, log every 100)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:llgs_balanced -s 1 -c 1 -o gpurun_out/prof_s1 -f \
     python tools/s1_run.py 100000 20000 100 2 > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+if [ "${CONFIGS:-0}" = "1" ]; then
+  echo "== per-configuration throughput (S2..S5)"; timeout 900 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; echo "configs rc=$?"; cut -c1-200 gpurun_out/configs.jsonl
+fi
 if [ "${PROFILE_CONFIGS:-0}" = "1" ]; then
   # one full capture per other kernel family (reduced sizes: ncu replays each kernel ~40 times)
   for spec in "s3:regex:llgs_:0.1" "s4:regex:llgs_:0.02" "s5s:regex:stack_kernel:0.25" "s5g:regex:group_:0.25"; do

@@ -133,6 +133,9 @@ def main():
     bj = os.path.join(OUT, "bench.json")
     if os.path.exists(bj) and os.path.getsize(bj):
         open(os.path.join(PROF, f"{tag}_bench.json"), "w").write(open(bj).read())
+    cj = os.path.join(OUT, "configs.jsonl")
+    if os.path.exists(cj) and os.path.getsize(cj):
+        open(os.path.join(PROF, f"{tag}_configs.jsonl"), "w").write(open(cj).read())
     if res:
         d = res[0]
         rd = to_bytes(*d["dram__bytes_read.sum"])
