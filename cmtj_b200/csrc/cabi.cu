@@ -199,6 +199,7 @@ const Variant *pick_variant(int nl, int solver, uint32_t need) {
 // sub-range of a run executed by one launch (time-chunked pipelining in cmtjb_run_host)
 struct Span {
   long long it_begin, it_end, first_sample;
+  long long n_samples = 0;  // > 0: `log` is a buffer of this many sample rows per channel (a time chunk), not the whole log
 };
 
 }  // namespace
@@ -376,7 +377,7 @@ void fill_run_params(RunParams &R, const cmtjb_junction_t *jn, int NL, const cmt
   R.n_custom = a->n_custom;
   R.B = a->n_instances;
   R.inst_offset = a->instance_offset;
-  R.n_samples = plan.n_samples;
+  R.n_samples = (span && span->n_samples > 0) ? span->n_samples : plan.n_samples;
   R.it_begin = span ? span->it_begin : a->start_iteration;
   R.it_end = span ? span->it_end : plan.total_iterations;
   R.total_iterations = plan.total_iterations;
@@ -662,6 +663,7 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
     sp.it_end = cuts[seg + 1];
     if (sp.it_end <= sp.it_begin) continue;
     sp.first_sample = fs0 + count_upto(sp.it_begin) - count_upto(it0);
+    sp.n_samples = span ? span->n_samples : 0;
     rc = launch_span(jn, seg == 1 ? layers : frozen.data(), ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log,
                      stream, &sp, post);
   }
@@ -839,12 +841,22 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   const size_t nm = (size_t)jn->n_layers * 3 * B * sizeof(double);
   const bool want_log = (args->log_mode == CMTJB_LOG_FULL || args->log_mode == CMTJB_LOG_ENERGY) && log && plan.n_samples > 0;
   const size_t nlog = want_log ? (size_t)plan.n_channels * plan.n_samples * B * sizeof(double) : 0;
+  // time chunking of large fixed-step logs (see below): ~768 MB per chunk, at least 16 chunks of >= 1 sample
+  int n_chunks = 1;
+  if (want_log && !plan.variable_samples && nlog > ((size_t)64 << 20) && plan.n_samples >= 16) {
+    const long long by_size = (long long)((nlog + ((size_t)768 << 20) - 1) / ((size_t)768 << 20));
+    n_chunks = (int)std::min<long long>(plan.n_samples, std::max<long long>(std::min<long long>(16, plan.n_samples / 4), by_size));
+  }
+  const bool chunked = n_chunks > 1;
+  const long long chunk_samples = chunked ? (plan.n_samples + n_chunks - 1) / n_chunks + 1 : plan.n_samples;
+  const size_t chunk_elems = (size_t)plan.n_channels * chunk_samples * B;
+  const size_t nlog_dev = chunked ? 2 * chunk_elems * sizeof(double) : nlog;
   // carve every device buffer of this call out of the per-device slab (256-byte aligned)
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t n_tlog = (plan.variable_samples && want_log && time_log) ? (size_t)plan.n_samples * B * sizeof(double) : 0;
   const size_t n_onef = args->onef_buffer ? (size_t)jn->n_layers * 3 * plan.total_iterations * B * sizeof(double) : 0;
   const size_t n_cust = (args->custom_table && args->n_custom > 0) ? (size_t)3 * plan.total_iterations * args->n_custom * sizeof(double) : 0;
-  const size_t total = al(nm) + al(nlog) + 2 * al(B * sizeof(int32_t)) + al(n_tlog) + al(n_onef) + al(n_cust) +
+  const size_t total = al(nm) + al(nlog_dev) + 2 * al(B * sizeof(int32_t)) + al(n_tlog) + al(n_onef) + al(n_cust) +
                        (size_t)n_overrides * al(B * sizeof(double)) + 256;
   std::lock_guard<std::mutex> lock(g_slab_mu);
   void *base = nullptr;
@@ -857,7 +869,7 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     return p;
   };
   double *d_m = (double *)take(nm);
-  double *d_log = want_log ? (double *)take(nlog) : nullptr;
+  double *d_log = want_log ? (double *)take(nlog_dev) : nullptr;
   int32_t *d_status = (int32_t *)take(B * sizeof(int32_t));
   int32_t *d_ns = plan.variable_samples ? (int32_t *)take(B * sizeof(int32_t)) : nullptr;
   double *d_tlog = n_tlog ? (double *)take(n_tlog) : nullptr;
@@ -880,40 +892,47 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     CUDA_TRY(cudaMemcpy(d_cust, args->custom_table, n_cust, cudaMemcpyHostToDevice));
     a.custom_table = d_cust;
   }
-  // Large fixed-step logs: run in time chunks and copy chunk k to the host while chunk k+1
-  // integrates (the copy engine overlaps the FP64 pipe; effective when `log` is pinned memory).
-  int n_chunks = 1;
-  if (want_log && !plan.variable_samples && nlog > ((size_t)64 << 20) && plan.n_samples >= 16)
-    n_chunks = (int)std::min<long long>(16, plan.n_samples / 4);
-  if (n_chunks == 1) {
+  if (!chunked) {
     rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, d_log, d_status, d_ns, d_tlog, nullptr, nullptr);
     if (rc) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
     if (want_log) CUDA_TRY(cudaMemcpy(log, d_log, nlog, cudaMemcpyDeviceToHost));
   } else {
+    // Large fixed-step logs: the run is cut into time chunks; chunk c integrates into device buffer c % 2
+    // while the copy engine streams chunk c-1 to the host (effective when `log` is pinned memory).  Device
+    // memory for the log is two chunk buffers whatever the length of the run, so a log larger than HBM
+    // (full-rate PIMM logs: 56 B per junction-step) streams through.
     cudaStream_t sc = nullptr, sd = nullptr;
     CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
     const long long we = plan.write_every, S0 = a.start_iteration;
     const long long i0 = ((S0 + we - 1) / we) * we;  // iteration of this run's sample 0
     std::vector<cudaEvent_t> evs;
+    cudaEvent_t copied[2] = {nullptr, nullptr};  // buffer b has been drained to the host
     for (int c = 0; c < n_chunks && rc == CMTJB_OK; c++) {
       const long long s0 = plan.n_samples * c / n_chunks, s1 = plan.n_samples * (c + 1) / n_chunks;
+      double *buf = d_log + (size_t)(c & 1) * chunk_elems;
       Span sp;
       sp.it_begin = (c == 0) ? S0 : i0 + s0 * we;
       sp.it_end = (c == n_chunks - 1) ? plan.total_iterations : i0 + s1 * we;
-      sp.first_sample = s0;
-      rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, d_log, d_status, d_ns, d_tlog, sc, nullptr, &sp);
+      sp.first_sample = 0;
+      sp.n_samples = chunk_samples;
+      if (copied[c & 1]) cudaStreamWaitEvent(sc, copied[c & 1], 0);
+      rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, buf, d_status, d_ns, d_tlog, sc, nullptr, &sp);
       if (rc) break;
       cudaEvent_t ev;
       cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
       evs.push_back(ev);
       cudaEventRecord(ev, sc);
       cudaStreamWaitEvent(sd, ev, 0);
-      for (int ch = 0; ch < plan.n_channels; ch++) {
-        const size_t off = ((size_t)ch * plan.n_samples + s0) * B;
-        cudaMemcpyAsync(log + off, d_log + off, (size_t)(s1 - s0) * B * sizeof(double), cudaMemcpyDeviceToHost, sd);
-      }
+      for (int ch = 0; ch < plan.n_channels; ch++)
+        cudaMemcpyAsync(log + ((size_t)ch * plan.n_samples + s0) * B, buf + (size_t)ch * chunk_samples * B,
+                        (size_t)(s1 - s0) * B * sizeof(double), cudaMemcpyDeviceToHost, sd);
+      cudaEvent_t done;
+      cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+      evs.push_back(done);
+      cudaEventRecord(done, sd);
+      copied[c & 1] = done;
     }
     cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sd);
     for (cudaEvent_t ev : evs) cudaEventDestroy(ev);

@@ -294,25 +294,27 @@ def PIMM_procedure(
     output: Dict[str, Any] = defaultdict(list)
     spectrum: List[np.ndarray] = []
     freqs = None
-    k = 0
-    for r in parts:
-        for i in range(r["Rx"].shape[0]):
-            output["H"].append(Hvecs[k])
-            output["Rx"].append(r["Rx"][i])
-            output["Ry"].append(r["Ry"][i])
-            output["m_avg"].append(r["m_avg"][i])
-            if not static_only:
-                spectrum.append(r["spectrum"][i][:, None])
-                freqs = r["freqs"]
-                if full_output:
-                    output["m_traj"].append(r["m_traj"][i])
-                    for li, lid in enumerate(layer_ids):
-                        output[lid].append(r["layer_spectra"][li][i][:, None])
-            k += 1
+    if not parts:
+        return np.squeeze(np.asarray(spectrum)), freqs, output
+
+    def cat(key):
+        return np.concatenate([r[key] for r in parts], axis=0)
+
+    # the reference appends one entry per field point (procedures.py:183-193); same lists, assembled
+    # from whole-batch arrays (row views) instead of 1e5 Python-level appends
+    n = sum(r["Rx"].shape[0] for r in parts)
+    output["H"] = list(Hvecs[:n])
+    output["Rx"] = list(cat("Rx"))
+    output["Ry"] = list(cat("Ry"))
+    output["m_avg"] = list(cat("m_avg"))
     spectrum_arr = np.squeeze(np.asarray(spectrum))
-    if full_output:
-        for lid in layer_ids:
-            output[lid] = np.asarray(output[lid]).squeeze()
+    if not static_only:
+        freqs = parts[-1]["freqs"]
+        spectrum_arr = np.squeeze(cat("spectrum")[:, :, None])
+        if full_output:
+            output["m_traj"] = list(cat("m_traj"))
+            for li, lid in enumerate(layer_ids):
+                output[lid] = np.concatenate([r["layer_spectra"][li] for r in parts], axis=0)[:, :, None].squeeze()
     return spectrum_arr, freqs, output
 
 

@@ -1,5 +1,5 @@
 """CPU restatement of the reductions the reference's sweep procedures apply to ONE runSimulation
-log -- TEST INFRASTRUCTURE ONLY (imported by tests/ and tools/bench_configs.py's cpu baseline leg;
+log -- TEST INFRASTRUCTURE ONLY (imported by tests/ only;
 never by the product, which does these reductions on the GPU).
 
 Follows cmtj/utils/procedures.py and cmtj/utils/resistance.py of the reference line by line, with

@@ -120,3 +120,22 @@ def test_balanced_fused_post_is_bit_identical(on_cuda):
         return {"proj": proj_log.cpu().numpy(), "sd": state.cpu().numpy(), "final": b._m_dev.cpu().numpy()}
 
     _same(_forced("1", run), _forced("0", run))
+
+
+def test_host_entry_streams_large_logs_in_time_chunks(on_cuda):
+    """cmtjb_run_host cuts logs above 64 MB into time chunks that integrate into two alternating device
+    buffers while the previous chunk is copied out; the assembled host log must equal the device-resident
+    log of the same run bit for bit (both forms, sample rows that do not divide evenly into chunks)."""
+    import torch
+
+    B, steps, we = 5000, 3030, 10  # 7 x 303 x 5000 doubles = 85 MB -> 16 chunks of 18.9 samples
+    b = _batch(helpers.two_layer_mtj, B, seed=9)
+    host = dict(b.run(steps * DT * (1 + 1e-9), DT, we * DT * (1 + 1e-9)))
+    final_host = b.m_state.copy()
+    b2 = _batch(helpers.two_layer_mtj, B, seed=9)
+    dev = b2.run_device(steps * DT * (1 + 1e-9), DT, we * DT * (1 + 1e-9))
+    torch.cuda.synchronize()
+    for k, v in host.items():
+        if k != "time":
+            assert np.array_equal(dev[k].cpu().numpy(), v), k
+    assert np.array_equal(b2._m_dev.cpu().numpy(), final_host)
