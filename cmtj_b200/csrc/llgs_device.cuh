@@ -209,6 +209,106 @@ __device__ __forceinline__ d3 dynamic_field(const DevLayer &Lr, const RunParams 
 }
 
 // ---------------------------------------------------------------------------------------
+// F_DYNI fast path.  Inline evaluation (per-instance frequency / phase / timing: a VSD map, one
+// instance per (field, frequency) pair) walks 12 field slots and their override tables at every
+// right-hand-side evaluation: ~1900 bookkeeping instructions per step against ~400 of arithmetic
+// (ncu, VSD 256 x 64).  Sweeps excite ONE field component per layer, so the driver of that slot is
+// resolved once per launch into registers (type, component, amplitude and three waveform parameters,
+// per-instance overrides applied) and the steppers add its value to the constant field at each of the
+// step's distinct stage times (three for RK4, not four).  Layers with several time-dependent field
+// slots keep the general path (type = kFastGeneric).
+// ---------------------------------------------------------------------------------------
+constexpr int kFastNone = -2, kFastGeneric = -1;
+struct FastDrv {
+  int type;  // cmtjb_update of the resolved slot, kFastNone (no time-dependent field) or kFastGeneric
+  int comp;  // field component 0..2
+  double amp, p0, p1, p2;
+};
+
+template <uint32_t F> __device__ __forceinline__ FastDrv resolve_fast(const DevLayer &Lr, const RunParams &R, long long i) {
+  FastDrv f{kFastNone, 0, 0.0, 0.0, 0.0, 0.0};
+  if constexpr ((F & F_DYNI) != 0) {
+    const uint32_t mask = Lr.dynmask & 0xFFFu;
+    if (mask == 0) return f;
+    if (mask & (mask - 1)) {
+      f.type = kFastGeneric;
+      return f;
+    }
+    const int s = __ffs((int)mask) - 1;
+    const DevDriver &d = Lr.drv[s];
+    f.type = d.type;
+    f.comp = s % 3;
+    f.amp = ovr_or<F>(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, d.amplitude);
+    switch (d.type) {
+    case CMTJB_UPD_PULSE:
+      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PERIOD, i, d.period);
+      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_CYCLE, i, d.cycle);
+      break;
+    case CMTJB_UPD_SINE:
+    case CMTJB_UPD_POSINE:
+    case CMTJB_UPD_HALFSINE:
+      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_FREQUENCY, i, d.frequency);
+      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PHASE, i, d.phase);
+      break;
+    case CMTJB_UPD_STEP:
+      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTOP, i, d.timeStop);
+      break;
+    case CMTJB_UPD_TRAPEZOID:
+      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
+      f.p2 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_STEADYTIME, i, d.steadyTime);
+      break;
+    case CMTJB_UPD_GAUSSIMPULSE:
+    case CMTJB_UPD_GAUSSSTEP:
+      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
+      break;
+    default: f.type = kFastGeneric; break;  // custom etc.: not evaluable inline
+    }
+  }
+  return f;
+}
+
+// same expressions as driver_shape, on the resolved parameters
+__device__ __forceinline__ double fast_shape(const FastDrv &f, double t) {
+  switch (f.type) {
+  case CMTJB_UPD_PULSE: {
+    const int n = (int)(t / f.p0);
+    const double nT = n * f.p0;
+    return (nT <= t && t <= (nT + f.p1 * f.p0)) ? 1.0 : 0.0;
+  }
+  case CMTJB_UPD_SINE:
+  case CMTJB_UPD_POSINE:
+  case CMTJB_UPD_HALFSINE: return sin(2 * M_PI * t * f.p0 + f.p1);
+  case CMTJB_UPD_STEP: return (t >= f.p0 && t <= f.p1) ? 1.0 : 0.0;
+  case CMTJB_UPD_TRAPEZOID: {
+    const double t0 = f.p0, e = f.p1, st = f.p2;
+    if (t < t0) return 0.0;
+    if (t <= t0 + e) return (t - t0) / e;
+    if (t <= t0 + e + st) return 1.0;
+    if (t <= t0 + 2 * e + st) return 1.0 - (t - (t0 + e + st)) / e;
+    return 0.0;
+  }
+  case CMTJB_UPD_GAUSSIMPULSE: {
+    const double x = t - f.p0;
+    return exp(-(x * x) / (2 * (f.p1 * f.p1)));
+  }
+  case CMTJB_UPD_GAUSSSTEP: return 0.5 * (1 + erf((t - f.p0) / (sqrt(2.0) * f.p1)));
+  default: return 0.0;
+  }
+}
+
+// constant field + time-dependent field of layer l at time t (F_DYNI variants)
+template <uint32_t F>
+__device__ __forceinline__ d3 stage_field(const DevLayer &Lr, const RunParams &R, int l, long long i, double t, d3 Hc, const FastDrv &f) {
+  if (f.type == kFastNone) return Hc;
+  if (f.type == kFastGeneric) return dynamic_field<F>(Lr, R, l, StageTime{t, nullptr}, i, Hc);
+  const double v = driver_post(f.type, f.amp * fast_shape(f, t));
+  return mk(Hc.x + (f.comp == 0 ? v : 0.0), Hc.y + (f.comp == 1 ? v : 0.0), Hc.z + (f.comp == 2 ? v : 0.0));
+}
+
+// ---------------------------------------------------------------------------------------
 // External per-thread inputs of the coupled-system kernels (coupled_kernels.cuh): a Stack
 // replaces every layer's current driver each step (stack.hpp:79-91).  NoExt = plain junction.
 // ---------------------------------------------------------------------------------------
@@ -222,11 +322,12 @@ struct NoExt {
 // fused with solveLLG (junction.hpp:716-815).
 //   HAS_BOT / HAS_TOP: the layer has a neighbour on that side (else the reference passes 0).
 // ---------------------------------------------------------------------------------------
-template <uint32_t F, bool HAS_BOT, bool HAS_TOP, class Ext = NoExt>
+//   PRE: Hc already holds the complete field of the four plain drivers at this stage time (stage_field).
+template <uint32_t F, bool HAS_BOT, bool HAS_TOP, class Ext = NoExt, bool PRE = false>
 __device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, int l, long long i, StageTime t, d3 m, d3 bot,
                                     d3 top, d3 Hc, const Ext &ext = Ext()) {
   static_assert((F & F_DEMAG_FULL) == 0 || (F & F_NOFOLD) != 0, "a full demag tensor cannot be folded into the diagonal operator");
-  d3 H = dynamic_field<F>(Lr, R, l, t, i, Hc);
+  d3 H = PRE ? Hc : dynamic_field<F>(Lr, R, l, t, i, Hc);
   const d3 a = ld3(Lr.anis);
   if constexpr ((F & F_NOFOLD) != 0) {  // K1 (junction.hpp:638-643)
     const double K = slot_value<F>(Lr, R, CMTJB_SLOT_K1, t, i);

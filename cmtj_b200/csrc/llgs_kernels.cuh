@@ -183,30 +183,53 @@ __device__ __forceinline__ d3 layer_u(const DevModel<NL> &M, const RunParams &R,
   const d3 top = (l < NL - 1) ? nb.m[l < NL - 1 ? l + 1 : 0] : zero;
   return llg_u<F, (l > 0), (l < NL - 1), Ext>(M.L[l], R, l, i, t, m, bot, top, Hc[l], ext);
 }
+// the same with the complete plain-driver field of this stage time handed in (F_DYNI fast path)
+template <int NL, uint32_t F, int l, class Ext = NoExt>
+__device__ __forceinline__ d3 layer_u_pre(const DevModel<NL> &M, const RunParams &R, long long i, StageTime t, d3 m,
+                                          const State<NL> &nb, d3 Hstage, const Ext &ext = Ext()) {
+  const d3 zero = mk(0, 0, 0);
+  const d3 bot = (l > 0) ? nb.m[l > 0 ? l - 1 : 0] : zero;
+  const d3 top = (l < NL - 1) ? nb.m[l < NL - 1 ? l + 1 : 0] : zero;
+  return llg_u<F, (l > 0), (l < NL - 1), Ext, true>(M.L[l], R, l, i, t, m, bot, top, Hstage, ext);
+}
 
 // RK4: Layer::rk4_step (junction.hpp:1017-1041) under runMultiLayerSolver (:1682-1696):
 // neighbours frozen at their pre-step values for all four stages (Jacobi).
 template <int NL, uint32_t F, int l, class Ext = NoExt>
 __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &R, long long i, const double *row, double t,
-                                        const State<NL> &S0, const d3 *Hc, d3 &m4, const Ext &ext = Ext()) {
+                                        const State<NL> &S0, const d3 *Hc, d3 &m4, const Ext &ext = Ext(),
+                                        const FastDrv *fd = nullptr) {
   const DevLayer &Lr = M.L[l];
   const double h = Lr.h;  // llg * dt: dm = h * u
   const d3 m0 = S0.m[l];
   const StageTime t0{t, row}, t1{t + 0.5 * R.dt, row + R.dyn_ncols}, t2{t + R.dt, row + 2 * R.dyn_ncols};
-  const d3 u1 = layer_u<NL, F, l, Ext>(M, R, i, t0, m0, S0, Hc, ext);
-  const d3 u2 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u1, Lr.h_half, m0), S0, Hc, ext);
-  const d3 u3 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u2, Lr.h_half, m0), S0, Hc, ext);
-  m4 = axpy(u3, h, m0);  // where the reference's cached log values come from (energy log)
-  const d3 u4 = layer_u<NL, F, l, Ext>(M, R, i, t2, m4, S0, Hc, ext);
+  d3 u1, u2, u3, u4;
+  if ((F & F_DYNI) != 0 && fd != nullptr) {
+    // the plain-driver field at the step's three distinct stage times, from the resolved driver
+    const d3 H0 = stage_field<F>(Lr, R, l, i, t0.t, Hc[l], fd[l]), H1 = stage_field<F>(Lr, R, l, i, t1.t, Hc[l], fd[l]),
+             H2 = stage_field<F>(Lr, R, l, i, t2.t, Hc[l], fd[l]);
+    u1 = layer_u_pre<NL, F, l, Ext>(M, R, i, t0, m0, S0, H0, ext);
+    u2 = layer_u_pre<NL, F, l, Ext>(M, R, i, t1, axpy(u1, Lr.h_half, m0), S0, H1, ext);
+    u3 = layer_u_pre<NL, F, l, Ext>(M, R, i, t1, axpy(u2, Lr.h_half, m0), S0, H1, ext);
+    m4 = axpy(u3, h, m0);
+    u4 = layer_u_pre<NL, F, l, Ext>(M, R, i, t2, m4, S0, H2, ext);
+  } else {
+    u1 = layer_u<NL, F, l, Ext>(M, R, i, t0, m0, S0, Hc, ext);
+    u2 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u1, Lr.h_half, m0), S0, Hc, ext);
+    u3 = layer_u<NL, F, l, Ext>(M, R, i, t1, axpy(u2, Lr.h_half, m0), S0, Hc, ext);
+    m4 = axpy(u3, h, m0);  // where the reference's cached log values come from (energy log)
+    u4 = layer_u<NL, F, l, Ext>(M, R, i, t2, m4, S0, Hc, ext);
+  }
   const d3 acc = mk(fma(2.0, u2.x + u3.x, u1.x + u4.x), fma(2.0, u2.y + u3.y, u1.y + u4.y), fma(2.0, u2.z + u3.z, u1.z + u4.z));
   return normalize3(axpy(acc, Lr.h_sixth, m0));
 }
 
 template <int NL, uint32_t F, int l = 0, class Ext = NoExt>
 __device__ __forceinline__ void rk4_all(const DevModel<NL> &M, const RunParams &R, long long i, const double *row, double t,
-                                        const State<NL> &S0, State<NL> &S1, const d3 *Hc, State<NL> &M4, const Ext &ext = Ext()) {
-  S1.m[l] = rk4_layer<NL, F, l, Ext>(M, R, i, row, t, S0, Hc, M4.m[l], ext);
-  if constexpr (l + 1 < NL) rk4_all<NL, F, l + 1, Ext>(M, R, i, row, t, S0, S1, Hc, M4, ext);
+                                        const State<NL> &S0, State<NL> &S1, const d3 *Hc, State<NL> &M4, const Ext &ext = Ext(),
+                                        const FastDrv *fd = nullptr) {
+  S1.m[l] = rk4_layer<NL, F, l, Ext>(M, R, i, row, t, S0, Hc, M4.m[l], ext, fd);
+  if constexpr (l + 1 < NL) rk4_all<NL, F, l + 1, Ext>(M, R, i, row, t, S0, S1, Hc, M4, ext, fd);
 }
 
 // Euler-Heun: Junction::eulerHeunSolverStep (junction.hpp:1709-1754)
@@ -273,10 +296,11 @@ __device__ __forceinline__ void heun_correct(const DevModel<NL> &M, const RunPar
 // them, everywhere else they are dead code.
 template <int NL, int SOLVER, uint32_t F>
 __device__ __forceinline__ void do_step(const DevModel<NL> &M, const RunParams &R, long long i, long long it,
-                                        const double *row, double t, State<NL> &S, const d3 *Hc, State<NL> &Em, State<NL> &Enb) {
+                                        const double *row, double t, State<NL> &S, const d3 *Hc, State<NL> &Em, State<NL> &Enb,
+                                        const FastDrv *fd) {
   State<NL> S1;
   if constexpr (SOLVER == CMTJB_RK4) {
-    rk4_all<NL, F>(M, R, i, row, t, S, S1, Hc, Em);
+    rk4_all<NL, F>(M, R, i, row, t, S, S1, Hc, Em, NoExt(), fd);
     Enb = S;
   } else if constexpr (SOLVER == CMTJB_EULER_HEUN) {
     euler_heun_all<NL, F>(M, R, i, it, row, t, S, S1, Hc);
@@ -307,6 +331,14 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
                 __ldcg(R.m_state + (3 * l + 2) * R.B + i));
     Hc[l] = constant_field(M.L[l], R, i);
   }
+  // F_DYNI RK4 variants (VSD maps): the single time-dependent field driver of each layer, resolved once
+  FastDrv fdrv[NL];
+  const FastDrv *fd = nullptr;
+  if constexpr ((F & F_DYNI) != 0 && SOLVER == CMTJB_RK4 && F != F_ALL) {
+#pragma unroll
+    for (int l = 0; l < NL; l++) fdrv[l] = resolve_fast<F>(M.L[l], R, i);
+    fd = fdrv;
+  }
   // sample k is written after step k*write_every (junction.hpp:1973-1980): step `it` writes when
   // it % write_every == 0, so ceil(x / write_every) samples precede step x
   const long long we = R.write_every;
@@ -328,7 +360,7 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
   for (long long it = it0; it < it1; ++it) {
     const double t = (double)it * R.dt;
     State<NL> Em, Enb;
-    do_step<NL, SOLVER, F>(M, R, i, it, row, t, S, Hc, Em, Enb);
+    do_step<NL, SOLVER, F>(M, R, i, it, row, t, S, Hc, Em, Enb, fd);
     if constexpr ((F & (F_DYN | F_DYNS)) != 0 && (F & F_DYNI) == 0) row += 3 * R.dyn_ncols;
     if (until_write == 0) {
       if (logging) write_sample<NL>(M, R, S, sample, i);

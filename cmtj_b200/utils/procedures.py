@@ -61,15 +61,22 @@ def _spectrum_bins(n: int, int_step: float, max_frequency: float):
     return findx, freqs[findx]
 
 
-def spectrum_device(signal, int_step: float, max_frequency: float):
+def spectrum_device(signal, int_step: float, max_frequency: float, slice_bytes: float = 2e9):
     """|FFT| of B real series stored [n, B] on the device, restricted like compute_spectrum_strip.
-    Returns (CUDA tensor [K, B], freqs [K,1])."""
+    Returns (CUDA tensor [K, B], freqs [K,1]).  The transform runs over column slices whose complex
+    half-spectrum stays below ``slice_bytes``: only the K bins up to ``max_frequency`` are kept, so a
+    whole-sweep projection log (tens of GB) never needs a second buffer of its own size."""
     torch = _torch()
-    n = int(signal.shape[0])
+    n, B = int(signal.shape[0]), int(signal.shape[1])
     findx, freqs = _spectrum_bins(n, int_step, max_frequency)
-    half = torch.fft.rfft(signal, dim=0)[: n // 2]
     idx = torch.from_numpy(findx.ravel()).to(signal.device)
-    return half.index_select(0, idx).abs(), freqs
+    out = torch.empty((int(idx.numel()), B), dtype=torch.float64, device=signal.device)
+    cols = max(1, int(slice_bytes // max(8 * n, 1)))
+    for lo in range(0, B, cols):
+        hi = min(B, lo + cols)
+        half = torch.fft.rfft(signal[:, lo:hi], dim=0)[: n // 2]
+        out[:, lo:hi] = half.index_select(0, idx).abs()
+    return out, freqs
 
 
 def compute_spectrum_strip(input_m, int_step: float, max_frequency: float):
@@ -241,7 +248,7 @@ def PIMM_procedure(
     static_only: bool = False,
     carry_state: bool = False,
     device: int = 0,
-    memory_budget: float = 24e9,
+    memory_budget: float = 100e9,
 ) -> Tuple[np.ndarray, np.ndarray, Dict[str, Any]]:
     """Pulse-induced microwave magnetometry over a field sweep (procedures.py:42-204): returns
     ``(spectrum [n_H, n_f], frequencies [n_f, 1], other_data)`` with other_data keys ``H``, ``Rx``,
@@ -281,7 +288,9 @@ def PIMM_procedure(
     else:
         m0 = _disturbed(junction, layer_ids, Hvecs.shape[0], disturbance)
         n_series = 0 if static_only else (1 + L if full_output else 1)
-        per_inst = 8.0 * n_total * (3.0 * n_series + (2.0 * (3 * L + 3) if full_output else 0.0)) + 8.0 * 200 * (3 * L + 3)
+        # device bytes per instance: the projection log(s), the full-rate log when full_output, the last-n log
+        # (twice: the weighted m_traj copy handed back to the host is staged on the device)
+        per_inst = 8.0 * n_total * (n_series + (2.0 * (3 * L + 3) if full_output else 0.0)) + 8.0 * 200 * (3 * L + 3)
         for lo, hi in _instance_chunks(Hvecs.shape[0], per_inst, memory_budget):
             parts.append(run(Hvecs[lo:hi], {k: v[lo:hi] for k, v in m0.items()}))
         if parts:

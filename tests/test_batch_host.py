@@ -79,3 +79,16 @@ def test_batch_argument_checks(on_oracle):
         b.run(1e-9, 1e-12, 1e-13)
     empty = cmtj_b200.JunctionBatch(j, 0)
     assert empty.run(1e-10, 1e-13, 1e-13)["free_mx"].shape == (1000, 0)
+
+
+def test_cpulist_parsing_and_affinity_helpers_are_safe_without_a_gpu():
+    from cmtj_b200 import _numa
+
+    assert _numa._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _numa._parse_cpulist("") == []
+    # no CUDA device here: nothing is known, nothing is changed
+    import os
+
+    before = os.sched_getaffinity(0)
+    assert _numa.bind_host_to_gpu(0) is None or os.sched_getaffinity(0) <= before
+    os.sched_setaffinity(0, before)
