@@ -145,7 +145,7 @@ def test_short_time_diffusion_variance(ref):
 def test_thermal_fmr_psd(ref):
     """Thermally excited precession: Welch-averaged PSD of m_x(t) around the resonance line, GPU
     (2048 trajectories) vs reference (48 trajectories); the ratio of the band-integrated power must
-    be within 4 sigma of 1 and the peak must sit in the same frequency bin (+-1)."""
+    be within 4 sigma of 1 and the line must sit at the same frequency (band centroid within 4 standard errors)."""
     steps, n_gpu, n_ref = 8192, 2048, 48
 
     def build(mod):
@@ -169,9 +169,16 @@ def test_thermal_fmr_psd(ref):
 
     Pg, Pr = psd(yg), psd(yr)
     pg, pr = Pg.mean(axis=1), Pr.mean(axis=1)
-    kg, kr = int(np.argmax(pg[1:])) + 1, int(np.argmax(pr[1:])) + 1
-    assert abs(kg - kr) <= 1, (kg, kr)
+    kg = int(np.argmax(pg[1:])) + 1  # 2048-trajectory average: the line position is well resolved
     lo, hi = max(kg - 6, 1), kg + 7
+    # line position: power-weighted centroid of the band per trajectory, means compared at 4 standard errors
+    # (the argmax of the 48-trajectory reference average alone wanders by a couple of bins: each bin of it
+    # is a chi-square estimate with a 14 % relative spread, and the reference cannot be seeded)
+    k = np.arange(lo, hi)[:, None]
+    cg, cr = (k * Pg[lo:hi]).sum(axis=0) / Pg[lo:hi].sum(axis=0), (k * Pr[lo:hi]).sum(axis=0) / Pr[lo:hi].sum(axis=0)
+    se_c = math.sqrt(cg.var() / n_gpu + cr.var() / n_ref)
+    assert abs(cg.mean() - cr.mean()) < max(4 * se_c, 0.25), (cg.mean(), cr.mean(), se_c)
+    assert abs(int(np.argmax(pr[lo:hi])) + lo - kg) <= 3, (kg, int(np.argmax(pr[lo:hi])) + lo)
     # band power per trajectory -> mean and standard error on both sides
     bg, br = Pg[lo:hi].sum(axis=0), Pr[lo:hi].sum(axis=0)
     se = math.sqrt(bg.var() / n_gpu / bg.mean() ** 2 + br.var() / n_ref / br.mean() ** 2)
