@@ -366,14 +366,22 @@ def main():
             bh.m_state[...] = m_init
             return bh.run(T, DT, wf, out=host_log)
 
-        for _ in range(2):
+        # warm-up: the pinned allocation above leaves the GPU idle for seconds; W untimed steps bring the
+        # clocks back up before the timed region (sampled below like the device leg)
+        for _ in range(max(args.warmup, 3)):
             e2e_step()
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
         barrier()
         t0 = time.perf_counter()
+        each = []
         for _ in range(args.steps):
+            t_s = time.perf_counter()
             out = e2e_step()
+            each.append(1e3 * (time.perf_counter() - t_s))
         torch.cuda.synchronize(dev)
         dt_e2e = time.perf_counter() - t0
+        clocks_e2e = sampler2.stop(t0, time.perf_counter())
         checksum = float(out["free_mz"][-1].sum())  # the result is read on the host
         t = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -386,6 +394,8 @@ def main():
             "ms_per_step": 1e3 * float(t.item()) / args.steps,
             "api": "JunctionBatch.run -> cmtjb_run_host (pinned host log buffer, time-chunked D2H overlap)",
             "checksum_free_mz_last": checksum,
+            "ms_each": each,
+            "clocks": clocks_e2e,
             "pcie_d2h_gbs_measured": d2h_gbs,
             "host_numa_binding": f"{len(bound)} GPU-local CPUs during pinned allocation" if bound else "none (single node or unknown)",
         }

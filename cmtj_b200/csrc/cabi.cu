@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cmath>
 #include <mutex>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -838,14 +839,19 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   CUDA_TRY(cudaSetDevice(device));
   const long long B = args->n_instances;
   if (B <= 0) return CMTJB_OK;
+  const bool trace_host = std::getenv("CMTJB_TRACE_HOST") != nullptr;
+  const auto wall0 = std::chrono::steady_clock::now();
+  auto wall_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
   const size_t nm = (size_t)jn->n_layers * 3 * B * sizeof(double);
   const bool want_log = (args->log_mode == CMTJB_LOG_FULL || args->log_mode == CMTJB_LOG_ENERGY) && log && plan.n_samples > 0;
   const size_t nlog = want_log ? (size_t)plan.n_channels * plan.n_samples * B * sizeof(double) : 0;
-  // time chunking of large fixed-step logs (see below): ~768 MB per chunk, at least 16 chunks of >= 1 sample
+  // time chunking of large fixed-step logs (see below): at most ~768 MB per chunk and at least 32 chunks (the
+  // copy of the LAST chunk is the only one not hidden behind compute), each of >= 1 sample
   int n_chunks = 1;
   if (want_log && !plan.variable_samples && nlog > ((size_t)64 << 20) && plan.n_samples >= 16) {
     const long long by_size = (long long)((nlog + ((size_t)768 << 20) - 1) / ((size_t)768 << 20));
-    n_chunks = (int)std::min<long long>(plan.n_samples, std::max<long long>(std::min<long long>(16, plan.n_samples / 4), by_size));
+    n_chunks = (int)std::min<long long>(plan.n_samples, std::max<long long>(std::min<long long>(32, plan.n_samples / 4), by_size));
+    if (const char *c = std::getenv("CMTJB_HOST_CHUNKS")) n_chunks = (int)std::max<long long>(2, std::min<long long>(std::atoll(c), plan.n_samples));  // tuning knob
   }
   const bool chunked = n_chunks > 1;
   const long long chunk_samples = chunked ? (plan.n_samples + n_chunks - 1) / n_chunks + 1 : plan.n_samples;
@@ -892,6 +898,7 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     CUDA_TRY(cudaMemcpy(d_cust, args->custom_table, n_cust, cudaMemcpyHostToDevice));
     a.custom_table = d_cust;
   }
+  if (trace_host) std::fprintf(stderr, "[cmtjb] host: inputs staged at %.2f ms\n", wall_ms());
   if (!chunked) {
     rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, d_log, d_status, d_ns, d_tlog, nullptr, nullptr);
     if (rc) return rc;
@@ -908,6 +915,12 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     const long long we = plan.write_every, S0 = a.start_iteration;
     const long long i0 = ((S0 + we - 1) / we) * we;  // iteration of this run's sample 0
     std::vector<cudaEvent_t> evs;
+    const bool trace = std::getenv("CMTJB_TRACE_HOST") != nullptr;
+    cudaEvent_t t_start = nullptr;
+    if (trace) {
+      cudaEventCreate(&t_start);
+      cudaEventRecord(t_start, sc);
+    }
     cudaEvent_t copied[2] = {nullptr, nullptr};  // buffer b has been drained to the host
     for (int c = 0; c < n_chunks && rc == CMTJB_OK; c++) {
       const long long s0 = plan.n_samples * c / n_chunks, s1 = plan.n_samples * (c + 1) / n_chunks;
@@ -921,7 +934,7 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
       rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, buf, d_status, d_ns, d_tlog, sc, nullptr, &sp);
       if (rc) break;
       cudaEvent_t ev;
-      cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev, trace ? cudaEventDefault : cudaEventDisableTiming);
       evs.push_back(ev);
       cudaEventRecord(ev, sc);
       cudaStreamWaitEvent(sd, ev, 0);
@@ -929,12 +942,23 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
         cudaMemcpyAsync(log + ((size_t)ch * plan.n_samples + s0) * B, buf + (size_t)ch * chunk_samples * B,
                         (size_t)(s1 - s0) * B * sizeof(double), cudaMemcpyDeviceToHost, sd);
       cudaEvent_t done;
-      cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&done, trace ? cudaEventDefault : cudaEventDisableTiming);
       evs.push_back(done);
       cudaEventRecord(done, sd);
       copied[c & 1] = done;
     }
+    if (trace_host) std::fprintf(stderr, "[cmtjb] host: all chunks enqueued at %.2f ms\n", wall_ms());
     cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sd);
+    if (trace_host) std::fprintf(stderr, "[cmtjb] host: streams drained at %.2f ms\n", wall_ms());
+    if (trace && rc == CMTJB_OK) {  // CMTJB_TRACE_HOST=1: when each chunk finished integrating / copying (ms from the start)
+      for (size_t k = 0; k + 1 < evs.size(); k += 2) {
+        float a_ms = 0, b_ms = 0;
+        cudaEventElapsedTime(&a_ms, t_start, evs[k]);
+        cudaEventElapsedTime(&b_ms, t_start, evs[k + 1]);
+        std::fprintf(stderr, "[cmtjb] chunk %zu: integrated %.1f ms, copied %.1f ms\n", k / 2, a_ms, b_ms);
+      }
+    }
+    if (t_start) cudaEventDestroy(t_start);
     for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
     cudaStreamDestroy(sc);
     cudaStreamDestroy(sd);
@@ -952,6 +976,7 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     st = st_local.data();
   }
   CUDA_TRY(cudaMemcpy(st, d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (trace_host) std::fprintf(stderr, "[cmtjb] host: done at %.2f ms\n", wall_ms());
   for (long long i = 0; i < B; i++)
     if (st[i]) return fail(CMTJB_ENAN, "NAN magnetisation");
   return CMTJB_OK;
