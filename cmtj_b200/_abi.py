@@ -385,6 +385,13 @@ _cuda: Optional[Backend] = None
 _cuda_lib: Optional[C.CDLL] = None
 
 
+def last_variant() -> str:
+    """Name of the kernel variant the calling thread's last sweep launch selected (``cmtjb_last_variant``)."""
+    lib = load_library()
+    lib.cmtjb_last_variant.restype = C.c_char_p
+    return (lib.cmtjb_last_variant() or b"").decode()
+
+
 def load_library() -> C.CDLL:
     """dlopen the in-tree CUDA library; raises if it has not been built."""
     global _cuda_lib

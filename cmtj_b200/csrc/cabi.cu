@@ -30,7 +30,8 @@ int variants_dopri(const Variant **out);
 int variants_post(const Variant **out);
 
 thread_local std::string g_err;
-std::atomic<long long> g_launches{0};  // kernels launched by this library (bench.py: gpu_launches)
+std::atomic<long long> g_launches{0};
+thread_local std::string g_last_variant;  // name of the kernel variant of the calling thread's last sweep launch  // kernels launched by this library (bench.py: gpu_launches)
 
 int fail(int code, const std::string &msg) {
   g_err = msg;
@@ -126,11 +127,12 @@ bool layer_foldable(const cmtjb_layer_t &L, int l, const cmtjb_override_t *ovr, 
   return T[1] == 0 && T[2] == 0 && T[3] == 0 && T[5] == 0 && T[6] == 0 && T[7] == 0;
 }
 
-// which terms does this model need compiled in?
+// which terms does this model need compiled in?  Returns the union over the layers; `per_layer`
+// (optional, [n_layers]) receives each layer's own set (split variants, dev_model.h: F_SPLIT).
 uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
-                         const cmtjb_run_args_t *a, int solver) {
-  uint32_t F = 0;
+                         const cmtjb_run_args_t *a, int solver, uint32_t *per_layer = nullptr) {
   const int n = jn->n_layers;
+  uint32_t Fl[CMTJB_MAX_LAYERS] = {0};
   // a slot is "live" if its constant is non-zero, it is time dependent, or it is overridden
   auto live = [&](int l, int s) {
     const cmtjb_driver_t &d = layers[l].drivers[s];
@@ -139,8 +141,9 @@ uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
       if ((ovr[k].layer < 0 || ovr[k].layer == l) && ovr[k].slot == s) return true;
     return false;
   };
-  for (int l = 0; l < n; l++) {
+  for (int l = 0; l < n && l < CMTJB_MAX_LAYERS; l++) {
     const cmtjb_layer_t &L = layers[l];
+    uint32_t F = 0;
     if (live(l, CMTJB_SLOT_K2)) F |= F_K2;
     for (int s = CMTJB_SLOT_IEC_TOP; s <= CMTJB_SLOT_IECQ_BOTTOM; s++)
       if (live(l, s)) F |= F_IEC;
@@ -158,23 +161,36 @@ uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
     for (int s = 0; s < CMTJB_NSLOTS; s++)
       if (slot_dynamic(L.drivers[s])) F |= (s < CMTJB_SLOT_K1) ? F_DYN : F_DYNS;
     if (!layer_foldable(L, l, ovr, n_ovr)) F |= F_NOFOLD;
+    for (int k = 0; k < n_ovr; k++) {
+      if (!(ovr[k].layer < 0 || ovr[k].layer == l)) continue;
+      if (!(ovr[k].field == CMTJB_FIELD_CONSTANT && ovr[k].slot < CMTJB_SLOT_K1)) F |= F_OVR;
+      if (ovr[k].field == CMTJB_FIELD_CONSTANT) continue;
+      // a per-instance waveform parameter makes the driver non-uniform across the batch: the shared
+      // stage table cannot hold it.  Scalar slots keep the table for per-instance AMPLITUDE only.
+      const bool field_slot = ovr[k].slot < CMTJB_SLOT_K1;
+      if (!field_slot && ovr[k].field == CMTJB_FIELD_AMPLITUDE) continue;
+      if (slot_dynamic(L.drivers[ovr[k].slot])) F |= F_DYNI;
+    }
+    Fl[l] = F;
   }
-  for (int k = 0; k < n_ovr; k++) {
-    if (!(ovr[k].field == CMTJB_FIELD_CONSTANT && ovr[k].slot < CMTJB_SLOT_K1)) F |= F_OVR;
-    if (ovr[k].field == CMTJB_FIELD_CONSTANT) continue;
-    // a per-instance waveform parameter makes the driver non-uniform across the batch: the shared
-    // stage table cannot hold it.  Scalar slots keep the table for per-instance AMPLITUDE only.
-    const bool field_slot = ovr[k].slot < CMTJB_SLOT_K1;
-    if (!field_slot && ovr[k].field == CMTJB_FIELD_AMPLITUDE) continue;
-    for (int l = 0; l < n; l++)
-      if ((ovr[k].layer < 0 || ovr[k].layer == l) && slot_dynamic(layers[l].drivers[ovr[k].slot])) F |= F_DYNI;
+  uint32_t U = 0;
+  for (int l = 0; l < n && l < CMTJB_MAX_LAYERS; l++) U |= Fl[l];
+  if ((U & (F_DYN | F_DYNS)) && solver == CMTJB_DORMAND_PRINCE) U |= F_DYNI;  // adaptive time: no stage table
+  // one evaluation mode per launch: if any layer evaluates inline, every time-dependent driver does
+  if (U & F_DYNI) {
+    for (int l = 0; l < n && l < CMTJB_MAX_LAYERS; l++)
+      if (Fl[l] & (F_DYN | F_DYNS | F_DYNI)) Fl[l] = (Fl[l] & ~(F_DYN | F_DYNS)) | F_DYNI;
+    U &= ~(F_DYN | F_DYNS);
   }
-  if ((F & (F_DYN | F_DYNS)) && solver == CMTJB_DORMAND_PRINCE) F |= F_DYNI;  // adaptive time: no stage table
-  if (F & F_DYNI) F &= ~(F_DYN | F_DYNS);
-  return F;
+  if (per_layer)
+    for (int l = 0; l < n && l < CMTJB_MAX_LAYERS; l++) per_layer[l] = Fl[l];
+  return U;
 }
 
-const Variant *pick_variant(int nl, int solver, uint32_t need) {
+// `need`: union of the layers' needs plus launch-wide bits (F_POST, forced F_ALL); `per_layer`: each layer's own
+// needs, or null.  A plain variant covers the model if it contains `need`; a split variant (F_SPLIT) if every
+// layer's needs are contained in the term set that variant compiles for that layer.
+const Variant *pick_variant(int nl, int solver, uint32_t need, const uint32_t *per_layer = nullptr) {
   const Variant *tab = nullptr;
   int n = 0;
   switch (solver) {
@@ -187,8 +203,25 @@ const Variant *pick_variant(int nl, int solver, uint32_t need) {
   int best_extra = 1 << 30;
   for (int i = 0; i < n; i++) {
     const Variant &v = tab[i];
-    if (v.nl != nl || (v.features & need) != need) continue;
-    const int extra = __builtin_popcount(v.features & ~need);
+    if (v.nl != nl) continue;
+    int extra = 0;
+    if (v.features & F_SPLIT) {
+      if (!per_layer) continue;
+      const uint32_t launch_wide = need & ~F_BASEMASK;  // none today besides what F_BASEMASK already holds
+      if (launch_wide || (need & F_POST) != (v.features & F_POST)) continue;
+      bool ok = true;
+      for (int l = 0; l < nl && ok; l++) {
+        const uint32_t have = layer_mask(v.features, l) & ~(uint32_t)F_POST;
+        ok = (per_layer[l] & ~have) == 0;
+        extra += __builtin_popcount(have & ~per_layer[l]);
+      }
+      // the launch-wide evaluation mode must match: table variants need a table, inline ones must not mix
+      if (ok && ((need & F_DYNI) != 0) != ((v.features & F_DYNI) != 0)) ok = false;
+      if (!ok) continue;
+    } else {
+      if ((v.features & need) != need) continue;
+      extra = nl * __builtin_popcount(v.features & ~need);  // every layer carries the superfluous terms
+    }
     if (extra < best_extra) {
       best_extra = extra;
       best = &v;
@@ -537,20 +570,27 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
   if (jn->n_layers > 4) {
     std::snprintf(plan.variant, sizeof(plan.variant), "wide/L%d/F_ALL", jn->n_layers);
     plan.feature_mask = (int32_t)F_ALL;
+    g_last_variant = plan.variant;
     return run_wide(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, stream, span, post);
   }
-  uint32_t need = needed_features(jn, layers, ovr, n_ovr, a, plan.effective_solver);
+  uint32_t per_layer[CMTJB_MAX_LAYERS] = {0};
+  uint32_t need = needed_features(jn, layers, ovr, n_ovr, a, plan.effective_solver, per_layer);
+  bool split_ok = true;  // per-layer matching only when nothing below rewrites the need
   if (need & (F_DYN | F_DYNS)) {
     // the stage table costs 24 B per column per step; beyond 2 GiB evaluate inline instead
     size_t n_cols = 3 * (size_t)jn->n_layers;
     for (int l = 0; l < jn->n_layers; l++)
       for (int s = CMTJB_SLOT_K1; s < CMTJB_NSLOTS; s++) n_cols += slot_dynamic(layers[l].drivers[s]) ? 1 : 0;
     const long long steps = span ? span->it_end - span->it_begin : plan.total_iterations - a->start_iteration;
-    if (n_cols * (size_t)std::max<long long>(steps, 0) * 24 > ((size_t)2 << 30)) need = (need & ~(F_DYN | F_DYNS)) | F_DYNI;
+    if (n_cols * (size_t)std::max<long long>(steps, 0) * 24 > ((size_t)2 << 30)) {
+      need = (need & ~(F_DYN | F_DYNS)) | F_DYNI;
+      split_ok = false;
+    }
   }
-  const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel (testing)
-  if (force && std::strcmp(force, "full") == 0) need = F_ALL;
-  if (a->log_mode == CMTJB_LOG_ENERGY) need = F_ALL;  // the energy log lives in the general variants only
+  const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel; "nosplit": no split variants (testing)
+  if (force && std::strcmp(force, "full") == 0) need = F_ALL, split_ok = false;
+  if (force && std::strcmp(force, "nosplit") == 0) split_ok = false;
+  if (a->log_mode == CMTJB_LOG_ENERGY) need = F_ALL, split_ok = false;  // the energy log lives in the general variants only
   if (post) need |= F_POST;
   {
     int max_col = -1;
@@ -564,13 +604,14 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
                                    "with per-instance timing overrides or a driver table beyond 2 GiB");
     }
   }
-  const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need);
+  const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need, split_ok ? per_layer : nullptr);
   if (!v) {
     char buf[160];
     std::snprintf(buf, sizeof(buf), "no compiled kernel variant for %d layers, solver %d, features 0x%x", jn->n_layers,
                   plan.effective_solver, need);
     return fail(CMTJB_ENOTSUP, buf);
   }
+  g_last_variant = v->name;
   // the plan reports the variant of the (last) segment that still evaluates time-dependent drivers
   if (plan.variant[0] == 0 || (v->features & (F_DYN | F_DYNS | F_DYNI))) {
     plan.feature_mask = (int32_t)v->features;
@@ -755,6 +796,7 @@ int cmtjb_abi_version(void) { return CMTJB_ABI_VERSION; }
 const char *cmtjb_last_error(void) { return g_err.c_str(); }
 
 long long cmtjb_launch_count(void) { return g_launches.load(); }
+const char *cmtjb_last_variant(void) { return g_last_variant.c_str(); }
 
 int cmtjb_release_cache(void) {
   std::lock_guard<std::mutex> lock(g_slab_mu);

@@ -37,8 +37,25 @@ enum : uint32_t {
   F_ALL_TAB = F_ALL & ~F_DYNI,
   // fused post-processing of the sweep procedures (projection log, spin-diode IIR; cmtjb_post_t).
   // Not part of F_ALL: only the variants of variants_post.cu carry it.
-  F_POST = 1u << 14
+  F_POST = 1u << 14,
+  // Split variants: only the layers named in the 4-bit heavy set (bits 15..18, bit l = layer l) carry the
+  // full term set; the others are compiled with the field terms only (F_LIGHTSET: constant, batch-uniform
+  // parameters, no torque, no noise, no time-dependent driver, no override).  A CIMS stack has its SOT
+  // drive, per-instance amplitudes and step drivers on the free layer alone: the two pinned layers then
+  // cost what they cost in the lean sweep kernel, and the loop body shrinks by a third.
+  F_SPLIT = 1u << 19,
+  F_HEAVY_SHIFT = 15,
+  F_LIGHTSET = F_K2 | F_IEC | F_IDMI | F_DIPOLE | F_DEMAG_FULL | F_NOFOLD,
+  F_BASEMASK = (1u << 15) - 1
 };
+#define CMTJB_SPLIT(heavy_layers) (cmtjb::F_SPLIT | ((uint32_t)(heavy_layers) << cmtjb::F_HEAVY_SHIFT))
+// the term set compiled into layer l of a variant
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr uint32_t layer_mask(uint32_t F, int l) {
+  return ((F & F_SPLIT) != 0 && ((F >> F_HEAVY_SHIFT >> l) & 1u) == 0) ? (F & F_LIGHTSET) : (F & F_BASEMASK);
+}
 
 struct DevDriver {
   int32_t type;  // cmtjb_update

@@ -181,7 +181,7 @@ __device__ __forceinline__ d3 layer_u(const DevModel<NL> &M, const RunParams &R,
   const d3 zero = mk(0, 0, 0);
   const d3 bot = (l > 0) ? nb.m[l > 0 ? l - 1 : 0] : zero;
   const d3 top = (l < NL - 1) ? nb.m[l < NL - 1 ? l + 1 : 0] : zero;
-  return llg_u<F, (l > 0), (l < NL - 1), Ext>(M.L[l], R, l, i, t, m, bot, top, Hc[l], ext);
+  return llg_u<layer_mask(F, l), (l > 0), (l < NL - 1), Ext>(M.L[l], R, l, i, t, m, bot, top, Hc[l], ext);
 }
 // the same with the complete plain-driver field of this stage time handed in (F_DYNI fast path)
 template <int NL, uint32_t F, int l, class Ext = NoExt>
@@ -190,7 +190,7 @@ __device__ __forceinline__ d3 layer_u_pre(const DevModel<NL> &M, const RunParams
   const d3 zero = mk(0, 0, 0);
   const d3 bot = (l > 0) ? nb.m[l > 0 ? l - 1 : 0] : zero;
   const d3 top = (l < NL - 1) ? nb.m[l < NL - 1 ? l + 1 : 0] : zero;
-  return llg_u<F, (l > 0), (l < NL - 1), Ext, true>(M.L[l], R, l, i, t, m, bot, top, Hstage, ext);
+  return llg_u<layer_mask(F, l), (l > 0), (l < NL - 1), Ext, true>(M.L[l], R, l, i, t, m, bot, top, Hstage, ext);
 }
 
 // RK4: Layer::rk4_step (junction.hpp:1017-1041) under runMultiLayerSolver (:1682-1696):
@@ -204,10 +204,11 @@ __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &
   const d3 m0 = S0.m[l];
   const StageTime t0{t, row}, t1{t + 0.5 * R.dt, row + R.dyn_ncols}, t2{t + R.dt, row + 2 * R.dyn_ncols};
   d3 u1, u2, u3, u4;
-  if ((F & F_DYNI) != 0 && fd != nullptr) {
+  if ((layer_mask(F, l) & F_DYNI) != 0 && fd != nullptr) {
     // the plain-driver field at the step's three distinct stage times, from the resolved driver
-    const d3 H0 = stage_field<F>(Lr, R, l, i, t0.t, Hc[l], fd[l]), H1 = stage_field<F>(Lr, R, l, i, t1.t, Hc[l], fd[l]),
-             H2 = stage_field<F>(Lr, R, l, i, t2.t, Hc[l], fd[l]);
+    constexpr uint32_t FL = layer_mask(F, l);
+    const d3 H0 = stage_field<FL>(Lr, R, l, i, t0.t, Hc[l], fd[l]), H1 = stage_field<FL>(Lr, R, l, i, t1.t, Hc[l], fd[l]),
+             H2 = stage_field<FL>(Lr, R, l, i, t2.t, Hc[l], fd[l]);
     u1 = layer_u_pre<NL, F, l, Ext>(M, R, i, t0, m0, S0, H0, ext);
     u2 = layer_u_pre<NL, F, l, Ext>(M, R, i, t1, axpy(u1, Lr.h_half, m0), S0, H1, ext);
     u3 = layer_u_pre<NL, F, l, Ext>(M, R, i, t1, axpy(u2, Lr.h_half, m0), S0, H1, ext);
@@ -242,8 +243,8 @@ __device__ __forceinline__ void euler_heun_all(const DevModel<NL> &M, const RunP
   const StageTime t0{t, row};
   const d3 f = layer_u<NL, F, l, Ext>(M, R, i, t0, m0, S0, Hc, ext);
   d3 mn = axpy(f, Lr.llg * R.dt, m0);
-  if constexpr ((F & (F_THERMAL | F_ONEF)) != 0) {
-    const d3 dW = noise_dW<F, NL>(Lr, R, l, i, it, t0);
+  if constexpr ((layer_mask(F, l) & (F_THERMAL | F_ONEF)) != 0) {
+    const d3 dW = noise_dW<layer_mask(F, l), NL>(Lr, R, l, i, it, t0);
     const double gs = Lr.llg * R.sqrt_dt;
     const d3 g = stoch_u(Lr, m0, dW);
     const d3 gp = stoch_u(Lr, axpy(g, gs, m0), dW);
@@ -265,8 +266,8 @@ __device__ __forceinline__ void heun_predict(const DevModel<NL> &M, const RunPar
   const d3 f = layer_u<NL, F, l>(M, R, i, t0, m0, S0, Hc);
   Fn.m[l] = f;
   d3 mp = axpy(f, Lr.llg * R.dt, m0);
-  if constexpr ((F & (F_THERMAL | F_ONEF)) != 0) {
-    const d3 dW = noise_dW<F, NL>(Lr, R, l, i, it, t0);
+  if constexpr ((layer_mask(F, l) & (F_THERMAL | F_ONEF)) != 0) {
+    const d3 dW = noise_dW<layer_mask(F, l), NL>(Lr, R, l, i, it, t0);
     const d3 g = stoch_u(Lr, m0, dW);
     dWs.m[l] = dW;
     Gn.m[l] = g;
@@ -283,7 +284,7 @@ __device__ __forceinline__ void heun_correct(const DevModel<NL> &M, const RunPar
   const StageTime t2{t + R.dt, row + 2 * R.dyn_ncols};
   const d3 f2 = layer_u<NL, F, l>(M, R, i, t2, P.m[l], P, Hc);
   d3 mn = axpy(Fn.m[l] + f2, 0.5 * (Lr.llg * R.dt), S0.m[l]);
-  if constexpr ((F & (F_THERMAL | F_ONEF)) != 0) {
+  if constexpr ((layer_mask(F, l) & (F_THERMAL | F_ONEF)) != 0) {
     const d3 g2 = stoch_u(Lr, P.m[l], dWs.m[l]);
     mn = axpy(Gn.m[l] + g2, 0.5 * (Lr.llg * R.sqrt_dt), mn);
   }

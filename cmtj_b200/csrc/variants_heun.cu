@@ -9,10 +9,14 @@ static const Variant kTable[] = {
     CMTJB_FIXED(1, CMTJB_HEUN, F_ALL_TAB),
     CMTJB_FIXED(1, CMTJB_HEUN, F_ALL),
     CMTJB_FIXED(2, CMTJB_HEUN, F_IEC),
+    CMTJB_FIXED(2, CMTJB_HEUN, F_ALL_TAB | CMTJB_SPLIT(1)),
     CMTJB_FIXED(2, CMTJB_HEUN, F_ALL_TAB),
     CMTJB_FIXED(2, CMTJB_HEUN, F_ALL),
     CMTJB_FIXED(3, CMTJB_HEUN, F_IEC),
     CMTJB_FIXED(3, CMTJB_HEUN, F_IEC | F_SOT | F_K2 | F_OVR | F_DYN | F_DYNS),
+    // split: SOT drive / overrides / step drivers on the free layer only (CIMS stability diagram, bench S4)
+    CMTJB_FIXED(3, CMTJB_HEUN, F_IEC | F_SOT | F_K2 | F_OVR | F_DYN | F_DYNS | CMTJB_SPLIT(1)),
+    CMTJB_FIXED(3, CMTJB_HEUN, F_ALL_TAB | CMTJB_SPLIT(1)),
     CMTJB_FIXED(3, CMTJB_HEUN, F_ALL_TAB),
     CMTJB_FIXED(3, CMTJB_HEUN, F_ALL),
     CMTJB_FIXED(4, CMTJB_HEUN, F_ALL_TAB),

@@ -12,10 +12,12 @@ static const Variant kTable[] = {
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN | F_DYNS | F_NOFOLD),
+    CMTJB_FIXED(2, CMTJB_RK4, F_ALL_TAB | CMTJB_SPLIT(1)),
     CMTJB_FIXED(2, CMTJB_RK4, F_ALL_TAB),
     CMTJB_FIXED(2, CMTJB_RK4, F_ALL),
     CMTJB_FIXED(3, CMTJB_RK4, F_IEC),
     CMTJB_FIXED(3, CMTJB_RK4, F_IEC | F_DYN),
+    CMTJB_FIXED(3, CMTJB_RK4, F_ALL_TAB | CMTJB_SPLIT(1)),  // torque / drivers / overrides on the free layer only
     CMTJB_FIXED(3, CMTJB_RK4, F_ALL_TAB),
     CMTJB_FIXED(3, CMTJB_RK4, F_ALL),
     CMTJB_FIXED(4, CMTJB_RK4, F_ALL_TAB),

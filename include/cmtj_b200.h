@@ -322,6 +322,9 @@ int cmtjb_compute_gmr_device(double Rp, double Rap, const double *m1, const doub
 
 /* Number of kernels this library has launched in this process (monotonic). */
 long long cmtjb_launch_count(void);
+/* Name of the kernel variant (layer count / solver / compiled term set) the calling thread's last sweep launch
+ * selected; diagnostic.  cmtjb_plan() cannot know it in general: per-instance overrides change the choice. */
+const char *cmtjb_last_variant(void);
 /* cmtjb_run_host keeps one device scratch slab per device between calls; this frees them. */
 int cmtjb_release_cache(void);
 

@@ -407,3 +407,35 @@ def test_many_layer_batch_with_overrides():
     for k in logs[1]:
         if k != "time":
             assert helpers.max_rel_err(logs[0][k], logs[1][k]) <= TOL, k
+
+
+@pytest.mark.parametrize("mode", ["Heun", "RK4"])
+def test_split_variant_torque_on_the_free_layer_only(mode):
+    """CIMS-like stack (bench S4 shape): SOT step drivers with per-instance amplitudes on the free layer,
+    per-instance field on all layers; the pinned layers run the field-only term set (split variant).
+    Switching trajectories amplify rounding, so the bound is the conditioning-aware one of _three."""
+    from cmtj_b200 import _abi
+
+    n = 12
+    cur, fld = np.meshgrid(np.linspace(-1, 1, n), np.linspace(-300e3, 300e3, n))
+    B = n * n
+    variants = []
+
+    def fn(eps):
+        j = helpers.tri_layer_mtj(cmtj_b200)
+        j.setLayerFieldLikeTorqueDriver("free", cmtj_b200.stepDriver(0, 1e3, 0, 0.2e-9))
+        j.setLayerDampingLikeTorqueDriver("free", cmtj_b200.stepDriver(0, 16e3, 0, 0.2e-9))
+        j.getLayer("free").setReferenceLayer(cmtj_b200.CVector(0, 1, 0))
+        if eps:
+            _perturb(j, eps)
+        b = cmtj_b200.JunctionBatch(j, B)
+        b.set_override("free", "fieldLike", "amplitude", 1e3 * cur.ravel() ** 2)
+        b.set_override("free", "dampingLike", "amplitude", 16e3 * cur.ravel())
+        b.set_external_field("all", np.stack([fld.ravel(), np.zeros(B), np.zeros(B)], axis=1))
+        out = dict(b.run(0.4e-9, 1e-12, 4e-12, solverMode=getattr(cmtj_b200.SolverMode, mode)))
+        variants.append(_abi.last_variant())
+        return out
+
+    g, w, sens = _three(fn)
+    assert "CMTJB_SPLIT(1)" in variants[0], variants
+    _check(g, w, sens=sens)

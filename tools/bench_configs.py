@@ -86,7 +86,7 @@ def s2(scale):
         out = b.run_device(T, 1e-13, we * 1e-13 * (1 + 1e-9))["_log"]
         secs = timed(lambda: b.run_device(T, 1e-13, we * 1e-13 * (1 + 1e-9), out=out))
         emit(f"S2 vsd 1-layer sine Oersted RK4, {tag}", B * steps, secs, 225.0, out.numel() * 8,
-             {"instances": B, "steps": steps, "variant": b.last_plan.variant.decode()})
+             {"instances": B, "steps": steps, "variant": _abi.last_variant()})
         del out
 
 
@@ -104,7 +104,7 @@ def s3(scale):
         sm = getattr(m.SolverMode, mode)
         secs = timed(lambda: b.run_device(T, 1e-13, T, solverMode=sm, log=False, seed=1))
         emit(f"S3 p-bit 1-layer STT 300 K {mode}, final state only", B * steps, secs, float(flop), 0,
-             {"instances": B, "steps": steps, "variant": b.last_plan.variant.decode()})
+             {"instances": B, "steps": steps, "variant": _abi.last_variant()})
 
 
 def s4(scale):
@@ -124,7 +124,7 @@ def s4(scale):
     T = steps * 1e-12 * (1 + 1e-9)
     secs = timed(lambda: b.run_device(T, 1e-12, T, solverMode=m.SolverMode.Heun, log=False), reps=2)
     emit("S4 CIMS 3-layer Heun, SOT step drivers, final state only", 3 * B * steps, secs, 2 * (3 + 9 + 20 + 27 + 34 + 8) + 33, 0,
-         {"instances": B, "grid": [n, n], "steps": steps, "variant": b.last_plan.variant.decode()})
+         {"instances": B, "grid": [n, n], "steps": steps, "variant": _abi.last_variant()})
 
 
 def _lattice(n_side, pitch=100e-9):
