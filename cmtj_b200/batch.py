@@ -184,6 +184,24 @@ class JunctionBatch:
             tab[k].layer, tab[k].slot, tab[k].field, tab[k].values = l, s, f, pointers[k]
         return tab, n
 
+    def selected_variant(self, totalTime: float, timeStep: float = 1e-13, writeFrequency: float = 1e-11,
+                         solverMode: SolverMode = SolverMode.RK4) -> str:
+        """Name of the compiled kernel variant a run with these arguments and the current per-instance overrides
+        would launch for its driver-evaluating segment (``cmtjb_select_variant``; host logic, no GPU needed)."""
+        lib = _abi.load_library()
+        jn, layers = self.junction._pack()
+        a = self._args(totalTime, timeStep, writeFrequency, solverMode, True, 0, None)
+        tab, n = self._override_table([v.ctypes.data for v in self._overrides.values()])
+        name = C.create_string_buffer(96)
+        f = lib.cmtjb_select_variant
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_char_p, C.c_int32]
+        rc = f(C.byref(jn), layers, tab, n, C.byref(a), name, 96)
+        if rc != _abi.OK:
+            lib.cmtjb_last_error.restype = C.c_char_p
+            raise RuntimeError((lib.cmtjb_last_error() or b"").decode())
+        return name.value.decode()
+
     def _check_onef(self):
         if any(l.noiseScale != 0 for l in self.junction._layers):
             raise NotImplementedError("1/f^alpha noise is only wired for single-instance Junction.runSimulation")

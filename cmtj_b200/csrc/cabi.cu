@@ -798,6 +798,27 @@ const char *cmtjb_last_error(void) { return g_err.c_str(); }
 long long cmtjb_launch_count(void) { return g_launches.load(); }
 const char *cmtjb_last_variant(void) { return g_last_variant.c_str(); }
 
+int cmtjb_select_variant(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *overrides,
+                         int32_t n_overrides, const cmtjb_run_args_t *args, char *name, int32_t name_size) {
+  if (!name || name_size <= 0) return fail(CMTJB_EINVAL, "null argument");
+  cmtjb_plan_t plan;
+  int rc = make_plan(jn, layers, args, &plan);
+  if (rc) return rc;
+  rc = check_overrides(jn, overrides, n_overrides);
+  if (rc) return rc;
+  if (jn->n_layers > 4) {
+    std::snprintf(name, name_size, "wide/L%d/F_ALL", jn->n_layers);
+    return CMTJB_OK;
+  }
+  uint32_t per_layer[CMTJB_MAX_LAYERS] = {0};
+  uint32_t need = needed_features(jn, layers, overrides, n_overrides, args, plan.effective_solver, per_layer);
+  if (args->log_mode == CMTJB_LOG_ENERGY) need = F_ALL;
+  const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need, args->log_mode == CMTJB_LOG_ENERGY ? nullptr : per_layer);
+  if (!v) return fail(CMTJB_ENOTSUP, "no compiled kernel variant covers this model");
+  std::snprintf(name, name_size, "%s", v->name);
+  return CMTJB_OK;
+}
+
 int cmtjb_release_cache(void) {
   std::lock_guard<std::mutex> lock(g_slab_mu);
   for (int d = 0; d < 64; d++)

@@ -325,6 +325,11 @@ long long cmtjb_launch_count(void);
 /* Name of the kernel variant (layer count / solver / compiled term set) the calling thread's last sweep launch
  * selected; diagnostic.  cmtjb_plan() cannot know it in general: per-instance overrides change the choice. */
 const char *cmtjb_last_variant(void);
+/* Which compiled variant a run of this model with these overrides would launch for its driver-evaluating
+ * segment (no CUDA call; host logic only, used by the CPU tests of the selection rules).  `overrides[k].values`
+ * are not dereferenced. */
+int cmtjb_select_variant(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *overrides,
+                         int32_t n_overrides, const cmtjb_run_args_t *args, char *name, int32_t name_size);
 /* cmtjb_run_host keeps one device scratch slab per device between calls; this frees them. */
 int cmtjb_release_cache(void);
 

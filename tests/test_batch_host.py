@@ -92,3 +92,45 @@ def test_cpulist_parsing_and_affinity_helpers_are_safe_without_a_gpu():
     before = os.sched_getaffinity(0)
     assert _numa.bind_host_to_gpu(0) is None or os.sched_getaffinity(0) <= before
     os.sched_setaffinity(0, before)
+
+
+def test_kernel_variant_selection_rules():
+    """Which compiled variant covers which model (cabi.cu: needed_features per layer + pick_variant).  Host
+    logic only: the library is dlopen'ed, no CUDA call is made."""
+    import cmtj_b200 as cm
+
+    dt = 1e-13
+    # S1: two-layer PIMM sweep, per-instance field, step pulse on all layers -> lean IEC + table
+    j = helpers.two_layer_mtj(cm)
+    j.setLayerOerstedFieldDriver("all", cm.AxialDriver(cm.NullDriver(), cm.NullDriver(), cm.ScalarDriver.getStepDriver(0, 50, 0, 3 * dt)))
+    b = cm.JunctionBatch(j, 4)
+    b.set_external_field("all", np.zeros((4, 3)))
+    assert b.selected_variant(1e-9, dt, 1e-11) == "CMTJB_RK4/L2/F_IEC | F_DYN"
+    # no time-dependent driver: the lean variant
+    b0 = cm.JunctionBatch(helpers.two_layer_mtj(cm), 4)
+    assert b0.selected_variant(1e-9, dt, 1e-11) == "CMTJB_RK4/L2/F_IEC"
+    # per-instance frequency: the shared stage table cannot hold it -> inline evaluation (general variant)
+    j = helpers.two_layer_mtj(cm)
+    j.setLayerOerstedFieldDriver("all", cm.AxialDriver(cm.NullDriver(), cm.ScalarDriver.getSineDriver(0, 50, 5e9, 0), cm.NullDriver()))
+    b = cm.JunctionBatch(j, 4)
+    b.set_override("all", "Hoe_y", "frequency", np.linspace(1e9, 4e9, 4))
+    assert "F_ALL" in b.selected_variant(1e-9, dt, 1e-11) and "SPLIT" not in b.selected_variant(1e-9, dt, 1e-11)
+    # CIMS shape: torque drivers and per-instance amplitudes on the free layer only -> split variant
+    j = helpers.tri_layer_mtj(cm)
+    j.setLayerFieldLikeTorqueDriver("free", cm.stepDriver(0, 1e3, 0, 1e-9))
+    j.setLayerDampingLikeTorqueDriver("free", cm.stepDriver(0, 16e3, 0, 1e-9))
+    j.getLayer("free").setReferenceLayer(cm.CVector(0, 1, 0))
+    b = cm.JunctionBatch(j, 4)
+    b.set_override("free", "dampingLike", "amplitude", np.ones(4))
+    b.set_external_field("all", np.zeros((4, 3)))
+    v = b.selected_variant(2e-9, 1e-12, 1e-11, cm.SolverMode.Heun)
+    assert v.startswith("CMTJB_HEUN/L3/") and "CMTJB_SPLIT(1)" in v, v
+    # the same drive on the BOTTOM layer: no split variant names that layer -> a plain variant
+    j = helpers.tri_layer_mtj(cm)
+    j.setLayerFieldLikeTorqueDriver("bottom", cm.stepDriver(0, 1e3, 0, 1e-9))
+    j.getLayer("bottom").setReferenceLayer(cm.CVector(0, 1, 0))
+    v = cm.JunctionBatch(j, 4).selected_variant(2e-9, 1e-12, 1e-11, cm.SolverMode.Heun)
+    assert "SPLIT" not in v, v
+    # thermal single layer -> Euler-Heun lean thermal variant; many layers -> the lane-per-layer kernel
+    assert "F_THERMAL" in cm.JunctionBatch(helpers.stt_layer_mtj(cm, temperature=300.0), 4).selected_variant(1e-9, dt, 1e-11)
+    assert cm.JunctionBatch(helpers.multi_layer(cm, 6), 4).selected_variant(1e-9, dt, 1e-11) == "wide/L6/F_ALL"

@@ -127,6 +127,23 @@ def s4(scale):
          {"instances": B, "grid": [n, n], "steps": steps, "variant": _abi.last_variant()})
 
 
+def dp(scale):
+    """Dormand-Prince (adaptive RK5(4), junction.hpp:866-1002): single-layer SOT junction, field x current
+    grid, 5 ns, final state only.  Throughput in accepted+rejected step ATTEMPTS is not observable from the
+    host; reported as simulated time per wall second and as equivalent fixed steps of the initial dt."""
+    n = int(1024 * math.sqrt(scale))
+    B, T, dt = n * n, 5e-9, 1e-12
+    j = helpers.sot_layer(m, dynamic=False)
+    b = m.JunctionBatch(j, B)
+    cur, fld = np.meshgrid(np.linspace(-1, 1, n), np.linspace(-200e3, 200e3, n))
+    b.set_override("free", "current", "constantValue", 1e11 * cur.ravel())
+    b.set_external_field("free", np.stack([fld.ravel(), np.zeros(B), np.zeros(B)], axis=1))
+    secs = timed(lambda: b.run_device(T, dt, T, solverMode=m.SolverMode.DormandPrince, log=False), reps=2)
+    emit("Dormand-Prince 1-layer SOT, current x field grid, final state only", B * (T / dt), secs, 7 * (3 + 9 + 27 + 34) + 90, 0,
+         {"instances": B, "sim_time_s": T, "initial_dt": dt, "simulated_seconds_per_wall_second": B * T / secs,
+          "variant": _abi.last_variant()})
+
+
 def _lattice(n_side, pitch=100e-9):
     js, pos = [], []
     rng = np.random.default_rng(0)
@@ -245,7 +262,7 @@ def procs(scale):
 
 
 if __name__ == "__main__":
-    which = [a for a in sys.argv[1:] if not a.replace(".", "").isdigit()] or ["s2", "s3", "s4", "s5g", "s5s", "procs"]
+    which = [a for a in sys.argv[1:] if not a.replace(".", "").isdigit()] or ["s2", "s3", "s4", "s5g", "s5s", "dp", "procs"]
     scale = [float(a) for a in sys.argv[1:] if a.replace(".", "").isdigit()]
     scale = scale[0] if scale else 1.0
     print(json.dumps({"fp64_peak_tflops_measured": PEAK / 1e12, "hbm_gbs": HBM}), flush=True)
