@@ -8,6 +8,8 @@ static const Variant kTable[] = {
     CMTJB_FIXED(1, CMTJB_EULER_HEUN, F_ALL_TAB),
     CMTJB_FIXED(1, CMTJB_EULER_HEUN, F_ALL),
     CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_IEC),
+    CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_IEC | F_THERMAL),          // two coupled layers at temperature
+    CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_IEC | F_STT | F_THERMAL),  // thermally assisted STT switching of a two-layer junction
     CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_ALL_TAB),
     CMTJB_FIXED(2, CMTJB_EULER_HEUN, F_ALL),
     CMTJB_FIXED(3, CMTJB_EULER_HEUN, F_IEC),

@@ -168,6 +168,24 @@ def stt_layer_mtj(mod, mag=None, temperature=None):
     return j
 
 
+def stt_two_layer_mtj(mod, current=None, temperature=None, mag=(0.1, 0.1, 0.95)):
+    """Free STT layer on a reference layer (IEC coupled): the usual two-layer MTJ under a current drive."""
+    demag = [(0.001, 0, 0), (0, 0.002, 0), (0, 0, 0.997)]
+    free = mod.Layer.createSTTLayer("free", mod.CVector(*mag), mod.CVector(0, 0, 1), 1.2, 1.5e-9, SURFACE, _demag(mod, demag), 0.02,
+                                    1.0, 0.1, 0.7)
+    free.setReferenceLayer(mod.Reference.bottom)
+    ref = mod.Layer("bottom", mod.CVector(0.05, 0.0, 1.0), mod.CVector(0, 0, 1), 1.4, 3e-9, SURFACE, _demag(mod, demag), 0.02)
+    j = mod.Junction([free, ref], 100, 200)
+    j.setLayerAnisotropyDriver("free", mod.ScalarDriver.getConstantDriver(0.6e6))
+    j.setLayerAnisotropyDriver("bottom", mod.ScalarDriver.getConstantDriver(1.5e6))
+    j.setIECDriver("free", "bottom", mod.ScalarDriver.getConstantDriver(2e-5))
+    j.setLayerCurrentDriver("free", current if current is not None else mod.ScalarDriver.getConstantDriver(-3e10))
+    j.setLayerExternalFieldDriver("all", mod.AxialDriver(10e3, 0.0, -30e3))
+    if temperature is not None:
+        j.setLayerTemperatureDriver("all", mod.ScalarDriver.getConstantDriver(temperature))
+    return j
+
+
 def sot_layer(mod, dynamic=True, mag=(0.1, 0.1, 0.9)):
     """1-layer SOT junction with K2 and step torque drivers (CIMS-like)."""
     demag = [(0, 0, 0), (0, 0, 0), (0, 0, 1)]

@@ -131,6 +131,12 @@ def test_kernel_variant_selection_rules():
     j.getLayer("bottom").setReferenceLayer(cm.CVector(0, 1, 0))
     v = cm.JunctionBatch(j, 4).selected_variant(2e-9, 1e-12, 1e-11, cm.SolverMode.Heun)
     assert "SPLIT" not in v, v
+    # two-layer STT junction: constant current, sine current (batch-uniform waveform), at temperature
+    sv = lambda j, *a: cm.JunctionBatch(j, 4).selected_variant(1e-9, dt, 1e-11, *a)  # noqa: E731
+    assert sv(helpers.stt_two_layer_mtj(cm)) == "CMTJB_RK4/L2/F_IEC | F_STT"
+    assert sv(helpers.stt_two_layer_mtj(cm, current=cm.sineDriver(0, 5e10, 2e9, 0))) == "CMTJB_RK4/L2/F_IEC | F_STT | F_DYNS"
+    assert sv(helpers.stt_two_layer_mtj(cm, temperature=300.0)) == "CMTJB_EULER_HEUN/L2/F_IEC | F_STT | F_THERMAL"
+    assert sv(helpers.stt_two_layer_mtj(cm, temperature=300.0), cm.SolverMode.Heun) == "CMTJB_HEUN/L2/F_IEC | F_STT | F_THERMAL"
     # thermal single layer -> Euler-Heun lean thermal variant; many layers -> the lane-per-layer kernel
     assert "F_THERMAL" in cm.JunctionBatch(helpers.stt_layer_mtj(cm, temperature=300.0), 4).selected_variant(1e-9, dt, 1e-11)
     assert cm.JunctionBatch(helpers.multi_layer(cm, 6), 4).selected_variant(1e-9, dt, 1e-11) == "wide/L6/F_ALL"

@@ -439,3 +439,15 @@ def test_split_variant_torque_on_the_free_layer_only(mode):
     g, w, sens = _three(fn)
     assert "CMTJB_SPLIT(1)" in variants[0], variants
     _check(g, w, sens=sens)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("drive", ["constant", "sine"])
+def test_two_layer_stt_junction(mode, drive):
+    """Lean two-layer STT variants (F_IEC | F_STT [| F_DYNS]); reference vector = the bottom layer's m."""
+    def tweak(mod, j):
+        if drive == "sine":
+            j.setLayerCurrentDriver("free", mod.ScalarDriver.getSineDriver(0, 5e10, 2e9, 0.0))
+
+    (g, _), (w, _) = _both(helpers.stt_two_layer_mtj, 0.5e-9, 1e-13, 5e-13, mode, tweak)
+    _check(g, w)

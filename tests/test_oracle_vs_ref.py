@@ -311,3 +311,16 @@ def test_many_layer_junctions_bit_exact(ref, on_oracle, n, strip, mode):
     layer count; on the GPU, L > 4 runs the lane-per-layer kernel (tests/test_gpu_parity.py)."""
     jr, jo = _run_both(ref, helpers.multi_layer, T=0.2e-9, wf=4e-13, mode=mode, n=n, strip=strip)
     _assert_same_logs(jr, jo)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_two_layer_stt_junction_bit_exact(ref, on_oracle, mode):
+    """Reference = bottom layer (referenceType BOTTOM, junction.hpp:727-740), constant and sine current."""
+    jr, jo = _run_both(ref, helpers.stt_two_layer_mtj, T=0.5e-9, wf=5e-13, mode=mode)
+    _assert_same_logs(jr, jo)
+
+    def sine(mod, j):
+        j.setLayerCurrentDriver("free", mod.ScalarDriver.getSineDriver(0, 5e10, 2e9, 0.0))
+
+    jr, jo = _run_both(ref, helpers.stt_two_layer_mtj, T=0.5e-9, wf=5e-13, mode=mode, tweak=sine)
+    _assert_same_logs(jr, jo)
