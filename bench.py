@@ -253,9 +253,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL writes its version banner (NCCL_DEBUG >= VERSION) and its
+        # warnings to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
