@@ -253,12 +253,24 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL writes its version banner (NCCL_DEBUG >= VERSION) and its
-        # warnings to stdout unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION / WARN
+        # (this image exports NCCL_DEBUG).  Only those two levels are silenced; INFO / TRACE stay as asked for.
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+        # ... and whatever native code still writes to fd 1 while the communicator comes up goes to stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         torch.cuda.synchronize(dev)
