@@ -88,8 +88,6 @@ int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
   p->effective_solver = mode;
   if (any_custom && mode == CMTJB_DORMAND_PRINCE)
     return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers need a fixed-step solver: Dormand-Prince evaluates drivers at adaptive times");
-  if (any_custom && a->log_mode == CMTJB_LOG_ENERGY)
-    return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers cannot be combined with the energy log");
   p->n_channels = 3 * jn->n_layers + (jn->mr_mode == CMTJB_MR_CLASSIC ? 1 : jn->mr_mode == CMTJB_MR_STRIP ? 3 : 0);
   if (a->log_mode == CMTJB_LOG_ENERGY)
     for (int i = 0; i < jn->n_layers; i++) p->n_channels += layers[i].includeSOT ? CMTJB_ENERGY_CHANNELS_SOT : CMTJB_ENERGY_CHANNELS;
@@ -491,6 +489,12 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
       }
     }
   }
+  if ((v->features & F_DYNI) && R.custom && R.n_custom > 0) {
+    // inline-evaluating variants read pre-evaluated callbacks straight from the caller's table, which has the
+    // stage table's [step][stage][column] layout: the row pointer of the time loop walks it instead
+    R.dyn_tab = R.custom + 3 * R.it_begin * R.n_custom;
+    R.dyn_ncols = R.n_custom;
+  }
   cudaError_t e = v->launch(&M, &R, stream);
   g_launches++;
   if (tab) cudaFreeAsync(tab, stream);
@@ -599,9 +603,6 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
         if (layers[l].drivers[s].update == CMTJB_UPD_CUSTOM) max_col = std::max(max_col, layers[l].drivers[s].custom_column);
     if (max_col >= 0) {
       if (!a->custom_table || max_col >= a->n_custom) return fail(CMTJB_EINVAL, "custom driver: custom_table is null or has too few columns");
-      if (need & F_DYNI)
-        return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are tabulated at the batch-uniform stage times and cannot be combined "
-                                   "with per-instance timing overrides or a driver table beyond 2 GiB");
     }
   }
   const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need, split_ok ? per_layer : nullptr);

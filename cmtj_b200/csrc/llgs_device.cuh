@@ -145,13 +145,22 @@ __device__ __noinline__ double driver_dynamic_inline(const DevLayer &Lr, const R
 // F_DYN variants read the waveform from a table built once per launch.
 struct StageTime {
   double t;
-  const double *row;  // this stage time's row of RunParams::dyn_tab (F_DYN / F_DYNS variants)
+  // this stage time's row of RunParams::dyn_tab (F_DYN / F_DYNS variants).  Inline-evaluating variants
+  // (F_DYNI) have no such table; for them the pointer walks the caller's custom_table instead (same
+  // [step][stage][column] layout), which is how CMTJB_UPD_CUSTOM drivers are read there; null otherwise.
+  const double *row;
 };
+// unit waveform of slot s in an inline-evaluating variant: pre-evaluated callbacks from the custom table
+template <uint32_t F>
+__device__ __forceinline__ double dynamic_inline_at(const DevLayer &Lr, const RunParams &R, int s, StageTime st, long long i) {
+  if (Lr.drv[s].type == CMTJB_UPD_CUSTOM) return st.row ? __ldg(st.row + Lr.drv[s].pad) : 0.0;
+  return driver_dynamic_inline<F>(Lr, R, s, st.t, i);
+}
 
 template <uint32_t F>
 __device__ __forceinline__ double driver_dynamic(const DevLayer &Lr, const RunParams &R, int s, StageTime st, long long i) {
   if constexpr ((F & F_DYNI) != 0) {
-    return driver_dynamic_inline<F>(Lr, R, s, st.t, i);
+    return dynamic_inline_at<F>(Lr, R, s, st, i);
   } else {
     const double A = ovr_or<F>(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, Lr.drv[s].amplitude);
     return driver_post(Lr.drv[s].type, A * __ldg(st.row + Lr.dyncol[s]));
@@ -196,7 +205,7 @@ __device__ __forceinline__ d3 dynamic_field(const DevLayer &Lr, const RunParams 
       for (int g = 0; g < 4; g++)
 #pragma unroll
         for (int c = 0; c < 3; c++)
-          if ((Lr.dynmask >> (g * 3 + c)) & 1u) h[c] += driver_dynamic_inline<F>(Lr, R, g * 3 + c, t.t, i);
+          if ((Lr.dynmask >> (g * 3 + c)) & 1u) h[c] += dynamic_inline_at<F>(Lr, R, g * 3 + c, t, i);
       return mk(h[0], h[1], h[2]);
     }
   } else if constexpr ((F & F_DYN) != 0) {
@@ -301,9 +310,11 @@ __device__ __forceinline__ double fast_shape(const FastDrv &f, double t) {
 
 // constant field + time-dependent field of layer l at time t (F_DYNI variants)
 template <uint32_t F>
-__device__ __forceinline__ d3 stage_field(const DevLayer &Lr, const RunParams &R, int l, long long i, double t, d3 Hc, const FastDrv &f) {
+__device__ __forceinline__ d3 stage_field(const DevLayer &Lr, const RunParams &R, int l, long long i, StageTime st, d3 Hc,
+                                          const FastDrv &f) {
+  const double t = st.t;
   if (f.type == kFastNone) return Hc;
-  if (f.type == kFastGeneric) return dynamic_field<F>(Lr, R, l, StageTime{t, nullptr}, i, Hc);
+  if (f.type == kFastGeneric) return dynamic_field<F>(Lr, R, l, st, i, Hc);
   const double v = driver_post(f.type, f.amp * fast_shape(f, t));
   return mk(Hc.x + (f.comp == 0 ? v : 0.0), Hc.y + (f.comp == 1 ? v : 0.0), Hc.z + (f.comp == 2 ? v : 0.0));
 }

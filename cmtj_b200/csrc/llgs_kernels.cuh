@@ -113,7 +113,7 @@ __device__ __forceinline__ void post_sample(const DevModel<NL> &M, const RunPara
 // General (F_ALL) variants only; off the hot path (__noinline__, runs on written samples).
 template <int NL, uint32_t F>
 __device__ __noinline__ void write_energy(const DevModel<NL> &M, const RunParams &R, const State<NL> &Sm, const State<NL> &Snb,
-                                          double t_eval, long long sample, long long i) {
+                                          double t_eval, const double *row_eval, long long sample, long long i) {
   const long long cs = R.n_samples * R.B;
   double *p = R.log + R.elog_ch0 * cs + sample * R.B + i;
   auto put = [&](double v) {
@@ -125,7 +125,7 @@ __device__ __noinline__ void write_energy(const DevModel<NL> &M, const RunParams
     put(v.y);
     put(v.z);
   };
-  const StageTime t{t_eval, nullptr};
+  const StageTime t{t_eval, row_eval};  // row_eval: the custom-table row of that evaluation (inline variants)
   const d3 zero = mk(0, 0, 0);
   for (int l = 0; l < NL; l++) {
     const DevLayer &Lr = M.L[l];
@@ -207,8 +207,8 @@ __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &
   if ((layer_mask(F, l) & F_DYNI) != 0 && fd != nullptr) {
     // the plain-driver field at the step's three distinct stage times, from the resolved driver
     constexpr uint32_t FL = layer_mask(F, l);
-    const d3 H0 = stage_field<FL>(Lr, R, l, i, t0.t, Hc[l], fd[l]), H1 = stage_field<FL>(Lr, R, l, i, t1.t, Hc[l], fd[l]),
-             H2 = stage_field<FL>(Lr, R, l, i, t2.t, Hc[l], fd[l]);
+    const d3 H0 = stage_field<FL>(Lr, R, l, i, t0, Hc[l], fd[l]), H1 = stage_field<FL>(Lr, R, l, i, t1, Hc[l], fd[l]),
+             H2 = stage_field<FL>(Lr, R, l, i, t2, Hc[l], fd[l]);
     u1 = layer_u_pre<NL, F, l, Ext>(M, R, i, t0, m0, S0, H0, ext);
     u2 = layer_u_pre<NL, F, l, Ext>(M, R, i, t1, axpy(u1, Lr.h_half, m0), S0, H1, ext);
     u3 = layer_u_pre<NL, F, l, Ext>(M, R, i, t1, axpy(u2, Lr.h_half, m0), S0, H1, ext);
@@ -362,12 +362,16 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
     const double t = (double)it * R.dt;
     State<NL> Em, Enb;
     do_step<NL, SOLVER, F>(M, R, i, it, row, t, S, Hc, Em, Enb, fd);
-    if constexpr ((F & (F_DYN | F_DYNS)) != 0 && (F & F_DYNI) == 0) row += 3 * R.dyn_ncols;
+    if constexpr ((F & (F_DYN | F_DYNS | F_DYNI)) != 0) {
+      if (row) row += 3 * R.dyn_ncols;  // table variants: the stage table; inline variants: the custom table, if any
+    }
     if (until_write == 0) {
       if (logging) write_sample<NL>(M, R, S, sample, i);
       if constexpr ((F & F_POST) != 0) post_sample<NL>(M, R, S, ps, t, sample, i);
       if constexpr (F == F_ALL) {
-        if (logging && R.elog_ch0 >= 0) write_energy<NL, F>(M, R, Em, Enb, SOLVER == CMTJB_EULER_HEUN ? t : t + R.dt, sample, i);
+        if (logging && R.elog_ch0 >= 0)
+          write_energy<NL, F>(M, R, Em, Enb, SOLVER == CMTJB_EULER_HEUN ? t : t + R.dt,
+                              row ? row - (SOLVER == CMTJB_EULER_HEUN ? 3 : 1) * R.dyn_ncols : nullptr, sample, i);
       }
       sample++;
       until_write = we;
@@ -677,7 +681,7 @@ __global__ void __launch_bounds__(kBlock) llgs_dopri_kernel(const __grid_constan
               State<1> Em, Enb;
               Em.m[0] = m5;
               Enb.m[0] = m5;
-              write_energy<1, F>(M, R, Em, Enb, t_last, sample, i);
+              write_energy<1, F>(M, R, Em, Enb, t_last, nullptr, sample, i);
             }
           }
           if (R.time_log) R.time_log[sample * R.B + i] = t;

@@ -505,8 +505,6 @@ int validate(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtj
   p->effective_solver = mode;
   if (any_custom && mode == CMTJB_DORMAND_PRINCE)
     return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers need a fixed-step solver: Dormand-Prince evaluates drivers at adaptive times");
-  if (any_custom && a->log_mode == CMTJB_LOG_ENERGY)
-    return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers cannot be combined with the energy log");
   p->n_channels = 3 * jn->n_layers + (jn->mr_mode == CMTJB_MR_CLASSIC ? 1 : jn->mr_mode == CMTJB_MR_STRIP ? 3 : 0);
   if (a->log_mode == CMTJB_LOG_ENERGY) p->n_channels += energy_channels(jn, layers);
   if (mode == CMTJB_DORMAND_PRINCE) {

@@ -451,3 +451,22 @@ def test_two_layer_stt_junction(mode, drive):
 
     (g, _), (w, _) = _both(helpers.stt_two_layer_mtj, 0.5e-9, 1e-13, 5e-13, mode, tweak)
     _check(g, w)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_custom_driver_with_the_energy_log(mode):
+    """The reference's own tests/test_drivers.py::test_custom_on_junction shape: a Python callback on the
+    anisotropy with calculateEnergies=True (general, inline-evaluating variant reading the custom table)."""
+    import test_oracle_vs_ref as t
+
+    logs = []
+    for be in (None, helpers.oracle_backend()):
+        with helpers.facade_on(be):
+            j = helpers.single_layer_mtj(cmtj_b200)
+            t._custom_tweak(cmtj_b200, j)
+            j.runSimulation(0.2e-9, 1e-13, 5e-13, calculateEnergies=True, solverMode=getattr(cmtj_b200.SolverMode, mode))
+            logs.append(helpers.log_arrays(j.getLog()))
+    assert set(logs[0]) == set(logs[1])
+    for k in logs[1]:
+        assert helpers.max_rel_err(logs[0][k], logs[1][k]) <= TOL, k
+    assert np.ptp(logs[0]["free_K"]) > 0  # the callback's value is what the energy log records as K

@@ -3,7 +3,9 @@ tests/assets/curated_examples/*.json of /root/reference) against this package: `
 to cmtj_b200 (install_as_cmtj), the reference's pure-Python `cmtj.utils` helpers are picked up
 from the reference tree on top of it, and the compute goes through our facade, packing code and
 the oracle restatement.  This is the "golden vectors of the reference" pin of SURVEY 8(c) for
-the CPU side; the same scripts run on the GPU path in tests/test_gpu_reference_suite.py.
+the CPU side.  The second half runs the reference's OTHER test files for the path (drivers, stack,
+group interaction, solvers, SOT torques, constants, sanity, basic, procedures) unmodified, in a
+subprocess, with `cmtj` aliased to this package (tests/ref_alias_plugin.py).
 
 CPU only, and only where /root/reference exists (it does not travel to the GPU box)."""
 import importlib.util
@@ -52,3 +54,22 @@ def test_reference_golden_vectors_through_our_facade(on_oracle, name):
     mod = load_reference_tests()
     assert mod.Junction is cmtj_b200.Junction and mod.cmtj is cmtj_b200  # really our facade, not the reference's
     getattr(mod, name)(False)  # update_reference=False: compare with the reference's committed JSON
+
+
+REF_TEST_FILES = ["test_basic", "test_drivers", "test_sanity", "test_stack", "test_group_interaction", "test_constants",
+                  "test_sot_torques", "test_solvers"]
+
+
+@pytest.mark.parametrize("name", REF_TEST_FILES + ["test_procedures"])
+def test_reference_test_file_passes_against_this_package(name, tmp_path):
+    """`pytest /root/reference/tests/<name>.py` with `import cmtj` resolving to cmtj_b200 (facade on the
+    oracle): the reference's own assertions on API surface, error messages and numbers."""
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([here, os.path.dirname(here), os.environ.get("PYTHONPATH", "")]))
+    cmd = [sys.executable, "-m", "pytest", os.path.join(REF, "tests", name + ".py"), "-p", "ref_alias_plugin", "-p", "no:cacheprovider",
+           "-q", "--rootdir", str(tmp_path), "-c", os.devnull]
+    r = subprocess.run(cmd, env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-500:]
