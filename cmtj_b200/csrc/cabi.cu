@@ -346,6 +346,9 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
   D.aJ_c = J.HBAR / (J.ELECTRON_CHARGE * L.Ms * L.thickness);
   D.lam = L.SlonczewskiSpacerLayerParameter;
   D.lam2 = D.lam * D.lam;
+  D.stt_num = L.alternativeSTT ? L.spinPolarisation : L.spinPolarisation * D.lam2;
+  D.stt_a = L.alternativeSTT ? D.lam : D.lam2 - 1.0;
+  D.stt_b = L.alternativeSTT ? 1.0 : D.lam2 + 1.0;
   D.P = L.spinPolarisation;
   D.beta = L.beta;
   D.kappa = L.kappa;
@@ -353,6 +356,7 @@ void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D
   D.dlT = L.dampingLikeTorque;
   const double V = L.cellSurface * L.thickness;
   D.sigma_c = (V != 0.0) ? (2.0 * L.damping * J.BOLTZMANN_CONST) / (L.Ms * V * gyro) : 0.0;
+  D.sigma0 = std::sqrt(D.sigma_c * L.drivers[CMTJB_SLOT_TEMPERATURE].constantValue);
   D.Rx0 = L.Rx0;
   D.Ry0 = L.Ry0;
   D.AMR_X = L.AMR_X;

@@ -74,6 +74,8 @@ struct DevLayer {
   double llg;                // -gamma/(1+alpha^2)
   double aJ_c;               // hbar/(e*Ms*thickness)
   double lam, lam2, P, beta, kappa;
+  double stt_num, stt_a, stt_b;  // Slonczewski eta = stt_num / (stt_a (m.p) + stt_b): P lam^2, lam^2 - 1, lam^2 + 1 (or P, lam, 1)
+  double sigma0;                 // sqrt(sigma_c * T) of a constant, batch-uniform temperature
   double flT, dlT;           // static SOT efficiencies
   double ref[3], ref2[3];
   double sigma_c;            // 2*alpha*kB/(Ms*V*gamma); sigma = sqrt(sigma_c*T)

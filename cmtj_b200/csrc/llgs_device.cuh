@@ -406,9 +406,9 @@ __device__ __forceinline__ d3 llg_u(const DevLayer &Lr, const RunParams &R, int 
       if (Lr.stt) {
         const double I = Ext::kCurrent ? ext.current(t.t) : slot_value<F>(Lr, R, CMTJB_SLOT_CURRENT, t, i);
         const double mp = dot(m, ref);
-        double eta;
-        if (Lr.altSTT) eta = Lr.P / fma(Lr.lam, mp, 1.0);
-        else eta = (Lr.P * Lr.lam2) / fma(Lr.lam2 - 1.0, mp, Lr.lam2 + 1.0);
+        // eta = P lam^2 / (lam^2 + 1 + (lam^2 - 1) m.p)  or  P / (1 + lam m.p)  (junction.hpp:748-757), the
+        // constants folded on the host; reciprocal + multiply instead of the library division
+        const double eta = Lr.stt_num * (1.0 / fma(Lr.stt_a, mp, Lr.stt_b));
         const double ae = Lr.aJ_c * I * eta;
         const d3 fl = cross(m, ref);
         const d3 dl = cross(m, fl);
@@ -506,8 +506,13 @@ __device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, i
   d3 dW = mk(0, 0, 0);
   if constexpr ((F & F_THERMAL) != 0) {
     if (Lr.thermal) {
-      const double T = slot_value<F>(Lr, R, CMTJB_SLOT_TEMPERATURE, t, i);
-      const double sigma = sqrt(Lr.sigma_c * T);
+      double sigma;
+      if constexpr ((F & (F_OVR | F_DYNS | F_DYNI)) == 0) {
+        sigma = Lr.sigma0;  // constant, batch-uniform temperature: the square root is taken on the host
+      } else {
+        const double T = slot_value<F>(Lr, R, CMTJB_SLOT_TEMPERATURE, t, i);
+        sigma = sqrt(Lr.sigma_c * T);
+      }
       dW = normal3(R.seed, (unsigned long long)(R.inst_offset + i), (unsigned)l, (unsigned long long)it) * sigma;
     }
   }
