@@ -273,7 +273,9 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
   const double waves = mean / cap;
   const double eff = mean <= cap ? mean / std::ceil(mean) : waves / std::ceil(waves);
   // a task is a whole number of log periods ...
-  const long long we = R.write_every > 0 ? R.write_every : 1;
+  // (nothing is written between tasks in a final-state-only run: any length will do)
+  const bool writes = R.log != nullptr || R.post.n_proj > 0 || R.post.sd_mode != CMTJB_SD_NONE;
+  const long long we = (writes && R.write_every > 0) ? R.write_every : 1;
   // ... and the launch is cut into about 64 rounds (tail <= 1/64 of the quantisation loss), 128 to 400 steps
   // each (measured on B200, S1: 100..400 steps per task within 0.1 % of each other, 1000+ slower)
   long long target = std::min<long long>(400, std::max<long long>(128, steps / 64));

@@ -24,9 +24,9 @@ out = None
 for r in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    res = b.run_device(T, 1e-13, we * 1e-13 * (1 + 1e-9), log=we > 0, out=out)
+    res = b.run_device(T, 1e-13, (we * 1e-13 * (1 + 1e-9)) if we > 0 else T, log=we > 0, out=out)
     e1.record(); torch.cuda.synchronize()
-    out = res["_log"]
+    out = res.get("_log")
     dt = e0.elapsed_time(e1) * 1e-3
     nbytes = 0 if out is None else out.numel() * 8
     print(f"rep {r} variant={b.last_plan.variant.decode()} B={B} steps={steps} we={we}: {dt*1e3:.2f} ms "
