@@ -60,16 +60,28 @@ REF_TEST_FILES = ["test_basic", "test_drivers", "test_sanity", "test_stack", "te
                   "test_sot_torques", "test_solvers"]
 
 
-@pytest.mark.parametrize("name", REF_TEST_FILES + ["test_procedures"])
-def test_reference_test_file_passes_against_this_package(name, tmp_path):
-    """`pytest /root/reference/tests/<name>.py` with `import cmtj` resolving to cmtj_b200 (facade on the
-    oracle): the reference's own assertions on API surface, error messages and numbers."""
+def _run_reference_files(names, tmp_path):
     import subprocess
 
     here = os.path.dirname(os.path.abspath(__file__))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([here, os.path.dirname(here), os.environ.get("PYTHONPATH", "")]))
-    cmd = [sys.executable, "-m", "pytest", os.path.join(REF, "tests", name + ".py"), "-p", "ref_alias_plugin", "-p", "no:cacheprovider",
-           "-q", "--rootdir", str(tmp_path), "-c", os.devnull]
-    r = subprocess.run(cmd, env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    cmd = [sys.executable, "-m", "pytest"] + [os.path.join(REF, "tests", n + ".py") for n in names] + [
+        "-p", "ref_alias_plugin", "-p", "no:cacheprovider", "-q", "--rootdir", str(tmp_path), "-c", os.devnull]
+    r = subprocess.run(cmd, env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-500:]
+    return r.stdout
+
+
+def test_reference_test_files_pass_against_this_package(tmp_path):
+    """`pytest /root/reference/tests/{test_basic,test_drivers,...}.py` with `import cmtj` resolving to cmtj_b200
+    (facade on the oracle): the reference's own assertions on API surface, error messages and numbers.
+    One subprocess for the eight files (42 tests)."""
+    out = _run_reference_files(REF_TEST_FILES, tmp_path)
+    n = int(out.strip().splitlines()[-1].split(" passed")[0].split()[-1])
+    assert n >= 42, out[-300:]
+
+
+def test_reference_procedures_test_file_passes_against_this_package(tmp_path):
+    """tests/test_procedures.py of the reference (PIMM / VSD procedures of cmtj.utils driving OUR Junction)."""
+    _run_reference_files(["test_procedures"], tmp_path)
