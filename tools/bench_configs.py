@@ -70,7 +70,7 @@ def emit(name, layer_steps, secs, flop_per_layer_step, log_bytes, extra):
 def s2(scale):
     """vsd-basic-field-scan (curated-examples/vsd-basic-field-scan.py:57-60,102-128): 1 layer, sine
     Oersted drive with per-instance frequency, logged EVERY step (HBM-write bound)."""
-    B, steps = int(262144 * scale), 2000
+    B, steps = int(262144 * scale), 5000  # 52 GB of log when every step is written; ~15 ms per call
     demag = [m.CVector(0, 0, 0), m.CVector(0, 0, 0), m.CVector(0, 0, 1)]
     l = m.Layer("free", m.CVector(0, 0, 1), m.CVector(0, 0, 1), 0.525, 1.45e-9, 0.0, demag, 0.03)
     l.setReferenceLayer(m.CVector(0, 1, 0))
@@ -84,7 +84,7 @@ def s2(scale):
     T = steps * 1e-13 * (1 + 1e-9)
     for tag, we in (("log every step", 1), ("log every 100", 100)):
         out = b.run_device(T, 1e-13, we * 1e-13 * (1 + 1e-9))["_log"]
-        secs = timed(lambda: b.run_device(T, 1e-13, we * 1e-13 * (1 + 1e-9), out=out))
+        secs = timed(lambda: b.run_device(T, 1e-13, we * 1e-13 * (1 + 1e-9), out=out), reps=7)
         emit(f"S2 vsd 1-layer sine Oersted RK4, {tag}", B * steps, secs, 225.0, out.numel() * 8,
              {"instances": B, "steps": steps, "variant": _abi.last_variant()})
         del out
