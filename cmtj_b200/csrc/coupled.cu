@@ -403,6 +403,69 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
     g_launches++;
     if (e != cudaSuccess) rc = cuda_fail(e, "group_block_kernel");
   } else {
+    const char *two_env = std::getenv("CMTJB_GROUP_TWO_KERNEL");
+    if (two_env && two_env[0] == '1') {
+      // EXPERIMENT (off by default, measured slower: 79 vs 61 us per step at N = 4096): two kernels per step,
+      // the pair sum at full occupancy, then the per-element step (coupled_kernels.cuh)
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      const int tiles = (N + 31) / 32;
+      const long long want_threads = (long long)sms * 2048;  // every SM full
+      const int P = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(64, N), want_threads / ((long long)tiles * 32)));
+      double *d_hpart = nullptr;
+      RunParams *d_R = nullptr;
+      e = cudaMallocAsync((void **)&d_hpart, (size_t)P * 3 * N * sizeof(double), stream);
+      if (e == cudaSuccess) e = upload(&R, 1, &d_R, stream);
+      if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync(pair-field partials)");
+      const long long we = R.write_every;
+      const long long Btot = R.B;
+      for (long long inst = 0; inst < n_inst && rc == CMTJB_OK; inst++) {
+        PairParams Q;
+        Q.N = N;
+        Q.P = P;
+        Q.pos = d_pos;
+        Q.pref = d_pref;
+        Q.mx = m_state + (size_t)(3 * g->top_layer + 0) * Btot + inst * N;
+        Q.my = m_state + (size_t)(3 * g->top_layer + 1) * Btot + inst * N;
+        Q.mz = m_state + (size_t)(3 * g->top_layer + 2) * Btot + inst * N;
+        Q.Hpart = d_hpart;
+        GroupStepParams G;
+        std::memset(&G, 0, sizeof(G));
+        G.N = N;
+        G.P = P;
+        G.interaction = g->interaction;
+        G.top = g->top_layer;
+        G.inst = inst;
+        G.Hpart = d_hpart;
+        long long sample = R.first_sample;
+        const long long pair_blocks = ((long long)tiles * 32 * P + 255) / 256;
+        for (long long it = R.it_begin; it < R.it_end && rc == CMTJB_OK; it++) {
+          if (g->interaction != CMTJB_INT_NULL) {
+            group_pair_kernel<<<(unsigned)pair_blocks, 256, 0, stream>>>(Q);
+            g_launches++;
+          }
+          G.it = it;
+          G.write = (it % we == 0) ? 1 : 0;
+          G.sample = sample;
+          if (G.write) sample++;
+          const unsigned sb = (unsigned)((N + 127) / 128);
+#define CMTJB_GSTEP(SOLVER)                                                                                              \
+  do {                                                                                                                   \
+    if (uni) group_step_kernel<NL, SOLVER, F_COUPLED_LEAN, true><<<sb, 128, 0, stream>>>(d_models, d_R, G);              \
+    else if (lean) group_step_kernel<NL, SOLVER, F_COUPLED_LEAN, false><<<sb, 128, 0, stream>>>(d_models, d_R, G);       \
+    else group_step_kernel<NL, SOLVER, F_ALL, false><<<sb, 128, 0, stream>>>(d_models, d_R, G);                          \
+  } while (0)
+          if (rk4) CMTJB_GSTEP(CMTJB_RK4);
+          else CMTJB_GSTEP(CMTJB_EULER_HEUN);
+#undef CMTJB_GSTEP
+          g_launches++;
+          e = cudaGetLastError();
+          if (e != cudaSuccess) rc = cuda_fail(e, "group pair/step kernels");
+        }
+      }
+      if (d_hpart) cudaFreeAsync(d_hpart, stream);
+      if (d_R) cudaFreeAsync(d_R, stream);
+    } else {
     // one array across the grid: cooperative launch, as many co-resident CTAs as the pair sum can use
 #define CMTJB_GRID_FN(SOLVER)                                                                    \
   (uni ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, true>                      \
@@ -433,6 +496,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
           if (e != cudaSuccess) rc = cuda_fail(e, "group_grid_kernel");
         }
       }
+    }
     }
   }
   cudaFreeAsync(d_models, stream);

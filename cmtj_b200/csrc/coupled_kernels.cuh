@@ -555,4 +555,98 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
   }
 }
 
+// ====================================================================================================
+// GroupInteraction, one large group: two kernels per time step instead of one persistent cooperative kernel.
+// EXPERIMENT, selected with CMTJB_GROUP_TWO_KERNEL=1; parity-tested, but measured SLOWER than the cooperative
+// kernel on B200 at N = 4096 (79 vs 61 us per step): the pair kernel takes 45-48 us (FP64 pipe 61 % busy at
+// 41 % occupancy) and the 4096-thread step kernel is pure single-thread latency (15-20 us).
+//
+// The cooperative form above inlines the junction's step next to the pair loop, which pins it at 128
+// registers, 16 warps per SM and one grid barrier per step (ncu: FP64 pipe 39 % busy, the rest latency).
+// Here the pair sum is its own kernel -- ~40 registers, every SM full, no shared memory, no barrier: a warp
+// is 32 CONSECUTIVE elements a sharing one partner slice, so every partner load is a warp-wide broadcast
+// served by L1 -- and the step is a second, small kernel (one thread per element, state in m_state).  The stream orders
+// them; 2 launches per step cost less than the grid barrier they replace.  Partial sums are written per
+// slice and added in slice order by the step kernel: deterministic, no atomics.
+// ====================================================================================================
+struct PairParams {
+  int N, P;                // elements, partner slices
+  const double *pos;       // device [3][N]
+  const double *pref;      // device [N]
+  const double *mx, *my, *mz;  // device [N] each: top-layer magnetisation at the start of the step (rows of m_state)
+  double *Hpart;           // device [P][3][N] partial pair fields
+};
+
+__global__ void __launch_bounds__(256) group_pair_kernel(const __grid_constant__ PairParams Q) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = Q.N;
+  const int tiles = (N + 31) / 32;       // warps per slice
+  const long long w = gt >> 5;
+  const int p = (int)(w / tiles);
+  if (p >= Q.P) return;
+  const int a_raw = (int)(w - (long long)p * tiles) * 32 + (int)(gt & 31);
+  const int a = a_raw < N ? a_raw : N - 1;
+  const d3 ra = mk(__ldg(Q.pos + a), __ldg(Q.pos + N + a), __ldg(Q.pos + 2 * N + a));
+  const int per = (N + Q.P - 1) / Q.P;
+  const int b0 = p * per, b1 = (b0 + per < N) ? b0 + per : N;
+  d3 H = mk(0, 0, 0);
+#pragma unroll 4
+  for (int b = b0; b < b1; b++) {
+    const d3 rb = mk(__ldg(Q.pos + b), __ldg(Q.pos + N + b), __ldg(Q.pos + 2 * N + b));
+    const d3 mb = mk(Q.mx[b], Q.my[b], Q.mz[b]);  // rewritten by the step kernel between launches: plain loads
+    pair_accumulate(H, ra - rb, mb, __ldg(Q.pref + b), b == a);
+  }
+  if (a_raw < N) {
+    double *o = Q.Hpart + (size_t)p * 3 * N + a;
+    o[0] = H.x;
+    o[N] = H.y;
+    o[2 * N] = H.z;
+  }
+}
+
+struct GroupStepParams {
+  int N, P, interaction, top;
+  long long inst;          // instance of the batch (state rows inst*N .. inst*N + N - 1)
+  long long it, sample;    // this step's index and, if `write`, the log row it produces
+  int write;
+  const double *Hpart;     // [P][3][N]
+};
+
+// Launched once per time step: its parameter block is kept to a few words (the models and the run
+// parameters are read through pointers) so that the two launches of a step cost the host less than the
+// kernels cost the device.
+template <int NL, int SOLVER, uint32_t F, bool UNIFORM>
+__global__ void __launch_bounds__(128) group_step_kernel(const DevModel<NL> *__restrict__ models, const RunParams *__restrict__ Rp,
+                                                         const __grid_constant__ GroupStepParams G) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= G.N) return;
+  const int N = G.N;
+  const long long i = G.inst * N + a;
+  const RunParams &R = *Rp;
+  const DevModel<NL> &M = models[UNIFORM ? 0 : a];
+  State<NL> S;
+  load_state<NL>(R, i, S);
+  d3 H = mk(0, 0, 0);
+  if (G.interaction != CMTJB_INT_NULL) {
+    for (int p = 0; p < G.P; p++) {
+      const double *q = G.Hpart + (size_t)p * 3 * N + a;
+      H = H + mk(q[0], q[N], q[2 * N]);
+    }
+    if (G.interaction == CMTJB_INT_DIPOLE_NOMURA) H = H * (1.0 / (4.0 * M_PI));
+  }
+  d3 Hl[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const d3 Hc = constant_field(M.L[l], R, i);
+    Hl[l] = (l == G.top) ? Hc + H : Hc;  // setLayerReservedInteractionField(topId, ...) (reservoir.hpp:145-146)
+  }
+  coupled_step<NL, SOLVER, F>(M, R, i, G.it, (double)G.it * R.dt, S, Hl, NoExt());
+  store_state<NL>(R, i, S);  // the next pair kernel reads the top layer's rows from here
+  if (G.write && R.log) write_sample<NL>(M, R, S, G.sample, i);
+  if (R.status) {
+    const int st = nan_status<NL, SOLVER>(S);
+    if (G.it == 0 || st) R.status[i] = st;
+  }
+}
+
 }  // namespace cmtjb
