@@ -258,3 +258,17 @@ def test_stack_kcl_reduction_shapes(n):
 
     g, w, p = _three(fn)
     _check(g, w, p)
+
+
+def test_group_two_kernel_experiment_matches_the_oracle(monkeypatch):
+    """CMTJB_GROUP_TWO_KERNEL=1: pair-sum kernel + per-element step kernel per time step (off by default)."""
+    monkeypatch.setenv("CMTJB_GROUP_TWO_KERNEL", "1")
+
+    def fn(eps):
+        g = _lattice_group(20, eps)
+        out = g.run_batch(1, 0.03e-9, 1e-13, 1e-12)
+        out.pop("m_state")
+        return out
+
+    g, w, p = _three(fn)
+    _check(g, w, p)
