@@ -470,3 +470,31 @@ def test_custom_driver_with_the_energy_log(mode):
     for k in logs[1]:
         assert helpers.max_rel_err(logs[0][k], logs[1][k]) <= TOL, k
     assert np.ptp(logs[0]["free_K"]) > 0  # the callback's value is what the energy log records as K
+
+
+def test_edge_cases_empty_batch_zero_steps_single_instance():
+    """Edges of the batched entry on the device: no instances, no steps (totalTime < timeStep), one instance,
+    and one more instance than a warp; shapes and values as on the oracle."""
+    import torch
+
+    j = helpers.two_layer_mtj(cmtj_b200)
+    assert cmtj_b200.JunctionBatch(j, 0).run(1e-10, 1e-13, 1e-12)["free_mx"].shape == (100, 0)
+    b = cmtj_b200.JunctionBatch(j, 3)
+    out = b.run(5e-14, 1e-13, 1e-13)
+    assert out["free_mx"].shape == (0, 3) and out["time"].shape == (0,)
+    assert np.array_equal(b.get_magnetisation("free"), np.tile([0.1, 0.1, 1.0], (3, 1)))  # untouched, un-normalised
+    dev = cmtj_b200.JunctionBatch(j, 3).run_device(5e-14, 1e-13, 1e-13)
+    torch.cuda.synchronize()
+    assert tuple(dev["_log"].shape) == (7, 0, 3)
+    for B in (1, 33):
+        logs = []
+        for be in (None, helpers.oracle_backend()):
+            with helpers.facade_on(be):
+                bb = cmtj_b200.JunctionBatch(helpers.two_layer_mtj(cmtj_b200), B)
+                bb.set_external_field("all", np.linspace(-2e5, 2e5, 3 * B).reshape(B, 3))
+                logs.append(dict(bb.run(0.2e-9, 1e-13, 1e-12)))
+        for k in logs[1]:
+            if k != "time":
+                assert helpers.max_rel_err(logs[0][k], logs[1][k]) <= TOL, (B, k)
+    with pytest.raises(RuntimeError, match="time step cannot be larger than write frequency"):
+        cmtj_b200.JunctionBatch(j, 2).run(1e-10, 1e-12, 1e-13)
