@@ -307,7 +307,7 @@ def PIMM_procedure(
         return np.squeeze(np.asarray(spectrum)), freqs, output
 
     def cat(key):
-        return np.concatenate([r[key] for r in parts], axis=0)
+        return parts[0][key] if len(parts) == 1 else np.concatenate([r[key] for r in parts], axis=0)
 
     # the reference appends one entry per field point (procedures.py:183-193); same lists, assembled
     # from whole-batch arrays (row views) instead of 1e5 Python-level appends
