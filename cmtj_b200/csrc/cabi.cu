@@ -125,6 +125,32 @@ bool layer_foldable(const cmtjb_layer_t &L, int l, const cmtjb_override_t *ovr, 
   return T[1] == 0 && T[2] == 0 && T[3] == 0 && T[5] == 0 && T[6] == 0 && T[7] == 0;
 }
 
+// Fast-field eligibility (dev_model.h: F_FAST): every time-dependent driver is a plain FIELD driver evaluable on
+// the device, at most one per layer, and every override other than a constant field component addresses such
+// a driver.  Then nothing but that one driver needs inline evaluation or the override tables in the time loop.
+bool fast_field_eligible(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr) {
+  bool any = false;
+  for (int l = 0; l < jn->n_layers; l++) {
+    int n_dyn = 0;
+    for (int s = 0; s < CMTJB_NSLOTS; s++) {
+      const cmtjb_driver_t &d = layers[l].drivers[s];
+      if (!slot_dynamic(d)) continue;
+      if (s >= CMTJB_SLOT_K1 || d.update == CMTJB_UPD_CUSTOM) return false;
+      n_dyn++;
+    }
+    if (n_dyn > 1) return false;
+    any = any || n_dyn == 1;
+  }
+  for (int k = 0; k < n_ovr; k++) {
+    const bool field_slot = ovr[k].slot < CMTJB_SLOT_K1;
+    if (ovr[k].field == CMTJB_FIELD_CONSTANT && field_slot) continue;  // summed into the constant field once per launch
+    if (!field_slot) return false;
+    for (int l = 0; l < jn->n_layers; l++)
+      if ((ovr[k].layer < 0 || ovr[k].layer == l) && !slot_dynamic(layers[l].drivers[ovr[k].slot])) return false;
+  }
+  return any;
+}
+
 // which terms does this model need compiled in?  Returns the union over the layers; `per_layer`
 // (optional, [n_layers]) receives each layer's own set (split variants, dev_model.h: F_SPLIT).
 uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
@@ -597,11 +623,17 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
       split_ok = false;
     }
   }
+  uint32_t need_fast = 0;  // alternative: the fast-field form of an inline-evaluating RK4 model
+  if ((need & F_DYNI) && plan.effective_solver == CMTJB_RK4 && a->log_mode != CMTJB_LOG_ENERGY &&
+      fast_field_eligible(jn, layers, ovr, n_ovr))
+    need_fast = (need & ~(uint32_t)(F_DYNI | F_OVR)) | F_FAST;
   const char *force = std::getenv("CMTJB_FORCE_VARIANT");  // "full": always the most general kernel; "nosplit": no split variants (testing)
+  if (force && (std::strcmp(force, "full") == 0 || std::strcmp(force, "nofast") == 0)) need_fast = 0;
   if (force && std::strcmp(force, "full") == 0) need = F_ALL, split_ok = false;
   if (force && std::strcmp(force, "nosplit") == 0) split_ok = false;
   if (a->log_mode == CMTJB_LOG_ENERGY) need = F_ALL, split_ok = false;  // the energy log lives in the general variants only
   if (post) need |= F_POST;
+  if (post && need_fast) need_fast |= F_POST;
   {
     int max_col = -1;
     for (int l = 0; l < jn->n_layers; l++)
@@ -611,7 +643,8 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
       if (!a->custom_table || max_col >= a->n_custom) return fail(CMTJB_EINVAL, "custom driver: custom_table is null or has too few columns");
     }
   }
-  const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need, split_ok ? per_layer : nullptr);
+  const Variant *v = need_fast ? pick_variant(jn->n_layers, plan.effective_solver, need_fast) : nullptr;
+  if (!v) v = pick_variant(jn->n_layers, plan.effective_solver, need, split_ok ? per_layer : nullptr);
   if (!v) {
     char buf[160];
     std::snprintf(buf, sizeof(buf), "no compiled kernel variant for %d layers, solver %d, features 0x%x", jn->n_layers,
@@ -820,7 +853,11 @@ int cmtjb_select_variant(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
   uint32_t per_layer[CMTJB_MAX_LAYERS] = {0};
   uint32_t need = needed_features(jn, layers, overrides, n_overrides, args, plan.effective_solver, per_layer);
   if (args->log_mode == CMTJB_LOG_ENERGY) need = F_ALL;
-  const Variant *v = pick_variant(jn->n_layers, plan.effective_solver, need, args->log_mode == CMTJB_LOG_ENERGY ? nullptr : per_layer);
+  const Variant *v = nullptr;
+  if ((need & F_DYNI) && plan.effective_solver == CMTJB_RK4 && args->log_mode != CMTJB_LOG_ENERGY &&
+      fast_field_eligible(jn, layers, overrides, n_overrides))
+    v = pick_variant(jn->n_layers, plan.effective_solver, (need & ~(uint32_t)(F_DYNI | F_OVR)) | F_FAST);
+  if (!v) v = pick_variant(jn->n_layers, plan.effective_solver, need, args->log_mode == CMTJB_LOG_ENERGY ? nullptr : per_layer);
   if (!v) return fail(CMTJB_ENOTSUP, "no compiled kernel variant covers this model");
   std::snprintf(name, name_size, "%s", v->name);
   return CMTJB_OK;

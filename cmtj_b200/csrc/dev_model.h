@@ -46,7 +46,12 @@ enum : uint32_t {
   F_SPLIT = 1u << 19,
   F_HEAVY_SHIFT = 15,
   F_LIGHTSET = F_K2 | F_IEC | F_IDMI | F_DIPOLE | F_DEMAG_FULL | F_NOFOLD,
-  F_BASEMASK = (1u << 15) - 1
+  F_BASEMASK = (1u << 15) - 1,
+  // Fast-field variants (RK4): every time-dependent driver is a FIELD driver, at most one per layer, and every
+  // per-instance waveform parameter belongs to it (a VSD map: Oersted sine with per-instance frequency).  The
+  // driver is resolved once per launch (resolve_fast) and added to the field at the three stage times, so
+  // the loop body is compiled WITHOUT inline-driver and override machinery (F_DYNI / F_OVR).
+  F_FAST = 1u << 20
 };
 #define CMTJB_SPLIT(heavy_layers) (cmtjb::F_SPLIT | ((uint32_t)(heavy_layers) << cmtjb::F_HEAVY_SHIFT))
 // the term set compiled into layer l of a variant

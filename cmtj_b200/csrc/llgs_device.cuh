@@ -236,7 +236,7 @@ struct FastDrv {
 
 template <uint32_t F> __device__ __forceinline__ FastDrv resolve_fast(const DevLayer &Lr, const RunParams &R, long long i) {
   FastDrv f{kFastNone, 0, 0.0, 0.0, 0.0, 0.0};
-  if constexpr ((F & F_DYNI) != 0) {
+  if constexpr ((F & (F_DYNI | F_FAST)) != 0) {
     const uint32_t mask = Lr.dynmask & 0xFFFu;
     if (mask == 0) return f;
     if (mask & (mask - 1)) {
@@ -247,31 +247,31 @@ template <uint32_t F> __device__ __forceinline__ FastDrv resolve_fast(const DevL
     const DevDriver &d = Lr.drv[s];
     f.type = d.type;
     f.comp = s % 3;
-    f.amp = ovr_or<F>(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, d.amplitude);
+    f.amp = ovr_always(Lr, R, s, CMTJB_FIELD_AMPLITUDE, i, d.amplitude);
     switch (d.type) {
     case CMTJB_UPD_PULSE:
-      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PERIOD, i, d.period);
-      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_CYCLE, i, d.cycle);
+      f.p0 = ovr_always(Lr, R, s, CMTJB_FIELD_PERIOD, i, d.period);
+      f.p1 = ovr_always(Lr, R, s, CMTJB_FIELD_CYCLE, i, d.cycle);
       break;
     case CMTJB_UPD_SINE:
     case CMTJB_UPD_POSINE:
     case CMTJB_UPD_HALFSINE:
-      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_FREQUENCY, i, d.frequency);
-      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_PHASE, i, d.phase);
+      f.p0 = ovr_always(Lr, R, s, CMTJB_FIELD_FREQUENCY, i, d.frequency);
+      f.p1 = ovr_always(Lr, R, s, CMTJB_FIELD_PHASE, i, d.phase);
       break;
     case CMTJB_UPD_STEP:
-      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
-      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTOP, i, d.timeStop);
+      f.p0 = ovr_always(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+      f.p1 = ovr_always(Lr, R, s, CMTJB_FIELD_TIMESTOP, i, d.timeStop);
       break;
     case CMTJB_UPD_TRAPEZOID:
-      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
-      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
-      f.p2 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_STEADYTIME, i, d.steadyTime);
+      f.p0 = ovr_always(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+      f.p1 = ovr_always(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
+      f.p2 = ovr_always(Lr, R, s, CMTJB_FIELD_STEADYTIME, i, d.steadyTime);
       break;
     case CMTJB_UPD_GAUSSIMPULSE:
     case CMTJB_UPD_GAUSSSTEP:
-      f.p0 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
-      f.p1 = ovr_or<F>(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
+      f.p0 = ovr_always(Lr, R, s, CMTJB_FIELD_TIMESTART, i, d.timeStart);
+      f.p1 = ovr_always(Lr, R, s, CMTJB_FIELD_EDGETIME, i, d.edgeTime);
       break;
     default: f.type = kFastGeneric; break;  // custom etc.: not evaluable inline
     }

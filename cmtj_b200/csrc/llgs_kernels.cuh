@@ -204,7 +204,7 @@ __device__ __forceinline__ d3 rk4_layer(const DevModel<NL> &M, const RunParams &
   const d3 m0 = S0.m[l];
   const StageTime t0{t, row}, t1{t + 0.5 * R.dt, row + R.dyn_ncols}, t2{t + R.dt, row + 2 * R.dyn_ncols};
   d3 u1, u2, u3, u4;
-  if ((layer_mask(F, l) & F_DYNI) != 0 && fd != nullptr) {
+  if (((layer_mask(F, l) & F_DYNI) != 0 || (F & F_FAST) != 0) && fd != nullptr) {
     // the plain-driver field at the step's three distinct stage times, from the resolved driver
     constexpr uint32_t FL = layer_mask(F, l);
     const d3 H0 = stage_field<FL>(Lr, R, l, i, t0, Hc[l], fd[l]), H1 = stage_field<FL>(Lr, R, l, i, t1, Hc[l], fd[l]),
@@ -335,7 +335,7 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
   // F_DYNI RK4 variants (VSD maps): the single time-dependent field driver of each layer, resolved once
   FastDrv fdrv[NL];
   const FastDrv *fd = nullptr;
-  if constexpr ((F & F_DYNI) != 0 && SOLVER == CMTJB_RK4 && F != F_ALL) {
+  if constexpr ((F & (F_DYNI | F_FAST)) != 0 && SOLVER == CMTJB_RK4 && F != F_ALL) {
 #pragma unroll
     for (int l = 0; l < NL; l++) fdrv[l] = resolve_fast<F>(M.L[l], R, i);
     fd = fdrv;

@@ -6,10 +6,12 @@ namespace cmtjb {
 static const Variant kTable[] = {
     CMTJB_FIXED(1, CMTJB_RK4, F_POST),            // the relaxation segment after the pulse window (constant drivers)
     CMTJB_FIXED(1, CMTJB_RK4, F_DYN | F_POST),    // PIMM / VSD of a single layer, batch-uniform excitation
-    CMTJB_FIXED(1, CMTJB_RK4, F_DYNI | F_OVR | F_POST),   // VSD with a per-instance excitation frequency
+    CMTJB_FIXED(1, CMTJB_RK4, F_FAST | F_POST),           // VSD with a per-instance excitation frequency (resolved once)
+    CMTJB_FIXED(1, CMTJB_RK4, F_DYNI | F_OVR | F_POST),   // ... the general inline-evaluating form
     CMTJB_FIXED(1, CMTJB_RK4, F_ALL | F_POST),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_POST),           // relaxation segment of the two-layer PIMM sweep
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN | F_POST),   // PIMM of the two-layer MTJ (bench S1)
+    CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_FAST | F_POST),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYNI | F_OVR | F_POST),
     CMTJB_FIXED(2, CMTJB_RK4, F_ALL | F_POST),
     CMTJB_FIXED(3, CMTJB_RK4, F_ALL_TAB | F_POST),

@@ -5,6 +5,7 @@ static const Variant kTable[] = {
     // lean: folded K1+demag diagonal operator + constant fields
     CMTJB_FIXED(1, CMTJB_RK4, 0),
     CMTJB_FIXED(1, CMTJB_RK4, F_DYN),
+    CMTJB_FIXED(1, CMTJB_RK4, F_FAST),           // one field driver per layer with per-instance waveform (VSD map)
     CMTJB_FIXED(1, CMTJB_RK4, F_STT),
     CMTJB_FIXED(1, CMTJB_RK4, F_STT | F_DYNS),   // current-driven switching: time-dependent current, batch-uniform waveform
     CMTJB_FIXED(1, CMTJB_RK4, F_SOT | F_DYNS),
@@ -13,6 +14,7 @@ static const Variant kTable[] = {
     CMTJB_FIXED(1, CMTJB_RK4, F_ALL),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN),
+    CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_FAST),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_STT),            // two-layer STT junction (free + reference layer)
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_STT | F_DYNS),
     CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_DYN | F_DYNS | F_NOFOLD),

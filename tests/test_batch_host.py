@@ -109,12 +109,15 @@ def test_kernel_variant_selection_rules():
     # no time-dependent driver: the lean variant
     b0 = cm.JunctionBatch(helpers.two_layer_mtj(cm), 4)
     assert b0.selected_variant(1e-9, dt, 1e-11) == "CMTJB_RK4/L2/F_IEC"
-    # per-instance frequency: the shared stage table cannot hold it -> inline evaluation (general variant)
+    # per-instance frequency: the shared stage table cannot hold it -> the fast-field variant, or the general
+    # inline-evaluating one when overrides reach beyond that driver
     j = helpers.two_layer_mtj(cm)
     j.setLayerOerstedFieldDriver("all", cm.AxialDriver(cm.NullDriver(), cm.ScalarDriver.getSineDriver(0, 50, 5e9, 0), cm.NullDriver()))
     b = cm.JunctionBatch(j, 4)
     b.set_override("all", "Hoe_y", "frequency", np.linspace(1e9, 4e9, 4))
-    assert "F_ALL" in b.selected_variant(1e-9, dt, 1e-11) and "SPLIT" not in b.selected_variant(1e-9, dt, 1e-11)
+    assert b.selected_variant(1e-9, dt, 1e-11) == "CMTJB_RK4/L2/F_IEC | F_FAST"  # one field driver per layer: resolved once
+    b.set_override("free", "K1", "constantValue", np.linspace(1e3, 2e3, 4))       # a per-instance SCALAR slot as well
+    assert "F_ALL" in b.selected_variant(1e-9, dt, 1e-11) and "F_FAST" not in b.selected_variant(1e-9, dt, 1e-11)
     # CIMS shape: torque drivers and per-instance amplitudes on the free layer only -> split variant
     j = helpers.tri_layer_mtj(cm)
     j.setLayerFieldLikeTorqueDriver("free", cm.stepDriver(0, 1e3, 0, 1e-9))
