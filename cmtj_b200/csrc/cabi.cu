@@ -760,7 +760,7 @@ struct Slab {
   void *p = nullptr;
   size_t bytes = 0;
 };
-std::mutex g_slab_mu;
+std::mutex g_slab_mu[64];  // one per device: host-entry calls on different devices run concurrently
 Slab g_slab[64];
 
 int slab_reserve(int device, size_t bytes, void **out) {
@@ -864,13 +864,14 @@ int cmtjb_select_variant(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
 }
 
 int cmtjb_release_cache(void) {
-  std::lock_guard<std::mutex> lock(g_slab_mu);
-  for (int d = 0; d < 64; d++)
+  for (int d = 0; d < 64; d++) {
+    std::lock_guard<std::mutex> lock(g_slab_mu[d]);
     if (g_slab[d].p) {
       cudaSetDevice(d);
       cudaFree(g_slab[d].p);
       g_slab[d] = Slab();
     }
+  }
   return CMTJB_OK;
 }
 
@@ -971,7 +972,8 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   const size_t n_cust = (args->custom_table && args->n_custom > 0) ? (size_t)3 * plan.total_iterations * args->n_custom * sizeof(double) : 0;
   const size_t total = al(nm) + al(nlog_dev) + 2 * al(B * sizeof(int32_t)) + al(n_tlog) + al(n_onef) + al(n_cust) +
                        (size_t)n_overrides * al(B * sizeof(double)) + 256;
-  std::lock_guard<std::mutex> lock(g_slab_mu);
+  if (device < 0 || device >= 64) return fail(CMTJB_EINVAL, "device index out of range");
+  std::lock_guard<std::mutex> lock(g_slab_mu[device]);
   void *base = nullptr;
   rc = slab_reserve(device, total, &base);
   if (rc) return rc;
