@@ -964,7 +964,18 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   const bool chunked = n_chunks > 1;
   const long long chunk_samples = chunked ? (plan.n_samples + n_chunks - 1) / n_chunks + 1 : plan.n_samples;
   const size_t chunk_elems = (size_t)plan.n_channels * chunk_samples * B;
-  const size_t nlog_dev = chunked ? 2 * chunk_elems * sizeof(double) : nlog;
+  // ring of chunk buffers: as many as fit in a quarter of the free device memory (at most 24 GB), at least two.
+  // With the whole log in the ring the integration never waits for a copy, so a transient slowdown of the host
+  // side (other tenants of the host's memory) only delays the copies; with two buffers it still streams.
+  int n_buf = 1;
+  if (chunked) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
+    const size_t budget = std::min<size_t>(free_b / 4, (size_t)24 << 30);
+    n_buf = (int)std::max<size_t>(2, std::min<size_t>((size_t)n_chunks, budget / std::max<size_t>(chunk_elems * sizeof(double), 1)));
+    if (const char *c = std::getenv("CMTJB_HOST_RING")) n_buf = std::max(2, std::min(n_chunks, std::atoi(c)));  // tests: force buffer reuse
+  }
+  const size_t nlog_dev = chunked ? (size_t)n_buf * chunk_elems * sizeof(double) : nlog;
   // carve every device buffer of this call out of the per-device slab (256-byte aligned)
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t n_tlog = (plan.variable_samples && want_log && time_log) ? (size_t)plan.n_samples * B * sizeof(double) : 0;
@@ -1014,9 +1025,9 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     CUDA_TRY(cudaDeviceSynchronize());
     if (want_log) CUDA_TRY(cudaMemcpy(log, d_log, nlog, cudaMemcpyDeviceToHost));
   } else {
-    // Large fixed-step logs: the run is cut into time chunks; chunk c integrates into device buffer c % 2
-    // while the copy engine streams chunk c-1 to the host (effective when `log` is pinned memory).  Device
-    // memory for the log is two chunk buffers whatever the length of the run, so a log larger than HBM
+    // Large fixed-step logs: the run is cut into time chunks; chunk c integrates into buffer c % n_buf of a ring
+    // while the copy engine streams the finished chunks to the host (effective when `log` is pinned memory).
+    // Device memory for the log is bounded by the ring whatever the length of the run, so a log larger than HBM
     // (full-rate PIMM logs: 56 B per junction-step) streams through.
     cudaStream_t sc = nullptr, sd = nullptr;
     CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
@@ -1030,16 +1041,17 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
       cudaEventCreate(&t_start);
       cudaEventRecord(t_start, sc);
     }
-    cudaEvent_t copied[2] = {nullptr, nullptr};  // buffer b has been drained to the host
+    std::vector<cudaEvent_t> copied(n_buf, nullptr);  // buffer b has been drained to the host
     for (int c = 0; c < n_chunks && rc == CMTJB_OK; c++) {
       const long long s0 = plan.n_samples * c / n_chunks, s1 = plan.n_samples * (c + 1) / n_chunks;
-      double *buf = d_log + (size_t)(c & 1) * chunk_elems;
+      const int bi = c % n_buf;
+      double *buf = d_log + (size_t)bi * chunk_elems;
       Span sp;
       sp.it_begin = (c == 0) ? S0 : i0 + s0 * we;
       sp.it_end = (c == n_chunks - 1) ? plan.total_iterations : i0 + s1 * we;
       sp.first_sample = 0;
       sp.n_samples = chunk_samples;
-      if (copied[c & 1]) cudaStreamWaitEvent(sc, copied[c & 1], 0);
+      if (copied[bi]) cudaStreamWaitEvent(sc, copied[bi], 0);
       rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, buf, d_status, d_ns, d_tlog, sc, nullptr, &sp);
       if (rc) break;
       cudaEvent_t ev;
@@ -1054,7 +1066,7 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
       cudaEventCreateWithFlags(&done, trace ? cudaEventDefault : cudaEventDisableTiming);
       evs.push_back(done);
       cudaEventRecord(done, sd);
-      copied[c & 1] = done;
+      copied[bi] = done;
     }
     if (trace_host) std::fprintf(stderr, "[cmtjb] host: all chunks enqueued at %.2f ms\n", wall_ms());
     cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sd);

@@ -122,13 +122,18 @@ def test_balanced_fused_post_is_bit_identical(on_cuda):
     _same(_forced("1", run), _forced("0", run))
 
 
-def test_host_entry_streams_large_logs_in_time_chunks(on_cuda):
-    """cmtjb_run_host cuts logs above 64 MB into time chunks that integrate into two alternating device
-    buffers while the previous chunk is copied out; the assembled host log must equal the device-resident
-    log of the same run bit for bit (both forms, sample rows that do not divide evenly into chunks)."""
+@pytest.mark.parametrize("ring", [None, "2", "3"])
+def test_host_entry_streams_large_logs_in_time_chunks(on_cuda, monkeypatch, ring):
+    """cmtjb_run_host cuts logs above 64 MB into time chunks that integrate into a ring of device buffers
+    while finished chunks are copied out; the assembled host log must equal the device-resident log of the
+    same run bit for bit (sample rows that do not divide evenly into chunks; ring forced down to 2 and 3
+    buffers so that buffers are reused while their previous content is still being copied)."""
     import torch
 
-    B, steps, we = 5000, 3030, 10  # 7 x 303 x 5000 doubles = 85 MB -> 16 chunks of 18.9 samples
+    if ring:
+        monkeypatch.setenv("CMTJB_HOST_RING", ring)
+
+    B, steps, we = 5000, 3030, 10  # 7 x 303 x 5000 doubles = 85 MB -> 32 chunks of 9.5 samples
     b = _batch(helpers.two_layer_mtj, B, seed=9)
     host = dict(b.run(steps * DT * (1 + 1e-9), DT, we * DT * (1 + 1e-9)))
     final_host = b.m_state.copy()
