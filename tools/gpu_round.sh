@@ -3,7 +3,7 @@
 # full ncu capture of the dominant kernel.  Outputs land in gpurun_out/ (scratch); summaries are
 # copied into profiles/ by tools/summarise_profiles.py afterwards.
 set -u
-mkdir -p gpurun_out
+rm -rf gpurun_out/summary; mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
