@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LAYERS = 8
 NSLOTS = 30
 

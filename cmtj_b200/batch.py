@@ -202,10 +202,6 @@ class JunctionBatch:
             raise RuntimeError((lib.cmtjb_last_error() or b"").decode())
         return name.value.decode()
 
-    def _check_onef(self):
-        if any(l.noiseScale != 0 for l in self.junction._layers):
-            raise NotImplementedError("1/f^alpha noise is only wired for single-instance Junction.runSimulation")
-
     def _package(self, plan: _abi.Plan, log: Optional[np.ndarray], timeStep: float, tlog, nsamp) -> BatchLog:
         out = BatchLog()
         if log is None:
@@ -234,7 +230,6 @@ class JunctionBatch:
     ) -> BatchLog:
         """Integrate every instance; host buffers in, host buffers out (H2D/D2H inside).
         ``out`` may be a preallocated (e.g. pinned) float64 array [n_channels, n_samples, B]."""
-        self._check_onef()
         self.sync_state_to_host()
         self._m_dev = None
         be = _abi.backend()
@@ -285,7 +280,6 @@ class JunctionBatch:
         run whose first steps were integrated by an earlier call (state carried on the device)."""
         import torch
 
-        self._check_onef()
         be = _abi.cuda_backend()
         lib = be.lib
         dev = torch.device("cuda", self.device)

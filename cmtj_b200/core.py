@@ -1244,21 +1244,6 @@ class Junction:
                     tab[3 * i + st, c] = d.getCurrentScalarValue(ts[st])
         return tab
 
-    def _make_onef(self, total_iterations: int) -> Optional[np.ndarray]:
-        """getSolver (junction.hpp:1905-1916): a fresh VectorAlphaNoise buffer per run for every
-        layer with scaleNoise != 0; generated on the host once (setup, not the hot path)."""
-        if not any(l.noiseScale != 0 for l in self._layers):
-            return None
-        from .noise import vector_alpha_noise
-
-        buf = np.zeros((self.layerNo * 3, max(total_iterations, 1), 1), dtype=np.float64)
-        for i, l in enumerate(self._layers):
-            if l.noiseScale != 0:
-                buf[3 * i : 3 * i + 3, :total_iterations, 0] = vector_alpha_noise(
-                    total_iterations, l.noiseAlpha, l.noiseStd, l.noiseScale, l.noiseAxis
-                )
-        return buf
-
     # -- the hot path entry ---------------------------------------------------------------------------
     def runSimulation(
         self,
@@ -1285,13 +1270,10 @@ class Junction:
         args.n_instances = 1
         args.instance_offset = 0
         args.start_iteration = 0
-        args.onef_buffer = None
+        args.onef_buffer = None  # 1/f^alpha noise (setAlphaNoise) is generated by the library on the device
         plan = be.plan(jn, layers, args)
         if plan.solver_overridden:
             print("[WARNING] Solver automatically changed to Euler Heun for stochastic calculation.")
-        onef = self._make_onef(int(plan.total_iterations))
-        if onef is not None:
-            args.onef_buffer = onef.ctypes.data
         custom = self._custom_table(layers, plan, timeStep)
         if custom is not None:
             args.custom_table = custom.ctypes.data

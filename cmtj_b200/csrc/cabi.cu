@@ -20,6 +20,7 @@
 #include "dev_model.h"
 #include "host_common.h"
 #include "llgs_kernels.cuh"
+#include "onef.h"
 
 namespace cmtjb {
 // variant tables, one per translation unit (variants_*.cu)
@@ -70,6 +71,12 @@ int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
         mode = CMTJB_EULER_HEUN;
         p->solver_overridden = 1;
       }
+    }
+    if (L.noiseScale != 0) {
+      // setAlphaNoise (junction.hpp:406-414) / VectorAlphaNoise (noise.hpp:285-287)
+      if (L.noiseAlpha < 0 || L.noiseAlpha > 2) return fail(CMTJB_ERUNTIME, "alpha must be between 0 and 2");
+      if (L.noiseAxis < CMTJB_AXIS_X || L.noiseAxis > CMTJB_AXIS_ALL)
+        return fail(CMTJB_ERUNTIME, "Invalid axis specified: " + std::to_string(L.noiseAxis));
     }
     if (L.temperatureSet && L.cellSurface * L.thickness == 0.0)
       return fail(CMTJB_ERUNTIME, "Cell surface cannot be 0 during temp. calculations!");
@@ -180,7 +187,7 @@ uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
     else if (L.includeSOT) F |= F_SOT;
     if (solver == CMTJB_HEUN || solver == CMTJB_EULER_HEUN) {
       if (L.temperatureSet) F |= F_THERMAL;
-      if (L.noiseScale != 0 && a->onef_buffer) F |= F_ONEF;
+      if (L.noiseScale != 0) F |= F_ONEF;  // the caller's buffer, or generated on the device (onef.cu)
     }
     for (int s = 0; s < CMTJB_NSLOTS; s++)
       if (slot_dynamic(L.drivers[s])) F |= (s < CMTJB_SLOT_K1) ? F_DYN : F_DYNS;
@@ -256,8 +263,12 @@ const Variant *pick_variant(int nl, int solver, uint32_t need, const uint32_t *p
 
 // sub-range of a run executed by one launch (time-chunked pipelining in cmtjb_run_host)
 struct Span {
-  long long it_begin, it_end, first_sample;
+  long long it_begin = 0, it_end = 0, first_sample = 0;
   long long n_samples = 0;  // > 0: `log` is a buffer of this many sample rows per channel (a time chunk), not the whole log
+  // instance sub-range of this launch (i_hi < 0: all) and the device-generated 1/f^alpha buffer covering it (onef.cu)
+  long long i_lo = 0, i_hi = -1;
+  const float *onef_gen = nullptr;
+  long long onef_i0 = 0, onef_B = 0;
 };
 
 }  // namespace
@@ -281,7 +292,8 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
   if (force && force[0] == '0') return bp;
   const bool forced = force && force[0] == '1';
   const long long steps = R.it_end - R.it_begin;
-  if (steps <= 0 || R.B <= 0) return bp;
+  const long long n_inst = R.i_hi - R.i_lo;  // instances of this launch (a sub-batch when noise buffers are generated in pieces)
+  if (steps <= 0 || n_inst <= 0) return bp;
   static int n_sm[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return bp;
@@ -293,7 +305,7 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
     return bp;
   }
   bal_blocks = std::min(bal_blocks, 8);  // kBalBlock = 4 warps: at most 8 resident warps per sub-partition
-  const long long W = (R.B + 31) / 32;
+  const long long W = (n_inst + 31) / 32;
   const double mean = (double)W / (4.0 * n_sm[dev]);
   const double cap = plain_blocks * (kBlock / 32) / 4.0;  // resident warps per sub-partition, plain form
   const double waves = mean / cap;
@@ -422,6 +434,18 @@ void set_step_products(DevLayer &D, double dt) {
   D.h_sixth = D.h * (1.0 / 6.0);
 }
 
+// where each layer's generated 1/f^alpha series sit in RunParams::onef_gen, and how tickVector combines them
+void set_onef_slots(const cmtjb_layer_t *layers, int n_layers, DevLayer *D) {
+  OnefSlot slots[3 * CMTJB_MAX_LAYERS];
+  int first[CMTJB_MAX_LAYERS];
+  if (onef_slots_of(layers, n_layers, slots, first) < 0) return;  // invalid axis: rejected in make_plan
+  for (int l = 0; l < n_layers; l++) {
+    D[l].onef_slot = first[l] < 0 ? 0 : first[l];
+    D[l].onef_axis = layers[l].noiseAxis;
+    D[l].onef_scale = layers[l].noiseScale;
+  }
+}
+
 namespace {
 
 // RunParams of one launch of a single-junction batch (everything except the override rows)
@@ -441,12 +465,20 @@ void fill_run_params(RunParams &R, const cmtjb_junction_t *jn, int NL, const cmt
   R.n_custom = a->n_custom;
   R.B = a->n_instances;
   R.inst_offset = a->instance_offset;
+  const bool ranged = span != nullptr;
   R.n_samples = (span && span->n_samples > 0) ? span->n_samples : plan.n_samples;
-  R.it_begin = span ? span->it_begin : a->start_iteration;
-  R.it_end = span ? span->it_end : plan.total_iterations;
+  R.it_begin = ranged ? span->it_begin : a->start_iteration;
+  R.it_end = ranged ? span->it_end : plan.total_iterations;
   R.total_iterations = plan.total_iterations;
   R.write_every = plan.write_every > 0 ? plan.write_every : 1;
-  R.first_sample = span ? span->first_sample : 0;
+  R.first_sample = ranged ? span->first_sample : 0;
+  R.i_lo = span ? span->i_lo : 0;
+  R.i_hi = (span && span->i_hi >= 0) ? span->i_hi : a->n_instances;
+  if (span && span->onef_gen) {
+    R.onef_gen = span->onef_gen;
+    R.onef_i0 = span->onef_i0;
+    R.onef_B = span->onef_B;
+  }
   R.dt = a->timeStep;
   R.sqrt_dt = std::sqrt(a->timeStep);
   R.total_time = a->totalTime;
@@ -495,7 +527,8 @@ int run_typed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmt
     }
   }
   fill_run_params(R, jn, NL, a, plan, m_state, log, status, n_samples_out, time_log, span, post);
-  if (R.B <= 0) return CMTJB_OK;
+  if (R.B <= 0 || R.i_hi <= R.i_lo) return CMTJB_OK;
+  set_onef_slots(layers, NL, M.L);
   // table of the time-dependent drivers at this launch's stage times (F_DYN / F_DYNS variants)
   double *tab = nullptr;
   if ((v->features & (F_DYN | F_DYNS)) && !(v->features & F_DYNI) && R.it_end > R.it_begin) {
@@ -545,7 +578,6 @@ int run_wide(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtj
   if (plan.effective_solver == CMTJB_DORMAND_PRINCE) return fail(CMTJB_ENOTSUP, "Dormand-Prince is single-layer only");
   std::vector<DevLayer> L(NL);
   for (int l = 0; l < NL; l++) {
-    if (layers[l].noiseScale != 0 && !a->onef_buffer) return fail(CMTJB_EINVAL, "1/f noise requested without a buffer");
     for (int s = 0; s < CMTJB_NSLOTS; s++)
       if (layers[l].drivers[s].update == CMTJB_UPD_CUSTOM)
         return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers support junctions of at most 4 layers");
@@ -563,7 +595,8 @@ int run_wide(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtj
     }
   }
   fill_run_params(R, jn, NL, a, plan, m_state, log, status, nullptr, nullptr, span, nullptr);
-  if (R.B <= 0 || R.it_end <= R.it_begin) return CMTJB_OK;
+  if (R.B <= 0 || R.it_end <= R.it_begin || R.i_hi <= R.i_lo) return CMTJB_OK;
+  set_onef_slots(layers, NL, L.data());
   DevLayer *dL = nullptr;
   cudaError_t e = cudaMallocAsync((void **)&dL, sizeof(DevLayer) * NL, stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(layer models)");
@@ -682,17 +715,12 @@ bool driver_window(const cmtjb_driver_t &d, double *t0, double *t1) {
   }
 }
 
-int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
-                    const cmtjb_run_args_t *a, double *m_state, double *log, int32_t *status, int32_t *n_samples_out,
-                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span = nullptr,
-                    const cmtjb_post_t *post = nullptr) {
-  cmtjb_plan_t plan;
-  int rc = make_plan(jn, layers, a, &plan);
-  if (rc) return rc;
-  rc = check_overrides(jn, ovr, n_ovr);
-  if (rc) return rc;
-  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
-  plan.variant[0] = 0;
+// Steps [span.it_begin, span.it_end) of instances [span.i_lo, span.i_hi): one launch, or three when the
+// time-dependent drivers have finite support (below).
+int run_device_spans(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                     const cmtjb_run_args_t *a, cmtjb_plan_t &plan, double *m_state, double *log, int32_t *status,
+                     int32_t *n_samples_out, double *time_log, cudaStream_t stream, const Span *span, const cmtjb_post_t *post) {
+  int rc = CMTJB_OK;
   // Time-window specialisation: when every time-dependent driver has finite support and none of its
   // timing fields varies per instance, only the steps inside the union of the windows run the
   // driver-evaluating variant; the steps before and after run the lean constant-driver variant
@@ -716,14 +744,9 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
       w1 = any_dynamic ? std::max(w1, t1) : t1;
       any_dynamic = true;
     }
-  const long long it0 = span ? span->it_begin : a->start_iteration;
-  const long long it1 = span ? span->it_end : plan.total_iterations;
-  const long long fs0 = span ? span->first_sample : 0;
-  if (!windowed || !any_dynamic || it1 <= it0) {
-    rc = launch_span(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log, stream, span, post);
-    if (plan_out) *plan_out = plan;
-    return rc;
-  }
+  const long long it0 = span->it_begin, it1 = span->it_end, fs0 = span->first_sample;
+  if (!windowed || !any_dynamic || it1 <= it0)
+    return launch_span(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log, stream, span, post);
   // step `it` touches times [it*dt, it*dt + dt]; two steps of margin absorb rounding at the edges
   const double dt = a->timeStep;
   long long a_on = (long long)std::floor(w0 / dt) - 2, a_off = (long long)std::ceil(w1 / dt) + 2;
@@ -740,15 +763,105 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
   auto count_upto = [&](long long m) { return m <= 0 ? 0LL : (m - 1) / we + 1; };
   const long long cuts[4] = {it0, a_on, a_off, it1};
   for (int seg = 0; seg < 3 && rc == CMTJB_OK; seg++) {
-    Span sp;
+    Span sp = *span;
     sp.it_begin = cuts[seg];
     sp.it_end = cuts[seg + 1];
     if (sp.it_end <= sp.it_begin) continue;
     sp.first_sample = fs0 + count_upto(sp.it_begin) - count_upto(it0);
-    sp.n_samples = span ? span->n_samples : 0;
     rc = launch_span(jn, seg == 1 ? layers : frozen.data(), ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log,
                      stream, &sp, post);
   }
+  return rc;
+}
+
+// Device memory a run may spend on generated 1/f^alpha buffers: half of what is free now (CMTJB_ONEF_BUDGET_MB
+// overrides, tests use it to force sub-batching).
+size_t onef_budget_bytes() {
+  if (const char *c = std::getenv("CMTJB_ONEF_BUDGET_MB")) return (size_t)std::max(1, std::atoi(c)) << 20;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
+  return free_b / 2;
+}
+
+// does this run draw 1/f^alpha noise that the library has to generate?
+int onef_needed(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a, const cmtjb_plan_t &plan,
+                OnefSlot *slots, int *n_slots) {
+  *n_slots = 0;
+  if (a->onef_buffer) return CMTJB_OK;
+  if (plan.effective_solver != CMTJB_HEUN && plan.effective_solver != CMTJB_EULER_HEUN) return CMTJB_OK;
+  int first[CMTJB_MAX_LAYERS];
+  const int ns = onef_slots_of(layers, jn->n_layers, slots, first);
+  if (ns < 0) return fail(CMTJB_ERUNTIME, "Invalid axis specified");
+  *n_slots = ns;
+  return CMTJB_OK;
+}
+
+int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
+                    const cmtjb_run_args_t *a, double *m_state, double *log, int32_t *status, int32_t *n_samples_out,
+                    double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span_in = nullptr,
+                    const cmtjb_post_t *post = nullptr) {
+  cmtjb_plan_t plan;
+  int rc = make_plan(jn, layers, a, &plan);
+  if (rc) return rc;
+  rc = check_overrides(jn, ovr, n_ovr);
+  if (rc) return rc;
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  plan.variant[0] = 0;
+  Span span;
+  if (span_in) {
+    span = *span_in;
+  } else {
+    span.it_begin = a->start_iteration;
+    span.it_end = plan.total_iterations;
+    span.first_sample = 0;
+  }
+  if (span.i_hi < 0) span.i_hi = a->n_instances;
+  OnefSlot slots[3 * CMTJB_MAX_LAYERS];
+  int n_slots = 0;
+  rc = onef_needed(jn, layers, a, plan, slots, &n_slots);
+  if (rc) return rc;
+  if (n_slots == 0 || span.onef_gen || span.i_hi <= span.i_lo || plan.total_iterations <= 0) {
+    rc = run_device_spans(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log, stream, &span, post);
+    if (plan_out) *plan_out = plan;
+    return rc;
+  }
+  // 1/f^alpha noise (junction.hpp:1905-1916): one float32 buffer of total_iterations samples per (instance, layer,
+  // axis).  When the buffers of the whole batch do not fit the budget, the batch is integrated in sub-batches of
+  // consecutive instances (a multiple of 32), each with its own generation; results do not depend on the split.
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const long long n = plan.total_iterations, n_inst = span.i_hi - span.i_lo;
+  const size_t per_inst = (size_t)n_slots * (size_t)n * sizeof(float);
+  const size_t budget = onef_budget_bytes();
+  long long Bc = (long long)std::min<size_t>((size_t)n_inst, budget / std::max<size_t>(per_inst, 1));
+  if (Bc < n_inst) Bc = (Bc / 32) * 32;
+  if (Bc <= 0) {
+    char buf[256];
+    std::snprintf(buf, sizeof(buf),
+                  "1/f^alpha noise: %zu bytes of noise buffer per instance (%d series x %lld iterations x 4 B) do not fit the "
+                  "%zu bytes available for 32 instances at a time; shorten the run or free device memory",
+                  per_inst, n_slots, n, budget);
+    return fail(CMTJB_ERUNTIME, buf);
+  }
+  float *gen = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&gen, per_inst * (size_t)Bc, stream);
+  if (e != cudaSuccess) {
+    char buf[200];
+    std::snprintf(buf, sizeof(buf), "1/f^alpha noise: cudaMallocAsync of %zu bytes failed (%s)", per_inst * (size_t)Bc, cudaGetErrorString(e));
+    return fail(CMTJB_ECUDA, buf);
+  }
+  for (long long i0 = span.i_lo; i0 < span.i_hi && rc == CMTJB_OK; i0 += Bc) {
+    Span sp = span;
+    sp.i_lo = i0;
+    sp.i_hi = std::min(i0 + Bc, span.i_hi);
+    rc = onef_generate(dev, stream, n, slots, n_slots, a->seed, (unsigned long long)(a->instance_offset + i0), sp.i_hi - sp.i_lo, gen);
+    if (rc) break;
+    sp.onef_gen = gen;
+    sp.onef_i0 = i0;
+    sp.onef_B = sp.i_hi - sp.i_lo;
+    rc = run_device_spans(jn, layers, ovr, n_ovr, a, plan, m_state, log, status, n_samples_out, time_log, stream, &sp, post);
+  }
+  cudaFreeAsync(gen, stream);
   if (plan_out) *plan_out = plan;
   return rc;
 }
@@ -760,6 +873,12 @@ struct Slab {
   void *p = nullptr;
   size_t bytes = 0;
 };
+// Where the last cmtjb_run_host call of this thread spent its time (cmtjb_host_stats; bench.py puts it into e2e).
+struct HostStats {
+  double total_ms = 0, integrate_ms = 0, ring_wait_ms = 0, copy_ms = 0, tail_copy_ms = 0, pipeline_ms = 0, log_bytes = 0;
+  int n_chunks = 1, n_ring = 1;
+};
+thread_local HostStats g_host_stats;
 std::mutex g_slab_mu[64];  // one per device: host-entry calls on different devices run concurrently
 Slab g_slab[64];
 
@@ -1018,11 +1137,46 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     CUDA_TRY(cudaMemcpy(d_cust, args->custom_table, n_cust, cudaMemcpyHostToDevice));
     a.custom_table = d_cust;
   }
+  // the staging copies above ran on the legacy stream; a pageable cudaMemcpy may return before its DMA has
+  // landed, and the streams below do not synchronise with the legacy stream
+  CUDA_TRY(cudaDeviceSynchronize());
   if (trace_host) std::fprintf(stderr, "[cmtjb] host: inputs staged at %.2f ms\n", wall_ms());
+  HostStats hs_stats;
+  hs_stats.n_chunks = n_chunks;
+  hs_stats.n_ring = n_buf;
+  // 1/f^alpha noise generated by the library: once for the whole run when it fits the budget (time chunks then
+  // share the buffer), in instance sub-batches by run_device_impl otherwise (the log is then kept resident)
+  float *d_gen = nullptr;
+  Span gen_span;  // carries the pre-generated buffer into every time chunk
+  {
+    OnefSlot slots[3 * CMTJB_MAX_LAYERS];
+    int n_slots = 0;
+    rc = onef_needed(jn, layers, &a, plan, slots, &n_slots);
+    if (rc) return rc;
+    if (n_slots > 0 && chunked) {
+      const size_t need = (size_t)n_slots * (size_t)plan.total_iterations * sizeof(float) * (size_t)B;
+      if (need > onef_budget_bytes())
+        return fail(CMTJB_ERUNTIME, "1/f^alpha noise: the noise buffers of this batch (" + std::to_string(need) +
+                                        " bytes) and a log of " + std::to_string(nlog) +
+                                        " bytes do not fit the device together; run fewer instances per call or decimate the log");
+      CUDA_TRY(cudaMalloc((void **)&d_gen, need));
+      rc = onef_generate(device, nullptr, plan.total_iterations, slots, n_slots, a.seed, (unsigned long long)a.instance_offset, B, d_gen);
+      if (rc == CMTJB_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(CMTJB_ECUDA, "1/f^alpha noise generation failed");
+      if (rc) {
+        cudaFree(d_gen);
+        return rc;
+      }
+      gen_span.onef_gen = d_gen;
+      gen_span.onef_i0 = 0;
+      gen_span.onef_B = B;
+    }
+  }
   if (!chunked) {
+    const double t_staged = wall_ms();
     rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, d_log, d_status, d_ns, d_tlog, nullptr, nullptr);
     if (rc) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
+    hs_stats.integrate_ms = wall_ms() - t_staged;
     if (want_log) CUDA_TRY(cudaMemcpy(log, d_log, nlog, cudaMemcpyDeviceToHost));
   } else {
     // Large fixed-step logs: the run is cut into time chunks; chunk c integrates into buffer c % n_buf of a ring
@@ -1030,63 +1184,84 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
     // Device memory for the log is bounded by the ring whatever the length of the run, so a log larger than HBM
     // (full-rate PIMM logs: 56 B per junction-step) streams through.
     cudaStream_t sc = nullptr, sd = nullptr;
-    CUDA_TRY(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+    cudaError_t es = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
+    if (es == cudaSuccess) es = cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking);
+    if (es != cudaSuccess) {
+      if (sc) cudaStreamDestroy(sc);
+      if (d_gen) cudaFree(d_gen);
+      return cuda_fail(es, "cudaStreamCreateWithFlags");
+    }
     const long long we = plan.write_every, S0 = a.start_iteration;
     const long long i0 = ((S0 + we - 1) / we) * we;  // iteration of this run's sample 0
-    std::vector<cudaEvent_t> evs;
-    const bool trace = std::getenv("CMTJB_TRACE_HOST") != nullptr;
-    cudaEvent_t t_start = nullptr;
-    if (trace) {
-      cudaEventCreate(&t_start);
-      cudaEventRecord(t_start, sc);
+    // per chunk: integration started / finished (compute stream), copy finished (copy stream)
+    std::vector<cudaEvent_t> ev_begin(n_chunks, nullptr), ev_end(n_chunks, nullptr), ev_copied(n_chunks, nullptr);
+    for (int c = 0; c < n_chunks; c++) {
+      cudaEventCreate(&ev_begin[c]);
+      cudaEventCreate(&ev_end[c]);
+      cudaEventCreate(&ev_copied[c]);
     }
-    std::vector<cudaEvent_t> copied(n_buf, nullptr);  // buffer b has been drained to the host
+    int enqueued = 0;
     for (int c = 0; c < n_chunks && rc == CMTJB_OK; c++) {
       const long long s0 = plan.n_samples * c / n_chunks, s1 = plan.n_samples * (c + 1) / n_chunks;
       const int bi = c % n_buf;
       double *buf = d_log + (size_t)bi * chunk_elems;
-      Span sp;
+      Span sp = gen_span;
       sp.it_begin = (c == 0) ? S0 : i0 + s0 * we;
       sp.it_end = (c == n_chunks - 1) ? plan.total_iterations : i0 + s1 * we;
       sp.first_sample = 0;
       sp.n_samples = chunk_samples;
-      if (copied[bi]) cudaStreamWaitEvent(sc, copied[bi], 0);
+      if (c >= n_buf) cudaStreamWaitEvent(sc, ev_copied[c - n_buf], 0);  // buffer bi has been drained to the host
+      cudaEventRecord(ev_begin[c], sc);
       rc = run_device_impl(jn, layers, d_ovr.data(), n_overrides, &a, d_m, buf, d_status, d_ns, d_tlog, sc, nullptr, &sp);
       if (rc) break;
-      cudaEvent_t ev;
-      cudaEventCreateWithFlags(&ev, trace ? cudaEventDefault : cudaEventDisableTiming);
-      evs.push_back(ev);
-      cudaEventRecord(ev, sc);
-      cudaStreamWaitEvent(sd, ev, 0);
+      cudaEventRecord(ev_end[c], sc);
+      cudaStreamWaitEvent(sd, ev_end[c], 0);
       for (int ch = 0; ch < plan.n_channels; ch++)
         cudaMemcpyAsync(log + ((size_t)ch * plan.n_samples + s0) * B, buf + (size_t)ch * chunk_samples * B,
                         (size_t)(s1 - s0) * B * sizeof(double), cudaMemcpyDeviceToHost, sd);
-      cudaEvent_t done;
-      cudaEventCreateWithFlags(&done, trace ? cudaEventDefault : cudaEventDisableTiming);
-      evs.push_back(done);
-      cudaEventRecord(done, sd);
-      copied[bi] = done;
+      cudaEventRecord(ev_copied[c], sd);
+      enqueued = c + 1;
     }
     if (trace_host) std::fprintf(stderr, "[cmtjb] host: all chunks enqueued at %.2f ms\n", wall_ms());
     cudaError_t e1 = cudaStreamSynchronize(sc), e2 = cudaStreamSynchronize(sd);
     if (trace_host) std::fprintf(stderr, "[cmtjb] host: streams drained at %.2f ms\n", wall_ms());
-    if (trace && rc == CMTJB_OK) {  // CMTJB_TRACE_HOST=1: when each chunk finished integrating / copying (ms from the start)
-      for (size_t k = 0; k + 1 < evs.size(); k += 2) {
-        float a_ms = 0, b_ms = 0;
-        cudaEventElapsedTime(&a_ms, t_start, evs[k]);
-        cudaEventElapsedTime(&b_ms, t_start, evs[k + 1]);
-        std::fprintf(stderr, "[cmtjb] chunk %zu: integrated %.1f ms, copied %.1f ms\n", k / 2, a_ms, b_ms);
+    if (rc == CMTJB_OK && e1 == cudaSuccess && e2 == cudaSuccess) {
+      // where the time went: integration, gaps on the compute stream (waiting for a ring buffer to drain), and the
+      // copy engine -- busy, or idle waiting for the next chunk
+      float ms = 0;
+      double prev_end = 0, prev_copied = 0;
+      for (int c = 0; c < enqueued; c++) {
+        cudaEventElapsedTime(&ms, ev_begin[0], ev_begin[c]);
+        const double tb = ms;
+        cudaEventElapsedTime(&ms, ev_begin[0], ev_end[c]);
+        const double te = ms;
+        cudaEventElapsedTime(&ms, ev_begin[0], ev_copied[c]);
+        const double tc = ms;
+        hs_stats.integrate_ms += te - tb;
+        if (c > 0) hs_stats.ring_wait_ms += std::max(0.0, tb - prev_end);
+        hs_stats.copy_ms += tc - std::max(te, prev_copied);
+        if (trace_host) std::fprintf(stderr, "[cmtjb] chunk %d: integration %.1f..%.1f ms, copied %.1f ms\n", c, tb, te, tc);
+        prev_end = te;
+        prev_copied = tc;
+        hs_stats.pipeline_ms = tc;
+        hs_stats.tail_copy_ms = tc - te;
       }
     }
-    if (t_start) cudaEventDestroy(t_start);
-    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+    for (int c = 0; c < n_chunks; c++) {
+      cudaEventDestroy(ev_begin[c]);
+      cudaEventDestroy(ev_end[c]);
+      cudaEventDestroy(ev_copied[c]);
+    }
     cudaStreamDestroy(sc);
     cudaStreamDestroy(sd);
+    if (d_gen) cudaFree(d_gen);
     if (rc) return rc;
     if (e1 != cudaSuccess) return cuda_fail(e1, "chunked run (compute stream)");
     if (e2 != cudaSuccess) return cuda_fail(e2, "chunked run (copy stream)");
   }
+  hs_stats.log_bytes = (double)nlog;
+  hs_stats.total_ms = wall_ms();
+  g_host_stats = hs_stats;
   CUDA_TRY(cudaMemcpy(m_state, d_m, nm, cudaMemcpyDeviceToHost));
   if (d_tlog) CUDA_TRY(cudaMemcpy(time_log, d_tlog, (size_t)plan.n_samples * B * sizeof(double), cudaMemcpyDeviceToHost));
   if (d_ns && n_samples_out) CUDA_TRY(cudaMemcpy(n_samples_out, d_ns, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -1100,6 +1275,15 @@ int cmtjb_run_host(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, cons
   if (trace_host) std::fprintf(stderr, "[cmtjb] host: done at %.2f ms\n", wall_ms());
   for (long long i = 0; i < B; i++)
     if (st[i]) return fail(CMTJB_ENAN, "NAN magnetisation");
+  return CMTJB_OK;
+}
+
+int cmtjb_host_stats(double *out, int32_t n) {
+  if (!out || n <= 0) return fail(CMTJB_EINVAL, "null argument");
+  const HostStats &h = g_host_stats;
+  const double v[CMTJB_HOST_NSTATS] = {h.total_ms,     h.integrate_ms, h.ring_wait_ms,     h.copy_ms,         h.tail_copy_ms,
+                                       h.pipeline_ms,  h.log_bytes,    (double)h.n_chunks, (double)h.n_ring};
+  for (int k = 0; k < n && k < CMTJB_HOST_NSTATS; k++) out[k] = v[k];
   return CMTJB_OK;
 }
 

@@ -11,6 +11,7 @@
 
 #include "coupled_kernels.cuh"
 #include "host_common.h"
+#include "onef.h"
 
 namespace cmtjb {
 namespace {
@@ -39,8 +40,6 @@ int validate_system(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *lay
     int rc = make_plan(&jns[j], layers + (size_t)j * c->nl, &aj, &p);
     if (rc) return rc;
     for (int l = 0; l < c->nl; l++) {
-      if (layers[(size_t)j * c->nl + l].noiseScale != 0)
-        return fail(CMTJB_ENOTSUP, "1/f^alpha noise inside a coupled system is not supported");
       for (int s = 0; s < CMTJB_NSLOTS; s++)
         if (layers[(size_t)j * c->nl + l].drivers[s].update == CMTJB_UPD_CUSTOM)
           return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers are not supported inside a coupled system");
@@ -108,9 +107,71 @@ template <int NL> bool models_uniform(const std::vector<DevModel<NL>> &m) {
   return true;
 }
 
+// 1/f^alpha noise of a coupled system (every junction's layers tick their own VectorAlphaNoise inside the
+// junction's stepper, junction.hpp:1725-1727): one series per (element, layer, axis).  The buffer has one slot
+// layout for the whole system, defined per layer index by the first junction that carries noise there; the
+// others must use the same axis, alpha and std (scale may differ, 0 = none).
+struct SystemNoise {
+  OnefSlot slots[3 * CMTJB_MAX_LAYERS];
+  int first[CMTJB_MAX_LAYERS];
+  int n_slots = 0;
+};
+int system_noise(int n, int nl, const cmtjb_layer_t *layers, int solver, SystemNoise *sn) {
+  sn->n_slots = 0;
+  if (solver != CMTJB_EULER_HEUN && solver != CMTJB_HEUN) return CMTJB_OK;
+  std::vector<cmtjb_layer_t> proto(nl);
+  for (int l = 0; l < nl; l++) {
+    proto[l] = layers[l];
+    proto[l].noiseScale = 0;
+    for (int j = 0; j < n; j++) {
+      const cmtjb_layer_t &L = layers[(size_t)j * nl + l];
+      if (L.noiseScale == 0) continue;
+      if (proto[l].noiseScale == 0) {
+        proto[l] = L;
+      } else if (L.noiseAxis != proto[l].noiseAxis || L.noiseAlpha != proto[l].noiseAlpha || L.noiseStd != proto[l].noiseStd) {
+        return fail(CMTJB_ENOTSUP, "1/f^alpha noise in a coupled system: junctions must share axis, alpha and std per layer in this build");
+      }
+    }
+  }
+  const int ns = onef_slots_of(proto.data(), nl, sn->slots, sn->first);
+  if (ns < 0) return fail(CMTJB_ERUNTIME, "Invalid axis specified");
+  sn->n_slots = ns;
+  return CMTJB_OK;
+}
+
+// generate the system's noise buffers for all n_elements elements (stream-ordered); *gen is freed by the caller
+int system_noise_generate(const SystemNoise &sn, const cmtjb_run_args_t *a, long long n_iter, long long n_elements, int n_junctions,
+                          RunParams &R, float **gen, cudaStream_t stream) {
+  *gen = nullptr;
+  if (sn.n_slots == 0 || n_iter <= 0) return CMTJB_OK;
+  const size_t bytes = (size_t)sn.n_slots * (size_t)n_iter * sizeof(float) * (size_t)n_elements;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes > free_b / 2) {
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "1/f^alpha noise: %zu bytes of noise buffers (%d series x %lld iterations x %lld elements x 4 B) exceed half of the %zu bytes free on the device; run fewer instances per call",
+                  bytes, sn.n_slots, n_iter, n_elements, free_b);
+    return fail(CMTJB_ERUNTIME, buf);
+  }
+  cudaError_t e = cudaMallocAsync((void **)gen, bytes, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(1/f noise buffers)");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int rc = onef_generate(dev, stream, n_iter, sn.slots, sn.n_slots, a->seed, (unsigned long long)a->instance_offset * (unsigned long long)n_junctions,
+                         n_elements, *gen);
+  if (rc) {
+    cudaFreeAsync(*gen, stream);
+    *gen = nullptr;
+    return rc;
+  }
+  R.onef_gen = *gen;
+  R.onef_i0 = 0;
+  R.onef_B = n_elements;
+  return CMTJB_OK;
+}
+
 template <int NL>
 void build_models(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr, int n_ovr,
-                  int clear_hres_layer, double dt, std::vector<DevModel<NL>> &out, RunParams &R) {
+                  int clear_hres_layer, double dt, std::vector<DevModel<NL>> &out, RunParams &R, const SystemNoise *sn = nullptr) {
   out.resize(n);
   for (int j = 0; j < n; j++) {
     DevModel<NL> &M = out[j];
@@ -126,6 +187,11 @@ void build_models(int n, const cmtjb_junction_t *jns, const cmtjb_layer_t *layer
       }
       derive_layer(jns[j], L, M.L[l]);
       set_step_products(M.L[l], dt);
+      if (sn && sn->n_slots > 0) {
+        M.L[l].onef_slot = sn->first[l] < 0 ? 0 : sn->first[l];
+        M.L[l].onef_axis = L.noiseAxis;
+        M.L[l].onef_scale = L.noiseScale;
+      }
     }
     M.Rp = jns[j].Rp;
     M.Rhalf = (jns[j].Rap - jns[j].Rp) / 2.0;
@@ -167,6 +233,8 @@ void fill_run_params(RunParams &R, const Common &c, const cmtjb_run_args_t *a, l
   R.log = (a->log_mode == CMTJB_LOG_FULL) ? jlog : nullptr;
   R.status = status;
   R.B = n_elements;
+  R.i_lo = 0;
+  R.i_hi = n_elements;
   R.inst_offset = a->instance_offset;
   R.n_samples = c.plan0.n_samples;
   R.it_begin = a->start_iteration;
@@ -234,8 +302,11 @@ int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmt
   RunParams R;
   std::memset(&R, 0, sizeof(R));
   fill_run_params(R, c, a, n_inst * N, m_state, jlog, status);
+  SystemNoise sn;
+  int rc_n = system_noise(N, NL, layers, c.solver, &sn);
+  if (rc_n) return rc_n;
   std::vector<DevModel<NL>> models;
-  build_models<NL>(N, jns, layers, ovr, n_ovr, -1, a->timeStep, models, R);
+  build_models<NL>(N, jns, layers, ovr, n_ovr, -1, a->timeStep, models, R, &sn);
   StackParams SP;
   std::memset(&SP, 0, sizeof(SP));
   SP.N = N;
@@ -272,6 +343,13 @@ int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmt
   if (e == cudaSuccess) e = upload(st->coupling, (size_t)(N - 1), &d_coupling, stream);
   if (e != cudaSuccess) return cuda_fail(e, "stack parameter upload");
   SP.coupling = d_coupling;
+  float *d_gen = nullptr;
+  rc_n = system_noise_generate(sn, a, c.plan0.total_iterations, n_inst * N, N, R, &d_gen, stream);
+  if (rc_n) {
+    cudaFreeAsync(d_models, stream);
+    cudaFreeAsync(d_coupling, stream);
+    return rc_n;
+  }
   const int threads = SP.spb * N;
   const long long blocks = (n_inst + SP.spb - 1) / SP.spb;
   const size_t smem = (3 * (size_t)threads + 2 * ((size_t)threads / 32 + 1)) * sizeof(double);
@@ -298,6 +376,7 @@ int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmt
   g_launches++;
   cudaFreeAsync(d_models, stream);
   cudaFreeAsync(d_coupling, stream);
+  if (d_gen) cudaFreeAsync(d_gen, stream);
   if (e != cudaSuccess) return cuda_fail(e, "stack_kernel");
   return CMTJB_OK;
 }
@@ -359,8 +438,11 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   RunParams R;
   std::memset(&R, 0, sizeof(R));
   fill_run_params(R, c, a, n_inst * N, m_state, jlog, status);
+  SystemNoise sn;
+  int rc_n = system_noise(N, NL, layers, c.solver, &sn);
+  if (rc_n) return rc_n;
   std::vector<DevModel<NL>> models;
-  build_models<NL>(N, jns, layers, ovr, n_ovr, g->top_layer, a->timeStep, models, R);
+  build_models<NL>(N, jns, layers, ovr, n_ovr, g->top_layer, a->timeStep, models, R, &sn);
   std::vector<double> pos(3 * (size_t)N), pref(N);
   for (int k = 0; k < N; k++) {
     for (int d = 0; d < 3; d++) pos[(size_t)d * N + k] = g->coordinates[3 * k + d];
@@ -381,7 +463,14 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   if (e != cudaSuccess) return cuda_fail(e, "group parameter upload");
   GP.pos = d_pos;
   GP.pref = d_pref;
-  int rc = CMTJB_OK;
+  float *d_gen = nullptr;
+  int rc = system_noise_generate(sn, a, c.plan0.total_iterations, n_inst * N, N, R, &d_gen, stream);
+  if (rc) {
+    cudaFreeAsync(d_models, stream);
+    cudaFreeAsync(d_pos, stream);
+    cudaFreeAsync(d_pref, stream);
+    return rc;
+  }
   const bool rk4 = (c.solver == CMTJB_RK4);
   const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver, false));
   const bool uni = lean && models_uniform<NL>(models);
@@ -503,6 +592,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   cudaFreeAsync(d_pos, stream);
   cudaFreeAsync(d_pref, stream);
   if (d_mbuf) cudaFreeAsync(d_mbuf, stream);
+  if (d_gen) cudaFreeAsync(d_gen, stream);
   return rc;
 }
 

@@ -92,6 +92,10 @@ struct DevLayer {
   int32_t stt, sot, dynamicSOT, altSTT, thermal, onef, pid;
   int32_t includeSOT;        // raw flag: the energy log writes Hfl/Hdl for these layers (junction.hpp:1604-1609)
   double lin[3];             // folded diagonal linear operator (valid when the variant lacks F_NOFOLD)
+  // 1/f^alpha noise generated on the device (onef.cu): first series of this layer in RunParams::onef_gen, the
+  // VectorAlphaNoise axis (cmtjb_axis; ALL = three components, normalised per sample) and scale (noise.hpp:291-301)
+  int32_t onef_slot, onef_axis;
+  double onef_scale;
   // per-launch products (run_typed): h = llg*dt and the IEC coefficients J/(Ms t), 2 J2/(Ms t) of
   // constant, batch-uniform couplings (used by variants without F_DYNS / F_DYNI / F_OVR)
   double h, h_half, h_sixth;
@@ -133,7 +137,10 @@ struct RunParams {
   int32_t *n_samples_out;    // [B] (DP)
   double *time_log;          // [n_samples][B] (DP)
   const double *ovr[kMaxOverrides];  // row k: [B] values of override k
-  const double *onef;        // [NL*3][total_iterations][B] or null
+  const double *onef;        // caller-provided, already scaled: [NL*3][total_iterations][B] or null
+  const float *onef_gen;     // generated on the device, raw float32: [n_slots][total_iterations][onef_B] or null
+  long long onef_i0, onef_B; // onef_gen covers instances onef_i0 .. onef_i0 + onef_B - 1
+  long long i_lo, i_hi;      // instances this launch integrates (a sub-batch of 0..B when noise buffers are generated in pieces)
   const double *custom;      // [3*total_iterations][n_custom] pre-evaluated CMTJB_UPD_CUSTOM drivers or null
   long long n_custom;
   // [it_end-it_begin][3][dyn_ncols]: time-dependent driver values at the three stage times

@@ -517,10 +517,27 @@ __device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, i
     }
   }
   if constexpr ((F & F_ONEF) != 0) {
-    if (Lr.onef && R.onef) {
-      const double *b = R.onef + ((long long)(l * 3) * R.total_iterations + it) * R.B + i;
-      const long long cs = R.total_iterations * R.B;
-      dW = dW + mk(__ldg(b), __ldg(b + cs), __ldg(b + 2 * cs));
+    if (Lr.onef) {
+      if (R.onef) {  // caller's buffer: VectorAlphaNoise::tickVector values, scaled
+        const double *b = R.onef + ((long long)(l * 3) * R.total_iterations + it) * R.B + i;
+        const long long cs = R.total_iterations * R.B;
+        dW = dW + mk(__ldg(b), __ldg(b + cs), __ldg(b + 2 * cs));
+      } else if (R.onef_gen) {
+        // tickVector (noise.hpp:291-301) on the raw component buffers: widen the float32 samples, normalise the
+        // vector when all three axes carry noise (CVector::normalize: no-op for the zero vector), scale
+        const float *b = R.onef_gen + ((long long)Lr.onef_slot * R.total_iterations + it) * R.onef_B + (i - R.onef_i0);
+        if (Lr.onef_axis == CMTJB_AXIS_ALL) {
+          const long long cs = R.total_iterations * R.onef_B;
+          const d3 v = mk((double)__ldg(b), (double)__ldg(b + cs), (double)__ldg(b + 2 * cs));
+          const double l2 = dot(v, v);
+          const double s = l2 != 0.0 ? Lr.onef_scale / sqrt(l2) : Lr.onef_scale;
+          dW = axpy(v, s, dW);
+        } else {
+          const double x = (double)__ldg(b) * Lr.onef_scale;
+          dW = mk(dW.x + (Lr.onef_axis == CMTJB_AXIS_X ? x : 0.0), dW.y + (Lr.onef_axis == CMTJB_AXIS_Y ? x : 0.0),
+                  dW.z + (Lr.onef_axis == CMTJB_AXIS_Z ? x : 0.0));
+        }
+      }
     }
   }
   return dW;

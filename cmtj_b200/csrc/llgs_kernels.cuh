@@ -408,8 +408,8 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
 template <int NL, int SOLVER, uint32_t F>
 __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constant__ DevModel<NL> M,
                                                             const __grid_constant__ RunParams R) {
-  const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= R.B) return;
+  const long long i = R.i_lo + (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= R.i_hi) return;
   run_span<NL, SOLVER, F>(M, R, i, R.it_begin, R.it_end);
 }
 
@@ -458,10 +458,10 @@ __global__ void __launch_bounds__(kBalBlock) llgs_balanced_kernel(const __grid_c
         while (ld_acquire_gpu(Q.done + w) < (int)round) __nanosleep(256);
       __syncwarp();
     }
-    const long long i = w * 32 + lane;
+    const long long i = R.i_lo + w * 32 + lane;
     const long long it0 = R.it_begin + round * Q.chunk;
     const long long it1 = (it0 + Q.chunk < R.it_end) ? it0 + Q.chunk : R.it_end;
-    if (i < R.B) run_span<NL, SOLVER, F>(M, R, i, it0, it1);
+    if (i < R.i_hi) run_span<NL, SOLVER, F>(M, R, i, it0, it1);
     __threadfence();
     __syncwarp();
     if (lane == 0) st_release_gpu(Q.done + w, (int)round + 1);
@@ -491,11 +491,11 @@ template <int SOLVER>
 __global__ void __launch_bounds__(128) llgs_wide_kernel(const __grid_constant__ WideModel W, const __grid_constant__ RunParams R) {
   constexpr uint32_t F = F_ALL;
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long i_raw = gt / kWideGroup;
-  const int l_raw = (int)(gt - i_raw * kWideGroup);
+  const long long i_raw = R.i_lo + gt / kWideGroup;
+  const int l_raw = (int)(gt % kWideGroup);
   const int NL = W.n_layers;
-  const bool live = i_raw < R.B && l_raw < NL;  // idle lanes still take part in the shuffles
-  const long long i = i_raw < R.B ? i_raw : R.B - 1;
+  const bool live = i_raw < R.i_hi && l_raw < NL;  // idle lanes still take part in the shuffles
+  const long long i = i_raw < R.i_hi ? i_raw : R.i_hi - 1;
   const int l = l_raw < NL ? l_raw : NL - 1;
   const DevLayer &Lr = W.L[l];
   const d3 zero = mk(0, 0, 0);
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(128) llgs_wide_kernel(const __grid_constant__ 
 }
 
 template <int SOLVER> cudaError_t launch_wide(const WideModel &W, const RunParams &R, cudaStream_t stream) {
-  const long long threads = R.B * kWideGroup;
+  const long long threads = (R.i_hi - R.i_lo) * kWideGroup;
   llgs_wide_kernel<SOLVER><<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(W, R);
   return cudaGetLastError();
 }
@@ -772,7 +772,7 @@ cudaError_t launch_fixed(const void *model, const RunParams *R, cudaStream_t str
     cudaFreeAsync(scratch, stream);
     return e;
   }
-  const long long blocks = (R->B + kBlock - 1) / kBlock;
+  const long long blocks = (R->i_hi - R->i_lo + kBlock - 1) / kBlock;
   llgs_fixed_kernel<NL, SOLVER, F><<<(unsigned)blocks, kBlock, 0, stream>>>(*M, *R);
   return cudaGetLastError();
 }

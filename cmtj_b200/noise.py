@@ -1,65 +1,35 @@
 """1/f^alpha noise generators: ``BufferedAlphaNoise`` / ``VectorAlphaNoise``
 (core/noise.hpp:138-308, python names cmtj.cpp:449-462).
 
-The reference fills one buffer of ``bufferSize = totalIterations`` samples per axis at the
-first tick (Kasdin's filter, float32, through kissfft).  It is set-up work, not the
-per-timestep path, so the buffer is generated here on the host with numpy's FFT (float32
-data, same filter and the same one-sided-spectrum quirks) and handed to the device as a
-read-only array (``cmtjb_run_args_t.onef_buffer``).  RNG streams differ from the
-reference's ``mt19937(random_device)``: parity is distributional.
+The reference fills one buffer of ``bufferSize`` float32 samples per component at the first tick
+(Kasdin's filter through a 2n-point kissfft).  Here the buffer comes from the same device generator the
+junction kernels draw from (``cmtjb_alpha_noise_host`` -> cmtj_b200/csrc/onef.cu: Philox white noise, cuFFT
+in float32, the reference's one-sided-spectrum product); these classes only keep the reference's tick
+bookkeeping.  Junction runs do not go through them: a layer with ``setAlphaNoise`` gets its buffers generated
+inside ``runSimulation`` / ``JunctionBatch.run``, one series per (instance, layer, axis).  RNG streams differ
+from the reference's ``mt19937(random_device)``: parity is distributional.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
-
-def _kasdin_weights(n: int, alpha: float) -> np.ndarray:
-    # noise.hpp:173-177: h0 = 1, h_i = h_{i-1} * (alpha/2 + i - 1) / i, in float32
-    h = np.empty(n, dtype=np.float32)
-    h[0] = 1.0
-    if n > 1:
-        i = np.arange(1, n, dtype=np.float32)
-        w = ((np.float32(0.5 * alpha) + (i - np.float32(1.0))) / i).astype(np.float32)
-        h[1:] = np.cumprod(w, dtype=np.float32)
-    return h
+from . import _abi
 
 
-def alpha_noise_buffer(n: int, alpha: float, std: float, rng=None) -> np.ndarray:
-    """One ``fillBuffer`` (noise.hpp:190-227): returns ``result`` (float32, length n)."""
-    if n <= 0:
-        return np.zeros(0, dtype=np.float32)
-    rng = np.random if rng is None else rng
-    white = np.zeros(2 * n, dtype=np.complex64)
-    white[:n] = rng.normal(0.0, std, n).astype(np.float32) if std > 0 else 0.0
-    col = np.zeros(2 * n, dtype=np.complex64)
-    col[:n] = _kasdin_weights(n, alpha)
-    W = np.fft.fft(white).astype(np.complex64)
-    Cc = np.fft.fft(col).astype(np.complex64)
-    P = np.zeros(2 * n, dtype=np.complex64)
-    P[:n] = Cc[:n] * W[:n]
-    P[0] = P[0] / 2.0
-    P[n - 1] = P[n - 1] / 2.0
-    # kissfft's inverse is unnormalised; numpy's ifft divides by 2n
-    y = (np.fft.ifft(P) * (2 * n)).astype(np.complex64)
-    return (y[:n].real / np.float32(n)).astype(np.float32)
-
-
-def vector_alpha_noise(n: int, alpha: float, std: float, scale: float, axis, rng=None) -> np.ndarray:
-    """All ``n`` ticks of ``VectorAlphaNoise::tickVector`` at once: float64 [3][n], scaled;
-    normalised to unit length per sample when axis == all (noise.hpp:291-301)."""
-    ax = int(axis)
-    out = np.zeros((3, n), dtype=np.float64)
-    if ax == 3:
-        for c in range(3):
-            out[c] = alpha_noise_buffer(n, alpha, std, rng)
-        norm = np.sqrt(out[0] ** 2 + out[1] ** 2 + out[2] ** 2)
-        nz = norm != 0
-        out[:, nz] /= norm[nz]
-    elif ax in (0, 1, 2):
-        out[ax] = alpha_noise_buffer(n, alpha, std, rng)
-    else:
-        raise RuntimeError("Invalid axis specified: " + str(ax))
-    return out * scale
+def alpha_noise(n: int, alpha: float, std: float, seed: int, n_series: int = 1, series0: int = 0, device: int = 0) -> np.ndarray:
+    """``n_series`` independent ``BufferedAlphaNoise::fillBuffer`` results of ``n`` samples each, generated on the GPU:
+    float32 [n_series, n], unscaled."""
+    out = np.zeros((int(n_series), int(n)), dtype=np.float32)
+    if n <= 0 or n_series <= 0:
+        return out
+    lib = _abi.cuda_backend().lib
+    f = lib.cmtjb_alpha_noise_host
+    f.restype = C.c_int
+    f.argtypes = [C.c_double, C.c_double, C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+    _abi.cuda_backend().check(f(float(alpha), float(std), int(n), int(seed), int(series0), int(n_series), out.ctypes.data, int(device)))
+    return out
 
 
 class BufferedAlphaNoise:
@@ -72,7 +42,9 @@ class BufferedAlphaNoise:
         self._result = np.zeros(self.bufferSize, dtype=np.float32)
 
     def fillBuffer(self) -> None:
-        self._result = alpha_noise_buffer(self.bufferSize, self.alpha, self.std)
+        from .core import _next_seed
+
+        self._result = alpha_noise(self.bufferSize, self.alpha, self.std, _next_seed())[0]
 
     def tick(self) -> float:
         if self._counter == 0:

@@ -70,18 +70,19 @@ class ShardedSweep:
         local = self.batch.run(totalTime, timeStep, writeFrequency, solverMode, log=log, seed=seed)
         if not gather or self.world == 1:
             return local
-        return gather_logs(local, self.n_global, self.rank, self.world)
+        return gather_logs(local, self.n_global, self.rank, self.world, self.batch.device)
 
     def gather_magnetisation(self, layer_id: str) -> Optional[np.ndarray]:
         m = self.batch.get_magnetisation(layer_id)
         if self.world == 1:
             return m
-        parts = _gather_arrays(np.ascontiguousarray(m.T), self.n_global, self.rank, self.world)
+        parts = _gather_arrays(np.ascontiguousarray(m.T), self.n_global, self.rank, self.world, self.batch.device)
         return None if parts is None else parts.T
 
 
-def _gather_arrays(a: np.ndarray, n_global: int, rank: int, world: int) -> Optional[np.ndarray]:
-    """Gather arrays [..., n_local] along the last axis onto rank 0 (shards padded to equal size)."""
+def _gather_arrays(a: np.ndarray, n_global: int, rank: int, world: int, device: Optional[int] = None) -> Optional[np.ndarray]:
+    """Gather arrays [..., n_local] along the last axis onto rank 0 (shards padded to equal size).  With the NCCL
+    backend the staging tensor lives on ``device`` (the sweep's own GPU), not on torch's current device."""
     import torch
 
     dist = _dist()
@@ -94,7 +95,7 @@ def _gather_arrays(a: np.ndarray, n_global: int, rank: int, world: int) -> Optio
     cuda = dist.get_backend() == "nccl"
     t = torch.from_numpy(buf)
     if cuda:
-        t = t.cuda()
+        t = t.to(torch.device("cuda", int(device if device is not None else os.environ.get("LOCAL_RANK", 0))))
     outs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
     dist.gather(t, outs, dst=0)
     if rank != 0:
@@ -106,11 +107,11 @@ def _gather_arrays(a: np.ndarray, n_global: int, rank: int, world: int) -> Optio
     return res
 
 
-def gather_logs(local: BatchLog, n_global: int, rank: int, world: int) -> Optional[BatchLog]:
+def gather_logs(local: BatchLog, n_global: int, rank: int, world: int, device: Optional[int] = None) -> Optional[BatchLog]:
     keys = [k for k in local if k != "time"]
     out = BatchLog() if rank == 0 else None
     if keys:
-        stacked = _gather_arrays(np.stack([local[k] for k in keys]), n_global, rank, world)
+        stacked = _gather_arrays(np.stack([local[k] for k in keys]), n_global, rank, world, device)
         if rank == 0:
             for i, k in enumerate(keys):
                 out[k] = stacked[i]

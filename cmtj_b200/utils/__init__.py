@@ -22,7 +22,7 @@ from .constants import (  # noqa: F401
 from .filters import Filters  # noqa: F401
 from .linear import FieldScan  # noqa: F401
 from .parallel import distribute, sweep_product  # noqa: F401
-from .procedures import PIMM_procedure, ResistanceParameters, VSD_procedure, compute_spectrum_strip  # noqa: F401
+from .procedures import PIMM_batch, PIMM_procedure, ResistanceParameters, VSD_batch, VSD_procedure, compute_spectrum_strip  # noqa: F401
 from .resistance import (  # noqa: F401
     calculate_magnetoresistance,
     calculate_resistance_parallel,

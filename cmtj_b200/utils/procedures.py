@@ -11,13 +11,20 @@ instance axis of ONE fused launch and the reductions happen on the GPU:
 * VSD: the mixing ``-I(t) R(t)``, the 10 MHz Butterworth low-pass and the mean run inside the time
   loop (``cmtjb_post_t.sd_*``); nothing is logged at all.
 
-Semantics.  The reference carries the magnetisation from one sweep point to the next (hysteresis).
-``carry_state=True`` reproduces exactly that (sweep points run one after another, each a batch of
-one); the default ``carry_state=False`` starts every point from the junction's current
-magnetisation (plus the same ``disturbance`` draws), which is what makes the sweep a batch.
+Semantics.  The reference carries the magnetisation from one sweep point to the next (hysteresis,
+cmtj/utils/procedures.py:120-141): AHE loops and up/down field scans depend on it.  That is the
+default here too (``carry_state=True``): points run one after another, each from the state the previous
+one left, consuming numpy's global RNG stream exactly as the reference does -- a chain of dependent runs,
+so no faster than the chain allows.  ``carry_state=False`` -- or the explicitly named ``PIMM_batch`` /
+``VSD_batch`` -- starts every point from the junction's current magnetisation (plus the same ``disturbance``
+draws) and integrates the whole sweep as ONE batch; use it when the points are independent (spectra and
+spin-diode maps away from hysteresis), it is what the GPU is for.
 Everything else -- arguments, validation, return shapes -- follows the reference.
 """
 from __future__ import annotations
+
+import functools
+import warnings
 
 import math
 from collections import defaultdict
@@ -152,6 +159,16 @@ def _instance_chunks(n: int, bytes_per_instance: float, budget: float) -> List[T
     return [(lo, min(n, lo + per)) for lo in range(0, n, per)]
 
 
+def _warn_sequential(name: str, batch_name: str, n_points: int) -> None:
+    if n_points >= 64:
+        warnings.warn(
+            f"{name}: integrating {n_points} sweep points one after another to carry the magnetisation from point to "
+            f"point like the reference does; if the points are independent, carry_state=False (or {batch_name}) runs "
+            "them as one batch",
+            stacklevel=3,
+        )
+
+
 # ---------------------------------------------------------------------------------------------------
 # PIMM
 # ---------------------------------------------------------------------------------------------------
@@ -246,7 +263,7 @@ def PIMM_procedure(
     full_output: bool = False,
     disable_tqdm: bool = False,
     static_only: bool = False,
-    carry_state: bool = False,
+    carry_state: bool = True,
     device: int = 0,
     memory_budget: float = 100e9,
 ) -> Tuple[np.ndarray, np.ndarray, Dict[str, Any]]:
@@ -280,6 +297,7 @@ def PIMM_procedure(
 
     parts: List[Dict[str, Any]] = []
     if carry_state:
+        _warn_sequential("PIMM_procedure", "PIMM_batch", len(Hvecs))
         for H in Hvecs:
             r = run(H[None], _disturbed(junction, layer_ids, 1, disturbance))
             for i, lid in enumerate(layer_ids):
@@ -365,7 +383,7 @@ def VSD_procedure(
     Rtype: str = "Rz",
     resistance_fn: Callable = calculate_resistance_series,
     disable_tqdm: bool = False,
-    carry_state: bool = False,
+    carry_state: bool = True,
     device: int = 0,
     max_batch: int = 1 << 22,
 ) -> np.ndarray:
@@ -405,6 +423,7 @@ def VSD_procedure(
     fall = np.tile(frequencies, nH)
     spectrum = np.zeros(nH * nF)
     if carry_state:
+        _warn_sequential("VSD_procedure", "VSD_batch", nH * nF)
         for i in range(nH * nF):
             v, getm = _vsd_batch(junction, Hall[i : i + 1], fall[i : i + 1], _disturbed(junction, layer_ids, 1, disturbance),
                                  int_step, sd_mode, rows, comp, simulation_duration, device, bool(disturbance))
@@ -422,3 +441,8 @@ def VSD_procedure(
             for lid in layer_ids:
                 junction.setLayerMagnetisation(lid, CVector(*getm(lid)[-1]))
     return spectrum.reshape(nH, nF)
+
+
+#: ``PIMM_procedure`` / ``VSD_procedure`` with every sweep point started fresh and the sweep integrated as one batch
+PIMM_batch = functools.partial(PIMM_procedure, carry_state=False)
+VSD_batch = functools.partial(VSD_procedure, carry_state=False)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CMTJB_ABI_VERSION 3
+#define CMTJB_ABI_VERSION 4
 #define CMTJB_MAX_LAYERS 8
 
 /* ---- error codes --------------------------------------------------------------- */
@@ -164,9 +164,17 @@ typedef struct cmtjb_run_args {
   int64_t n_instances;
   int64_t instance_offset;  /* global index of instance 0 (RNG stream id; multi-GPU shards) */
   int64_t start_iteration;  /* first step index; >0 continues a run in time chunks */
-  /* Pre-generated 1/f^alpha vector noise (VectorAlphaNoise::tickVector, core/noise.hpp:291-301),
-   * already scaled; [n_layers*3][total_iterations][n_instances] or NULL.  Host or device
-   * pointer according to the entry point. */
+  /* 1/f^alpha noise of layers with noiseScale != 0 (setAlphaNoise, core/junction.hpp:406-414; one fresh
+   * VectorAlphaNoise of bufferSize = total_iterations per layer and run, getSolver :1905-1916).
+   * NULL (the normal case): the library generates the buffers on the device -- one independent series per
+   * (instance, layer, axis): Philox4x32-10 white noise keyed by (seed, instance_offset + instance, layer,
+   * axis, sample), Kasdin's filter in float32 exactly as BufferedAlphaNoise::fillBuffer does it
+   * (core/noise.hpp:190-227, 2n-point complex FFT, one-sided spectrum with both end bins halved), then
+   * tickVector's normalisation and scale (noise.hpp:291-301) inside the time loop.  Batches whose buffers
+   * exceed the free device memory are integrated in sub-batches of instances; a run that cannot fit even
+   * 32 instances fails with CMTJB_ERUNTIME and the byte counts.
+   * Non-NULL: the caller's own tickVector values, already scaled, double [n_layers*3][total_iterations]
+   * [n_instances] (host or device pointer according to the entry point; sweep entry points only). */
   const double *onef_buffer;
   /* CMTJB_UPD_CUSTOM drivers (ScalarDriver::getCustomDriver, drivers.hpp:247-260, :294-303).  A callback
    * cannot cross this boundary, but a fixed-step solver only ever asks a driver for its value at the
@@ -331,6 +339,22 @@ int cmtjb_select_variant(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
                          int32_t n_overrides, const cmtjb_run_args_t *args, char *name, int32_t name_size);
 /* cmtjb_run_host keeps one device scratch slab per device between calls; this frees them. */
 int cmtjb_release_cache(void);
+
+/* Where the calling thread's last cmtjb_run_host call spent its time, in the order of cmtjb_host_stat
+ * (milliseconds unless named otherwise).  A time-chunked run reports device-timed figures: integration, gaps
+ * on the compute stream while a ring buffer was still draining, the copy engine's busy time and the part of
+ * the last chunk's copy that nothing could hide. */
+enum cmtjb_host_stat {
+  CMTJB_HOST_TOTAL_MS = 0, CMTJB_HOST_INTEGRATE_MS, CMTJB_HOST_RING_WAIT_MS, CMTJB_HOST_COPY_MS, CMTJB_HOST_TAIL_COPY_MS,
+  CMTJB_HOST_PIPELINE_MS, CMTJB_HOST_LOG_BYTES, CMTJB_HOST_N_CHUNKS, CMTJB_HOST_N_RING, CMTJB_HOST_NSTATS
+};
+int cmtjb_host_stats(double *out, int32_t n);
+
+/* BufferedAlphaNoise::fillBuffer (core/noise.hpp:190-227) for n_series independent series of n samples on the
+ * device: out (HOST, float32 [n_series][n]) receives each series' `result` buffer (getFullBuffer), unscaled.
+ * Series k is the one a sweep instance series0 + k draws for layer 0, x axis, under `seed`. */
+int cmtjb_alpha_noise_host(double alpha, double std, int64_t n, uint64_t seed, int64_t series0, int64_t n_series,
+                           float *out, int device);
 
 /* ScalarDriver::getCurrentScalarValue (core/drivers.hpp:262-305) evaluated on the device
  * for n times (host pointers); used by the parity tests of the inline driver code. */

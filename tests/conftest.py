@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: long-running")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """write the achieved-parity ledger of this session (tests/parity_report.py)"""
+    import parity_report
+
+    path = parity_report.write()
+    if path:
+        print(f"\nparity ledger: {path} ({len(parity_report.ENTRIES)} entries)")
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """ctypes Backend over oracle/liboracle.so (the CPU restatement; checker only)."""

@@ -5,7 +5,7 @@ cmtj_b200.utils.procedures.  `m` exposes the core API, `P` the procedures module
 
 "fresh" scenarios give every sweep point its own junction (what the batched device procedure
 computes); "carried" scenarios pass the whole sweep to one call (the reference's hysteresis
-semantics; ours with carry_state=True)."""
+semantics; ours with the default carry_state=True; the fresh-start scenarios pass carry_state=False to ours)."""
 import sys
 
 import numpy as np
@@ -48,7 +48,7 @@ def pimm_fresh(m, P, batched):
     out = {}
     kw = dict(PIMM_KW, resistance_params=rparams(P, 2), disturbance=0, disable_tqdm=True)
     if batched:
-        _pack_pimm("", out, *P.PIMM_procedure(helpers.two_layer_mtj(m), H_PIMM, **kw))
+        _pack_pimm("", out, *P.PIMM_procedure(helpers.two_layer_mtj(m), H_PIMM, carry_state=False, **kw))
     else:
         parts = [P.PIMM_procedure(helpers.two_layer_mtj(m), H_PIMM[i : i + 1], **kw) for i in range(len(H_PIMM))]
         other = {k: [p[2][k][0] for p in parts] for k in ("Rx", "Ry", "m_avg", "H")}
@@ -64,7 +64,7 @@ def pimm_fresh_full(m, P, batched):
     H = H_PIMM[1:4]
     ids = ["free", "middle", "bottom"]
     if batched:
-        _pack_pimm("", out, *P.PIMM_procedure(helpers.tri_layer_mtj(m), H, **kw), layer_ids=ids)
+        _pack_pimm("", out, *P.PIMM_procedure(helpers.tri_layer_mtj(m), H, carry_state=False, **kw), layer_ids=ids)
     else:
         parts = [P.PIMM_procedure(helpers.tri_layer_mtj(m), H[i : i + 1], **kw) for i in range(len(H))]
         other = {k: [p[2][k][0] for p in parts] for k in ("Rx", "Ry", "m_avg", "H", "m_traj")}
@@ -78,7 +78,7 @@ def pimm_carried(m, P, batched):
     """The reference's own semantics: one call over the sweep, state carried, seeded disturbance."""
     out = {}
     kw = dict(PIMM_KW, resistance_params=rparams(P, 2), disable_tqdm=True)
-    extra = dict(carry_state=True) if batched else {}
+    extra = {}  # carried state is the default of both implementations
     np.random.seed(11)
     _pack_pimm("", out, *P.PIMM_procedure(helpers.two_layer_mtj(m), H_PIMM[:4], disturbance=1e-3, **kw, **extra))
     return out
@@ -87,7 +87,7 @@ def pimm_carried(m, P, batched):
 def pimm_static(m, P, batched):
     """static_only=True: no spectrum, resistances and m_avg only (AHE-loop use of the procedure)."""
     kw = dict(PIMM_KW, resistance_params=rparams(P, 2), disable_tqdm=True, disturbance=0, static_only=True)
-    extra = dict(carry_state=True) if batched else {}
+    extra = {}  # carried state is the default of both implementations
     spectrum, freqs, other = P.PIMM_procedure(helpers.two_layer_mtj(m), H_PIMM[:3], **kw, **extra)
     assert freqs is None and np.asarray(spectrum).size == 0
     return {k: np.asarray(other[k], dtype=np.float64) for k in ("Rx", "Ry", "m_avg")}
@@ -95,7 +95,7 @@ def pimm_static(m, P, batched):
 
 def _vsd(m, P, batched, build, **kw):
     if batched:
-        return {"spectrum": P.VSD_procedure(build(m), H_VSD, F_VSD, disturbance=0, disable_tqdm=True, **VSD_KW, **kw)}
+        return {"spectrum": P.VSD_procedure(build(m), H_VSD, F_VSD, disturbance=0, disable_tqdm=True, carry_state=False, **VSD_KW, **kw)}
     s = np.zeros((len(H_VSD), len(F_VSD)))
     for i in range(len(H_VSD)):
         for k in range(len(F_VSD)):
@@ -121,7 +121,7 @@ def vsd_ry_parallel_single(m, P, batched):
 
 
 def vsd_carried(m, P, batched):
-    extra = dict(carry_state=True) if batched else {}
+    extra = {}  # carried state is the default of both implementations
     np.random.seed(5)
     return {"spectrum": P.VSD_procedure(helpers.two_layer_mtj(m), H_VSD, F_VSD[:2], disturbance=1e-3, disable_tqdm=True,
                                         resistance_params=rparams(P, 2), Rtype="Rz", **VSD_KW, **extra)}

@@ -27,7 +27,31 @@ def oracle_backend():
         if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
             subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"])
         lib = ctypes.CDLL(so)
-        _oracle = _abi.Backend(lib, "oracle_", has_device_arg=False)
+
+        class OracleBackend(_abi.Backend):
+            """The CPU oracle behind the facade's backend interface.  The product passes no 1/f^alpha buffer (its
+            library generates one on the device); the oracle takes the noise as an input, so this adapter draws it
+            from the numpy restatement of the reference's generator (oracle/noise_oracle.py)."""
+
+            def run_host(self, jn, layers, overrides, n_overrides, args, m_state, log, status, n_samples_out, time_log, device=0):
+                keep = None
+                if not args.onef_buffer and any(layers[i].noiseScale != 0 for i in range(jn.n_layers)):
+                    import sys
+
+                    if ORACLE_DIR not in sys.path:
+                        sys.path.insert(0, ORACLE_DIR)
+                    import noise_oracle
+
+                    plan = self.plan(jn, layers, args)
+                    keep = noise_oracle.junction_buffer(layers, jn.n_layers, int(plan.total_iterations), int(args.n_instances))
+                    args.onef_buffer = keep.ctypes.data
+                try:
+                    return super().run_host(jn, layers, overrides, n_overrides, args, m_state, log, status, n_samples_out, time_log, device)
+                finally:
+                    if keep is not None:
+                        args.onef_buffer = None
+
+        _oracle = OracleBackend(lib, "oracle_", has_device_arg=False)
     return _oracle
 
 

@@ -10,6 +10,7 @@ import pytest
 import cmtj_b200
 import helpers
 import test_coupled_oracle_vs_ref as T
+from parity_report import record
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -28,6 +29,7 @@ def _three(fn):
 
 def _check(g, w, p, tol=TOL):
     assert set(g) == set(w)
+    worst, worst_bound, widened = 0.0, tol, False
     for k in w:
         assert g[k].shape == w[k].shape, k
         if k == "time":
@@ -36,8 +38,12 @@ def _check(g, w, p, tol=TOL):
         scale = max(np.max(np.abs(w[k])), 1e-300)
         err = np.abs(g[k] - w[k]) / scale
         sens = np.maximum.accumulate(np.abs(p[k] - w[k]) / scale, axis=0)
-        bad = err > np.maximum(tol, 10 * sens)
+        bound = np.maximum(tol, 10 * sens)
+        worst, worst_bound = max(worst, float(err.max())), max(worst_bound, float(bound.max()))
+        widened = widened or bool((err > tol).any())
+        bad = err > bound
         assert not bad.any(), (k, float(err.max()), float(sens.max()))
+    record("coupled system", max_rel_err=worst, bound_1e9=tol, max_bound_applied=worst_bound, widened=widened)
 
 
 def _perturb(j, eps):

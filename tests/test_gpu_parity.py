@@ -13,6 +13,7 @@ import pytest
 import cmtj_b200
 import helpers
 from cmtj_b200 import _abi
+from parity_report import record
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -71,22 +72,33 @@ def _both(build, T, dt, wf, mode, tweak=None, **kw):
     return (g, keep["j"][0]), (w, keep["j"][1])
 
 
-def _check(got, want, tol=TOL, sens=None):
+def _check(got, want, tol=TOL, sens=None, what=""):
+    """Asserts the bound and records what was ACHIEVED (tests/parity_report.py): the largest relative error over
+    all channels and samples, the largest bound any sample was allowed, and `widened` = some sample exceeded the
+    plain 1e-9 and passed only under the sensitivity-widened bound."""
     want = dict(want)
     sens = want.pop("__sens__", {}) if sens is None else sens
     assert set(got) == set(want)
-    worst = 0.0
+    worst, worst_bound, widened, worst_key = 0.0, tol, False, ""
     for k in want:
         assert got[k].shape == want[k].shape, k
         if k == "time":
             assert np.array_equal(got[k], want[k])
             continue
+        if want[k].size == 0:
+            continue
         scale = max(np.max(np.abs(want[k])), 1e-300)
         err = np.abs(got[k] - want[k]) / scale
-        bound = np.maximum(tol, 10 * sens[k]) if k in sens else tol
-        worst = max(worst, float(err.max()))
+        bound = np.maximum(tol, 10 * sens[k]) if k in sens else np.full_like(err, tol)
+        if float(err.max()) > worst:
+            worst, worst_key = float(err.max()), k
+        worst_bound = max(worst_bound, float(np.max(bound)))
+        widened = widened or bool(np.any(err > tol))
         bad = err > bound
+        if np.any(bad):
+            record(what or "trajectory", max_rel_err=worst, bound_1e9=tol, max_bound_applied=worst_bound, widened=True, failed=True, channel=k)
         assert not np.any(bad), (k, float(err.max()), int(np.argmax(bad)), float(np.max(bound)))
+    record(what or "trajectory", max_rel_err=worst, bound_1e9=tol, max_bound_applied=worst_bound, widened=widened, channel=worst_key)
     return worst
 
 

@@ -49,7 +49,7 @@ def test_pimm_batched_vs_oracle_random_sweep(on_cuda, oracle):
     H = rng.uniform(-400e3, 400e3, (64, 3))
     rp = ps.rparams(P, 1)
     kw = dict(Hoe_direction=cm.Axis.xaxis, Hoe_excitation=300, simulation_duration=0.3e-9, max_frequency=60e9, take_last_n=10)
-    spectrum, freqs, out = P.PIMM_procedure(helpers.single_layer_mtj(cm), H, 1e-13, rp, disturbance=0, memory_budget=2e6, **kw)
+    spectrum, freqs, out = P.PIMM_procedure(helpers.single_layer_mtj(cm), H, 1e-13, rp, disturbance=0, memory_budget=2e6, carry_state=False, **kw)
     assert spectrum.shape[0] == 64 and freqs.shape == (spectrum.shape[1], 1)
     with helpers.facade_on(oracle):
         for i in rng.choice(64, 8, replace=False):
@@ -130,7 +130,7 @@ def test_vsd_fused_equals_standalone_kernels(on_cuda):
     H = np.repeat(ps.H_VSD, 3, axis=0)
     f = np.tile(ps.F_VSD, 2)
     got = P.VSD_procedure(helpers.two_layer_mtj(cm), ps.H_VSD, ps.F_VSD, disturbance=0, resistance_params=ps.rparams(P, 2),
-                          Rtype="Rz", **ps.VSD_KW).ravel()
+                          Rtype="Rz", carry_state=False, **ps.VSD_KW).ravel()
     oe = cm.ScalarDriver.getSineDriver(0, ps.VSD_KW["Hoe_excitation"], float(f[0]), 0)
     j.setLayerOerstedFieldDriver("all", cm.AxialDriver(cm.NullDriver(), oe, cm.NullDriver()))
     b = cm.JunctionBatch(j, 6)

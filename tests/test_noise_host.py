@@ -1,11 +1,17 @@
-"""Host restatement of the Kasdin 1/f^alpha generator (cmtj_b200/noise.py) against the reference's
+"""CPU restatement of the Kasdin 1/f^alpha generator (oracle/noise_oracle.py) against the reference's
 BufferedAlphaNoise / VectorAlphaNoise (core/noise.hpp:138-308, kissfft in float32): RNG streams
 differ, so the comparison is spectral.  CPU only."""
 import numpy as np
 import pytest
 
+import os
+import sys
+
 import cmtj_b200
-from cmtj_b200 import noise
+import helpers
+
+sys.path.insert(0, helpers.ORACLE_DIR)
+import noise_oracle as noise  # noqa: E402
 
 
 def _slope(x):

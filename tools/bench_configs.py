@@ -240,7 +240,7 @@ def procs(scale):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         spec, freqs, out = P.PIMM_procedure(helpers.two_layer_mtj(m), H, 1e-13, rp, simulation_duration=steps * 1e-13 * (1 + 1e-9),
-                                            disturbance=1e-3, disable_tqdm=True)
+                                            disturbance=1e-3, disable_tqdm=True, carry_state=False)
         torch.cuda.synchronize()
         secs = time.perf_counter() - t0
     emit("PIMM_procedure end to end: 2-layer MTJ, field sweep, 5 ns, spectrum + Rx/Ry on the host", 2 * nH * steps, secs, 337.0, 0,
@@ -254,7 +254,7 @@ def procs(scale):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         vm = P.VSD_procedure(helpers.two_layer_mtj(m), Hv, fs, 1e-13, rp, simulation_duration=steps2 * 1e-13 * (1 + 1e-9), Rtype="Rz",
-                             disable_tqdm=True)
+                             disable_tqdm=True, carry_state=False)
         torch.cuda.synchronize()
         secs = time.perf_counter() - t0
     emit("VSD_procedure end to end: 2-layer MTJ, field x frequency map, 10 ns, mixing + low-pass fused", 2 * nH2 * nF * steps2, secs,

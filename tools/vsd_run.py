@@ -12,6 +12,6 @@ Hv = np.zeros((nH, 3)); Hv[:, 0] = np.linspace(50e3, 400e3, nH); Hv[:, 2] = 20e3
 fs = np.linspace(2e9, 20e9, nF)
 for r in range(2):
     t0 = time.perf_counter()
-    vm = P.VSD_procedure(helpers.two_layer_mtj(m), Hv, fs, 1e-13, rp, simulation_duration=steps * 1e-13 * (1 + 1e-9), Rtype="Rz", disable_tqdm=True)
+    vm = P.VSD_procedure(helpers.two_layer_mtj(m), Hv, fs, 1e-13, rp, simulation_duration=steps * 1e-13 * (1 + 1e-9), Rtype="Rz", disable_tqdm=True, carry_state=False)
     torch.cuda.synchronize()
     print(f"VSD {nH}x{nF} x {steps} steps: {time.perf_counter()-t0:.3f} s  {2*nH*nF*steps/(time.perf_counter()-t0):.3e} layer-steps/s", flush=True)
