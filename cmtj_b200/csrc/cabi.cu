@@ -287,7 +287,7 @@ uint32_t model_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
 //     last, partly filled one costs a full wave  ->  efficiency waves / ceil(waves).
 // Balance when that model loses more than 3 % and the launch is long enough to be cut into >= 8 rounds.
 BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const void *plain_kernel) {
-  BalancePlan bp{false, 0, 0, 0, 0};
+  BalancePlan bp{false, 0, 0, 0, 0, 0, 0};
   const char *force = std::getenv("CMTJB_BALANCE");
   if (force && force[0] == '0') return bp;
   const bool forced = force && force[0] == '1';
@@ -320,12 +320,10 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
   if (const char *c = std::getenv("CMTJB_BALANCE_CHUNK")) target = std::max<long long>(1, std::atoll(c));  // tuning knob
   const long long chunk = we * ((target + we - 1) / we);
   const long long rounds = (steps + chunk - 1) / chunk;
-  // Resident warps per sub-partition of the balanced form: at most 0.9 W / S, so that a warp drawing a
-  // ticket (almost) always finds the predecessor task finished -- tickets are issued round-major, and
-  // the W - S k instance-warps not being integrated at any moment are the slack that keeps the queue
-  // from stalling (measured on B200, S1 with W / S = 5.28: k = 4 -> 1.151e11 layer-steps/s, k = 5 ->
-  // 1.105e11, plain -> 1.044e11).  Below four the FP64 pipe is latency- rather than throughput-bound
-  // and time-slicing would serialise what the plain form overlaps.
+  // Resident warps per sub-partition of the balanced form: the largest k below W / S.  The W - S k instance-warps
+  // that nobody holds at any moment are what a free warp picks from (llgs_balanced_kernel); a twentieth of W is
+  // kept in reserve so that the search stays short.  Below four the FP64 pipe is latency- rather than throughput-
+  // bound and time-slicing would serialise what the plain form overlaps.
   long long k = std::min<long long>(bal_blocks, (long long)std::floor(0.9 * mean));
   if (const char *c = std::getenv("CMTJB_BALANCE_WARPS")) k = std::max<long long>(1, std::min<long long>(std::atoll(c), bal_blocks));
   if (!forced && (eff > 0.97 || rounds < 8 || k < 4)) return bp;
@@ -335,6 +333,8 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
   bp.n_rounds = (steps + bp.chunk - 1) / bp.chunk;
   bp.n_wtasks = W;
   bp.blocks = (int)std::min<long long>(k * n_sm[dev], (W + 3) / 4);
+  bp.per_sm = std::getenv("CMTJB_BALANCE_NOPIN") ? 0 : (int)k;
+  if (const char *c = std::getenv("CMTJB_BALANCE_SCHED")) bp.sched = (c[0] == 'c') ? 1 : 0;  // "claim" / "ticket" (tuning knob)
   return bp;
 }
 
@@ -484,6 +484,8 @@ void fill_run_params(RunParams &R, const cmtjb_junction_t *jn, int NL, const cmt
   R.total_time = a->totalTime;
   R.write_frequency = a->writeFrequency;
   R.seed = a->seed;
+  R.pk = make_philox_keys(a->seed);
+  if (const char *c = std::getenv("CMTJB_TUNE")) R.tune_flags = std::atoi(c);
   if (post) {
     PostParams &P = R.post;
     P.proj_log = post->proj_log;
@@ -918,31 +920,49 @@ __global__ void normals_kernel(unsigned long long seed, long long inst0, long lo
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_inst * n_steps) return;
   const long long st = q / n_inst, i = q - st * n_inst;
-  const d3 v = normal3(seed, (unsigned long long)(inst0 + i), layer, (unsigned long long)(step0 + st));
+  const PhiloxKeys K = philox_keys(seed);
+  const d3 v = normal3(K, (unsigned long long)(inst0 + i), layer, (unsigned long long)(step0 + st));
   out[3 * q + 0] = v.x;
   out[3 * q + 1] = v.y;
   out[3 * q + 2] = v.z;
 }
 
-// 8 independent DFMA chains per thread; 2 flop per DFMA
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, long long iters, double a, double b) {
-  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+// CH independent DFMA chains per thread, 8 links per chain and iteration; 2 flop per DFMA
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// out[1..4]: SM cycle counter and global nanosecond timer at the start and the end of block 0 (the SM clock the
+// microbenchmark actually ran at: sustained DFMA issue is power-limited on this part)
+template <int CH> __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, long long iters, double a, double b) {
+  long long c0 = 0;
+  unsigned long long n0 = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    c0 = clock64();
+    n0 = global_ns();
+  }
+  double x[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) x[c] = threadIdx.x * 1e-3 + c;
   for (long long k = 0; k < iters; k++) {
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      x0 = fma(x0, a, b);
-      x1 = fma(x1, a, b);
-      x2 = fma(x2, a, b);
-      x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b);
-      x5 = fma(x5, a, b);
-      x6 = fma(x6, a, b);
-      x7 = fma(x7, a, b);
+#pragma unroll
+      for (int c = 0; c < CH; c++) x[c] = fma(x[c], a, b);
     }
   }
-  const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < CH; c++) s += x[c];
   if (s == 123.456) out[0] = s;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[1] = (double)(clock64() - c0);
+    out[2] = (double)(global_ns() - n0);
+  }
 }
+
+thread_local double g_peak_mhz = 0.0;
 
 }  // namespace
 }  // namespace cmtjb
@@ -1287,6 +1307,8 @@ int cmtjb_host_stats(double *out, int32_t n) {
   return CMTJB_OK;
 }
 
+double cmtjb_fp64_peak_sm_mhz(void) { return g_peak_mhz; }
+
 int cmtjb_eval_driver_host(const cmtjb_driver_t *driver, const double *times, int64_t n, double *out, int device) {
   if (!driver || !times || !out) return fail(CMTJB_EINVAL, "null argument");
   if (driver->update == CMTJB_UPD_CUSTOM) return fail(CMTJB_ENOTSUP, "custom drivers are host-only");
@@ -1348,26 +1370,45 @@ int cmtjb_fp64_peak(int device, int64_t iters, double *flops, double *ms) {
   CUDA_TRY(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  const int blocks = prop.multiProcessorCount * 4, threads = 256;
   double *d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, 8));
+  CUDA_TRY(cudaMalloc(&d, 4 * sizeof(double)));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  fp64_peak_kernel<<<blocks, threads>>>(d, iters / 8 + 1, 0.999999, 1e-7);  // warm-up
-  cudaEventRecord(e0);
-  fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
-  cudaEventRecord(e1);
-  cudaError_t e = cudaEventSynchronize(e1);
-  float t = 0;
-  cudaEventElapsedTime(&t, e0, e1);
+  // the FP64 pipe only saturates with enough independent DFMAs per sub-partition: 8 or 16 chains per thread at 8 or
+  // 16 warps per sub-partition; the best of the four shapes is the measured peak
+  double best = 0.0, best_ms = 0.0;
+  cudaError_t e = cudaSuccess;
+  for (int shape = 0; shape < 4 && e == cudaSuccess; shape++) {
+    const int chains = (shape & 1) ? 16 : 8, blocks_per_sm = (shape & 2) ? 8 : 4;
+    const int blocks = prop.multiProcessorCount * blocks_per_sm, threads = 256;
+    const long long it = std::max<long long>(1, iters * 8 / chains);
+    auto launch = [&](long long n) {
+      if (chains == 8) fp64_peak_kernel<8><<<blocks, threads>>>(d, n, 0.999999, 1e-7);
+      else fp64_peak_kernel<16><<<blocks, threads>>>(d, n, 0.999999, 1e-7);
+    };
+    launch(it / 8 + 1);  // warm-up
+    cudaEventRecord(e0);
+    launch(it);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    const double n_fma = (double)blocks * threads * (double)it * 8.0 * chains;
+    const double f = 2.0 * n_fma / (t * 1e-3);
+    if (e == cudaSuccess && f > best) {
+      best = f;
+      best_ms = t;
+      double probe[4] = {0, 0, 0, 0};
+      if (cudaMemcpy(probe, d, sizeof(probe), cudaMemcpyDeviceToHost) == cudaSuccess && probe[2] > 0) g_peak_mhz = probe[1] / probe[2] * 1e3;
+    }
+  }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(d);
   if (e != cudaSuccess) return cuda_fail(e, "fp64_peak_kernel");
-  const double n_fma = (double)blocks * threads * (double)iters * 64.0;
-  if (flops) *flops = 2.0 * n_fma / (t * 1e-3);
-  if (ms) *ms = t;
+  if (flops) *flops = best;
+  if (ms) *ms = best_ms;
   return CMTJB_OK;
 }
 

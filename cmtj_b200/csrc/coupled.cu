@@ -248,6 +248,7 @@ void fill_run_params(RunParams &R, const Common &c, const cmtjb_run_args_t *a, l
   R.total_time = a->totalTime;
   R.write_frequency = a->writeFrequency;
   R.seed = a->seed;
+  R.pk = make_philox_keys(a->seed);
 }
 
 // stream-ordered upload of a small host array
@@ -310,7 +311,11 @@ int stack_launch(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, const cmt
   StackParams SP;
   std::memset(&SP, 0, sizeof(SP));
   SP.N = N;
-  SP.spb = std::max(1, 128 / N);
+  // stacks per block: the per-step barriers are block-wide, so a block holds as few stacks as fill two warps
+  // (CMTJB_STACK_BLOCK overrides the thread target; tuning knob)
+  int block_target = 64;
+  if (const char *c = std::getenv("CMTJB_STACK_BLOCK")) block_target = std::max(32, std::atoi(c));
+  SP.spb = std::max(1, block_target / N);
   SP.kind = st->kind;
   SP.use_kcl = st->use_kcl;
   SP.delayed = st->delayed;
@@ -407,16 +412,27 @@ int validate_group(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cm
   if (c->nl > 4) return fail(CMTJB_ENOTSUP, "coupled junctions with more than 4 layers are not supported by this build");
   if (g->top_layer < 0 || g->top_layer >= c->nl) return fail(CMTJB_EINVAL, "layer index out of range");
   if (g->interaction < CMTJB_INT_NULL || g->interaction > CMTJB_INT_DIPOLE_NOMURA) return fail(CMTJB_EINVAL, "unknown interaction function");
-  // reservoir.hpp:171-177 (unique coordinates) and the per-pair distance guards (:84-87, :39-42)
+  // reservoir.hpp:171-177 (unique coordinates) and the per-pair distance guards (:84-87, :39-42): the reference tests
+  // every pair; points closer than `lim` are adjacent in x within `lim`, so a sort and a sliding window find them
   const double lim = (g->interaction == CMTJB_INT_DIPOLE_NOMURA) ? 1e-14 : 1e-10;
   const double *r = g->coordinates;
-  for (int i = 0; i < n; i++)
-    for (int j = i + 1; j < n; j++) {
-      const double dx = r[3 * i] - r[3 * j], dy = r[3 * i + 1] - r[3 * j + 1], dz = r[3 * i + 2] - r[3 * j + 2];
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (r[3 * a] != r[3 * b]) return r[3 * a] < r[3 * b];
+    if (r[3 * a + 1] != r[3 * b + 1]) return r[3 * a + 1] < r[3 * b + 1];
+    return r[3 * a + 2] < r[3 * b + 2];
+  });
+  bool too_close = false;
+  for (int u = 0; u < n; u++)
+    for (int v = u + 1; v < n; v++) {
+      const int i = order[u], j = order[v];
+      const double dx = r[3 * j] - r[3 * i], dy = r[3 * i + 1] - r[3 * j + 1], dz = r[3 * i + 2] - r[3 * j + 2];
+      if (dx > lim && dx != 0) break;
       if (dx == 0 && dy == 0 && dz == 0) return fail(CMTJB_ERUNTIME, "Coordinate vectors must be unique!");
-      if (g->interaction != CMTJB_INT_NULL && std::sqrt(dx * dx + dy * dy + dz * dz) < lim)
-        return fail(CMTJB_ERUNTIME, "Points are too close for stable dipole calculation");
+      if (g->interaction != CMTJB_INT_NULL && std::sqrt(dx * dx + dy * dy + dz * dz) < lim) too_close = true;
     }
+  if (too_close) return fail(CMTJB_ERUNTIME, "Points are too close for stable dipole calculation");
   return CMTJB_OK;
 }
 
@@ -555,35 +571,46 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
       if (d_hpart) cudaFreeAsync(d_hpart, stream);
       if (d_R) cudaFreeAsync(d_R, stream);
     } else {
-    // one array across the grid: cooperative launch, as many co-resident CTAs as the pair sum can use
-#define CMTJB_GRID_FN(SOLVER)                                                                    \
-  (uni ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, true>                      \
-       : lean ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, false> : (const void *)group_grid_kernel<NL, SOLVER, F_ALL, false>)
+    // one array across the grid: cooperative launch, one block per SM, every block the same share of the N^2 pairs
+    // lean single-layer arrays (the reservoir case) run 768 threads per block; CMTJB_GROUP_THREADS=512 forces the 512 form
+    const char *thr_env = std::getenv("CMTJB_GROUP_THREADS");
+    const bool wide_block = NL == 1 && uni && !(thr_env && std::atoi(thr_env) == 512);
+    const int n_threads = wide_block ? kGroupThreadsLean : kGroupThreads;
+#define CMTJB_GRID_FN(SOLVER)                                                                                          \
+  (wide_block ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, true, kGroupThreadsLean>                   \
+   : uni      ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, true, kGroupThreads>                       \
+   : lean     ? (const void *)group_grid_kernel<NL, SOLVER, F_COUPLED_LEAN, false, kGroupThreads>                      \
+              : (const void *)group_grid_kernel<NL, SOLVER, F_ALL, false, kGroupThreads>)
     const void *fn = rk4 ? CMTJB_GRID_FN(CMTJB_RK4) : CMTJB_GRID_FN(CMTJB_EULER_HEUN);
 #undef CMTJB_GRID_FN
     int per_sm = 0, sms = 0, coop = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0);
-    if (e != cudaSuccess || per_sm <= 0 || !coop) {
+    // elements per block: at least 8 (tiny arrays use fewer blocks: the barrier, not the pair sum, is their cost)
+    int n_blocks = std::max(1, std::min(sms, (N + 7) / 8));
+    GP.A = (N + n_blocks - 1) / n_blocks;
+    n_blocks = (N + GP.A - 1) / GP.A;
+    GP.P = GP.A <= n_threads ? n_threads / GP.A : 0;
+    GP.tile = kGroupTileMax;
+    const size_t smem = ((size_t)7 * GP.tile + 3 * (size_t)GP.A) * sizeof(double);
+    if (coop && GP.P > 0) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && coop && GP.P > 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, n_threads, smem);
+    if (!coop || e != cudaSuccess || (GP.P > 0 && per_sm <= 0)) {
+      cudaGetLastError();
       rc = fail(CMTJB_ECUDA, "cooperative launch is not available for the group kernel on this device");
+    } else if (GP.P == 0 || n_blocks > per_sm * sms) {
+      rc = fail(CMTJB_ENOTSUP, "dipole-coupled array exceeds one GPU's co-resident thread capacity (" + std::to_string((long long)sms * n_threads) +
+                                   " elements); shard it over several GPUs (cmtj_b200.reservoir.ShardedGroup)");
     } else {
-      const long long max_threads = (long long)per_sm * sms * 256;
-      if (N > max_threads) {
-        rc = fail(CMTJB_ENOTSUP, "dipole-coupled array exceeds one GPU's co-resident thread capacity");
-      } else {
-        GP.P = std::min(32, pow2_floor(max_threads / N));
-        const long long blocks = ((long long)N * GP.P + 255) / 256;
-        e = cudaMallocAsync((void **)&d_mbuf, 6 * (size_t)N * sizeof(double), stream);
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync(group exchange buffer)");
-        GP.mbuf = d_mbuf;
-        for (long long inst = 0; inst < n_inst && rc == CMTJB_OK; inst++) {
-          GP.inst = inst;
-          void *args[] = {(void *)&d_models, (void *)&M0, (void *)&GP, (void *)&R};
-          e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(256), args, 0, stream);
-          g_launches++;
-          if (e != cudaSuccess) rc = cuda_fail(e, "group_grid_kernel");
-        }
+      e = cudaMallocAsync((void **)&d_mbuf, 6 * (size_t)N * sizeof(double), stream);
+      if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync(group exchange buffer)");
+      GP.mbuf = d_mbuf;
+      for (long long inst = 0; inst < n_inst && rc == CMTJB_OK; inst++) {
+        GP.inst = inst;
+        void *args[] = {(void *)&d_models, (void *)&M0, (void *)&GP, (void *)&R};
+        e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)n_blocks), dim3(n_threads), args, smem, stream);
+        g_launches++;
+        if (e != cudaSuccess) rc = cuda_fail(e, "group_grid_kernel");
       }
     }
     }

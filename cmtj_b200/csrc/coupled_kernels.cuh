@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(kCoupledBlockMax) stack_kernel(const DevModel<
 // ====================================================================================================
 struct GroupParams {
   int N;             // elements per group
-  int P;             // threads cooperating on one element's pair sum (power of two <= 32)
+  int P;             // threads cooperating on one element's pair sum (block kernel: a power of two <= 32)
+  int A, tile;       // grid kernel: elements per block, partners per shared-memory tile
   int interaction;   // cmtjb_interaction
   int top;           // layer index of topId
   long long n_inst;
@@ -341,28 +342,28 @@ struct GroupParams {
 // field at a from the dipole at b (reservoir.hpp:79-97); r = r_a - r_b:
 //   H += pref (3 (m.r) r / r^5 - m / r^3)
 // 1/sqrt(x) without the library routine's special-case branches (BSSY/BSYNC + slow path around every
-// call): the SFU seed rsqrt.approx.ftz.f64 (MUFU.RSQ64H, ~2^-22) refined by two Newton steps, each
-// y <- y (1.5 - 0.5 x y^2): 2^-22 -> 2^-43 -> rounding level.  Inputs are squared pair distances,
-// validated on the host to be >= 1e-28 (reservoir.hpp:84-87, :39-42 guards): no zero / inf / NaN.
+// call): the SFU seed rsqrt.approx.ftz.f64 (MUFU.RSQ64H, relative error ~2^-22) refined by ONE third-order
+// (Halley) step  y <- y (1 + e/2 + 3 e^2/8),  e = 1 - x y^2:  the residual is (5/16) e^3 ~ 2^-65, i.e. rounding
+// level, in five FP64 instructions (two Newton steps take seven).  Inputs are squared pair distances, validated
+// on the host to be >= 1e-28 (reservoir.hpp:84-87, :39-42 guards): no zero / inf / NaN.
 __device__ __forceinline__ double rsqrt_nr(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  y = y * fma(-hx * y, y, 1.5);
-  y = y * fma(-hx * y, y, 1.5);
-  return y;
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y, fma(0.375, e, 0.5) * e, y);
 }
 
 // `self`: the pair (a, a) contributes nothing; handled without a branch (r2 -> 1, pref -> 0) so that the
-// pair loop unrolls into independent chains.
+// pair loop unrolls into independent chains.  25 FP64 instructions per pair:
+//   H += p3 (g r - m),   p3 = pref / r^3,   g = 3 (m.r) / r^2
 __device__ __forceinline__ void pair_accumulate(d3 &H, d3 r, d3 mb, double pref, bool self) {
   const double r2 = self ? 1.0 : dot(r, r);
   pref = self ? 0.0 : pref;
   const double inv = rsqrt_nr(r2);
   const double inv2 = inv * inv;
-  const double p3 = pref * (inv2 * inv);          // pref / r^3
-  const double a = (3.0 * inv2) * dot(mb, r) * p3;  // 3 pref (m.r) / r^5
-  H = mk(fma(a, r.x, fma(-p3, mb.x, H.x)), fma(a, r.y, fma(-p3, mb.y, H.y)), fma(a, r.z, fma(-p3, mb.z, H.z)));
+  const double p3 = (pref * inv) * inv2;
+  const double g = (3.0 * inv2) * dot(mb, r);
+  H = mk(fma(p3, fma(g, r.x, -mb.x), H.x), fma(p3, fma(g, r.y, -mb.y), H.y), fma(p3, fma(g, r.z, -mb.z), H.z));
 }
 
 // GroupInteraction, one group per block: blockDim.x = N * P rounded up to a warp multiple.  Two roles per
@@ -458,42 +459,68 @@ __global__ void __launch_bounds__(kCoupledBlockMax) group_block_kernel(const Dev
   }
 }
 
-// GroupInteraction, one large group across the whole grid (cooperative launch).  Thread
-// (a, p) as above with a = global_thread / P; the j-loop walks shared-memory tiles of kTile
-// partners; the top-layer magnetisation is exchanged through a double-buffered global array with
-// ONE grid-wide barrier per time step.
-constexpr int kGroupTile = 512;  // 7 arrays x 512 x 8 B = 28 KB of static shared memory
+// GroupInteraction, one large group across the whole grid (cooperative launch, ONE grid-wide barrier per step).
+//
+// Decomposition: block k owns A = ceil(N / gridDim) consecutive elements and sums their pair fields over ALL N
+// partners -- no reduction across blocks, and with gridDim = the SM count every SM carries the same 1/gridDim of
+// the N^2 pairs.  Inside the block thread (a, p) = (tid % A, tid / A) walks partners p, p + P, ... (P = 512 / A lanes
+// per element; the lanes of a warp mostly share the partner, so its seven shared-memory loads are broadcasts),
+// the P partial fields meet in shared memory, and the A elements are then stepped on A CONSECUTIVE lanes (one
+// element per lane, state in registers) -- not on one lane in P with the others parked.
+//
+// Shared memory holds the partners' x, y, z, prefactor and top-layer m: 7 x 8 B x TB.  Up to TB = 4096 partners
+// the geometry is staged ONCE and only the three m rows are re-staged per step (N = 4096 exactly fills the 227 KB);
+// larger arrays walk tiles of 4096 partners and re-stage all seven rows per tile.  The top-layer magnetisation is
+// exchanged through a double-buffered global array.
+constexpr int kGroupThreads = 512;   // general term set (128 registers)
+constexpr int kGroupThreadsLean = 768;  // lean term set: 6 warps per sub-partition at <= 85 registers
+constexpr int kGroupTileMax = 4096;
 
-template <int NL, int SOLVER, uint32_t F, bool UNIFORM>
-__global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__restrict__ models,
-                                                         const __grid_constant__ DevModel<NL> Mu,
-                                                         const __grid_constant__ GroupParams GP,
-                                                         const __grid_constant__ RunParams R) {
+template <int NL, int SOLVER, uint32_t F, bool UNIFORM, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) group_grid_kernel(const DevModel<NL> *__restrict__ models,
+                                                                      const __grid_constant__ DevModel<NL> Mu,
+                                                                      const __grid_constant__ GroupParams GP,
+                                                                      const __grid_constant__ RunParams R) {
   cg::grid_group grid = cg::this_grid();
-  // one array, so that the seven loads of a pair share one address register (immediate offsets)
-  __shared__ double tile[7][kGroupTile];  // x, y, z, prefactor, mx, my, mz of the staged partners
-  const int N = GP.N, P = GP.P;
-  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long a_raw = gt / P;
-  const int p = (int)(gt - a_raw * P);
-  const bool valid = a_raw < N;
-  const int a = valid ? (int)a_raw : N - 1;
-  const bool owner = valid && p == 0;
-  const long long i = GP.inst * N + a;
-  const DevModel<NL> &M = UNIFORM ? Mu : models[a];
+  extern __shared__ double sm[];
+  const int N = GP.N, A = GP.A, P = GP.P;
+  constexpr int TB = kGroupTileMax;  // compile-time row stride: the seven loads of a pair share one address register
+  double *tx = sm, *ty = tx + TB, *tz = ty + TB, *tp = tz + TB;  // static rows
+  double *tm = tp + TB;                                          // [3][TB] partners' m; reused for the P partial sums
+  double *Hs = tm + 3 * TB;                                      // [3][A] reduced fields of this block's elements
+  const int tid = threadIdx.x;
+  const int a_loc = tid % A, p = tid / A;
+  const int a0 = blockIdx.x * A;
+  const bool pair_lane = p < P;                  // the last (blockDim - A P) threads have no pairs
+  const int a_raw = a0 + a_loc;
+  const int a = a_raw < N ? a_raw : N - 1;       // lanes past the end shadow element N-1 (their sums are dropped)
+  const bool stepper = tid < A && a0 + tid < N;  // element a0 + tid is stepped by thread tid
+  const int e = stepper ? a0 + tid : N - 1;
+  const long long i = GP.inst * N + e;
+  const DevModel<NL> &M = UNIFORM ? Mu : models[e];
+  const bool resident = N <= TB;
   State<NL> S;
   d3 Hc[NL];
-  if (owner) {
+  if (stepper) {
     load_state<NL>(R, i, S);
 #pragma unroll
     for (int l = 0; l < NL; l++) Hc[l] = constant_field(M.L[l], R, i);
     const d3 mt = layer_m2<NL>(S, GP.top);
-    GP.mbuf[a] = mt.x;
-    GP.mbuf[N + a] = mt.y;
-    GP.mbuf[2 * N + a] = mt.z;
+    GP.mbuf[e] = mt.x;
+    GP.mbuf[N + e] = mt.y;
+    GP.mbuf[2 * N + e] = mt.z;
   }
   const d3 ra = mk(__ldg(GP.pos + a), __ldg(GP.pos + N + a), __ldg(GP.pos + 2 * N + a));
   const double scale = (GP.interaction == CMTJB_INT_DIPOLE_NOMURA) ? 1.0 / (4.0 * M_PI) : 1.0;
+  const bool interacting = GP.interaction != CMTJB_INT_NULL;
+  if (resident && interacting) {
+    for (int k = tid; k < N; k += blockDim.x) {
+      tx[k] = __ldg(GP.pos + k);
+      ty[k] = __ldg(GP.pos + N + k);
+      tz[k] = __ldg(GP.pos + 2 * N + k);
+      tp[k] = __ldg(GP.pref + k);
+    }
+  }
   long long until_write = (R.write_every - (R.it_begin % R.write_every)) % R.write_every;
   long long sample = R.first_sample;
   int cur = 0;
@@ -501,44 +528,64 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
   for (long long it = R.it_begin; it < R.it_end; ++it) {
     const double t = (double)it * R.dt;
     const double *mcur = GP.mbuf + (size_t)cur * 3 * N;
-    d3 H = mk(0, 0, 0);
-    if (GP.interaction != CMTJB_INT_NULL) {
-      for (int b0 = 0; b0 < N; b0 += kGroupTile) {
-        const int nb = min(kGroupTile, N - b0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-          tile[0][k] = __ldg(GP.pos + b0 + k);
-          tile[1][k] = __ldg(GP.pos + N + b0 + k);
-          tile[2][k] = __ldg(GP.pos + 2 * N + b0 + k);
-          tile[3][k] = __ldg(GP.pref + b0 + k);
-          tile[4][k] = __ldcg(mcur + b0 + k);  // written by other SMs last step: read through L2
-          tile[5][k] = __ldcg(mcur + N + b0 + k);
-          tile[6][k] = __ldcg(mcur + 2 * N + b0 + k);
+    if (interacting) {
+      d3 H = mk(0, 0, 0);
+      for (int b0 = 0; b0 < N; b0 += TB) {
+        const int nb = min(TB, N - b0);
+        if (b0 > 0) __syncthreads();  // the previous tile is still being read
+        for (int k = tid; k < nb; k += blockDim.x) {
+          if (!resident) {
+            tx[k] = __ldg(GP.pos + b0 + k);
+            ty[k] = __ldg(GP.pos + N + b0 + k);
+            tz[k] = __ldg(GP.pos + 2 * N + b0 + k);
+            tp[k] = __ldg(GP.pref + b0 + k);
+          }
+          tm[k] = __ldcg(mcur + b0 + k);  // written by other SMs last step: read through L2
+          tm[TB + k] = __ldcg(mcur + N + b0 + k);
+          tm[2 * TB + k] = __ldcg(mcur + 2 * N + b0 + k);
         }
         __syncthreads();
-#pragma unroll 4
-        for (int k = p; k < nb; k += P) {
-          const double *q = &tile[0][k];
-          pair_accumulate(H, mk(ra.x - q[0], ra.y - q[kGroupTile], ra.z - q[2 * kGroupTile]),
-                          mk(q[4 * kGroupTile], q[5 * kGroupTile], q[6 * kGroupTile]), q[3 * kGroupTile], b0 + k == a);
+        if (pair_lane) {
+          // two partners per iteration into separate accumulators: two independent dependency chains per thread
+          d3 H2 = mk(0, 0, 0);
+          int k = p;
+          for (; k + P < nb; k += 2 * P) {
+            const int k2 = k + P;
+            pair_accumulate(H, mk(ra.x - tx[k], ra.y - ty[k], ra.z - tz[k]), mk(tm[k], tm[TB + k], tm[2 * TB + k]), tp[k], b0 + k == a);
+            pair_accumulate(H2, mk(ra.x - tx[k2], ra.y - ty[k2], ra.z - tz[k2]), mk(tm[k2], tm[TB + k2], tm[2 * TB + k2]), tp[k2], b0 + k2 == a);
+          }
+          if (k < nb) pair_accumulate(H, mk(ra.x - tx[k], ra.y - ty[k], ra.z - tz[k]), mk(tm[k], tm[TB + k], tm[2 * TB + k]), tp[k], b0 + k == a);
+          H = H + H2;
         }
       }
-      for (int off = P >> 1; off > 0; off >>= 1) {
-        H.x += __shfl_xor_sync(0xffffffffu, H.x, off);
-        H.y += __shfl_xor_sync(0xffffffffu, H.y, off);
-        H.z += __shfl_xor_sync(0xffffffffu, H.z, off);
+      __syncthreads();  // every lane is done with the m rows: their space takes the partial sums
+      if (pair_lane) {
+        double *q = tm + (size_t)(p * A + a_loc) * 3;
+        q[0] = H.x;
+        q[1] = H.y;
+        q[2] = H.z;
       }
+      __syncthreads();
+      if (tid < 3 * A) {  // component c of element a_loc: sum over the P lanes in lane order (deterministic)
+        const int c = tid / A, al = tid - c * A;
+        double acc = 0.0;
+        for (int q = 0; q < P; q++) acc += tm[(size_t)(q * A + al) * 3 + c];
+        Hs[c * A + al] = acc;
+      }
+      __syncthreads();
     }
-    if (owner) {
-      d3 Hs[NL];
+    if (stepper) {
+      // setLayerReservedInteractionField(topId, AxialDriver(H_extra)) (reservoir.hpp:145-146)
+      const d3 H = interacting ? mk(Hs[tid], Hs[A + tid], Hs[2 * A + tid]) : mk(0, 0, 0);
+      d3 Hl[NL];
 #pragma unroll
-      for (int l = 0; l < NL; l++) Hs[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
-      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hs, NoExt());
+      for (int l = 0; l < NL; l++) Hl[l] = (l == GP.top) ? axpy(H, scale, Hc[l]) : Hc[l];
+      coupled_step<NL, SOLVER, F>(M, R, i, it, t, S, Hl, NoExt());
       double *nx = GP.mbuf + (size_t)(cur ^ 1) * 3 * N;
       const d3 mt = layer_m2<NL>(S, GP.top);
-      __stcg(nx + a, mt.x);
-      __stcg(nx + N + a, mt.y);
-      __stcg(nx + 2 * N + a, mt.z);
+      __stcg(nx + e, mt.x);
+      __stcg(nx + N + e, mt.y);
+      __stcg(nx + 2 * N + e, mt.z);
       if (until_write == 0 && R.log) write_sample<NL>(M, R, S, sample, i);
     }
     if (until_write == 0) {
@@ -549,7 +596,7 @@ __global__ void __launch_bounds__(256) group_grid_kernel(const DevModel<NL> *__r
     cur ^= 1;
     grid.sync();
   }
-  if (owner) {
+  if (stepper) {
     store_state<NL>(R, i, S);
     if (R.status) R.status[i] = nan_status<NL, SOLVER>(S);
   }

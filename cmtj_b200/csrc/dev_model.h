@@ -129,6 +129,22 @@ struct PostParams {
   double sd_b[4], sd_a[4];
 };
 
+// the ten Philox4x32 round keys of a run's seed (key + r * Weyl constant)
+struct PhiloxKeys {
+  uint32_t x[10], y[10];
+};
+inline PhiloxKeys make_philox_keys(unsigned long long seed) {
+  PhiloxKeys K;
+  uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; r++) {
+    K.x[r] = kx;
+    K.y[r] = ky;
+    kx += 0x9E3779B9u;
+    ky += 0xBB67AE85u;
+  }
+  return K;
+}
+
 // run parameters (also constant bank)
 struct RunParams {
   double *m_state;           // [NL*3][B]
@@ -158,6 +174,8 @@ struct RunParams {
   long long elog_ch0;        // first CMTJB_LOG_ENERGY channel, or -1 (general variants only)
   double dt, sqrt_dt, total_time, write_frequency;
   unsigned long long seed;
+  PhiloxKeys pk;             // round keys of `seed` (thermal noise)
+  int32_t tune_flags;        // CMTJB_TUNE bits (experiments): 1 = stateless thermal normals in the sweep kernels
   PostParams post;
 };
 

@@ -485,24 +485,112 @@ __device__ __forceinline__ float unit_open_low(uint32_t r) {
   const float lo = __uint_as_float(0x4b000000u | (r & 0x1ffu)) - 8388608.0f;    // 0 .. 511
   return fmaf(lo, -2.3283064365386963e-10f, hi) - 1.1641532182693481e-10f;      // - lo 2^-32 - 2^-33
 }
-__device__ __forceinline__ d3 normal3(unsigned long long seed, unsigned long long inst, unsigned int layer,
-                                      unsigned long long step) {
-  const uint4 ctr = make_uint4((uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)step,
-                               ((uint32_t)(step >> 32) << 8) | (layer & 0xFFu));
-  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  // radius sqrt(-2 ln u), u in (0, 1]: t = -2 ln 2 * log2(u) >= 0; sqrt(t) = t * rsqrt(t), 0 at t = 0
+// the same hash with the ten round keys taken from the constant bank (RunParams::pk, filled on the host from the
+// seed): the key schedule costs nothing in the time loop
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys &K) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ K.x[r], lo1, hi0 ^ ctr.w ^ K.y[r], lo0);
+  }
+  return ctr;
+}
+__device__ __forceinline__ PhiloxKeys philox_keys(unsigned long long seed) {
+  PhiloxKeys K;
+  uint32_t kx = (uint32_t)seed, ky = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    K.x[r] = kx;
+    K.y[r] = ky;
+    kx += 0x9E3779B9u;
+    ky += 0xBB67AE85u;
+  }
+  return K;
+}
+
+// four N(0,1) float32 values from one Philox block: two Box-Muller pairs, radius sqrt(-2 ln u) with u in (0, 1],
+// t = -2 ln 2 * log2(u) >= 0 and sqrt(t) = t * rsqrt(t) (0 at t = 0); angle uniform on [-pi, pi), where the SFU sine
+// and cosine are most accurate
+__device__ __forceinline__ float4 normal4(uint4 r) {
   const float t0 = -1.3862943611198906f * __log2f(unit_open_low(r.x));
   const float t1 = -1.3862943611198906f * __log2f(unit_open_low(r.z));
   const float r0 = t0 * rsqrtf(fmaxf(t0, 1e-30f)), r1 = t1 * rsqrtf(fmaxf(t1, 1e-30f));
-  // angle uniform on [-pi, pi): the SFU sine/cosine are most accurate there
   const float a0 = 6.283185307179586f * (__uint_as_float(0x3f800000u | (r.y >> 9)) - 1.5f);
   const float a1 = 6.283185307179586f * (__uint_as_float(0x3f800000u | (r.w >> 9)) - 1.5f);
-  return mk((double)(r0 * __cosf(a0)), (double)(r0 * __sinf(a0)), (double)(r1 * __cosf(a1)));
+  return make_float4(r0 * __cosf(a0), r0 * __sinf(a0), r1 * __cosf(a1), r1 * __sinf(a1));
+}
+
+// ---- the thermal stream ----------------------------------------------------------------------------------------
+// Normal n = 3 j + c (component c of step s = 4 q + j) of a (seed, instance, layer) stream is element n % 4 of
+// Philox block (q, n / 4): the twelve normals of four consecutive steps come from THREE blocks, every normal of
+// every block is used, and each value is a pure function of (seed, instance, layer, step, component) -- shards,
+// sub-batches and the persistent kernel's task boundaries reproduce the same numbers.
+__device__ __forceinline__ float4 thermal_block(const PhiloxKeys &K, unsigned long long inst, unsigned layer, unsigned long long q,
+                                                unsigned sub) {
+  const uint4 ctr = make_uint4((uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)q, ((uint32_t)(q >> 32) << 8) | (sub << 4) | (layer & 0xFu));
+  return normal4(philox4x32_10(ctr, K));
+}
+__device__ __forceinline__ float pick4(float4 v, unsigned k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// stateless form: one or two blocks per step (coupled and lane-per-layer kernels, test hook)
+__device__ __forceinline__ d3 normal3(const PhiloxKeys &K, unsigned long long inst, unsigned layer, unsigned long long step) {
+  const unsigned n0 = 3u * (unsigned)(step & 3ull);
+  const unsigned long long q = step >> 2;
+  const unsigned s0 = n0 >> 2, s1 = (n0 + 2u) >> 2;
+  const float4 b0 = thermal_block(K, inst, layer, q, s0);
+  float4 b1 = b0;
+  if (s1 != s0) b1 = thermal_block(K, inst, layer, q, s1);
+  float v[3];
+#pragma unroll
+  for (unsigned c = 0; c < 3; c++) v[c] = pick4(((n0 + c) >> 2) == s0 ? b0 : b1, (n0 + c) & 3u);
+  return mk((double)v[0], (double)v[1], (double)v[2]);
+}
+
+// carried form (time loops that own a layer for consecutive steps): the spare normals of a block wait in three
+// registers for the following steps, so a block is hashed exactly once -- 0.75 Philox blocks per layer-step.
+struct NoiseCarry {
+  float a, b, c;
+};
+// the spares as they stand BEFORE step `step` (a time loop that starts in the middle of a quad)
+__device__ __forceinline__ NoiseCarry carry_before(const PhiloxKeys &K, unsigned long long inst, unsigned layer, unsigned long long step) {
+  NoiseCarry nc{0.f, 0.f, 0.f};
+  const unsigned j = (unsigned)(step & 3ull);
+  if (j != 0) {
+    const float4 v = thermal_block(K, inst, layer, step >> 2, j - 1);
+    if (j == 1) nc.a = v.w;                  // normal 3
+    else if (j == 2) nc.a = v.z, nc.b = v.w; // normals 6, 7
+    else nc.a = v.y, nc.b = v.z, nc.c = v.w; // normals 9, 10, 11
+  }
+  return nc;
+}
+__device__ __forceinline__ d3 normal3_carried(const PhiloxKeys &K, unsigned long long inst, unsigned layer, unsigned long long step,
+                                              NoiseCarry &nc) {
+  const unsigned j = (unsigned)(step & 3ull);  // uniform across the warp: no divergence
+  if (j == 3) return mk((double)nc.a, (double)nc.b, (double)nc.c);
+  const float4 v = thermal_block(K, inst, layer, step >> 2, j);
+  d3 out;
+  if (j == 0) {
+    out = mk((double)v.x, (double)v.y, (double)v.z);
+    nc.a = v.w;
+  } else if (j == 1) {
+    out = mk((double)nc.a, (double)v.x, (double)v.y);
+    nc.a = v.z;
+    nc.b = v.w;
+  } else {
+    out = mk((double)nc.a, (double)nc.b, (double)v.x);
+    nc.a = v.y;
+    nc.b = v.z;
+    nc.c = v.w;
+  }
+  return out;
 }
 
 // the step's noise vector dW (junction.hpp:1121-1136): Langevin + 1/f^alpha buffer
 template <uint32_t F, int NL>
-__device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, int l, long long i, long long it, StageTime t) {
+__device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, int l, long long i, long long it, StageTime t,
+                                       NoiseCarry *nc = nullptr) {
   d3 dW = mk(0, 0, 0);
   if constexpr ((F & F_THERMAL) != 0) {
     if (Lr.thermal) {
@@ -513,7 +601,8 @@ __device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, i
         const double T = slot_value<F>(Lr, R, CMTJB_SLOT_TEMPERATURE, t, i);
         sigma = sqrt(Lr.sigma_c * T);
       }
-      dW = normal3(R.seed, (unsigned long long)(R.inst_offset + i), (unsigned)l, (unsigned long long)it) * sigma;
+      const unsigned long long inst = (unsigned long long)(R.inst_offset + i);
+      dW = (nc ? normal3_carried(R.pk, inst, (unsigned)l, (unsigned long long)it, *nc) : normal3(R.pk, inst, (unsigned)l, (unsigned long long)it)) * sigma;
     }
   }
   if constexpr ((F & F_ONEF) != 0) {

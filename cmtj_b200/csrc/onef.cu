@@ -28,17 +28,6 @@
 namespace cmtjb {
 namespace {
 
-// four N(0,1) float32 values from one Philox block (two Box-Muller pairs; same uniform construction and
-// SFU evaluation as normal3, llgs_device.cuh)
-__device__ __forceinline__ float4 normal4(uint4 r) {
-  const float t0 = -1.3862943611198906f * __log2f(unit_open_low(r.x));
-  const float t1 = -1.3862943611198906f * __log2f(unit_open_low(r.z));
-  const float r0 = t0 * rsqrtf(fmaxf(t0, 1e-30f)), r1 = t1 * rsqrtf(fmaxf(t1, 1e-30f));
-  const float a0 = 6.283185307179586f * (__uint_as_float(0x3f800000u | (r.y >> 9)) - 1.5f);
-  const float a1 = 6.283185307179586f * (__uint_as_float(0x3f800000u | (r.w >> 9)) - 1.5f);
-  return make_float4(r0 * __cosf(a0), r0 * __sinf(a0), r1 * __cosf(a1), r1 * __sinf(a1));
-}
-
 // W[g][t] = (std * N(0,1), 0) for t < n, 0 for n <= t < 2n.  One thread per four consecutive samples.
 // Series g belongs to global element elem0 + g (sweeps: instances; coupled systems: junctions of all instances).
 __global__ void onef_fill_kernel(float2 *W, long long n, long long G, unsigned long long seed, unsigned long long elem0,

@@ -60,6 +60,27 @@ def _torch():
     return torch
 
 
+class _Phases:
+    """CMTJB_TRACE_PROC=1: wall time of each phase of a procedure call (device synchronised at every mark)."""
+
+    def __init__(self, name):
+        import os
+        import time
+
+        self.on = bool(os.environ.get("CMTJB_TRACE_PROC"))
+        self.name, self.t, self.time = name, None, time
+        self.mark(None)
+
+    def mark(self, what):
+        if not self.on:
+            return
+        _torch().cuda.synchronize()
+        now = self.time.perf_counter()
+        if what is not None:
+            print(f"[cmtjb] {self.name}: {what} {1e3 * (now - self.t):.1f} ms", flush=True)
+        self.t = now
+
+
 def _spectrum_bins(n: int, int_step: float, max_frequency: float):
     """The bins compute_spectrum_strip keeps (procedures.py:29-40): first n//2 of fftfreq(n, dt),
     then those <= max_frequency.  Returns (findx [K,1], freqs[findx] [K,1])."""
@@ -68,22 +89,41 @@ def _spectrum_bins(n: int, int_step: float, max_frequency: float):
     return findx, freqs[findx]
 
 
-def spectrum_device(signal, int_step: float, max_frequency: float, slice_bytes: float = 2e9):
-    """|FFT| of B real series stored [n, B] on the device, restricted like compute_spectrum_strip.
-    Returns (CUDA tensor [K, B], freqs [K,1]).  The transform runs over column slices whose complex
-    half-spectrum stays below ``slice_bytes``: only the K bins up to ``max_frequency`` are kept, so a
-    whole-sweep projection log (tens of GB) never needs a second buffer of its own size."""
+def spectrum_device(signal, int_step: float, max_frequency: float):
+    """|FFT| of B real series stored time-major [n, B] on the device (rows may be a view with a pitch), restricted
+    like compute_spectrum_strip.  Returns (CUDA tensor [B, K], freqs [K, 1]).  ``cmtjb_rfft_abs_device``: cuFFT in
+    double precision over column slices of the buffer as it lies (no transposed copy), only the K bins up to
+    ``max_frequency`` are kept, so a whole-sweep projection log (tens of GB) never needs a second buffer of its
+    own size."""
+    import ctypes as C
+
     torch = _torch()
     n, B = int(signal.shape[0]), int(signal.shape[1])
     findx, freqs = _spectrum_bins(n, int_step, max_frequency)
-    idx = torch.from_numpy(findx.ravel()).to(signal.device)
-    out = torch.empty((int(idx.numel()), B), dtype=torch.float64, device=signal.device)
-    cols = max(1, int(slice_bytes // max(8 * n, 1)))
-    for lo in range(0, B, cols):
-        hi = min(B, lo + cols)
-        half = torch.fft.rfft(signal[:, lo:hi], dim=0)[: n // 2]
-        out[:, lo:hi] = half.index_select(0, idx).abs()
+    K = int(findx.size)
+    assert signal.dtype == torch.float64 and signal.stride(1) == 1 and (n == 1 or signal.stride(0) >= B)
+    if K and not np.array_equal(findx.ravel(), np.arange(K)):  # fftfreq is increasing on [0, n/2): always a prefix
+        raise RuntimeError("unexpected frequency selection")
+    out = torch.empty((B, K), dtype=torch.float64, device=signal.device)
+    if K == 0 or B == 0:
+        return out, freqs
+    be = _abi.cuda_backend()
+    f = be.lib.cmtjb_rfft_abs_device
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    ld = int(signal.stride(0)) if n > 1 else B
+    stream = torch.cuda.current_stream(signal.device).cuda_stream
+    be.check(f(signal.data_ptr(), n, B, ld, K, out.data_ptr(), signal.device.index or 0, C.c_void_p(stream)))
     return out, freqs
+
+
+def _to_host(t):
+    """device tensor -> numpy through page-locked memory (torch caches the pinned blocks between calls)"""
+    torch = _torch()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
 
 
 def compute_spectrum_strip(input_m, int_step: float, max_frequency: float):
@@ -91,7 +131,7 @@ def compute_spectrum_strip(input_m, int_step: float, max_frequency: float):
     torch = _torch()
     x = torch.from_numpy(np.ascontiguousarray(np.asarray(input_m, dtype=np.float64))).cuda().reshape(-1, 1)
     yf, freqs = spectrum_device(x, int_step, max_frequency)
-    return yf.cpu().numpy(), freqs
+    return yf.cpu().numpy().reshape(-1, 1), freqs
 
 
 def _steps(total: float, dt: float) -> int:
@@ -176,6 +216,7 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
                 wait_time, max_frequency, take_last_n, full_output, static_only, device, normalise):
     """One batch of field points (all start from m0).  Returns a dict of host arrays."""
     torch = _torch()
+    ph = _Phases("PIMM batch")
     B = Hc.shape[0]
     L = junction.layerNo
     layer_ids = junction.getLayerIds()
@@ -211,6 +252,7 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
             batch.run_device(_time_for_steps(n_a, int_step), int_step, int_step, log=False, post=spec(0))
         res = batch.run_device(simulation_duration, int_step, int_step, post=spec(n_a), start_iteration=n_a)
         log_last = res["_log"]
+    ph.mark(f"set-up + integration of {B} instances x {n_total} steps")
     m_last = log_last[: 3 * L].contiguous()  # [3L, n_last, B]
     w_dev = torch.tensor(weights, dtype=torch.float64, device=dev)
     # static resistance over the last samples, from the thickness*Ms-weighted m (procedures.py:152-162)
@@ -232,15 +274,17 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
     final = m_last[:, -1, :].reshape(L, 3, B)
     out["m_avg"] = (final * w_dev[:, None, None]).sum(0).cpu().numpy().T  # [B,3]
     out["m_final"] = final.cpu().numpy()  # [L,3,B]
+    ph.mark("static resistances + final state to the host")
     if not static_only:
         time = np.arange(n_total, dtype=np.float64) * float(int_step)
         n0 = int(np.argwhere(time >= wait_time).ravel()[0]) if np.any(time >= wait_time) else n_total
         yf, freqs = spectrum_device(proj_log[0, n0:, :], int_step, max_frequency)
-        out["spectrum"] = yf.cpu().numpy().T  # [B,K]
+        ph.mark("spectrum (batched FFT)")
+        out["spectrum"] = _to_host(yf)  # [B,K]
         out["freqs"] = freqs
+        ph.mark("spectrum to the host")
         if full_output:
-            out["layer_spectra"] = [spectrum_device(proj_log[1 + l, n0:, :], int_step, max_frequency)[0].cpu().numpy().T
-                                    for l in range(L)]
+            out["layer_spectra"] = [_to_host(spectrum_device(proj_log[1 + l, n0:, :], int_step, max_frequency)[0]) for l in range(L)]
             mt = out.pop("m_traj_dev").reshape(L, 3, n_total, B) * w_dev[:, None, None, None]
             out["m_traj"] = mt.permute(3, 0, 1, 2).cpu().numpy()  # [B,L,3,T]
     return out
@@ -265,7 +309,7 @@ def PIMM_procedure(
     static_only: bool = False,
     carry_state: bool = True,
     device: int = 0,
-    memory_budget: float = 100e9,
+    memory_budget: Optional[float] = None,
 ) -> Tuple[np.ndarray, np.ndarray, Dict[str, Any]]:
     """Pulse-induced microwave magnetometry over a field sweep (procedures.py:42-204): returns
     ``(spectrum [n_H, n_f], frequencies [n_f, 1], other_data)`` with other_data keys ``H``, ``Rx``,
@@ -306,6 +350,12 @@ def PIMM_procedure(
     else:
         m0 = _disturbed(junction, layer_ids, Hvecs.shape[0], disturbance)
         n_series = 0 if static_only else (1 + L if full_output else 1)
+        if memory_budget is None:
+            # everything that is free now, less what the spectrum slices, their cuFFT work area and the small logs take:
+            # splitting a sweep into instance chunks costs throughput (fewer warps per SM sub-partition), so the whole
+            # sweep stays one batch whenever its projection log fits (1e5 points x 20 ns: 160 GB)
+            free_b, _ = _torch().cuda.mem_get_info(device)
+            memory_budget = max(free_b - 8e9, 0.25 * free_b)
         # device bytes per instance: the projection log(s), the full-rate log when full_output, the last-n log
         # (twice: the weighted m_traj copy handed back to the host is staged on the device)
         per_inst = 8.0 * n_total * (n_series + (2.0 * (3 * L + 3) if full_output else 0.0)) + 8.0 * 200 * (3 * L + 3)

@@ -327,6 +327,13 @@ int cmtjb_compute_sd_device(const double *R, const double *I, int32_t current_pe
 int cmtjb_compute_gmr_device(double Rp, double Rap, const double *m1, const double *m2, int64_t n, double *out,
                              int device, void *stream);
 
+/* compute_spectrum_strip (cmtj/utils/procedures.py:29-40) for B series at once: x is DEVICE, time-major,
+ * x[t * ld + b] for t < n, b < B (the projection log of cmtjb_run_device_post, or any row range of it);
+ * out (DEVICE, [B][K]) receives |FFT(x_b)[k]| for the K lowest bins, K <= n/2 + 1.  Double-precision cuFFT over
+ * column slices, no transposed copy of the input. */
+int cmtjb_rfft_abs_device(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
+                          void *stream);
+
 /* Number of kernels this library has launched in this process (monotonic). */
 long long cmtjb_launch_count(void);
 /* Name of the kernel variant (layer count / solver / compiled term set) the calling thread's last sweep launch
@@ -450,6 +457,9 @@ int cmtjb_normals_host(uint64_t seed, int64_t inst0, int64_t n_inst, int32_t lay
 /* FP64 FMA-pipe microbenchmark used for the roofline denominator: runs `iters` dependent
  * DFMA chains on every SM and returns achieved FLOP/s in *flops (2 flop per DFMA). */
 int cmtjb_fp64_peak(int device, int64_t iters, double *flops, double *ms);
+/* SM clock (MHz) at which the calling thread's last cmtjb_fp64_peak actually ran, from the cycle counter and the global
+ * nanosecond timer read inside the kernel (0 before the first call). */
+double cmtjb_fp64_peak_sm_mhz(void);
 
 #ifdef __cplusplus
 }
