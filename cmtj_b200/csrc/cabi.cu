@@ -287,7 +287,7 @@ uint32_t model_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers,
 //     last, partly filled one costs a full wave  ->  efficiency waves / ceil(waves).
 // Balance when that model loses more than 3 % and the launch is long enough to be cut into >= 8 rounds.
 BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const void *plain_kernel) {
-  BalancePlan bp{false, 0, 0, 0, 0, 0, 0};
+  BalancePlan bp{false, 0, 0, 0, 0, 0};
   const char *force = std::getenv("CMTJB_BALANCE");
   if (force && force[0] == '0') return bp;
   const bool forced = force && force[0] == '1';
@@ -320,10 +320,12 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
   if (const char *c = std::getenv("CMTJB_BALANCE_CHUNK")) target = std::max<long long>(1, std::atoll(c));  // tuning knob
   const long long chunk = we * ((target + we - 1) / we);
   const long long rounds = (steps + chunk - 1) / chunk;
-  // Resident warps per sub-partition of the balanced form: the largest k below W / S.  The W - S k instance-warps
-  // that nobody holds at any moment are what a free warp picks from (llgs_balanced_kernel); a twentieth of W is
-  // kept in reserve so that the search stays short.  Below four the FP64 pipe is latency- rather than throughput-
-  // bound and time-slicing would serialise what the plain form overlaps.
+  // Resident warps per sub-partition of the balanced form: at most 0.9 W / S, so that a warp drawing a
+  // ticket (almost) always finds the predecessor task finished -- tickets are issued round-major, and
+  // the W - S k instance-warps not being integrated at any moment are the slack that keeps the queue
+  // from stalling (measured on B200, S1 with W / S = 5.28: k = 4 -> 1.15e11 layer-steps/s, k = 5 ->
+  // 0.6e11, plain -> 1.04e11).  Below four the FP64 pipe is latency- rather than throughput-bound
+  // and time-slicing would serialise what the plain form overlaps.
   long long k = std::min<long long>(bal_blocks, (long long)std::floor(0.9 * mean));
   if (const char *c = std::getenv("CMTJB_BALANCE_WARPS")) k = std::max<long long>(1, std::min<long long>(std::atoll(c), bal_blocks));
   if (!forced && (eff > 0.97 || rounds < 8 || k < 4)) return bp;
@@ -334,7 +336,6 @@ BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const 
   bp.n_wtasks = W;
   bp.blocks = (int)std::min<long long>(k * n_sm[dev], (W + 3) / 4);
   bp.per_sm = std::getenv("CMTJB_BALANCE_NOPIN") ? 0 : (int)k;
-  if (const char *c = std::getenv("CMTJB_BALANCE_SCHED")) bp.sched = (c[0] == 'c') ? 1 : 0;  // "claim" / "ticket" (tuning knob)
   return bp;
 }
 

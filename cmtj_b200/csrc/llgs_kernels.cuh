@@ -414,9 +414,16 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
   }
 }
 
+// Register budget: left to the compiler for every variant.  Tried and dropped (round 2): capping the stochastic single-
+// layer kernels at 64 registers for 8 warps per sub-partition instead of 5 (ncu: `wait` is their top stall) made
+// them slower, 7.3 -> 6.5e10 (Heun) and 9.0 -> 8.2e10 (Euler-Heun) layer-steps/s: the spilled state costs more than
+// the extra warps hide.  NB a second __launch_bounds__ argument of 1 is NOT neutral: it lifts the S1 kernel from 87 to
+// 116 registers and the 3-layer Heun kernel from 120 to 192, 9 % slower each.
+constexpr int min_blocks(int, int, int, uint32_t) { return 0; }  // 0 = no constraint
+
 // One thread per instance, whole step range of the launch.
 template <int NL, int SOLVER, uint32_t F>
-__global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constant__ DevModel<NL> M,
+__global__ void __launch_bounds__(kBlock, min_blocks(kBlock, NL, SOLVER, F)) llgs_fixed_kernel(const __grid_constant__ DevModel<NL> M,
                                                             const __grid_constant__ RunParams R) {
   const long long i = R.i_lo + (long long)blockIdx.x * kBlock + threadIdx.x;
   if (i >= R.i_hi) return;
@@ -428,26 +435,20 @@ __global__ void __launch_bounds__(kBlock) llgs_fixed_kernel(const __grid_constan
 // partition for its lifetime.  A sweep of W = ceil(B/32) warps that is not a multiple of 592 leaves
 // the run time set by the sub-partitions carrying ceil(W/592) warps while the others idle at the
 // end: W = 3125 (the 1e5-point PIMM sweep) is 5.28 per sub-partition, i.e. 12 % lost to the ones
-// that carry 6.  Here the run is cut into (round, instance-warp) tasks of `chunk` steps and k x 592
-// persistent warps (k < W / 592) work through them, so every sub-partition carries exactly k warps
-// until the work runs out.
+// that carry 6.  Here the run is cut into (round, instance-warp) tasks of `chunk` steps; resident
+// warps draw tasks from a ticket counter in (round-major) order, so every sub-partition stays busy
+// until the queue drains.  Task (r, w) may start once (r-1, w) has published the state of its 32
+// instances: a per-instance-warp round counter, release/acquire at gpu scope.  Tickets are handed
+// out in dependency order, so a waiting warp only ever waits on a warp that is already running.
 //
-// Scheduling: an instance-warp is CLAIMED for one round at a time.  A free warp walks a shared cursor
-// over the instance-warps and takes the first one that nobody holds (atomicCAS on its claim word), runs
-// that instance-warp's next round from the state left in m_state, publishes the round count and lets
-// go.  There are always W - k x 592 unheld instance-warps, so a free warp never waits for another
-// warp to finish (the round-major ticket queue this replaces made a warp sleep until the predecessor
-// task of its ticket was published: 13 % of all warp time on the S1 sweep, ncu `stall_sleeping`); the
-// cursor visits instance-warps cyclically, which keeps their progress even.  Which warp runs which
-// round does not affect any result: a round is a pure function of the state it starts from.
+// Tried and dropped (round 2, S1 sweep, same box): claiming any unheld instance-warp instead of
+// waiting for the ticket's predecessor removes the `sleeping` stall (1.07 -> 0.02 per issue) but the
+// lane-0 search executes 19 % more warp instructions and the kernel gets 8 % slower (376 vs 348 ms).
 struct Balance {
-  unsigned long long *cursor;    // zeroed before the launch
-  unsigned long long *finished;  // tasks completed, zeroed before the launch
-  int *done;                     // [n_wtasks] rounds completed per instance-warp, zeroed before the launch
-  int *claim;                    // [n_wtasks] 1 while a warp holds the instance-warp (and for good once it is finished)
-  long long chunk;               // steps per task
+  unsigned long long *ticket;  // zeroed before the launch
+  int *done;                   // [n_wtasks] rounds completed per instance-warp, zeroed before the launch
+  long long chunk;             // steps per task
   long long n_rounds, n_wtasks;
-  int sched;                     // 0: round-major ticket queue (wait for the predecessor task), 1: claim an unheld instance-warp
 };
 constexpr int kBalBlock = 128;  // one warp per sub-partition per block
 
@@ -456,86 +457,35 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_release_gpu(int *p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int cas_acquire_gpu(int *p, int expect, int val) {
-  int old;
-  asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(expect), "r"(val) : "memory");
-  return old;
-}
 
 template <int NL, int SOLVER, uint32_t F>
-__global__ void __launch_bounds__(kBalBlock) llgs_balanced_kernel(const __grid_constant__ DevModel<NL> M,
-                                                                  const __grid_constant__ RunParams R,
-                                                                  const __grid_constant__ Balance Q) {
+__global__ void __launch_bounds__(kBalBlock, min_blocks(kBalBlock, NL, SOLVER, F)) llgs_balanced_kernel(const __grid_constant__ DevModel<NL> M,
+                                                                                                        const __grid_constant__ RunParams R,
+                                                                                                        const __grid_constant__ Balance Q) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long total = (unsigned long long)Q.n_wtasks * (unsigned long long)Q.n_rounds;
-  if (Q.sched == 0) {
-    // round-major ticket queue: ticket id is task (id / W, id % W); it may start once the same instance-warp's previous
-    // round has been published.  Tickets are issued in dependency order, so a waiting warp only ever waits on a warp that
-    // already runs: no deadlock for any grid size.
-    for (;;) {
-      unsigned long long id = 0;
-      if (lane == 0) id = atomicAdd(Q.cursor, 1ULL);
-      id = __shfl_sync(0xffffffffu, id, 0);
-      if (id >= total) break;
-      const long long round = (long long)(id / (unsigned long long)Q.n_wtasks);
-      const long long w = (long long)(id - (unsigned long long)round * (unsigned long long)Q.n_wtasks);
-      if (round > 0) {
-        if (lane == 0)
-          while (ld_acquire_gpu(Q.done + w) < (int)round) __nanosleep(256);
-        __syncwarp();
-      }
-      const long long i = R.i_lo + w * 32 + lane;
-      const long long it0 = R.it_begin + round * Q.chunk;
-      const long long it1 = (it0 + Q.chunk < R.it_end) ? it0 + Q.chunk : R.it_end;
-      if (i < R.i_hi) run_span<NL, SOLVER, F>(M, R, i, it0, it1);
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release_gpu(Q.done + w, (int)round + 1);
-    }
-    return;
-  }
   for (;;) {
-    long long w = -1;
-    int round = 0;
-    if (lane == 0) {
-      int misses = 0;
-      for (;;) {
-        if (ld_acquire_gpu(Q.finished) >= total) break;
-        const long long idx = (long long)(atomicAdd(Q.cursor, 1ULL) % (unsigned long long)Q.n_wtasks);
-        if (ld_acquire_gpu(Q.claim + idx) == 0 && cas_acquire_gpu(Q.claim + idx, 0, 1) == 0) {
-          round = __ldcg(Q.done + idx);  // only the holder of the claim reads or writes it (L2: written from another SM)
-          w = idx;
-          break;
-        }
-        // everything left is held by someone (the tail of the run): do not hammer the cursor
-        if (++misses >= 64) {
-          __nanosleep(2000);
-          misses = 0;
-        }
-      }
+    unsigned long long id = 0;
+    if (lane == 0) id = atomicAdd(Q.ticket, 1ULL);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= total) break;
+    const long long round = (long long)(id / (unsigned long long)Q.n_wtasks);
+    const long long w = (long long)(id - (unsigned long long)round * (unsigned long long)Q.n_wtasks);
+    if (round > 0) {
+      if (lane == 0)
+        while (ld_acquire_gpu(Q.done + w) < (int)round) __nanosleep(256);
+      __syncwarp();
     }
-    w = __shfl_sync(0xffffffffu, w, 0);
-    round = __shfl_sync(0xffffffffu, round, 0);
-    if (w < 0) break;
     const long long i = R.i_lo + w * 32 + lane;
-    const long long it0 = R.it_begin + (long long)round * Q.chunk;
+    const long long it0 = R.it_begin + round * Q.chunk;
     const long long it1 = (it0 + Q.chunk < R.it_end) ? it0 + Q.chunk : R.it_end;
     if (i < R.i_hi) run_span<NL, SOLVER, F>(M, R, i, it0, it1);
     __threadfence();
     __syncwarp();
-    if (lane == 0) {
-      __stcg(Q.done + w, round + 1);
-      if (round + 1 < Q.n_rounds) st_release_gpu(Q.claim + w, 0);  // a finished instance-warp stays claimed: skipped for good
-      atomicAdd(Q.finished, 1ULL);
-    }
+    if (lane == 0) st_release_gpu(Q.done + w, (int)round + 1);
   }
 }
 
@@ -820,7 +770,6 @@ struct BalancePlan {
   long long chunk, n_rounds, n_wtasks;
   int blocks;
   int per_sm;  // resident blocks (= warps per sub-partition) the plan assumes on EVERY SM
-  int sched;   // Balance::sched
 };
 BalancePlan plan_balance(const RunParams &R, const void *balanced_kernel, const void *plain_kernel);
 
@@ -829,24 +778,22 @@ cudaError_t launch_fixed(const void *model, const RunParams *R, cudaStream_t str
   const DevModel<NL> *M = static_cast<const DevModel<NL> *>(model);
   const BalancePlan bp = plan_balance(*R, (const void *)&llgs_balanced_kernel<NL, SOLVER, F>, (const void *)&llgs_fixed_kernel<NL, SOLVER, F>);
   if (bp.use) {
-    const size_t bytes = 256 + 2 * (size_t)bp.n_wtasks * sizeof(int);
+    const size_t bytes = 256 + (size_t)bp.n_wtasks * sizeof(int);
     char *scratch = nullptr;
     cudaError_t e = cudaMallocAsync((void **)&scratch, bytes, stream);
     if (e != cudaSuccess) return e;
     cudaMemsetAsync(scratch, 0, bytes, stream);
     Balance Q;
-    Q.cursor = (unsigned long long *)scratch;
-    Q.finished = (unsigned long long *)(scratch + 128);
+    Q.ticket = (unsigned long long *)scratch;
     Q.done = (int *)(scratch + 256);
-    Q.claim = Q.done + bp.n_wtasks;
-    Q.sched = bp.sched;
     Q.chunk = bp.chunk;
     Q.n_rounds = bp.n_rounds;
     Q.n_wtasks = bp.n_wtasks;
     // The plan counts on exactly per_sm blocks on every SM (one warp per sub-partition each).  The block scheduler
     // only guarantees that when no SM can take more: each block asks for 1/per_sm of the SM's shared memory, which
     // it never touches, so that a (per_sm + 1)-th block does not fit.  Without this some SMs carry 5 warps per
-    // sub-partition and others 3; the slow ones then publish late and every waiter of theirs sleeps.
+    // sub-partition and others 3; the slow ones then publish late and every waiter of theirs sleeps (S1: 354-362 ms
+    // unpinned, 348 ms pinned).
     size_t pin = 0;
     if (bp.per_sm > 0 && bp.blocks >= bp.per_sm * 8) {
       pin = ((size_t)227 * 1024 / (size_t)bp.per_sm - 1024) & ~(size_t)1023;

@@ -9,6 +9,7 @@
 #include <cufft.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -48,6 +49,177 @@ __global__ void abs_transpose_kernel(const double2 *half, long long cols, long l
   }
 }
 
+
+// ---- single-pass pruned DFT -------------------------------------------------------------------------------------
+// A sweep's spectra keep only the K lowest bins of n-sample series (PIMM: 1601 of 100 001 at 20 ns / 80 GHz), but a
+// library FFT computes them all, in several passes over a buffer that is most of the GPU's memory (160 GB).  With
+// n = N1 N2 and N1 >= K, Cooley-Tukey's first split needs no second index for those bins:
+//     X[k] = sum_{n2 < N2} W_n^(n2 k) Y_n2[k],    Y_n2 = FFT_N1( x[N2 n1 + n2], n1 < N1 ),    k < K <= N1
+// so one block can walk ONE series once: for each pair of decimated sequences (n2, n2 + 1), packed as one complex
+// sequence, an N1-point mixed-radix FFT in shared memory (in place: samples are scattered to their digit-reversed
+// slots as they arrive), the two real-sequence spectra un-packed by Hermitian symmetry, and K running sums with the
+// twiddle carried by recurrence (W_n^(2k) per pair, N2 / 2 multiplications: 1e-14).  Every sample is read exactly
+// once, nothing but |X[k]|, k < K, is written; the transform itself is exact to rounding like any FFT.
+constexpr int kPrunedThreads = 256;
+constexpr int kMaxStages = 12;
+struct PrunedPlan {
+  int n1, n2, K, n_stages;
+  int radix[kMaxStages];  // outermost first: n1 = radix[0] * radix[1] * ...
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }  // a * (-i)
+
+// r-point DFT (forward, e^{-2 pi i jk / r}) of v[0..r) in place
+template <int R> __device__ __forceinline__ void dft_small(double2 *v);
+template <> __device__ __forceinline__ void dft_small<2>(double2 *v) {
+  const double2 a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <> __device__ __forceinline__ void dft_small<3>(double2 *v) {
+  const double c = -0.5, s = 0.86602540378443864676;  // cos, sin of 2 pi / 3
+  const double2 t1 = cadd(v[1], v[2]), t2 = csub(v[1], v[2]);
+  const double2 m = make_double2(fma(c, t1.x, v[0].x), fma(c, t1.y, v[0].y));
+  const double2 r = make_double2(s * t2.y, -s * t2.x);  // -i s t2
+  v[0] = cadd(v[0], t1);
+  v[1] = cadd(m, r);
+  v[2] = csub(m, r);
+}
+template <> __device__ __forceinline__ void dft_small<4>(double2 *v) {
+  const double2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]), c = cadd(v[1], v[3]), d = mul_mi(csub(v[1], v[3]));
+  v[0] = cadd(a, c);
+  v[1] = cadd(b, d);
+  v[2] = csub(a, c);
+  v[3] = csub(b, d);
+}
+template <> __device__ __forceinline__ void dft_small<5>(double2 *v) {
+  const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;  // cos 2pi/5, cos 4pi/5
+  const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;   // sin 2pi/5, sin 4pi/5
+  const double2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]), a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+  const double2 m1 = make_double2(fma(c1, a1.x, fma(c2, a2.x, v[0].x)), fma(c1, a1.y, fma(c2, a2.y, v[0].y)));
+  const double2 m2 = make_double2(fma(c2, a1.x, fma(c1, a2.x, v[0].x)), fma(c2, a1.y, fma(c1, a2.y, v[0].y)));
+  // -i (s1 b1 + s2 b2) and -i (s2 b1 - s1 b2)
+  const double2 q1 = make_double2(fma(s1, b1.y, s2 * b2.y), -fma(s1, b1.x, s2 * b2.x));
+  const double2 q2 = make_double2(fma(s2, b1.y, -(s1 * b2.y)), -fma(s2, b1.x, -(s1 * b2.x)));
+  v[0] = cadd(v[0], cadd(a1, a2));
+  v[1] = cadd(m1, q1);
+  v[4] = csub(m1, q1);
+  v[2] = cadd(m2, q2);
+  v[3] = csub(m2, q2);
+}
+
+// one in-place decimation-in-time stage: sub-transforms of size M (already done, stored blockwise) are combined R at a time
+template <int R> __device__ __forceinline__ void stage(double2 *buf, int n1, int M, const double2 *__restrict__ wtab, int tid) {
+  const int step = n1 / (R * M);  // W_{RM}^j = W_n1^(j * step)
+  for (int u = tid; u < n1 / R; u += kPrunedThreads) {
+    const int blk = u / M, k1 = u - blk * M;
+    double2 *p = buf + (size_t)blk * R * M + k1;
+    double2 v[R];
+    v[0] = p[0];
+#pragma unroll
+    for (int sgm = 1; sgm < R; sgm++) v[sgm] = (k1 == 0) ? p[sgm * M] : cmul(p[sgm * M], __ldg(wtab + (size_t)sgm * k1 * step));
+    dft_small<R>(v);
+#pragma unroll
+    for (int sgm = 0; sgm < R; sgm++) p[sgm * M] = v[sgm];
+  }
+}
+
+__global__ void __launch_bounds__(kPrunedThreads) pruned_dft_kernel(const double *__restrict__ x, long long B, long long ld,
+                                                                    const __grid_constant__ PrunedPlan P,
+                                                                    const double2 *__restrict__ wtab,   // W_n1^j, j < n1
+                                                                    const double2 *__restrict__ wk,     // W_n^k,  k < K
+                                                                    double *__restrict__ out) {
+  extern __shared__ double2 sm2[];
+  double2 *buf = sm2;              // [n1]  the packed pair, transformed in place
+  double2 *acc = buf + P.n1;       // [K]   running sums X[k]
+  double2 *tw = acc + P.K;         // [K]   W_n^(n2 k) of the current pair's even member
+  unsigned short *perm = (unsigned short *)(tw + P.K);  // [n1] digit-reversed slot of sample n1
+  const int tid = threadIdx.x;
+  const long long b = blockIdx.x;
+  const int n1 = P.n1, n2 = P.n2, K = P.K;
+  for (int q = tid; q < n1; q += kPrunedThreads) {
+    // sample q = r0 q0' + s0 goes to block s0 of size n1 / r0, and so on inwards
+    int rem = q, span = n1, pos = 0;
+    for (int st = 0; st < P.n_stages; st++) {
+      const int r = P.radix[st];
+      span /= r;
+      pos += (rem % r) * span;
+      rem /= r;
+    }
+    perm[q] = (unsigned short)pos;
+  }
+  for (int k = tid; k < K; k += kPrunedThreads) {
+    acc[k] = make_double2(0.0, 0.0);
+    tw[k] = make_double2(1.0, 0.0);
+  }
+  __syncthreads();
+  const double *xb = x + b;
+  for (int j = 0; j < n2; j += 2) {
+    const bool has_odd = j + 1 < n2;
+    for (int q = tid; q < n1; q += kPrunedThreads) {
+      const double *p = xb + ((long long)n2 * q + j) * ld;
+      buf[perm[q]] = make_double2(__ldcs(p), has_odd ? __ldcs(p + ld) : 0.0);
+    }
+    __syncthreads();
+    int M = 1;
+    for (int st = P.n_stages - 1; st >= 0; st--) {
+      const int r = P.radix[st];
+      if (r == 4) stage<4>(buf, n1, M, wtab, tid);
+      else if (r == 5) stage<5>(buf, n1, M, wtab, tid);
+      else if (r == 2) stage<2>(buf, n1, M, wtab, tid);
+      else stage<3>(buf, n1, M, wtab, tid);
+      M *= r;
+      __syncthreads();
+    }
+    // un-pack the two real spectra (Z = E + i O:  E[k] = (Z[k] + conj Z[n1-k]) / 2,  O[k] = (Z[k] - conj Z[n1-k]) / 2i) and add
+    // W^(j k) E[k] + W^((j+1) k) O[k]
+    for (int k = tid; k < K; k += kPrunedThreads) {
+      const double2 zk = buf[k], zm = buf[k == 0 ? 0 : n1 - k];
+      const double2 E = make_double2(0.5 * (zk.x + zm.x), 0.5 * (zk.y - zm.y));
+      const double2 O = make_double2(0.5 * (zk.y + zm.y), -0.5 * (zk.x - zm.x));
+      const double2 w = __ldg(wk + k);
+      const double2 t = tw[k];
+      acc[k] = cadd(acc[k], cmul(t, cadd(E, cmul(w, O))));
+      tw[k] = cmul(t, cmul(w, w));
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < K; k += kPrunedThreads) out[b * K + k] = hypot(acc[k].x, acc[k].y);
+}
+
+// n = n1 n2 with K <= n1 <= n1_max and n1 a product of 2, 3, 4, 5: the smallest such n1, or false
+bool plan_pruned(long long n, long long K, int n1_max, PrunedPlan *P) {
+  for (long long n1 = std::max<long long>(K, 2); n1 <= n1_max && n1 <= n; n1++) {
+    if (n % n1) continue;
+    long long rem = n1;
+    int st = 0, radix[kMaxStages];
+    while (rem % 4 == 0 && st < kMaxStages) radix[st++] = 4, rem /= 4;
+    while (rem % 2 == 0 && st < kMaxStages) radix[st++] = 2, rem /= 2;
+    while (rem % 5 == 0 && st < kMaxStages) radix[st++] = 5, rem /= 5;
+    while (rem % 3 == 0 && st < kMaxStages) radix[st++] = 3, rem /= 3;
+    if (rem != 1) continue;
+    P->n1 = (int)n1;
+    P->n2 = (int)(n / n1);
+    P->K = (int)K;
+    P->n_stages = st;
+    for (int i = 0; i < st; i++) P->radix[i] = radix[i];
+    return true;
+  }
+  return false;
+}
+
+// e^{-2 pi i j / m}, j < count, with the argument reduced exactly (j mod m in integers, octant symmetry left to sincospi)
+void unit_roots(long long m, long long count, std::vector<double2> &w) {
+  w.resize((size_t)count);
+  for (long long j = 0; j < count; j++) {
+    const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)(j % m) / (long double)m;
+    w[(size_t)j] = make_double2((double)cosl(a), (double)sinl(a));
+  }
+}
+
 }  // namespace
 }  // namespace cmtjb
 
@@ -60,6 +232,38 @@ extern "C" int cmtjb_rfft_abs_device(const double *x, int64_t n, int64_t B, int6
   if (n > (1LL << 30) || ld > (1LL << 30)) return fail(CMTJB_ENOTSUP, "series too long for the 32-bit cuFFT plan interface");
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t stream = (cudaStream_t)stream_;
+  {
+    // single pass over the buffer when n factors suitably (pruned_dft_kernel); CMTJB_SPECTRUM=cufft forces the library path
+    PrunedPlan P;
+    const char *force = std::getenv("CMTJB_SPECTRUM");
+    const bool want = !(force && force[0] == 'c');
+    // shared memory: n1 + 2 K complex doubles + n1 shorts; two blocks per SM up to n1 = 2048 at K <= 1.7k
+    if (want && n >= 64 && plan_pruned(n, K, 8192, &P)) {
+      const size_t smem = ((size_t)P.n1 + 2 * (size_t)P.K) * sizeof(double2) + (size_t)P.n1 * sizeof(unsigned short) + 16;
+      int max_smem = 0;
+      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+      if (smem <= (size_t)max_smem && P.n1 < 65536) {
+        std::vector<double2> wt, wkv;
+        unit_roots(P.n1, P.n1, wt);
+        unit_roots(n, K, wkv);
+        double2 *d_w = nullptr;
+        cudaError_t e = cudaMallocAsync((void **)&d_w, (wt.size() + wkv.size()) * sizeof(double2), stream);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(twiddles)");
+        e = cudaMemcpyAsync(d_w, wt.data(), wt.size() * sizeof(double2), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_w + wt.size(), wkv.data(), wkv.size() * sizeof(double2), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the host vectors go out of scope
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pruned_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+          pruned_dft_kernel<<<(unsigned)B, kPrunedThreads, smem, stream>>>(x, B, ld, P, d_w, d_w + wt.size(), out);
+          g_launches++;
+          e = cudaGetLastError();
+        }
+        cudaFreeAsync(d_w, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "pruned_dft_kernel");
+        return CMTJB_OK;
+      }
+    }
+  }
   const long long nh = n / 2 + 1;
   // column slices: the complex half-spectra of a slice stay below ~1 GiB (CMTJB_SPECTRUM_SLICE_MB overrides)
   size_t slice_bytes = (size_t)1 << 30;

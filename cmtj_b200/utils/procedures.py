@@ -354,7 +354,9 @@ def PIMM_procedure(
             # everything that is free now, less what the spectrum slices, their cuFFT work area and the small logs take:
             # splitting a sweep into instance chunks costs throughput (fewer warps per SM sub-partition), so the whole
             # sweep stays one batch whenever its projection log fits (1e5 points x 20 ns: 160 GB)
-            free_b, _ = _torch().cuda.mem_get_info(device)
+            torch = _torch()
+            free_b, _ = torch.cuda.mem_get_info(device)
+            free_b += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)  # torch's own cache is reusable
             memory_budget = max(free_b - 8e9, 0.25 * free_b)
         # device bytes per instance: the projection log(s), the full-rate log when full_output, the last-n log
         # (twice: the weighted m_traj copy handed back to the host is staged on the device)

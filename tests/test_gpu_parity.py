@@ -245,7 +245,7 @@ def test_batch_matches_oracle_per_instance():
         b = cmtj_b200.JunctionBatch(j, B)
         b.set_external_field("all", H)
         mf = m_free.copy()
-        mf[:, 0] = mf[:, 0] * (1 + eps) + eps
+        mf = mf * (1 + eps) + eps * np.array([1.0, -2.0, 3.0])  # every component: m0 may lie along any axis
         b.set_magnetisation("free", mf)
         b.set_magnetisation("bottom", m_bot)
         out = dict(b.run(1e-9, 1e-13, 1e-12))

@@ -98,9 +98,13 @@ def launches(tag):
 
 def ncu_full(tag, rep, title, launch_units=None):
     path = os.path.join(OUT, rep)
-    if not os.path.exists(path):
+    csv_path = os.path.join(OUT, os.path.splitext(rep)[0] + ".raw.csv")  # tools/ncu_summary.sh exports this on the box
+    if os.path.exists(csv_path):
+        raw = open(csv_path).read()
+    elif os.path.exists(path):
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return None
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader([l for l in raw.splitlines() if l.startswith('"')]))
     hdr, units = rows[0], rows[1]
     out = [f"# {tag}: {title}", "", "`ncu --set full --clock-control none --import-source on`, read with `--page raw --csv`.", ""]
