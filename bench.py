@@ -683,40 +683,34 @@ def main():
         import helpers
 
         # parity gate: 16 instances spread over the sweep, ALL 200 000 steps, every logged sample, CUDA vs the oracle
-        # restatement; the third run perturbs m0 by 1e-12 on the oracle: how far the REFERENCE arithmetic itself moves
+        # restatement; three more oracle runs perturb one component of m0 by 1e-12 each: how far the REFERENCE arithmetic
+        # itself moves (tests/parity_report.py: the bound is max(1e-9, 10 x that response) until the response reaches 1e-3)
+        from parity_report import compare_with_sensitivity
+
         sel = np.linspace(0, B - 1, 16).astype(int)
         logs = []
-        for be, eps in ((None, 0.0), (helpers.oracle_backend(), 0.0), (helpers.oracle_backend(), 1e-12)):
+        for be, axis in ((None, None), (helpers.oracle_backend(), None), (helpers.oracle_backend(), 0), (helpers.oracle_backend(), 1),
+                         (helpers.oracle_backend(), 2)):
             with helpers.facade_on(be):
                 bb = cmtj_b200.JunctionBatch(j, len(sel))
                 bb.set_external_field("all", H[sel])
                 mf = m_free[sel].copy()
-                mf = mf * (1 + eps) + eps * np.array([1.0, -2.0, 3.0])  # every component: m0 may lie along any axis
+                if axis is not None:
+                    mf[:, axis] = mf[:, axis] * (1 + 1e-12) + 1e-12
                 bb.set_magnetisation("free", mf)
                 bb.set_magnetisation("bottom", m_bot[sel])
                 logs.append(bb.run(T, DT, wf))
-        per_inst = np.zeros(len(sel))
-        sens_inst = np.zeros(len(sel))
-        for k in logs[1]:
-            if k == "time":
-                continue
-            scale = np.maximum(np.max(np.abs(logs[1][k]), axis=0), 1e-300)
-            per_inst = np.maximum(per_inst, np.max(np.abs(logs[0][k] - logs[1][k]), axis=0) / scale)
-            sens_inst = np.maximum(sens_inst, np.max(np.abs(logs[2][k] - logs[1][k]), axis=0) / scale)
-        well = sens_inst < 1e-10  # instances on which the reference itself is well conditioned over the whole run
-        parity = {
-            "instances": int(len(sel)),
-            "steps": int(steps),
-            "bound": 1e-9,
-            "max_rel_err_vs_oracle_per_instance": [float(v) for v in per_inst],
-            "reference_sensitivity_to_1e-12_per_instance": [float(v) for v in sens_inst],
-            "well_conditioned_instances": int(well.sum()),
-            "max_rel_err_well_conditioned": float(per_inst[well].max()) if well.any() else None,
-            "note": "where a 1e-12 perturbation of m0 moves the REFERENCE by more than 1e-10 over the run, the trajectories of any "
-                    "two implementations separate; the 1e-9 bound is asserted on the other instances",
-        }
-        if well.any() and parity["max_rel_err_well_conditioned"] > 1e-9:
-            raise SystemExit("bench.py parity gate: CUDA vs oracle %.3e > 1e-9" % parity["max_rel_err_well_conditioned"])
+        keys = [k for k in logs[1] if k != "time"]
+        try:
+            parity = dict(compare_with_sensitivity("bench.py parity gate: 16 of the sweep's instances, all %d RK4 steps" % steps, keys,
+                                                   logs[0], logs[1], logs[2:]))
+            parity["gate"] = "passed"
+        except AssertionError as e:  # reported in the line (and on stderr), so that the measurement is not lost with it
+            parity = {"gate": "FAILED", "detail": "CUDA vs oracle outside max(1e-9, 10 x reference sensitivity): %r" % (e.args,)}
+            print("bench.py parity gate FAILED: %s" % parity["detail"], file=sys.stderr)
+        parity.pop("test", None)
+        parity["note"] = ("max_rel_err_of_the_others: the instances that meet 1e-9 outright; the rest sit where a 1e-12 change of m0 moves the "
+                          "REFERENCE itself by more than 1e-10 (reference_sensitivity_per_instance): asserted against 10 x that response")
         if helpers.reference_module() is not None:
             cores = os.cpu_count() or 1
             ctx = mp.get_context("fork")

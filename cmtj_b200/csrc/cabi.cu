@@ -963,6 +963,107 @@ template <int CH> __global__ void __launch_bounds__(256) fp64_peak_kernel(double
   }
 }
 
+
+// FP64 pipe probe (cmtjb_fp64_pipe_probe): what fraction of the pipe's issue slots (64 lanes per SM and clock) a stream of
+// independent chains sustains at a given number of warps per sub-partition, for the operand shapes the integration kernels use.
+//   KIND 0: x = fma(x, a, b), a and b kernel parameters (constant bank): one register source operand
+//   KIND 1: x = fma(x, y, z), all three in registers (y, z differ per chain)
+//   KIND 2: the S1 step's instruction mix on three-register operands: 12 DFMA : 3 DMUL : 1 DADD
+//   KIND 3: the step's own dependency shape: cross products, dot products and axpy on 3-vectors (ILP 3), neighbour and field
+//           terms included (28 FP64 instructions per round, like one right-hand-side evaluation of the two-layer IEC model)
+//   KIND 4: KIND 3 on two independent vectors per thread, interleaved (what two layers, or two instances, per thread give)
+//   KIND 5: independent chains like KIND 1, but every DFMA reads three registers of THREE different chains, rotating from
+//           instruction to instruction (operand variety of real code without its short dependencies)
+template <int KIND, int CH> __global__ void __launch_bounds__(128) fp64_probe_kernel(double *out, const double *seed, long long iters, double a, double b) {
+  long long c0 = 0;
+  unsigned long long n0 = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    c0 = clock64();
+    n0 = global_ns();
+  }
+  double x[CH], y[CH], z[CH];
+#pragma unroll
+  for (int c = 0; c < CH; c++) {
+    x[c] = seed[c] + threadIdx.x * 1e-6;
+    y[c] = seed[CH + c];
+    z[c] = seed[2 * CH + c];
+  }
+  if constexpr (KIND == 3) {
+    // state m (x[0..2]), neighbour (y[0..2]), field (z[0..2]); constants from registers
+    double mx = x[0], my = x[1], mz = x[2];
+    const double nx = y[0], ny = y[1], nz = y[2], hx = z[0], hy = z[1], hz = z[2];
+    const double l0 = y[3], l1 = y[4], l2 = y[5], ib = z[3], ia = z[4], al = z[5], h = z[6];
+    for (long long k = 0; k < iters; k++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        double Hx = fma(l0, mx, hx), Hy = fma(l1, my, hy), Hz = fma(l2, mz, hz);               // 3
+        const double d = fma(nz, mz, fma(ny, my, nx * mx));                                        // 3
+        const double sc = fma(ib, d, ia);                                                          // 1
+        Hx = fma(nx, sc, Hx), Hy = fma(ny, sc, Hy), Hz = fma(nz, sc, Hz);                           // 3
+        const double px = fma(my, Hz, -(mz * Hy)), py = fma(mz, Hx, -(mx * Hz)), pz = fma(mx, Hy, -(my * Hx));  // 6
+        const double ax = al * mx, ay = al * my, az = al * mz;                                     // 3
+        const double ux = fma(ay, pz, fma(-az, py, px)), uy = fma(az, px, fma(-ax, pz, py)), uz = fma(ax, py, fma(-ay, px, pz));  // 6
+        mx = fma(ux, h, mx), my = fma(uy, h, my), mz = fma(uz, h, mz);                              // 3  -> 28
+      }
+    }
+    x[0] = mx, x[1] = my, x[2] = mz;
+  } else if constexpr (KIND == 4) {
+    double mx = x[0], my = x[1], mz = x[2], qx = x[2], qy = x[0], qz = x[1];
+    const double nx = y[0], ny = y[1], nz = y[2], hx = z[0], hy = z[1], hz = z[2];
+    const double l0 = y[3], l1 = y[4], l2 = y[5], ib = z[3], ia = z[4], al = z[5], h = z[6];
+    auto rhs = [&](double &ax_, double &ay_, double &az_) {
+      double Hx = fma(l0, ax_, hx), Hy = fma(l1, ay_, hy), Hz = fma(l2, az_, hz);
+      const double d = fma(nz, az_, fma(ny, ay_, nx * ax_));
+      const double sc = fma(ib, d, ia);
+      Hx = fma(nx, sc, Hx), Hy = fma(ny, sc, Hy), Hz = fma(nz, sc, Hz);
+      const double px = fma(ay_, Hz, -(az_ * Hy)), py = fma(az_, Hx, -(ax_ * Hz)), pz = fma(ax_, Hy, -(ay_ * Hx));
+      const double ax = al * ax_, ay = al * ay_, az = al * az_;
+      const double ux = fma(ay, pz, fma(-az, py, px)), uy = fma(az, px, fma(-ax, pz, py)), uz = fma(ax, py, fma(-ay, px, pz));
+      ax_ = fma(ux, h, ax_), ay_ = fma(uy, h, ay_), az_ = fma(uz, h, az_);
+    };
+    for (long long k = 0; k < iters; k++) {
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        rhs(mx, my, mz);
+        rhs(qx, qy, qz);
+      }
+    }
+    x[0] = mx + qx, x[1] = my + qy, x[2] = mz + qz;
+  } else if constexpr (KIND == 5) {
+    for (long long k = 0; k < iters; k++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+#pragma unroll
+        for (int c = 0; c < CH; c++) x[c] = fma(y[(c + u) % CH], z[(c + 3 * u + 1) % CH], x[c]);
+      }
+    }
+  } else {
+    for (long long k = 0; k < iters; k++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+          if constexpr (KIND == 0) x[c] = fma(x[c], a, b);
+          else if constexpr (KIND == 1) x[c] = fma(x[c], y[c], z[c]);
+          else {
+            if (u % 16 == 15) x[c] = x[c] + z[c];
+            else if (u % 4 == 3) x[c] = x[c] * y[c];
+            else x[c] = fma(x[c], y[c], z[c]);
+          }
+        }
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < CH; c++) s += x[c];
+  if (s == 123.456) out[0] = s;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[1] = (double)(clock64() - c0);
+    out[2] = (double)(global_ns() - n0);
+  }
+}
+
 thread_local double g_peak_mhz = 0.0;
 
 }  // namespace
@@ -1309,6 +1410,68 @@ int cmtjb_host_stats(double *out, int32_t n) {
 }
 
 double cmtjb_fp64_peak_sm_mhz(void) { return g_peak_mhz; }
+
+int cmtjb_fp64_pipe_probe(int device, int kind, int warps_per_subpartition, int64_t iters, double *issue_slot_frac,
+                          double *sm_mhz) {
+  if (kind < 0 || kind > 5 || warps_per_subpartition < 1 || warps_per_subpartition > 16 || iters <= 0 || !issue_slot_frac)
+    return fail(CMTJB_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  constexpr int CH = 8;
+  double h_seed[3 * CH];
+  for (int c = 0; c < CH; c++) {
+    h_seed[c] = 0.5 + 0.01 * c;
+    h_seed[CH + c] = 0.999999 - 1e-7 * c;
+    h_seed[2 * CH + c] = 1e-7 * (c + 1);
+  }
+  if (kind == 3 || kind == 4) {  // a slowly precessing unit vector: field 1, damping 0.01, h = 1e-3
+    const double m[3] = {0.6, 0.0, 0.8}, nb[3] = {0.0, 0.6, 0.8}, H[3] = {0.0, 0.0, 1.0};
+    for (int c = 0; c < 3; c++) h_seed[c] = m[c], h_seed[CH + c] = nb[c], h_seed[2 * CH + c] = H[c];
+    h_seed[CH + 3] = -0.1, h_seed[CH + 4] = -0.1, h_seed[CH + 5] = -1.0;
+    h_seed[2 * CH + 3] = 1e-3, h_seed[2 * CH + 4] = 1e-2, h_seed[2 * CH + 5] = 0.01, h_seed[2 * CH + 6] = 1e-3;
+  }
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, (4 + 3 * CH) * sizeof(double)));
+  cudaMemcpy(d + 4, h_seed, sizeof(h_seed), cudaMemcpyHostToDevice);
+  const int blocks = prop.multiProcessorCount * warps_per_subpartition;
+  auto launch = [&](long long n) {
+    switch (kind) {
+    case 0: fp64_probe_kernel<0, CH><<<blocks, 128>>>(d, d + 4, n, 0.999999, 1e-7); break;
+    case 1: fp64_probe_kernel<1, CH><<<blocks, 128>>>(d, d + 4, n, 0.0, 0.0); break;
+    case 2: fp64_probe_kernel<2, CH><<<blocks, 128>>>(d, d + 4, n, 0.0, 0.0); break;
+    case 3: fp64_probe_kernel<3, CH><<<blocks, 128>>>(d, d + 4, n, 0.0, 0.0); break;
+    case 4: fp64_probe_kernel<4, CH><<<blocks, 128>>>(d, d + 4, n, 0.0, 0.0); break;
+    default: fp64_probe_kernel<5, CH><<<blocks, 128>>>(d, d + 4, n, 0.0, 0.0); break;
+    }
+  };
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  launch(iters / 8 + 1);
+  cudaEventRecord(e0);
+  launch(iters);
+  cudaEventRecord(e1);
+  cudaError_t e = cudaEventSynchronize(e1);
+  float t_ms = 0;
+  cudaEventElapsedTime(&t_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double probe[4] = {0, 0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(probe, d, sizeof(probe), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "fp64_probe_kernel");
+  // the kernel's duration (events; the warp scheduler favours the oldest warp, so one block's own cycle count says nothing
+  // about the others) at the clock block 0 saw (cycle counter against the global nanosecond timer)
+  const double mhz = probe[2] > 0 ? probe[1] / probe[2] * 1e3 : 0.0;
+  const double cycles = (double)t_ms * 1e-3 * mhz * 1e6;
+  const double per_thread = (kind == 3 || kind == 4) ? 28.0 * 4.0 * (double)iters : 16.0 * CH * (double)iters;
+  const double per_sm = per_thread * 128.0 * warps_per_subpartition;  // thread-instructions on one SM
+  *issue_slot_frac = cycles > 0 ? per_sm / (64.0 * cycles) : 0.0;
+  if (sm_mhz) *sm_mhz = mhz;
+  return CMTJB_OK;
+}
+
 
 int cmtjb_eval_driver_host(const cmtjb_driver_t *driver, const double *times, int64_t n, double *out, int device) {
   if (!driver || !times || !out) return fail(CMTJB_EINVAL, "null argument");

@@ -65,6 +65,8 @@ constexpr int kMaxStages = 12;
 struct PrunedPlan {
   int n1, n2, K, n_stages;
   int radix[kMaxStages];  // outermost first: n1 = radix[0] * radix[1] * ...
+  // four-instance kernel: ceil(2^32 / d) for d = n1 / radix (butterflies per buffer) and d = M (sub-transform size) of each stage
+  uint32_t magic_per[kMaxStages], magic_M[kMaxStages];
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
@@ -190,6 +192,186 @@ __global__ void __launch_bounds__(kPrunedThreads) pruned_dft_kernel(const double
   for (int k = tid; k < K; k += kPrunedThreads) out[b * K + k] = hypot(acc[k].x, acc[k].y);
 }
 
+
+// ---- the same transform, four instances per block ------------------------------------------------------------------
+// pruned_dft_kernel reads ONE double of every 64-byte DRAM burst of the time-major log (ncu: 5.9 bytes fetched per
+// byte used, 8 % FP64 pipe, top stall long_scoreboard).  Here a block owns FOUR neighbouring instances, i.e. one whole
+// 32-byte sector of every row it touches (the neighbouring block, running beside it, takes the other half of the
+// burst), packs them as two complex sequences (instances 0/1 and 2/3), and walks the decimated sequences j < n2 one
+// per pass: an N1-point FFT of both packed buffers, the four real spectra un-packed by Hermitian symmetry, and
+// X_g[k] += W_n^(j k) Y_g,j[k mod N1] with the twiddle (shared by the four instances) carried by recurrence.  Y_j is
+// N1-periodic in k, so N1 need not reach K; the plan still prefers N1 >= K (fewest passes).  The samples of pass
+// j + 1 are fetched into registers while pass j is transformed, so the DRAM latency hides behind the butterflies.
+constexpr int kG = 4;
+constexpr int kGThreads = 512;
+constexpr int kGSlots = 16;  // register-staged samples per thread and pass: kG * n1 <= kGSlots * kGThreads
+
+// n / d for n < 2^14, d < 2^14 by one multiply-high: magic = ceil(2^32 / d) (d >= 2; d == 1 is handled by the caller)
+__device__ __forceinline__ int div_magic(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
+
+// One decimation-in-time stage over n_buf buffers, sub-transforms of size M combined R at a time.  Two butterflies per
+// thread and trip (independent loads in flight), index arithmetic by multiply-high, the R - 1 twiddles W_{RM}^(s k1)
+// from ONE table read and powers of it; the first stage (M == 1) has no twiddles at all.
+template <int R>
+__device__ __forceinline__ void stage_multi(double2 *buf, int n1, int n_buf, int M, uint32_t magic_per, uint32_t magic_M,
+                                            const double2 *__restrict__ wtab, int tid) {
+  const int per = n1 / R, total = n_buf * per;
+  const int step = per / M;  // W_{RM}^j = W_n1^(j * step)
+  for (int ub = tid; ub < total; ub += 2 * kGThreads) {
+    double2 v[2][R];
+    double2 *p[2];
+    bool on[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int u = ub + h * kGThreads;
+      on[h] = u < total;
+      const int uc = on[h] ? u : 0;
+      const int b = div_magic(uc, magic_per), uu = uc - b * per;
+      const int blk = (M == 1) ? uu : div_magic(uu, magic_M), k1 = uu - blk * M;
+      p[h] = buf + b * n1 + blk * R * M + k1;
+      double2 w1 = make_double2(1.0, 0.0);
+      if (M > 1) w1 = __ldg(wtab + k1 * step);
+#pragma unroll
+      for (int sgm = 0; sgm < R; sgm++) v[h][sgm] = p[h][sgm * M];
+      if (M > 1) {
+        const double2 w2 = cmul(w1, w1);
+        v[h][1] = cmul(v[h][1], w1);
+        if (R > 2) v[h][2] = cmul(v[h][2], w2);
+        if (R > 3) v[h][3] = cmul(v[h][3], cmul(w2, w1));
+        if (R > 4) v[h][4] = cmul(v[h][4], cmul(w2, w2));
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      dft_small<R>(v[h]);
+      if (on[h]) {
+#pragma unroll
+        for (int sgm = 0; sgm < R; sgm++) p[h][sgm * M] = v[h][sgm];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGThreads, 1) pruned_dft4_kernel(const double *__restrict__ x, long long B, long long ld,
+                                                                   const __grid_constant__ PrunedPlan P,
+                                                                   const double2 *__restrict__ wtab,   // W_n1^j, j < n1
+                                                                   const double2 *__restrict__ wk,     // W_n^k,  k < K
+                                                                   double *__restrict__ out) {
+  extern __shared__ double2 sm2[];
+  const int n1 = P.n1, n2 = P.n2, K = P.K;
+  double2 *buf = sm2;                    // [2][n1]  instances (0,1) and (2,3), each packed re/im, transformed in place
+  double2 *acc = buf + 2 * (size_t)n1;   // [kG][K]  running sums X_g[k]
+  double2 *tw = acc + (size_t)kG * K;    // [K]      W_n^(j k) of the current pass
+  const int tid = threadIdx.x;
+  const long long b0 = (long long)blockIdx.x * kG;
+  const int g = tid & (kG - 1), q0 = tid >> 2;
+  const bool g_ok = b0 + g < B;
+  // slot s of this thread: sample q = q0 + 128 s of instance g; its digit-reversed place in buf (in doubles, < 2^16), two
+  // places per register, 0xffff = no such sample
+  uint32_t dst2[kGSlots / 2];
+#pragma unroll
+  for (int s = 0; s < kGSlots; s++) {
+    const int q = q0 + s * (kGThreads / kG);
+    int rem = q, span = n1, pos = 0;
+    for (int st = 0; st < P.n_stages; st++) {
+      const int r = P.radix[st];
+      span /= r;
+      pos += (rem % r) * span;
+      rem /= r;
+    }
+    const uint32_t d = (q < n1) ? (uint32_t)(2 * ((g >> 1) * n1 + pos) + (g & 1)) : 0xffffu;
+    if (s & 1) dst2[s >> 1] |= d << 16;
+    else dst2[s >> 1] = d;
+  }
+  auto dst = [&](int s) { return (dst2[s >> 1] >> ((s & 1) * 16)) & 0xffffu; };
+  for (int k = tid; k < K; k += kGThreads) {
+    tw[k] = make_double2(1.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < kG; i++) acc[(size_t)i * K + k] = make_double2(0.0, 0.0);
+  }
+  const double *xg = x + b0 + g + (long long)n2 * q0 * ld;
+  const long long slot_stride = (long long)(kGThreads / kG) * n2 * ld;
+  double v[kGSlots];
+#pragma unroll
+  for (int s = 0; s < kGSlots; s++) v[s] = (g_ok && dst(s) != 0xffffu) ? __ldcs(xg + s * slot_stride) : 0.0;
+  for (int j = 0; j < n2; j++) {
+    double *bd = reinterpret_cast<double *>(buf);
+#pragma unroll
+    for (int s = 0; s < kGSlots; s++)
+      if (dst(s) != 0xffffu) bd[dst(s)] = v[s];
+    __syncthreads();
+    if (j + 1 < n2) {
+      const double *xn = xg + (long long)(j + 1) * ld;
+#pragma unroll
+      for (int s = 0; s < kGSlots; s++) v[s] = (g_ok && dst(s) != 0xffffu) ? __ldcs(xn + s * slot_stride) : 0.0;
+    }
+    int M = 1;
+    for (int st = P.n_stages - 1; st >= 0; st--) {
+      const int r = P.radix[st];
+      if (r == 4) stage_multi<4>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
+      else if (r == 5) stage_multi<5>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
+      else if (r == 2) stage_multi<2>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
+      else stage_multi<3>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
+      M *= r;
+      __syncthreads();
+    }
+    // Z = Y_a + i Y_b of two real sequences:  2 Y_a[k] = Z[k] + conj Z[-k],  2 Y_b[k] = -i (Z[k] - conj Z[-k])   (the 1/2 is applied at the end)
+    for (int k = tid; k < K; k += kGThreads) {
+      int km = k;
+      if (K > n1) km = k % n1;
+      const int kr = (km == 0) ? 0 : n1 - km;
+      const double2 t = tw[k];
+#pragma unroll
+      for (int pr = 0; pr < 2; pr++) {
+        const double2 zk = buf[(size_t)pr * n1 + km], zm = buf[(size_t)pr * n1 + kr];
+        const double2 Ya = make_double2(zk.x + zm.x, zk.y - zm.y);
+        const double2 Yb = make_double2(zk.y + zm.y, zm.x - zk.x);
+        double2 *a = acc + (size_t)(2 * pr) * K + k;
+        a[0] = cadd(a[0], cmul(t, Ya));
+        a[K] = cadd(a[K], cmul(t, Yb));
+      }
+      tw[k] = cmul(t, __ldg(wk + k));
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < K; k += kGThreads)
+#pragma unroll
+    for (int i = 0; i < kG; i++)
+      if (b0 + i < B) out[(b0 + i) * K + k] = 0.5 * hypot(acc[(size_t)i * K + k].x, acc[(size_t)i * K + k].y);
+}
+
+// n = n1 n2 for the four-instance kernel: n1 a product of 2, 3, 4, 5 with n1 <= n1_max; the smallest n1 >= K if there is
+// one, else the largest
+bool plan_grouped(long long n, long long K, int n1_max, PrunedPlan *P) {
+  auto factor = [&](long long n1) {
+    long long rem = n1;
+    int st = 0, radix[kMaxStages];
+    while (rem % 4 == 0 && st < kMaxStages) radix[st++] = 4, rem /= 4;
+    while (rem % 2 == 0 && st < kMaxStages) radix[st++] = 2, rem /= 2;
+    while (rem % 5 == 0 && st < kMaxStages) radix[st++] = 5, rem /= 5;
+    while (rem % 3 == 0 && st < kMaxStages) radix[st++] = 3, rem /= 3;
+    if (rem != 1) return false;
+    P->n1 = (int)n1;
+    P->n2 = (int)(n / n1);
+    P->K = (int)K;
+    P->n_stages = st;
+    for (int i = 0; i < st; i++) P->radix[i] = radix[i];
+    long long M = 1;
+    auto magic = [](long long d) { return d <= 1 ? 0u : (uint32_t)((((unsigned long long)1 << 32) + d - 1) / d); };
+    for (int i = st - 1; i >= 0; i--) {  // the kernel runs the stages innermost (M = 1) first
+      P->magic_per[i] = magic(n1 / radix[i]);
+      P->magic_M[i] = magic(M);
+      M *= radix[i];
+    }
+    return true;
+  };
+  for (long long n1 = std::max<long long>(K, 8); n1 <= n1_max && n1 <= n; n1++)
+    if (n % n1 == 0 && factor(n1)) return true;
+  for (long long n1 = std::min<long long>(n1_max, n); n1 >= 8; n1--)
+    if (n % n1 == 0 && factor(n1)) return true;
+  return false;
+}
+
 // n = n1 n2 with K <= n1 <= n1_max and n1 a product of 2, 3, 4, 5: the smallest such n1, or false
 bool plan_pruned(long long n, long long K, int n1_max, PrunedPlan *P) {
   for (long long n1 = std::max<long long>(K, 2); n1 <= n1_max && n1 <= n; n1++) {
@@ -233,35 +415,47 @@ extern "C" int cmtjb_rfft_abs_device(const double *x, int64_t n, int64_t B, int6
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t stream = (cudaStream_t)stream_;
   {
-    // single pass over the buffer when n factors suitably (pruned_dft_kernel); CMTJB_SPECTRUM=cufft forces the library path
+    // single pass over the buffer when n factors suitably: four instances per block (pruned_dft4_kernel) when its shared
+    // memory fits, else one (pruned_dft_kernel); CMTJB_SPECTRUM=cufft forces the library path, =single the one-instance kernel
     PrunedPlan P;
     const char *force = std::getenv("CMTJB_SPECTRUM");
     const bool want = !(force && force[0] == 'c');
-    // shared memory: n1 + 2 K complex doubles + n1 shorts; two blocks per SM up to n1 = 2048 at K <= 1.7k
-    if (want && n >= 64 && plan_pruned(n, K, 8192, &P)) {
-      const size_t smem = ((size_t)P.n1 + 2 * (size_t)P.K) * sizeof(double2) + (size_t)P.n1 * sizeof(unsigned short) + 16;
-      int max_smem = 0;
-      cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-      if (smem <= (size_t)max_smem && P.n1 < 65536) {
-        std::vector<double2> wt, wkv;
-        unit_roots(P.n1, P.n1, wt);
-        unit_roots(n, K, wkv);
-        double2 *d_w = nullptr;
-        cudaError_t e = cudaMallocAsync((void **)&d_w, (wt.size() + wkv.size()) * sizeof(double2), stream);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(twiddles)");
-        e = cudaMemcpyAsync(d_w, wt.data(), wt.size() * sizeof(double2), cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_w + wt.size(), wkv.data(), wkv.size() * sizeof(double2), cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the host vectors go out of scope
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(pruned_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) {
-          pruned_dft_kernel<<<(unsigned)B, kPrunedThreads, smem, stream>>>(x, B, ld, P, d_w, d_w + wt.size(), out);
-          g_launches++;
-          e = cudaGetLastError();
-        }
-        cudaFreeAsync(d_w, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "pruned_dft_kernel");
-        return CMTJB_OK;
+    const bool want_grouped = !(force && force[0] == 's');
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    bool grouped = false;
+    size_t smem = 0;
+    if (want && want_grouped && n >= 64 && plan_grouped(n, K, kGSlots * kGThreads / kG, &P) && (long long)P.n1 * 8 >= K) {
+      smem = (2 * (size_t)P.n1 + (kG + 1) * (size_t)P.K) * sizeof(double2);
+      grouped = smem <= (size_t)max_smem;
+    }
+    bool single = false;
+    if (want && !grouped && n >= 64 && plan_pruned(n, K, 8192, &P)) {
+      smem = ((size_t)P.n1 + 2 * (size_t)P.K) * sizeof(double2) + (size_t)P.n1 * sizeof(unsigned short) + 16;
+      single = smem <= (size_t)max_smem && P.n1 < 65536;
+    }
+    if (grouped || single) {
+      std::vector<double2> wt, wkv;
+      unit_roots(P.n1, P.n1, wt);
+      unit_roots(n, K, wkv);
+      double2 *d_w = nullptr;
+      cudaError_t e = cudaMallocAsync((void **)&d_w, (wt.size() + wkv.size()) * sizeof(double2), stream);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(twiddles)");
+      e = cudaMemcpyAsync(d_w, wt.data(), wt.size() * sizeof(double2), cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_w + wt.size(), wkv.data(), wkv.size() * sizeof(double2), cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the host vectors go out of scope
+      if (e == cudaSuccess)
+        e = grouped ? cudaFuncSetAttribute(pruned_dft4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : cudaFuncSetAttribute(pruned_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess) {
+        if (grouped) pruned_dft4_kernel<<<(unsigned)((B + kG - 1) / kG), kGThreads, smem, stream>>>(x, B, ld, P, d_w, d_w + wt.size(), out);
+        else pruned_dft_kernel<<<(unsigned)B, kPrunedThreads, smem, stream>>>(x, B, ld, P, d_w, d_w + wt.size(), out);
+        g_launches++;
+        e = cudaGetLastError();
       }
+      cudaFreeAsync(d_w, stream);
+      if (e != cudaSuccess) return cuda_fail(e, grouped ? "pruned_dft4_kernel" : "pruned_dft_kernel");
+      return CMTJB_OK;
     }
   }
   const long long nh = n / 2 + 1;

@@ -241,6 +241,7 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
     def spec(sample0):
         return PostSpec(proj=proj[:n_proj], proj_log=proj_log, proj_sample0=sample0) if n_proj else None
 
+    ph.mark("set-up (batch, inputs, projection log buffer)")
     if full_output and not static_only:
         res = batch.run_device(simulation_duration, int_step, int_step, post=spec(0))
         log_all = res["_log"]
@@ -252,7 +253,7 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
             batch.run_device(_time_for_steps(n_a, int_step), int_step, int_step, log=False, post=spec(0))
         res = batch.run_device(simulation_duration, int_step, int_step, post=spec(n_a), start_iteration=n_a)
         log_last = res["_log"]
-    ph.mark(f"set-up + integration of {B} instances x {n_total} steps")
+    ph.mark(f"integration of {B} instances x {n_total} steps")
     m_last = log_last[: 3 * L].contiguous()  # [3L, n_last, B]
     w_dev = torch.tensor(weights, dtype=torch.float64, device=dev)
     # static resistance over the last samples, from the thickness*Ms-weighted m (procedures.py:152-162)

@@ -460,6 +460,14 @@ int cmtjb_fp64_peak(int device, int64_t iters, double *flops, double *ms);
 /* SM clock (MHz) at which the calling thread's last cmtjb_fp64_peak actually ran, from the cycle counter and the global
  * nanosecond timer read inside the kernel (0 before the first call). */
 double cmtjb_fp64_peak_sm_mhz(void);
+/* FP64 pipe probe: the fraction of the pipe's issue slots (64 lanes per SM and clock, measured with the in-kernel cycle
+ * counter) that independent chains sustain at `warps_per_subpartition` resident warps.  kind 0: DFMA with two constant-bank
+ * operands; 1: DFMA with three register operands; 2: the S1 step's 12 DFMA : 3 DMUL : 1 DADD mix on register operands;
+ * 3: the dependency shape of one right-hand-side evaluation (3-vector cross/dot/axpy, 28 instructions); 4: the same on two
+ * independent vectors per thread; 5: independent chains whose DFMAs read registers of three different chains.  Diagnostics
+ * only: it bounds what the integration kernels can reach. */
+int cmtjb_fp64_pipe_probe(int device, int kind, int warps_per_subpartition, int64_t iters, double *issue_slot_frac,
+                          double *sm_mhz);
 
 #ifdef __cplusplus
 }

@@ -176,6 +176,35 @@ def test_spectrum_strip_matches_scipy(on_cuda):
     _close(yf, wy, tol=1e-12)
 
 
+@pytest.mark.parametrize("n,B,K_freq,pitch,mode", [
+    (200000, 9, 80e9, 0, ""),        # PIMM shape: n1 = 2000 >= K = 1601, four instances per block, ragged last group
+    (8000, 5, 400e9, 3, ""),         # a row view with a pitch, K = 320
+    (4096, 4, 4e12, 0, ""),          # K = 1639 of a power of two
+    (10000, 3, 2.0995e12, 0, ""),    # K = 2100 > n1 = 2000: aliased first-stage index
+    (6000, 3, 4.9e12, 0, ""),        # K = 2941: too many bins for four instances' sums, one instance per block
+    (6561, 2, 1e12, 0, ""),          # 3^8: radix-3 stages only
+    (10007, 3, 1e12, 0, ""),         # prime length: library path
+    (200000, 3, 80e9, 0, "single"),  # one instance per block
+    (5000, 6, 80e9, 0, "cufft"),
+])
+def test_spectrum_device_shapes(on_cuda, monkeypatch, n, B, K_freq, pitch, mode):
+    """|rfft| of time-major [n, B] series, K lowest bins: pruned single-pass kernels and the cuFFT path vs numpy"""
+    import torch
+
+    if mode:
+        monkeypatch.setenv("CMTJB_SPECTRUM", mode)
+    rng = np.random.default_rng(n + B)
+    t = np.arange(n)[:, None]
+    x = rng.normal(size=(n, B)) + 3.0 * np.sin(2 * np.pi * t * (7.25 + np.arange(B)[None, :]) / n) + 0.5
+    full = torch.zeros((n, B + pitch), dtype=torch.float64, device="cuda")
+    full[:, :B] = torch.from_numpy(x).cuda()
+    yf, fr = P.spectrum_device(full[:, :B], 1e-13, K_freq)
+    want = np.abs(np.fft.rfft(x, axis=0))[: fr.size].T
+    assert yf.shape == want.shape and fr.size > 0
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    assert np.max(np.abs(yf.cpu().numpy() - want) / scale) < 1e-12
+
+
 def test_distribute_covers_the_product(on_cuda, oracle):
     j = helpers.two_layer_mtj(cm)
     Hx, Hz = [-100e3, 50e3, 200e3], [0.0, 30e3]
