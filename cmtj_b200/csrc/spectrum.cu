@@ -372,6 +372,260 @@ bool plan_grouped(long long n, long long K, int n1_max, PrunedPlan *P) {
   return false;
 }
 
+
+// ---- pruned DFT through Chebyshev moments ---------------------------------------------------------------------------
+// When K << n / 2 (PIMM keeps 1601 of 100 001 bins) most of the single-pass kernels' work is wasted on resolution the
+// output never sees.  Cut the series into N1 blocks of N2 consecutive samples, t = N2 q + j.  Inside a block the kernel
+// e^{-2 pi i k j / n} turns by at most phi = pi k (N2 - 1) / n (a fraction of a cycle to a few cycles), so with
+// s = (2 j - (N2 - 1)) / (N2 - 1) in [-1, 1] the Jacobi-Anger expansion
+//     e^{-i phi s} = J_0(phi) + 2 sum_{d >= 1} (-i)^d J_d(phi) T_d(s)
+// converges super-exponentially once d > phi: D = 20 terms leave 1e-17 at phi = 2.5.  Hence, exactly up to that tail,
+//     X[k] = e^{-i phi_k} sum_{d < D} eps_d (-i)^d J_d(phi_k) C_d[k mod N1],   C_d = FFT_N1( c[q][d] ),
+//     c[q][d] = sum_{j < N2} T_d(s_j) x[N2 q + j]                              (the block's Chebyshev moments)
+// i.e. D real sequences of N1 points per series instead of N2 of them (20 instead of 100 for PIMM), and the moments are
+// a streaming reduction: one coalesced pass over the time-major log (cheb_moments_kernel, HBM-bound), after which the
+// transforms run on a fifth of the data laid out per series (cheb_combine_kernel: two moments packed per complex FFT,
+//     S[k] += alpha_p[k] Z_p[k] + beta_p[k] conj Z_p[-k],  alpha, beta = (-1)^p (a_2p -+ a_2p+1) / 2,  a_d = eps_d J_d(phi_k)
+// ).  The tail bound is evaluated on the host (Miller recurrence in long double) and D chosen for 2e-17.
+constexpr int kMomThreads = 256;
+constexpr int kMomMaxD = 32;
+
+struct MomentPlan {
+  PrunedPlan fft;  // n1 (FFT length), n2 (block length), K, radices
+  int D;           // moments per block (even)
+};
+
+// J_0 .. J_{count-1} at x by Miller's backward recurrence, normalised with J_0 + 2 sum J_2m = 1
+void bessel_j(long double x, int count, std::vector<long double> &J) {
+  J.assign((size_t)count, 0.0L);
+  if (x == 0.0L) {
+    J[0] = 1.0L;
+    return;
+  }
+  const int start = count + 60 + (int)(2.0L * x);
+  long double jp1 = 0.0L, jc = 1e-300L, norm = 0.0L;
+  for (int d = start; d >= 1; d--) {
+    const long double jm1 = (2.0L * d / x) * jc - jp1;  // J_{d-1}
+    jp1 = jc;
+    jc = jm1;
+    if (d - 1 < count) J[(size_t)(d - 1)] = jc;
+    if ((d - 1) % 2 == 0) norm += (d - 1 == 0 ? 1.0L : 2.0L) * jc;
+    if (fabsl(jc) > 1e250L) {  // rescale
+      const long double sc = 1e-250L;
+      jc *= sc, jp1 *= sc, norm *= sc;
+      for (int i = d - 1; i < count; i++) J[(size_t)i] *= sc;
+    }
+  }
+  for (auto &v : J) v /= norm;
+}
+
+bool factor_radices(long long n1, PrunedPlan *P) {
+  long long rem = n1;
+  int st = 0;
+  while (rem % 4 == 0 && st < kMaxStages) P->radix[st++] = 4, rem /= 4;
+  while (rem % 2 == 0 && st < kMaxStages) P->radix[st++] = 2, rem /= 2;
+  while (rem % 5 == 0 && st < kMaxStages) P->radix[st++] = 5, rem /= 5;
+  while (rem % 3 == 0 && st < kMaxStages) P->radix[st++] = 3, rem /= 3;
+  if (rem != 1) return false;
+  P->n_stages = st;
+  return true;
+}
+
+// block length N2 | n (8 <= N2 <= 1024) with N1 = n / N2 a product of 2, 3, 4, 5 that fits shared memory, D <= min(32, N2 / 2):
+// the plan with the least estimated work, or false
+bool plan_moments(long long n, long long K, size_t max_smem, MomentPlan *out) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  double best = 0.0;
+  bool found = false;
+  for (long long n2 = 8; n2 <= 1024 && n2 * 16 <= n; n2++) {
+    if (n % n2) continue;
+    const long long n1 = n / n2;
+    if (n1 < 16 || n1 > 32768) continue;
+    MomentPlan M;
+    if (!factor_radices(n1, &M.fft)) continue;
+    const size_t smem = ((size_t)n1 + (size_t)K) * sizeof(double2) + (size_t)n1 * sizeof(unsigned short) + 16;
+    if (smem > max_smem) continue;
+    const long double phi = pi * (long double)(K - 1) * (long double)(n2 - 1) / (long double)n;
+    std::vector<long double> J;
+    bessel_j(phi, kMomMaxD + 48, J);
+    int D = -1;
+    long double tail = 0.0L;
+    for (int d = kMomMaxD + 47; d >= 2; d--) {
+      tail += 2.0L * fabsl(J[(size_t)d]);
+      if (tail > 2e-17L) {
+        D = d + 1;
+        break;
+      }
+    }
+    if (D < 0) D = 2;
+    D = (D + 3) / 4 * 4;
+    if (D > kMomMaxD || 2 * D > n2) continue;
+    double lg = std::log2((double)n1);
+    const double cost = (double)n * (0.5 * D + 2.0) + 3.0 * (0.5 * D) * (double)n1 * lg + 2.0 * D * (double)K;
+    if (!found || cost < best) {
+      best = cost;
+      found = true;
+      M.fft.n1 = (int)n1, M.fft.n2 = (int)n2, M.fft.K = (int)K;
+      M.D = D;
+      *out = M;
+    }
+  }
+  return found;
+}
+
+// Host tables of a plan: T[(n2 + 1) / 2][D] (T_d at s_j, j < n2 / 2, then the middle sample of an odd block) and
+// ab[D / 2][K] = (alpha_p[k], beta_p[k])
+void moment_tables(long long n, const MomentPlan &M, std::vector<double> &T, std::vector<double2> &ab) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  const int n2 = M.fft.n2, D = M.D, K = M.fft.K;
+  const int rows = (n2 + 1) / 2;
+  T.resize((size_t)rows * D);
+  for (int j = 0; j < rows; j++) {
+    const long double sj = (long double)(2 * j - (n2 - 1)) / (long double)(n2 - 1);
+    const long double th = acosl(sj);
+    for (int d = 0; d < D; d++) T[(size_t)j * D + d] = (double)cosl((long double)d * th);
+  }
+  ab.resize((size_t)(D / 2) * K);
+  std::vector<long double> J;
+  for (int k = 0; k < K; k++) {
+    const long double phi = pi * (long double)k * (long double)(n2 - 1) / (long double)n;
+    bessel_j(phi, D, J);
+    for (int p = 0; p < D / 2; p++) {
+      const long double a0 = (2 * p == 0 ? 1.0L : 2.0L) * J[(size_t)(2 * p)], a1 = 2.0L * J[(size_t)(2 * p + 1)];
+      const long double sg = (p % 2) ? -0.5L : 0.5L;
+      ab[(size_t)p * K + k] = make_double2((double)(sg * (a0 - a1)), (double)(sg * (a0 + a1)));
+    }
+  }
+}
+
+// Moments of two consecutive blocks (q, q + 1) of one series per thread: lane = series (rows of the time-major log are read
+// coalesced), warp = block pair.  Samples j and N2 - 1 - j share |T_d| (T_d(-s) = (-1)^d T_d(s)): their sum feeds the even
+// moments, their difference the odd ones, D / 2 + 1 FP64 instructions per sample.  mom[series][p][q] = (c[q][2p], c[q][2p+1]).
+template <int D>
+__global__ void __launch_bounds__(kMomThreads) cheb_moments_kernel(const double *__restrict__ x, long long ld, long long b_lo,
+                                                                   long long b_hi, int n1, int n2, int pairs_per_block,
+                                                                   const double *__restrict__ Ttab, double2 *__restrict__ mom) {
+  extern __shared__ double sT[];  // [(n2 + 1) / 2][D]
+  const int rows = (n2 + 1) / 2;
+  for (int i = threadIdx.x; i < rows * D; i += kMomThreads) sT[i] = Ttab[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long b = b_lo + (long long)blockIdx.x * 32 + lane;
+  if (b >= b_hi) return;
+  const int half = n2 / 2;
+  const int n_pairs = (n1 + 1) / 2;
+  for (int it = 0; it < pairs_per_block; it += kMomThreads / 32) {
+    const int qp = blockIdx.y * pairs_per_block + it + warp;
+    if (qp >= n_pairs) break;
+    const int q = 2 * qp;
+    const bool two = q + 1 < n1;
+    const double *x0 = x + (long long)n2 * q * ld + b;
+    const double *x1 = two ? x0 + (long long)n2 * ld : x0;
+    double c0[D], c1[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) c0[d] = 0.0, c1[d] = 0.0;
+#pragma unroll 2
+    for (int j = 0; j < half; j++) {
+      const long long lo = (long long)j * ld, hi = (long long)(n2 - 1 - j) * ld;
+      const double a0 = __ldcs(x0 + lo), a1 = __ldcs(x0 + hi), g0 = __ldcs(x1 + lo), g1 = __ldcs(x1 + hi);
+      const double e0 = a0 + a1, o0 = a0 - a1, e1 = g0 + g1, o1 = g0 - g1;
+      const double2 *t2 = reinterpret_cast<const double2 *>(sT + j * D);
+#pragma unroll
+      for (int d = 0; d < D; d += 2) {
+        const double2 t = t2[d / 2];  // (T_d, T_{d+1}) at s_j, d even
+        c0[d] = fma(t.x, e0, c0[d]);
+        c0[d + 1] = fma(t.y, o0, c0[d + 1]);
+        c1[d] = fma(t.x, e1, c1[d]);
+        c1[d + 1] = fma(t.y, o1, c1[d + 1]);
+      }
+    }
+    if (n2 & 1) {  // the middle sample, s = 0: T_d(0) = 0 for odd d
+      const double a0 = __ldcs(x0 + (long long)half * ld), g0 = __ldcs(x1 + (long long)half * ld);
+#pragma unroll
+      for (int d = 0; d < D; d += 2) {
+        const double t = sT[half * D + d];
+        c0[d] = fma(t, a0, c0[d]);
+        c1[d] = fma(t, g0, c1[d]);
+      }
+    }
+    double2 *m = mom + ((b - b_lo) * (D / 2)) * (long long)n1 + q;
+#pragma unroll
+    for (int p = 0; p < D / 2; p++) {
+      m[(long long)p * n1] = make_double2(c0[2 * p], c0[2 * p + 1]);
+      if (two) m[(long long)p * n1 + 1] = make_double2(c1[2 * p], c1[2 * p + 1]);
+    }
+  }
+}
+
+// One series per block: the D / 2 packed moment sequences are transformed one after another in shared memory (mixed-radix,
+// in place, loaded straight to their digit-reversed slots) and folded into the K running sums.
+__global__ void __launch_bounds__(kPrunedThreads) cheb_combine_kernel(const double2 *__restrict__ mom, long long b_lo, int n_passes,
+                                                                      const __grid_constant__ PrunedPlan P,
+                                                                      const double2 *__restrict__ wtab,  // W_n1^j, j < n1
+                                                                      const double2 *__restrict__ ab,    // [n_passes][K]
+                                                                      double *__restrict__ out) {
+  extern __shared__ double2 sm2[];
+  const int n1 = P.n1, K = P.K;
+  double2 *buf = sm2;                                       // [n1]
+  double2 *acc = buf + n1;                                  // [K]
+  unsigned short *perm = (unsigned short *)(acc + K);       // [n1]
+  const int tid = threadIdx.x;
+  for (int q = tid; q < n1; q += kPrunedThreads) {
+    int rem = q, span = n1, pos = 0;
+    for (int st = 0; st < P.n_stages; st++) {
+      const int r = P.radix[st];
+      span /= r;
+      pos += (rem % r) * span;
+      rem /= r;
+    }
+    perm[q] = (unsigned short)pos;
+  }
+  for (int k = tid; k < K; k += kPrunedThreads) acc[k] = make_double2(0.0, 0.0);
+  __syncthreads();
+  const double2 *mb = mom + (long long)blockIdx.x * n_passes * n1;
+  for (int p = 0; p < n_passes; p++) {
+    const double2 *z = mb + (long long)p * n1;
+    for (int q = tid; q < n1; q += kPrunedThreads) buf[perm[q]] = __ldcs(z + q);
+    __syncthreads();
+    int M = 1;
+    for (int st = P.n_stages - 1; st >= 0; st--) {
+      const int r = P.radix[st];
+      if (r == 4) stage<4>(buf, n1, M, wtab, tid);
+      else if (r == 5) stage<5>(buf, n1, M, wtab, tid);
+      else if (r == 2) stage<2>(buf, n1, M, wtab, tid);
+      else stage<3>(buf, n1, M, wtab, tid);
+      M *= r;
+      __syncthreads();
+    }
+    const double2 *abp = ab + (long long)p * K;
+    for (int k = tid; k < K; k += kPrunedThreads) {
+      const int km = (K > n1) ? k % n1 : k;
+      const double2 zk = buf[km], zm = buf[km == 0 ? 0 : n1 - km];
+      const double2 c = __ldg(abp + k);
+      double2 a = acc[k];
+      a.x = fma(c.x, zk.x, fma(c.y, zm.x, a.x));
+      a.y = fma(c.x, zk.y, fma(-c.y, zm.y, a.y));
+      acc[k] = a;
+    }
+    __syncthreads();
+  }
+  const long long b = b_lo + blockIdx.x;
+  for (int k = tid; k < K; k += kPrunedThreads) out[b * K + k] = hypot(acc[k].x, acc[k].y);
+}
+
+template <int D>
+cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long long b_hi, int n1, int n2, const double *Ttab,
+                           double2 *mom, cudaStream_t stream) {
+  const size_t smem = (size_t)((n2 + 1) / 2) * D * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(cheb_moments_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int n_pairs = (n1 + 1) / 2;
+  const int per_block = 2 * (kMomThreads / 32);  // two block pairs per warp: the table load is amortised over 32 blocks
+  const dim3 grid((unsigned)((b_hi - b_lo + 31) / 32), (unsigned)((n_pairs + per_block - 1) / per_block));
+  cheb_moments_kernel<D><<<grid, kMomThreads, smem, stream>>>(x, ld, b_lo, b_hi, n1, n2, per_block, Ttab, mom);
+  return cudaGetLastError();
+}
+
 // n = n1 n2 with K <= n1 <= n1_max and n1 a product of 2, 3, 4, 5: the smallest such n1, or false
 bool plan_pruned(long long n, long long K, int n1_max, PrunedPlan *P) {
   for (long long n1 = std::max<long long>(K, 2); n1 <= n1_max && n1 <= n; n1++) {
