@@ -623,6 +623,99 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   return rc;
 }
 
+// One array sharded over `world` ranks (one process per GPU): this rank integrates elements [e_lo, e_hi) and exchanges
+// the top-layer magnetisation of all elements once per step through `exchange` (an in-place all-gather of the
+// [world][3][per] device buffer, stream-ordered; NCCL in cmtj_b200.reservoir.ShardedGroup).  Device pointers, sized
+// for this rank's elements only.
+template <int NL>
+int group_shard_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a,
+                       const Common &c, int rank, int world, cmtjb_exchange_fn exchange, void *ctx, double *m_state, double *jlog,
+                       int32_t *status, int device, cudaStream_t stream) {
+  const int N = g->n_junctions;
+  const int per = (N + world - 1) / world;
+  const int e_lo = std::min(N, rank * per), e_hi = std::min(N, e_lo + per), own = e_hi - e_lo;
+  RunParams R;
+  std::memset(&R, 0, sizeof(R));
+  fill_run_params(R, c, a, own, m_state, jlog, status);
+  R.inst_offset = a->instance_offset + e_lo;  // Philox streams are keyed by the global element index
+  std::vector<DevModel<NL>> models;
+  if (own > 0) build_models<NL>(own, jns + e_lo, layers + (size_t)e_lo * NL, nullptr, 0, g->top_layer, a->timeStep, models, R, nullptr);
+  std::vector<double> pos(3 * (size_t)N), pref(N);
+  for (int k = 0; k < N; k++) {
+    for (int d = 0; d < 3; d++) pos[(size_t)d * N + k] = g->coordinates[3 * k + d];
+    const cmtjb_layer_t &L = layers[(size_t)k * NL + g->top_layer];
+    pref[k] = (L.Ms / jns[k].MAGNETIC_PERMEABILITY) * (L.thickness * L.cellSurface);
+  }
+  DevModel<NL> *d_models = nullptr;
+  double *d_pos = nullptr, *d_pref = nullptr, *d_x = nullptr, *d_hpart = nullptr;
+  RunParams *d_R = nullptr;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int tiles = std::max(1, (own + 31) / 32);
+  // partner slices: a function of N alone (the sum order must not depend on the number of ranks), enough of them to fill
+  // one GPU's share of the machine when the array is small
+  const int P = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(64, N), ((long long)sms * 2048) / (((long long)N + 31) / 32 * 32)));
+  cudaError_t e = upload(models.data(), models.size(), &d_models, stream);
+  if (e == cudaSuccess) e = upload(pos.data(), pos.size(), &d_pos, stream);
+  if (e == cudaSuccess) e = upload(pref.data(), pref.size(), &d_pref, stream);
+  if (e == cudaSuccess) e = upload(&R, 1, &d_R, stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_x, (size_t)world * 3 * per * sizeof(double), stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_x, 0, (size_t)world * 3 * per * sizeof(double), stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_hpart, (size_t)P * 3 * std::max(own, 1) * sizeof(double), stream);
+  int rc = (e == cudaSuccess) ? CMTJB_OK : cuda_fail(e, "sharded group set-up");
+  double *x_own = d_x ? d_x + (size_t)rank * 3 * per : nullptr;
+  // initial exchange: the top-layer rows of the incoming state
+  for (int cpt = 0; cpt < 3 && rc == CMTJB_OK && own > 0; cpt++) {
+    e = cudaMemcpyAsync(x_own + (size_t)cpt * per, m_state + (size_t)(3 * g->top_layer + cpt) * own, (size_t)own * sizeof(double),
+                        cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "sharded group initial state");
+  }
+  if (rc == CMTJB_OK && exchange(ctx, d_x, (int64_t)3 * per, (int64_t)-1, (void *)stream) != 0) rc = fail(CMTJB_ERUNTIME, "exchange callback failed");
+  const bool rk4 = (c.solver == CMTJB_RK4);
+  const bool lean = own > 0 && lean_ok(system_features(own, NL, jns + e_lo, layers + (size_t)e_lo * NL, nullptr, 0, a, c.solver, false));
+  PairShardParams Q;
+  Q.N = N, Q.P = P, Q.own = own, Q.e_lo = e_lo, Q.per = per;
+  Q.pos = d_pos, Q.pref = d_pref, Q.xbuf = d_x, Q.Hpart = d_hpart;
+  GroupStepParams G;
+  std::memset(&G, 0, sizeof(G));
+  G.N = own, G.P = P, G.interaction = g->interaction, G.top = g->top_layer, G.inst = 0, G.Hpart = d_hpart;
+  G.xout = x_own, G.xpitch = per;
+  long long sample = R.first_sample;
+  const long long we = R.write_every;
+  const long long pair_blocks = ((long long)tiles * 32 * P + 255) / 256;
+  for (long long it = R.it_begin; it < R.it_end && rc == CMTJB_OK; it++) {
+    if (own > 0) {
+      if (g->interaction != CMTJB_INT_NULL) {
+        group_pair_shard_kernel<<<(unsigned)pair_blocks, 256, 0, stream>>>(Q);
+        g_launches++;
+      }
+      G.it = it;
+      G.write = (it % we == 0) ? 1 : 0;
+      G.sample = sample;
+      const unsigned sb = (unsigned)((own + 127) / 128);
+      if (rk4) {
+        if (lean) group_step_kernel<NL, CMTJB_RK4, F_COUPLED_LEAN, false><<<sb, 128, 0, stream>>>(d_models, d_R, G);
+        else group_step_kernel<NL, CMTJB_RK4, F_ALL, false><<<sb, 128, 0, stream>>>(d_models, d_R, G);
+      } else {
+        if (lean) group_step_kernel<NL, CMTJB_EULER_HEUN, F_COUPLED_LEAN, false><<<sb, 128, 0, stream>>>(d_models, d_R, G);
+        else group_step_kernel<NL, CMTJB_EULER_HEUN, F_ALL, false><<<sb, 128, 0, stream>>>(d_models, d_R, G);
+      }
+      g_launches++;
+      e = cudaGetLastError();
+      if (e != cudaSuccess) rc = cuda_fail(e, "sharded group pair/step kernels");
+    }
+    if (it % we == 0) sample++;
+    if (rc == CMTJB_OK && exchange(ctx, d_x, (int64_t)3 * per, (int64_t)it, (void *)stream) != 0) rc = fail(CMTJB_ERUNTIME, "exchange callback failed");
+  }
+  cudaFreeAsync(d_models, stream);
+  cudaFreeAsync(d_pos, stream);
+  cudaFreeAsync(d_pref, stream);
+  if (d_R) cudaFreeAsync(d_R, stream);
+  if (d_x) cudaFreeAsync(d_x, stream);
+  if (d_hpart) cudaFreeAsync(d_hpart, stream);
+  return rc;
+}
+
 int group_run(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_override_t *ovr,
               int n_ovr, const cmtjb_run_args_t *a, double *m_state, double *jlog, int32_t *status, int device,
               cudaStream_t stream) {
@@ -787,6 +880,27 @@ int cmtjb_group_run_host(const cmtjb_group_t *g, const cmtjb_junction_t *jns, co
   CUDA_TRY(cudaMemcpy(m_state, d_m, nm * sizeof(double), cudaMemcpyDeviceToHost));
   if (njl) CUDA_TRY(cudaMemcpy(junction_log, d_jl, njl * sizeof(double), cudaMemcpyDeviceToHost));
   return finish_status(d_st, status, E);
+}
+
+int cmtjb_group_run_sharded(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                            const cmtjb_run_args_t *args, int32_t rank, int32_t world, cmtjb_exchange_fn exchange, void *ctx,
+                            double *m_state, double *junction_log, int32_t *status, int device, void *stream) {
+  if (!exchange || world < 1 || rank < 0 || rank >= world) return fail(CMTJB_EINVAL, "bad rank / world / exchange callback");
+  if (!args || args->n_instances != 1) return fail(CMTJB_EINVAL, "a sharded array is one instance");
+  Common c;
+  int rc = validate_group(g, jns, layers, args, &c);
+  if (rc) return rc;
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  if (args->onef_buffer) return fail(CMTJB_ENOTSUP, "1/f noise buffers are not supported for sharded arrays");
+  for (long long k = 0; k < (long long)g->n_junctions * c.nl; k++)
+    if (layers[k].noiseScale != 0.0)
+      return fail(CMTJB_ENOTSUP, "1/f noise is not supported for sharded arrays");
+  CUDA_TRY(cudaSetDevice(device));
+  switch (c.nl) {
+  case 1: return group_shard_launch<1>(g, jns, layers, args, c, rank, world, exchange, ctx, m_state, junction_log, status, device, (cudaStream_t)stream);
+  case 2: return group_shard_launch<2>(g, jns, layers, args, c, rank, world, exchange, ctx, m_state, junction_log, status, device, (cudaStream_t)stream);
+  default: return fail(CMTJB_ENOTSUP, "dipole-coupled junctions with more than 2 layers are not supported by this build");
+  }
 }
 
 } /* extern "C" */

@@ -657,7 +657,55 @@ struct GroupStepParams {
   long long it, sample;    // this step's index and, if `write`, the log row it produces
   int write;
   const double *Hpart;     // [P][3][N]
+  double *xout;            // sharded arrays: this rank's rows [3][xpitch] of the exchange buffer (else null)
+  int xpitch;
 };
+
+// ---- one array sharded over several GPUs (reservoir.hpp:129-152 with the elements split into contiguous ranges) ---------
+// Rank r owns elements [e_lo, e_lo + own); the top-layer magnetisation of EVERY element lives in an exchange buffer
+// [world][3][per] (per = elements per rank, the last rank's tail unused) that the host all-gathers after each step
+// (NCCL, in place: each rank's step kernel writes its own rows).  Pair sums: a warp is 32 consecutive own elements
+// sharing one slice of the N partners, partner loads are warp-wide broadcasts; partial sums per slice, added in slice
+// order by the step kernel (deterministic, independent of the number of ranks because slices are ranges of the global index).
+struct PairShardParams {
+  int N, P, own, e_lo, per;
+  const double *pos;   // device [3][N]
+  const double *pref;  // device [N]
+  const double *xbuf;  // device [world][3][per]
+  double *Hpart;       // device [P][3][own]
+};
+
+__global__ void __launch_bounds__(256) group_pair_shard_kernel(const __grid_constant__ PairShardParams Q) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = Q.N, own = Q.own, per = Q.per;
+  const int tiles = (own + 31) / 32;
+  const long long w = gt >> 5;
+  const int p = (int)(w / tiles);
+  if (p >= Q.P) return;
+  const int a_raw = (int)(w - (long long)p * tiles) * 32 + (int)(gt & 31);
+  const int a = Q.e_lo + (a_raw < own ? a_raw : own - 1);
+  const d3 ra = mk(__ldg(Q.pos + a), __ldg(Q.pos + N + a), __ldg(Q.pos + 2 * N + a));
+  const int len = (N + Q.P - 1) / Q.P;
+  const int b0 = p * len, b1 = (b0 + len < N) ? b0 + len : N;
+  int r = b0 / per, o = b0 - r * per;
+  const double *base = Q.xbuf + (size_t)r * 3 * per;
+  d3 H = mk(0, 0, 0);
+  for (int b = b0; b < b1; b++) {
+    const d3 rb = mk(__ldg(Q.pos + b), __ldg(Q.pos + N + b), __ldg(Q.pos + 2 * N + b));
+    const d3 mb = mk(base[o], base[per + o], base[2 * per + o]);  // rewritten between launches: plain loads
+    pair_accumulate(H, ra - rb, mb, __ldg(Q.pref + b), b == a);
+    if (++o == per) {
+      o = 0;
+      base += (size_t)3 * per;
+    }
+  }
+  if (a_raw < own) {
+    double *q = Q.Hpart + (size_t)p * 3 * own + a_raw;
+    q[0] = H.x;
+    q[own] = H.y;
+    q[2 * own] = H.z;
+  }
+}
 
 // Launched once per time step: its parameter block is kept to a few words (the models and the run
 // parameters are read through pointers) so that the two launches of a step cost the host less than the
@@ -689,6 +737,12 @@ __global__ void __launch_bounds__(128) group_step_kernel(const DevModel<NL> *__r
   }
   coupled_step<NL, SOLVER, F>(M, R, i, G.it, (double)G.it * R.dt, S, Hl, NoExt());
   store_state<NL>(R, i, S);  // the next pair kernel reads the top layer's rows from here
+  if (G.xout) {
+    const d3 mt = layer_m2<NL>(S, G.top);
+    G.xout[a] = mt.x;
+    G.xout[G.xpitch + a] = mt.y;
+    G.xout[2 * G.xpitch + a] = mt.z;
+  }
   if (G.write && R.log) write_sample<NL>(M, R, S, G.sample, i);
   if (R.status) {
     const int st = nan_status<NL, SOLVER>(S);

@@ -11,7 +11,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -212,18 +214,18 @@ __device__ __forceinline__ int div_magic(int n, uint32_t magic) { return (int)__
 // One decimation-in-time stage over n_buf buffers, sub-transforms of size M combined R at a time.  Two butterflies per
 // thread and trip (independent loads in flight), index arithmetic by multiply-high, the R - 1 twiddles W_{RM}^(s k1)
 // from ONE table read and powers of it; the first stage (M == 1) has no twiddles at all.
-template <int R>
+template <int R, int THREADS = 512>
 __device__ __forceinline__ void stage_multi(double2 *buf, int n1, int n_buf, int M, uint32_t magic_per, uint32_t magic_M,
                                             const double2 *__restrict__ wtab, int tid) {
   const int per = n1 / R, total = n_buf * per;
   const int step = per / M;  // W_{RM}^j = W_n1^(j * step)
-  for (int ub = tid; ub < total; ub += 2 * kGThreads) {
+  for (int ub = tid; ub < total; ub += 2 * THREADS) {
     double2 v[2][R];
     double2 *p[2];
     bool on[2];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      const int u = ub + h * kGThreads;
+      const int u = ub + h * THREADS;
       on[h] = u < total;
       const int uc = on[h] ? u : 0;
       const int b = div_magic(uc, magic_per), uu = uc - b * per;
@@ -428,6 +430,13 @@ bool factor_radices(long long n1, PrunedPlan *P) {
   while (rem % 3 == 0 && st < kMaxStages) P->radix[st++] = 3, rem /= 3;
   if (rem != 1) return false;
   P->n_stages = st;
+  long long M = 1;
+  auto magic = [](long long d) { return d <= 1 ? 0u : (uint32_t)((((unsigned long long)1 << 32) + d - 1) / d); };
+  for (int i = st - 1; i >= 0; i--) {  // the kernels run the stages innermost (M = 1) first
+    P->magic_per[i] = magic(n1 / P->radix[i]);
+    P->magic_M[i] = magic(M);
+    M *= P->radix[i];
+  }
   return true;
 }
 
@@ -437,14 +446,16 @@ bool plan_moments(long long n, long long K, size_t max_smem, MomentPlan *out) {
   const long double pi = 3.14159265358979323846264338327950288L;
   double best = 0.0;
   bool found = false;
+  long long only_n2 = 0;  // CMTJB_SPECTRUM_N2: pin the block length (tests)
+  if (const char *c = std::getenv("CMTJB_SPECTRUM_N2")) only_n2 = std::atoll(c);
   for (long long n2 = 8; n2 <= 1024 && n2 * 16 <= n; n2++) {
-    if (n % n2) continue;
+    if (n % n2 || (only_n2 > 0 && n2 != only_n2)) continue;
     const long long n1 = n / n2;
     if (n1 < 16 || n1 > 32768) continue;
     MomentPlan M;
     if (!factor_radices(n1, &M.fft)) continue;
-    const size_t smem = ((size_t)n1 + (size_t)K) * sizeof(double2) + (size_t)n1 * sizeof(unsigned short) + 16;
-    if (smem > max_smem) continue;
+    const size_t smem = (2 * (size_t)n1 + (size_t)K) * sizeof(double2) + (size_t)n1 * sizeof(unsigned short) + 16;
+    if (smem > max_smem || n1 >= 16384) continue;
     const long double phi = pi * (long double)(K - 1) * (long double)(n2 - 1) / (long double)n;
     std::vector<long double> J;
     bessel_j(phi, kMomMaxD + 48, J);
@@ -461,7 +472,9 @@ bool plan_moments(long long n, long long K, size_t max_smem, MomentPlan *out) {
     D = (D + 3) / 4 * 4;
     if (D > kMomMaxD || 2 * D > n2) continue;
     double lg = std::log2((double)n1);
-    const double cost = (double)n * (0.5 * D + 2.0) + 3.0 * (0.5 * D) * (double)n1 * lg + 2.0 * D * (double)K;
+    // measured on B200 (PIMM shape): the moments pass is bound by the bytes it moves (the log once, the moments written and
+    // read back), the transforms by their butterflies at about twice the cost per unit
+    const double cost = (double)n * (1.0 + 2.5 * D / (double)n2) + 2.0 * (0.5 * D) * (double)n1 * lg + 2.0 * D * (double)K;
     if (!found || cost < best) {
       best = cost;
       found = true;
@@ -498,13 +511,14 @@ void moment_tables(long long n, const MomentPlan &M, std::vector<double> &T, std
   }
 }
 
-// Moments of two consecutive blocks (q, q + 1) of one series per thread: lane = series (rows of the time-major log are read
-// coalesced), warp = block pair.  Samples j and N2 - 1 - j share |T_d| (T_d(-s) = (-1)^d T_d(s)): their sum feeds the even
-// moments, their difference the odd ones, D / 2 + 1 FP64 instructions per sample.  mom[series][p][q] = (c[q][2p], c[q][2p+1]).
+// Moments of one block q of one series per thread: lane = series (rows of the time-major log are read coalesced), warp =
+// block.  Samples j and N2 - 1 - j share |T_d| (T_d(-s) = (-1)^d T_d(s)): their sum feeds the even moments, their difference
+// the odd ones, D / 2 + 1 FP64 instructions per sample.  mom[series][p][q] = (c[q][2p], c[q][2p+1]); the 16-byte halves of
+// a sector come from neighbouring warps of one block and merge in L2.
 template <int D>
-__global__ void __launch_bounds__(kMomThreads) cheb_moments_kernel(const double *__restrict__ x, long long ld, long long b_lo,
-                                                                   long long b_hi, int n1, int n2, int pairs_per_block,
-                                                                   const double *__restrict__ Ttab, double2 *__restrict__ mom) {
+__global__ void __launch_bounds__(kMomThreads, (D > 24 ? 2 : 3)) cheb_moments_kernel(const double *__restrict__ x, long long ld, long long b_lo,
+                                                                      long long b_hi, int n1, int n2, int q_per_block,
+                                                                      const double *__restrict__ Ttab, double2 *__restrict__ mom) {
   extern __shared__ double sT[];  // [(n2 + 1) / 2][D]
   const int rows = (n2 + 1) / 2;
   for (int i = threadIdx.x; i < rows * D; i += kMomThreads) sT[i] = Ttab[i];
@@ -513,61 +527,158 @@ __global__ void __launch_bounds__(kMomThreads) cheb_moments_kernel(const double 
   const long long b = b_lo + (long long)blockIdx.x * 32 + lane;
   if (b >= b_hi) return;
   const int half = n2 / 2;
-  const int n_pairs = (n1 + 1) / 2;
-  for (int it = 0; it < pairs_per_block; it += kMomThreads / 32) {
-    const int qp = blockIdx.y * pairs_per_block + it + warp;
-    if (qp >= n_pairs) break;
-    const int q = 2 * qp;
-    const bool two = q + 1 < n1;
-    const double *x0 = x + (long long)n2 * q * ld + b;
-    const double *x1 = two ? x0 + (long long)n2 * ld : x0;
-    double c0[D], c1[D];
+  for (int it = 0; it < q_per_block; it += kMomThreads / 32) {
+    const int q = blockIdx.y * q_per_block + it + warp;
+    if (q >= n1) break;
+    const double *lo = x + (long long)n2 * q * ld + b;
+    const double *hi = lo + (long long)(n2 - 1) * ld;
+    double c[D];
 #pragma unroll
-    for (int d = 0; d < D; d++) c0[d] = 0.0, c1[d] = 0.0;
-#pragma unroll 2
+    for (int d = 0; d < D; d++) c[d] = 0.0;
+#pragma unroll 4
     for (int j = 0; j < half; j++) {
-      const long long lo = (long long)j * ld, hi = (long long)(n2 - 1 - j) * ld;
-      const double a0 = __ldcs(x0 + lo), a1 = __ldcs(x0 + hi), g0 = __ldcs(x1 + lo), g1 = __ldcs(x1 + hi);
-      const double e0 = a0 + a1, o0 = a0 - a1, e1 = g0 + g1, o1 = g0 - g1;
+      const double a0 = __ldcs(lo), a1 = __ldcs(hi);
+      lo += ld;
+      hi -= ld;
+      const double e = a0 + a1, o = a0 - a1;
       const double2 *t2 = reinterpret_cast<const double2 *>(sT + j * D);
 #pragma unroll
       for (int d = 0; d < D; d += 2) {
         const double2 t = t2[d / 2];  // (T_d, T_{d+1}) at s_j, d even
-        c0[d] = fma(t.x, e0, c0[d]);
-        c0[d + 1] = fma(t.y, o0, c0[d + 1]);
-        c1[d] = fma(t.x, e1, c1[d]);
-        c1[d + 1] = fma(t.y, o1, c1[d + 1]);
+        c[d] = fma(t.x, e, c[d]);
+        c[d + 1] = fma(t.y, o, c[d + 1]);
       }
     }
     if (n2 & 1) {  // the middle sample, s = 0: T_d(0) = 0 for odd d
-      const double a0 = __ldcs(x0 + (long long)half * ld), g0 = __ldcs(x1 + (long long)half * ld);
+      const double a0 = __ldcs(lo);
 #pragma unroll
-      for (int d = 0; d < D; d += 2) {
-        const double t = sT[half * D + d];
-        c0[d] = fma(t, a0, c0[d]);
-        c1[d] = fma(t, g0, c1[d]);
-      }
+      for (int d = 0; d < D; d += 2) c[d] = fma(sT[half * D + d], a0, c[d]);
     }
     double2 *m = mom + ((b - b_lo) * (D / 2)) * (long long)n1 + q;
 #pragma unroll
-    for (int p = 0; p < D / 2; p++) {
-      m[(long long)p * n1] = make_double2(c0[2 * p], c0[2 * p + 1]);
-      if (two) m[(long long)p * n1 + 1] = make_double2(c1[2 * p], c1[2 * p + 1]);
-    }
+    for (int p = 0; p < D / 2; p++) m[(long long)p * n1] = make_double2(c[2 * p], c[2 * p + 1]);
   }
 }
 
-// One series per block: the D / 2 packed moment sequences are transformed one after another in shared memory (mixed-radix,
-// in place, loaded straight to their digit-reversed slots) and folded into the K running sums.
-__global__ void __launch_bounds__(kPrunedThreads) cheb_combine_kernel(const double2 *__restrict__ mom, long long b_lo, int n_passes,
+// ---- the same reduction with the log staged through shared memory by asynchronous copies ------------------------------
+// The register version above keeps at most a few KB per warp in flight and stalls on DRAM latency (ncu: 35 % of the HBM
+// peak, long_scoreboard 24 per issue).  Here a warp owns a ring of kMomStages shared-memory stages; one stage holds up to
+// S front rows j and their mirror rows N2 - 1 - j of a 32-series tile (256 bytes per row, 16 bytes per lane and
+// cp.async, two rows per warp instruction, one commit group per stage), so a block of 8 warps keeps ~200 KB of loads in
+// flight with no registers tied up.  Each warp is its own producer and consumer; warps never synchronise with each other.
+// A warp walks an even number of consecutive blocks q and writes the moments of a pair (q, q + 1) as whole 32-byte sectors.
+// (Tried first: one 256-byte cp.async.bulk per row, completion on an mbarrier -- the bulk-copy unit retires about one such
+// operation per 35 cycles and SM, 2.1 TB/s in all, slower than the register version.)
+constexpr int kMomStages = 4;
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(kMomThreads, 1) cheb_moments_async_kernel(const double *__restrict__ x, long long ld, int n1, int n2,
+                                                                            int S, int q_per_warp, const double *__restrict__ Ttab,
+                                                                            double2 *__restrict__ mom) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int rows_T = (n2 + 1) / 2;
+  const int stage_rows = 2 * S + 1;
+  double *sT = reinterpret_cast<double *>(smraw);                                            // [(n2 + 1) / 2][D]
+  const size_t t_bytes = (((size_t)rows_T * D * sizeof(double)) + 127) / 128 * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *ring = reinterpret_cast<double *>(smraw + t_bytes) + (size_t)warp * kMomStages * stage_rows * 32;  // [stage][row][32]
+  for (int i = threadIdx.x; i < rows_T * D; i += kMomThreads) sT[i] = Ttab[i];
+  __syncthreads();
+  const int half = n2 / 2;
+  const int nst = (half + S - 1) / S;  // stages per block of samples
+  const int q_begin = (blockIdx.y * (kMomThreads / 32) + warp) * q_per_warp;
+  const int q_end = min(n1, q_begin + q_per_warp);
+  if (q_begin >= q_end) return;
+  const int total = (q_end - q_begin) * nst;
+  const double *xt = x + (long long)blockIdx.x * 32 + 2 * (lane & 15);  // this lane's 16 bytes of the tile's rows
+  const int hw = lane >> 4;
+  auto issue = [&](int t) {
+    const int q = q_begin + t / nst, k = t - (t / nst) * nst;
+    const int j0 = k * S, cnt = min(S, half - j0);
+    const int rows = 2 * cnt + (((n2 & 1) && k == nst - 1) ? 1 : 0);
+    double *dst = ring + (size_t)(t % kMomStages) * stage_rows * 32 + 2 * (lane & 15);
+    const long long r0 = (long long)n2 * q;
+    for (int ri = hw; ri < rows; ri += 2) {
+      long long row;
+      int slot;
+      if (ri < cnt) row = r0 + j0 + ri, slot = ri;
+      else if (ri < 2 * cnt) row = r0 + (n2 - 1 - (j0 + ri - cnt)), slot = S + ri - cnt;
+      else row = r0 + half, slot = 2 * S;
+      cp_async16(dst + slot * 32, xt + row * ld);
+    }
+  };
+  for (int t = 0; t < kMomStages; t++) {
+    if (t < total) issue(t);
+    cp_async_commit();
+  }
+  double c[D], cprev[D];
+#pragma unroll
+  for (int d = 0; d < D; d++) c[d] = 0.0, cprev[d] = 0.0;
+  double2 *mrow = mom + ((long long)blockIdx.x * 32 + lane) * (D / 2) * (long long)n1;
+  for (int t = 0; t < total; t++) {
+    const int q = q_begin + t / nst, k = t - (t / nst) * nst;
+    const int j0 = k * S, cnt = min(S, half - j0);
+    cp_async_wait<kMomStages - 1>();  // this lane's copies of stage t have landed ...
+    __syncwarp();                     // ... and so have the other lanes'
+    const double *st = ring + (size_t)(t % kMomStages) * stage_rows * 32 + lane;
+#pragma unroll 2
+    for (int jj = 0; jj < cnt; jj++) {
+      const double a0 = st[jj * 32], a1 = st[(S + jj) * 32];
+      const double e = a0 + a1, o = a0 - a1;
+      const double2 *t2 = reinterpret_cast<const double2 *>(sT + (j0 + jj) * D);
+#pragma unroll
+      for (int d = 0; d < D; d += 2) {
+        const double2 tt = t2[d / 2];
+        c[d] = fma(tt.x, e, c[d]);
+        c[d + 1] = fma(tt.y, o, c[d + 1]);
+      }
+    }
+    if ((n2 & 1) && k == nst - 1) {
+      const double a0 = st[2 * S * 32];
+#pragma unroll
+      for (int d = 0; d < D; d += 2) c[d] = fma(sT[half * D + d], a0, c[d]);
+    }
+    __syncwarp();  // every lane has read the stage: it may be refilled
+    if (t + kMomStages < total) issue(t + kMomStages);
+    cp_async_commit();
+    if (k == nst - 1) {  // block q complete
+      const bool second = ((q - q_begin) & 1) != 0;
+      if (second) {
+#pragma unroll
+        for (int p = 0; p < D / 2; p++) {
+          double2 *m = mrow + (long long)p * n1 + (q - 1);
+          m[0] = make_double2(cprev[2 * p], cprev[2 * p + 1]);
+          m[1] = make_double2(c[2 * p], c[2 * p + 1]);
+        }
+      } else if (q + 1 >= q_end) {
+#pragma unroll
+        for (int p = 0; p < D / 2; p++) mrow[(long long)p * n1 + q] = make_double2(c[2 * p], c[2 * p + 1]);
+      }
+#pragma unroll
+      for (int d = 0; d < D; d++) cprev[d] = c[d], c[d] = 0.0;
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// One series per block: the D / 2 packed moment sequences are transformed two at a time in shared memory (mixed-radix, in
+// place, loaded straight to their digit-reversed slots; two butterflies per thread and trip, index arithmetic by
+// multiply-high, one twiddle read per butterfly) and folded into the K running sums.
+__global__ void __launch_bounds__(kPrunedThreads, 3) cheb_combine_kernel(const double2 *__restrict__ mom, long long b_lo, int n_passes,
                                                                       const __grid_constant__ PrunedPlan P,
                                                                       const double2 *__restrict__ wtab,  // W_n1^j, j < n1
                                                                       const double2 *__restrict__ ab,    // [n_passes][K]
                                                                       double *__restrict__ out) {
   extern __shared__ double2 sm2[];
   const int n1 = P.n1, K = P.K;
-  double2 *buf = sm2;                                       // [n1]
-  double2 *acc = buf + n1;                                  // [K]
+  double2 *buf = sm2;                                       // [2][n1]
+  double2 *acc = buf + 2 * n1;                              // [K]
   unsigned short *perm = (unsigned short *)(acc + K);       // [n1]
   const int tid = threadIdx.x;
   for (int q = tid; q < n1; q += kPrunedThreads) {
@@ -583,28 +694,36 @@ __global__ void __launch_bounds__(kPrunedThreads) cheb_combine_kernel(const doub
   for (int k = tid; k < K; k += kPrunedThreads) acc[k] = make_double2(0.0, 0.0);
   __syncthreads();
   const double2 *mb = mom + (long long)blockIdx.x * n_passes * n1;
-  for (int p = 0; p < n_passes; p++) {
+  for (int p = 0; p < n_passes; p += 2) {  // n_passes is even (D is a multiple of 4)
     const double2 *z = mb + (long long)p * n1;
-    for (int q = tid; q < n1; q += kPrunedThreads) buf[perm[q]] = __ldcs(z + q);
+    for (int q = tid; q < n1; q += kPrunedThreads) {
+      const int d = perm[q];
+      buf[d] = __ldcs(z + q);
+      buf[n1 + d] = __ldcs(z + n1 + q);
+    }
     __syncthreads();
     int M = 1;
     for (int st = P.n_stages - 1; st >= 0; st--) {
       const int r = P.radix[st];
-      if (r == 4) stage<4>(buf, n1, M, wtab, tid);
-      else if (r == 5) stage<5>(buf, n1, M, wtab, tid);
-      else if (r == 2) stage<2>(buf, n1, M, wtab, tid);
-      else stage<3>(buf, n1, M, wtab, tid);
+      if (r == 4) stage_multi<4, kPrunedThreads>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
+      else if (r == 5) stage_multi<5, kPrunedThreads>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
+      else if (r == 2) stage_multi<2, kPrunedThreads>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
+      else stage_multi<3, kPrunedThreads>(buf, n1, 2, M, P.magic_per[st], P.magic_M[st], wtab, tid);
       M *= r;
       __syncthreads();
     }
     const double2 *abp = ab + (long long)p * K;
     for (int k = tid; k < K; k += kPrunedThreads) {
       const int km = (K > n1) ? k % n1 : k;
-      const double2 zk = buf[km], zm = buf[km == 0 ? 0 : n1 - km];
-      const double2 c = __ldg(abp + k);
+      const int kr = km == 0 ? 0 : n1 - km;
       double2 a = acc[k];
-      a.x = fma(c.x, zk.x, fma(c.y, zm.x, a.x));
-      a.y = fma(c.x, zk.y, fma(-c.y, zm.y, a.y));
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const double2 zk = buf[h * n1 + km], zm = buf[h * n1 + kr];
+        const double2 c = __ldg(abp + (long long)h * K + k);
+        a.x = fma(c.x, zk.x, fma(c.y, zm.x, a.x));
+        a.y = fma(c.x, zk.y, fma(-c.y, zm.y, a.y));
+      }
       acc[k] = a;
     }
     __syncthreads();
@@ -615,14 +734,47 @@ __global__ void __launch_bounds__(kPrunedThreads) cheb_combine_kernel(const doub
 
 template <int D>
 cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long long b_hi, int n1, int n2, const double *Ttab,
-                           double2 *mom, cudaStream_t stream) {
-  const size_t smem = (size_t)((n2 + 1) / 2) * D * sizeof(double);
+                           double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream) {
+  const int rows_T = (n2 + 1) / 2;
+  long long full_tiles = 0;
+  // asynchronous-copy form: whole 32-series tiles whose rows start on 16-byte boundaries
+  if (allow_tma && (ld % 2) == 0 && (reinterpret_cast<uintptr_t>(x + b_lo) % 16) == 0 && n2 >= 4) {
+    const size_t t_bytes = (((size_t)rows_T * D * sizeof(double)) + 127) / 128 * 128;
+    const size_t bar_bytes = 0;
+    const size_t avail = (size_t)max_smem > t_bytes + bar_bytes + 1024 ? (size_t)max_smem - t_bytes - bar_bytes - 1024 : 0;
+    // per warp: kMomStages stages of (2 S + 1) rows of 256 bytes
+    int S = (int)std::min<size_t>(15, (avail / ((size_t)(kMomThreads / 32) * kMomStages * 256) - 1) / 2);
+    const int half = n2 / 2;
+    if (S >= 2) {
+      S = std::min(S, half);
+      const int nst = (half + S - 1) / S;
+      S = (half + nst - 1) / nst;  // even out the stages of a block
+      const size_t smem = t_bytes + (size_t)(kMomThreads / 32) * kMomStages * (2 * S + 1) * 256 + bar_bytes;
+      cudaError_t e = cudaFuncSetAttribute(cheb_moments_async_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      full_tiles = (b_hi - b_lo) / 32;
+      if (full_tiles > 0) {
+        // an even number of blocks per warp, enough warps for every SM: ~4 waves of 148 blocks at least when the slab allows
+        int q_per_warp = 8;
+        while (q_per_warp > 2 && full_tiles * ((n1 + 8 * q_per_warp - 1) / (8 * q_per_warp)) < 4 * 148) q_per_warp -= 2;
+        const dim3 grid((unsigned)full_tiles, (unsigned)((n1 + 8 * q_per_warp - 1) / (8 * q_per_warp)));
+        cheb_moments_async_kernel<D><<<grid, kMomThreads, smem, stream>>>(x + b_lo, ld, n1, n2, S, q_per_warp, Ttab, mom);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        g_launches++;
+      }
+    }
+  }
+  const long long b_rest = b_lo + full_tiles * 32;
+  if (b_rest >= b_hi) return cudaSuccess;
+  const size_t smem = (size_t)rows_T * D * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(cheb_moments_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int n_pairs = (n1 + 1) / 2;
-  const int per_block = 2 * (kMomThreads / 32);  // two block pairs per warp: the table load is amortised over 32 blocks
-  const dim3 grid((unsigned)((b_hi - b_lo + 31) / 32), (unsigned)((n_pairs + per_block - 1) / per_block));
-  cheb_moments_kernel<D><<<grid, kMomThreads, smem, stream>>>(x, ld, b_lo, b_hi, n1, n2, per_block, Ttab, mom);
+  const int per_block = 4 * (kMomThreads / 32);  // four blocks of samples per warp: the table load is amortised over 32 of them
+  const dim3 grid((unsigned)((b_hi - b_rest + 31) / 32), (unsigned)((n1 + per_block - 1) / per_block));
+  cheb_moments_kernel<D><<<grid, kMomThreads, smem, stream>>>(x, ld, b_rest, b_hi, n1, n2, per_block, Ttab,
+                                                              mom + full_tiles * 32 * (D / 2) * (long long)n1);
+  g_launches++;
   return cudaGetLastError();
 }
 
@@ -661,13 +813,151 @@ void unit_roots(long long m, long long count, std::vector<double2> &w) {
 
 using namespace cmtjb;
 
+extern "C" int cmtjb_rfft_abs_device_ws(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
+                                        void *stream_, void *workspace, int64_t workspace_bytes);
+
+namespace {
+// device tables of the moment plans used so far (a sweep procedure calls with the same shape again and again)
+struct MomentTables {
+  int device;
+  long long n, K, pinned_n2;
+  bool found;
+  MomentPlan M;
+  double *d_T;
+  double2 *d_ab, *d_w;
+};
+std::mutex g_mom_mu;
+std::vector<MomentTables> g_mom_tables;
+
+// plan + tables for (n, K) on `device`, built on first use; nullptr when the moment path does not apply
+const MomentTables *moment_tables_for(long long n, long long K, int device, int max_smem, cudaError_t *err) {
+  *err = cudaSuccess;
+  long long pinned = 0;
+  if (const char *c = std::getenv("CMTJB_SPECTRUM_N2")) pinned = std::atoll(c);
+  std::lock_guard<std::mutex> lock(g_mom_mu);
+  for (const MomentTables &t : g_mom_tables)
+    if (t.device == device && t.n == n && t.K == K && t.pinned_n2 == pinned) return t.found ? &t : nullptr;
+  MomentTables t;
+  std::memset(&t, 0, sizeof(t));
+  t.device = device, t.n = n, t.K = K, t.pinned_n2 = pinned;
+  t.found = n >= 512 && K >= 1 && plan_moments(n, K, (size_t)max_smem, &t.M);
+  if (t.found) {
+    std::vector<double> T;
+    std::vector<double2> ab, wt;
+    moment_tables(n, t.M, T, ab);
+    unit_roots(t.M.fft.n1, t.M.fft.n1, wt);
+    cudaError_t e = cudaMalloc((void **)&t.d_T, T.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&t.d_ab, ab.size() * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&t.d_w, wt.size() * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMemcpy(t.d_T, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t.d_ab, ab.data(), ab.size() * sizeof(double2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t.d_w, wt.data(), wt.size() * sizeof(double2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(t.d_T), cudaFree(t.d_ab), cudaFree(t.d_w);
+      *err = e;
+      return nullptr;
+    }
+  }
+  if (g_mom_tables.size() >= 8) {  // oldest out; its kernels may still be running
+    cudaDeviceSynchronize();
+    cudaFree(g_mom_tables.front().d_T), cudaFree(g_mom_tables.front().d_ab), cudaFree(g_mom_tables.front().d_w);
+    g_mom_tables.erase(g_mom_tables.begin());
+  }
+  g_mom_tables.reserve(9);  // pointers into the vector stay valid while at most 8 + 1 entries live
+  g_mom_tables.push_back(t);
+  return t.found ? &g_mom_tables.back() : nullptr;
+}
+
+bool moments_wanted() {
+  const char *force = std::getenv("CMTJB_SPECTRUM");
+  return !force || force[0] == 'm' || force[0] == '\0';
+}
+}  // namespace
+
+extern "C" int cmtjb_rfft_abs_workspace(int64_t n, int64_t K, int device, int64_t *bytes_per_series) {
+  if (!bytes_per_series || n <= 0 || K < 0) return fail(CMTJB_EINVAL, "bad argument");
+  *bytes_per_series = 0;
+  if (K == 0 || !moments_wanted()) return CMTJB_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaError_t e;
+  const MomentTables *t = moment_tables_for(n, K, device, max_smem, &e);
+  if (e != cudaSuccess) return cuda_fail(e, "moment tables");
+  if (t) *bytes_per_series = (int64_t)(t->M.D / 2) * t->M.fft.n1 * (int64_t)sizeof(double2);
+  return CMTJB_OK;
+}
+
 extern "C" int cmtjb_rfft_abs_device(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
                                      void *stream_) {
+  return cmtjb_rfft_abs_device_ws(x, n, B, ld, K, out, device, stream_, nullptr, 0);
+}
+
+extern "C" int cmtjb_rfft_abs_device_ws(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
+                                        void *stream_, void *workspace, int64_t workspace_bytes) {
   if (!x || !out || n <= 0 || B <= 0 || ld < B || K < 0 || K > n / 2 + 1) return fail(CMTJB_EINVAL, "bad argument");
   if (K == 0) return CMTJB_OK;
   if (n > (1LL << 30) || ld > (1LL << 30)) return fail(CMTJB_ENOTSUP, "series too long for the 32-bit cuFFT plan interface");
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (moments_wanted()) {
+    // strongly pruned spectra (K << n / 2): Chebyshev moments of blocks of consecutive samples, then short transforms of
+    // the moments (see cheb_moments_kernel).  CMTJB_SPECTRUM=moments or unset: used where a plan exists; any other value skips it.
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaError_t e;
+    const MomentTables *mt = moment_tables_for(n, K, device, max_smem, &e);
+    if (e != cudaSuccess) return cuda_fail(e, "moment tables");
+    if (mt) {
+      const MomentPlan &M = mt->M;
+      const int n1 = M.fft.n1, n2 = M.fft.n2, D = M.D, Pn = D / 2;
+      const char *tma_env = std::getenv("CMTJB_SPECTRUM_TMA");  // =0: register-staged moments kernel only
+      const bool allow_tma = !(tma_env && tma_env[0] == '0');
+      // slab of series whose packed moments fit the caller's workspace, else an allocation of this call
+      // (CMTJB_SPECTRUM_SLAB_MB; default: a quarter of the free memory, <= 2 GiB)
+      const size_t per_series = (size_t)Pn * n1 * sizeof(double2);
+      double2 *d_mom = reinterpret_cast<double2 *>(workspace);
+      size_t budget = (size_t)std::max<int64_t>(0, workspace_bytes);
+      const bool own = !workspace || budget < per_series || (reinterpret_cast<uintptr_t>(workspace) % 32) != 0;
+      if (own) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        budget = std::min<size_t>(free_b / 4, (size_t)2 << 30);
+        if (const char *c = std::getenv("CMTJB_SPECTRUM_SLAB_MB")) budget = (size_t)std::max(1, std::atoi(c)) << 20;
+      }
+      long long slab = (long long)std::max<size_t>(1, budget / per_series);
+      if (slab >= 32) slab = slab / 32 * 32;
+      slab = std::min<long long>(slab, B);
+      if (own) {
+        d_mom = nullptr;
+        e = cudaMallocAsync((void **)&d_mom, (size_t)slab * per_series, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(moment slab)");
+      }
+      const double *d_T = mt->d_T;
+      const size_t smem_c = (2 * (size_t)n1 + (size_t)K) * sizeof(double2) + (size_t)n1 * sizeof(unsigned short) + 16;
+      e = cudaFuncSetAttribute(cheb_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+      for (long long b_lo = 0; b_lo < B && e == cudaSuccess; b_lo += slab) {
+        const long long b_hi = std::min<long long>(B, b_lo + slab);
+        switch (D) {
+        case 4: e = launch_moments<4>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        case 8: e = launch_moments<8>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        case 12: e = launch_moments<12>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        case 16: e = launch_moments<16>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        case 20: e = launch_moments<20>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        case 24: e = launch_moments<24>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        case 28: e = launch_moments<28>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        default: e = launch_moments<32>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
+        }
+        if (e != cudaSuccess) break;
+        cheb_combine_kernel<<<(unsigned)(b_hi - b_lo), kPrunedThreads, smem_c, stream>>>(d_mom, b_lo, Pn, M.fft, mt->d_w, mt->d_ab, out);
+        g_launches++;
+        e = cudaGetLastError();
+      }
+      if (own && d_mom) cudaFreeAsync(d_mom, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "cheb_moments_kernel / cheb_combine_kernel");
+      return CMTJB_OK;
+    }
+  }
   {
     // single pass over the buffer when n factors suitably: four instances per block (pruned_dft4_kernel) when its shared
     // memory fits, else one (pruned_dft_kernel); CMTJB_SPECTRUM=cufft forces the library path, =single the one-instance kernel
@@ -677,6 +967,7 @@ extern "C" int cmtjb_rfft_abs_device(const double *x, int64_t n, int64_t B, int6
     const bool want_grouped = !(force && force[0] == 's');
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (force && force[0] == 'm') force = nullptr;
     bool grouped = false;
     size_t smem = 0;
     if (want && want_grouped && n >= 64 && plan_grouped(n, K, kGSlots * kGThreads / kG, &P) && (long long)P.n1 * 8 >= K) {

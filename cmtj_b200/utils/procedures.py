@@ -108,12 +108,31 @@ def spectrum_device(signal, int_step: float, max_frequency: float):
     if K == 0 or B == 0:
         return out, freqs
     be = _abi.cuda_backend()
-    f = be.lib.cmtjb_rfft_abs_device
+    dev = signal.device.index or 0
+    q = be.lib.cmtjb_rfft_abs_workspace
+    q.restype = C.c_int
+    q.argtypes = [C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+    per_series = C.c_int64(0)
+    be.check(q(n, K, dev, C.byref(per_series)))
+    ws, ws_ptr, ws_bytes = None, None, 0
+    import os
+
+    if per_series.value > 0 and not os.environ.get("CMTJB_SPECTRUM_NO_WS"):
+        # moments of a slab of series: from torch's caching allocator, so that a sweep's repeated calls do not allocate;
+        # a quarter of the free memory, at most 2 GiB, at least 1024 series where that fits
+        free_b = torch.cuda.mem_get_info(signal.device)[0]
+        cap = max(min(free_b // 4, 2 << 30), min(free_b // 2, 1024 * per_series.value))
+        if os.environ.get("CMTJB_SPECTRUM_SLAB_MB"):
+            cap = int(os.environ["CMTJB_SPECTRUM_SLAB_MB"]) << 20
+        slab = max(1, min(B, cap // per_series.value))
+        ws = torch.empty(slab * per_series.value, dtype=torch.uint8, device=signal.device)
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+    f = be.lib.cmtjb_rfft_abs_device_ws
     f.restype = C.c_int
-    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
     ld = int(signal.stride(0)) if n > 1 else B
     stream = torch.cuda.current_stream(signal.device).cuda_stream
-    be.check(f(signal.data_ptr(), n, B, ld, K, out.data_ptr(), signal.device.index or 0, C.c_void_p(stream)))
+    be.check(f(signal.data_ptr(), n, B, ld, K, out.data_ptr(), dev, C.c_void_p(stream), ws_ptr, ws_bytes))
     return out, freqs
 
 
@@ -259,7 +278,7 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
     # static resistance over the last samples, from the thickness*Ms-weighted m (procedures.py:152-162)
     if kind is not None:
         Rx, Ry = _res.strip_resistance_device(res_rows, m_last, kind, weights=weights, device=device)
-        out["Rx"], out["Ry"] = Rx.cpu().numpy().T, Ry.cpu().numpy().T  # [B, n_last]
+        out["Rx"], out["Ry"] = _to_host(Rx.t().contiguous()), _to_host(Ry.t().contiguous())  # [B, n_last]
     else:
         mh = (m_last.reshape(L, 3, n_last, B) * w_dev[:, None, None, None]).cpu().numpy()
         rx, ry = [], []
@@ -273,8 +292,8 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
             ry.append(b)
         out["Rx"], out["Ry"] = np.asarray(rx), np.asarray(ry)
     final = m_last[:, -1, :].reshape(L, 3, B)
-    out["m_avg"] = (final * w_dev[:, None, None]).sum(0).cpu().numpy().T  # [B,3]
-    out["m_final"] = final.cpu().numpy()  # [L,3,B]
+    out["m_avg"] = _to_host((final * w_dev[:, None, None]).sum(0).t().contiguous())  # [B,3]
+    out["m_final"] = _to_host(final.contiguous())  # [L,3,B]
     ph.mark("static resistances + final state to the host")
     if not static_only:
         time = np.arange(n_total, dtype=np.float64) * float(int_step)

@@ -329,10 +329,19 @@ int cmtjb_compute_gmr_device(double Rp, double Rap, const double *m1, const doub
 
 /* compute_spectrum_strip (cmtj/utils/procedures.py:29-40) for B series at once: x is DEVICE, time-major,
  * x[t * ld + b] for t < n, b < B (the projection log of cmtjb_run_device_post, or any row range of it);
- * out (DEVICE, [B][K]) receives |FFT(x_b)[k]| for the K lowest bins, K <= n/2 + 1.  Double-precision cuFFT over
- * column slices, no transposed copy of the input. */
+ * out (DEVICE, [B][K]) receives |FFT(x_b)[k]| for the K lowest bins, K <= n/2 + 1, in double precision.
+ * Strongly pruned spectra (K << n/2, the sweep-procedure case) reduce blocks of consecutive samples to Chebyshev
+ * moments in one pass over x and transform the moments (truncation below 2e-17 of the series' l1 norm); otherwise a
+ * single-pass pruned mixed-radix transform when n factors into 2, 3, 4, 5, else cuFFT over column slices.  No
+ * transposed copy of the input in any case. */
 int cmtjb_rfft_abs_device(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
                           void *stream);
+/* The same with a caller-owned DEVICE workspace (32-byte aligned) for the moments of a slab of series, so that repeated
+ * calls do not allocate: cmtjb_rfft_abs_workspace reports the bytes one series needs (0: this (n, K) takes a path that
+ * needs no workspace); any multiple of it is accepted, series are processed workspace_bytes / bytes_per_series at a time. */
+int cmtjb_rfft_abs_workspace(int64_t n, int64_t K, int device, int64_t *bytes_per_series);
+int cmtjb_rfft_abs_device_ws(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
+                             void *stream, void *workspace, int64_t workspace_bytes);
 
 /* Number of kernels this library has launched in this process (monotonic). */
 long long cmtjb_launch_count(void);
@@ -444,6 +453,20 @@ int cmtjb_group_run_host(const cmtjb_group_t *g, const cmtjb_junction_t *jns, co
 int cmtjb_group_run_device(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
                            const cmtjb_override_t *overrides, int32_t n_overrides, const cmtjb_run_args_t *args,
                            double *m_state, double *junction_log, int32_t *status, int device, void *stream);
+
+/* One dipole-coupled array sharded over `world` ranks, one process per GPU (reservoir.hpp:129-152 with the elements
+ * split into contiguous ranges of ceil(n_junctions / world)): this rank integrates its own elements and, after the
+ * initial state (step = -1) and after every step, calls `exchange` to all-gather the top-layer magnetisations in place:
+ * buf is a DEVICE buffer [world][count] doubles whose slice `rank` this rank has just written on `stream`; the callback
+ * must enqueue the all-gather on that stream (NCCL: ncclAllGather(buf + rank*count, buf, count, ncclDouble, comm, stream))
+ * and return 0.  g / jns / layers describe the WHOLE array on every rank; m_state [3*n_layers][own], junction_log
+ * [channels][n_samples][own] and status [own] are DEVICE pointers sized for this rank's elements.  The pair sums are
+ * accumulated in an order that depends on n_junctions alone, so the result is bit-identical for every world size.
+ * args->n_instances must be 1; thermal noise is keyed by the global element index; 1/f noise is not supported here. */
+typedef int (*cmtjb_exchange_fn)(void *ctx, double *buf, int64_t count, int64_t step, void *stream);
+int cmtjb_group_run_sharded(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                            const cmtjb_run_args_t *args, int32_t rank, int32_t world, cmtjb_exchange_fn exchange, void *ctx,
+                            double *m_state, double *junction_log, int32_t *status, int device, void *stream);
 
 /* RNG test hooks.  cmtjb_philox_host: one Philox4x32-10 block for counter ctr[4] / key key[2]
  * (known-answer tests).  cmtjb_normals_host: the N(0,1) triples the stochastic steppers draw for

@@ -177,7 +177,13 @@ def test_spectrum_strip_matches_scipy(on_cuda):
 
 
 @pytest.mark.parametrize("n,B,K_freq,pitch,mode", [
-    (200000, 9, 80e9, 0, ""),        # PIMM shape: n1 = 2000 >= K = 1601, four instances per block, ragged last group
+    (200000, 9, 80e9, 0, ""),        # PIMM shape, K = 1601 of 100 001 bins: Chebyshev moments of 100-sample blocks, 2000-point transforms
+    (200000, 70, 80e9, 2, "moments:250"),  # blocks of 250: transforms of 800 points < K (aliased index), D = 32, more than one 32-series tile
+    (200000, 5, 10e9, 0, "moments:40:nows"),  # K = 201, short blocks; the library allocates the moment slab itself
+    (6561, 3, 1e11, 0, "moments:27"),      # odd block length (middle sample), radix-3 transforms
+    (6561, 40, 1e11, 0, "moments:27"),     # the same through the bulk-copy kernel (one whole 32-series tile) + 8 ragged series
+    (200000, 33, 80e9, 1, "moments"),      # odd pitch: rows are not 16-byte aligned, register-staged kernel only
+    (200000, 9, 80e9, 0, "grouped"), # single pass, n1 = 2000 >= K = 1601, four instances per block, ragged last group
     (8000, 5, 400e9, 3, ""),         # a row view with a pitch, K = 320
     (4096, 4, 4e12, 0, ""),          # K = 1639 of a power of two
     (10000, 3, 2.0995e12, 0, ""),    # K = 2100 > n1 = 2000: aliased first-stage index
@@ -192,7 +198,12 @@ def test_spectrum_device_shapes(on_cuda, monkeypatch, n, B, K_freq, pitch, mode)
     import torch
 
     if mode:
-        monkeypatch.setenv("CMTJB_SPECTRUM", mode)
+        monkeypatch.setenv("CMTJB_SPECTRUM", mode.split(":")[0])
+        if ":" in mode:
+            monkeypatch.setenv("CMTJB_SPECTRUM_N2", mode.split(":")[1])
+            if mode.endswith(":nows"):
+                monkeypatch.setenv("CMTJB_SPECTRUM_NO_WS", "1")
+            monkeypatch.setenv("CMTJB_SPECTRUM_SLAB_MB", "8")  # several slabs
     rng = np.random.default_rng(n + B)
     t = np.arange(n)[:, None]
     x = rng.normal(size=(n, B)) + 3.0 * np.sin(2 * np.pi * t * (7.25 + np.arange(B)[None, :]) / n) + 0.5
