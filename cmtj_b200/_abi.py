@@ -251,6 +251,10 @@ def raise_for_status(rc: int, message: str) -> None:
     raise RuntimeError(message)
 
 
+# cmtjb_exchange_fn (include/cmtj_b200.h): (ctx, buf, count, step, stream) -> 0 on success
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p)
+
+
 class Backend:
     """Uniform view over a shared library exporting the run/plan entry points.
 
@@ -332,6 +336,19 @@ class Backend:
         return f(
             C.byref(g), C.cast(jns, C.c_void_p), C.cast(layers, C.c_void_p), C.cast(overrides, C.c_void_p), n_overrides,
             C.byref(args), self._ptr(m_state), self._ptr(jlog), self._ptr(status), *extra,
+        )  # fmt: skip
+
+    def group_run_sharded(self, g, jns, layers, args, rank, world, exchange, m_state_ptr, jlog_ptr, status_ptr, device=0, stream=0) -> int:
+        """``cmtjb_group_run_sharded``: one rank of a dipole array split over ``world`` processes.  The state / log /
+        status arguments are raw addresses (device memory for the CUDA library); ``exchange`` is an ``EXCHANGE_FN``."""
+        f = self._fn(
+            "group_run_sharded",
+            [_P(Group), C.c_void_p, C.c_void_p, _P(RunArgs), C.c_int32, C.c_int32, EXCHANGE_FN, C.c_void_p]
+            + [C.c_void_p] * 3 + [C.c_int, C.c_void_p],
+        )  # fmt: skip
+        return f(
+            C.byref(g), C.cast(jns, C.c_void_p), C.cast(layers, C.c_void_p), C.byref(args), int(rank), int(world), exchange, None,
+            C.c_void_p(m_state_ptr), C.c_void_p(jlog_ptr), C.c_void_p(status_ptr), int(device), C.c_void_p(stream),
         )  # fmt: skip
 
     def last_error(self) -> str:

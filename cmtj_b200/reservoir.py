@@ -124,6 +124,117 @@ class GroupInteraction:
             _coupled.write_back(self.junctionList, m, jlog[:, :ns, :], times)
         be.check(rc)
 
+    def run_sharded(
+        self,
+        totalTime: float,
+        timeStep: float = 1e-13,
+        writeFrequency: float = 1e-11,
+        rank: Optional[int] = None,
+        world: Optional[int] = None,
+        device: Optional[int] = None,
+        seed: Optional[int] = None,
+        exchange: Optional[Callable] = None,
+        gather: bool = True,
+        _host_memory: bool = False,
+    ) -> Dict[str, np.ndarray]:
+        """``runSimulation`` for an array split over the ranks of a ``torch.distributed`` job, one process per GPU
+        (core/reservoir.hpp:129-152 with the element loop cut into contiguous ranges of ceil(N / world)).  Every rank
+        constructs the SAME GroupInteraction and calls this; rank r integrates its own elements and the top-layer
+        magnetisations are all-gathered once per step (NCCL, in place on the device, stream-ordered: no host
+        synchronisation inside the time loop).  The pair sums are accumulated in an order that depends on N alone, so
+        the trajectories are bit-identical for every world size.
+
+        ``exchange(buf_address, count, step, stream_address) -> 0`` replaces the collective (tests, other transports).
+        With ``gather`` every rank ends up with all junction logs, as after the reference's runSimulation; without it
+        only this rank's junctions are written back.  Returns this rank's ``{"lo", "hi", "m_state", "log"}``."""
+        import os
+
+        from .sweep import _dist
+
+        be = _abi.backend()
+        dist = _dist()
+        rank = int(rank if rank is not None else (dist.get_rank() if dist else int(os.environ.get("RANK", 0))))
+        world = int(world if world is not None else (dist.get_world_size() if dist else int(os.environ.get("WORLD_SIZE", 1))))
+        dev = int(device if device is not None else os.environ.get("LOCAL_RANK", 0))
+        if seed is None:
+            box = [_coupled._next_seed() if rank == 0 else None]
+            if dist is not None and world > 1:
+                dist.broadcast_object_list(box, src=0)  # one Philox key for the whole array
+            seed = box[0] if box[0] is not None else 0
+        g, jns, layers, nl, xyz = self._pack()
+        a = _coupled.run_args(totalTime, timeStep, writeFrequency, 1, seed=seed)
+        plan = be.group_plan(g, jns, layers, a)
+        if plan.solver_overridden and rank == 0:
+            print("[WARNING] Solver automatically changed to Euler Heun for stochastic calculation.")
+        N, ns, ch = self.noElements, int(plan.n_samples), int(plan.n_junction_channels)
+        per = -(-N // world)
+        lo = min(N, rank * per)
+        hi = min(N, lo + per)
+        own = hi - lo
+        m_host = np.ascontiguousarray(_coupled.initial_state(self.junctionList, 1)[:, lo:hi])
+        if _host_memory:  # a host-memory stand-in for the library (CPU tests of this plumbing)
+            torch = None
+            m_dev, jlog_dev = m_host, np.zeros((ch, max(ns, 1), max(own, 1)), dtype=np.float64)
+            st_dev = np.zeros(max(own, 1), dtype=np.int32)
+            addr = lambda t: t.ctypes.data  # noqa: E731
+            stream_ptr = 0
+        else:
+            import torch
+
+            tdev = torch.device("cuda", dev)
+            stream = torch.cuda.Stream(tdev)
+            stream_ptr = stream.cuda_stream
+            with torch.cuda.stream(stream):
+                m_dev = torch.from_numpy(m_host).to(tdev)
+                jlog_dev = torch.zeros((ch, max(ns, 1), max(own, 1)), dtype=torch.float64, device=tdev)
+                st_dev = torch.zeros(max(own, 1), dtype=torch.int32, device=tdev)
+            addr = lambda t: t.data_ptr()  # noqa: E731
+        failure: List[BaseException] = []
+        if exchange is None:
+            exchange = _collective_exchange(dist, rank, world, None if _host_memory else dev)
+
+        def _cb(ctx, buf, count, step, stream_arg):
+            try:
+                return int(exchange(buf, int(count), int(step), stream_arg or 0) or 0)
+            except BaseException as e:  # an exception must not unwind through the C frames
+                failure.append(e)
+                return 1
+
+        cb = _abi.EXCHANGE_FN(_cb)
+        rc = be.group_run_sharded(g, jns, layers, a, rank, world, cb, addr(m_dev), addr(jlog_dev), addr(st_dev), dev, stream_ptr)
+        if failure:
+            raise failure[0]
+        if torch is not None:
+            stream.synchronize()
+            m_own, jlog_own = m_dev.cpu().numpy(), jlog_dev.cpu().numpy()[:, :ns, :own]
+        else:
+            m_own, jlog_own = m_dev, jlog_dev[:, :ns, :own]
+        times = _coupled.sample_times(plan, timeStep)[:ns]
+        ok = rc in (_abi.OK, _abi.ENAN)
+        if ok and gather and world > 1:
+            if dist is None:
+                raise RuntimeError("gather=True needs an initialised torch.distributed job")
+            import torch as _t
+
+            rows = np.zeros((3 * nl + ch * ns, per), dtype=np.float64)
+            rows[: 3 * nl, :own] = m_own
+            rows[3 * nl :, :own] = jlog_own.reshape(ch * ns, own)
+            t = _t.from_numpy(rows)
+            if dist.get_backend() == "nccl":
+                t = t.to(_t.device("cuda", dev))
+            parts = [_t.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            for r, part in enumerate(parts):
+                r_lo = min(N, r * per)
+                r_hi = min(N, r_lo + per)
+                if r_hi > r_lo:
+                    pr = part.cpu().numpy()[:, : r_hi - r_lo]
+                    _coupled.write_back(self.junctionList[r_lo:r_hi], pr[: 3 * nl], pr[3 * nl :].reshape(ch, ns, r_hi - r_lo), times)
+        elif ok and own > 0:
+            _coupled.write_back(self.junctionList[lo:hi], m_own, jlog_own, times)
+        be.check(rc)
+        return {"lo": lo, "hi": hi, "m_state": m_own, "log": jlog_own, "time": times}
+
     def run_batch(
         self,
         n_instances: int,
@@ -165,3 +276,50 @@ class GroupInteraction:
             for ch, name in enumerate(self.junctionList[0]._channel_names()):
                 out[name] = jl[ch]
         return out
+
+
+class _DeviceSpan:
+    """A raw device address as a ``__cuda_array_interface__`` object (float64, 1-D), so that torch can view it."""
+
+    def __init__(self, address: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(address), False), "version": 2}
+
+
+def _collective_exchange(dist, rank: int, world: int, device: Optional[int]):
+    """The default ``cmtjb_exchange_fn``: an in-place all-gather of the [world][count] exchange buffer over
+    ``torch.distributed`` -- NCCL on the library's stream for device buffers (``device`` given), the job's CPU backend
+    for host buffers.  A single rank has nothing to exchange."""
+    if world == 1:
+        return lambda buf, count, step, stream: 0
+    if dist is None:
+        raise RuntimeError("a sharded array over more than one rank needs an initialised torch.distributed job")
+    import ctypes as C
+
+    import torch
+
+    if device is None:
+
+        def host_exchange(buf, count, step, stream):
+            full = torch.from_numpy(np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(world * count,)))
+            parts = [torch.empty(count, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(parts, full[rank * count : (rank + 1) * count].clone())
+            for r, p in enumerate(parts):
+                full[r * count : (r + 1) * count] = p
+            return 0
+
+        return host_exchange
+
+    tdev = torch.device("cuda", device)
+    cache: Dict[tuple, tuple] = {}
+
+    def device_exchange(buf, count, step, stream):
+        key = (buf, count, stream)
+        if key not in cache:
+            full = torch.as_tensor(_DeviceSpan(buf, world * count), device=tdev)
+            cache[key] = (full, full[rank * count : (rank + 1) * count], torch.cuda.ExternalStream(stream, device=tdev))
+        full, mine, ext = cache[key]
+        with torch.cuda.stream(ext):
+            dist.all_gather_into_tensor(full, mine)  # in place: NCCL's sendbuff == recvbuff + rank * count case
+        return 0
+
+    return device_exchange

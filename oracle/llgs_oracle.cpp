@@ -1022,4 +1022,97 @@ int oracle_group_run_host(const cmtjb_group_t *g, const cmtjb_junction_t *jns, c
   return CMTJB_OK;
 }
 
+/* The sharded form of cmtjb_group_run_sharded (include/cmtj_b200.h) with HOST pointers: rank `rank` steps elements
+ * [rank*per, rank*per + own) of reservoir.hpp:129-152's loop and reads every partner's top-layer magnetisation from the
+ * exchange buffer [world][3][per] that `exchange` all-gathers after each step.  Stand-in for the device library in the
+ * world_size-2 gloo test of the host-side plumbing (tests/test_sharded_group.py); `device` and `stream` are ignored. */
+typedef int (*oracle_exchange_fn)(void *ctx, double *buf, int64_t count, int64_t step, void *stream);
+int oracle_group_run_sharded(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                             const cmtjb_run_args_t *args, int32_t rank, int32_t world, oracle_exchange_fn exchange, void *ctx,
+                             double *m_state, double *jlog, int32_t *status, int device, void *stream) {
+  (void)device;
+  if (!exchange || world < 1 || rank < 0 || rank >= world) return fail(CMTJB_EINVAL, "bad rank / world / exchange callback");
+  if (!args || args->n_instances != 1) return fail(CMTJB_EINVAL, "a sharded array is one instance");
+  cmtjb_coupled_plan_t plan;
+  int rc = oracle_group_plan(g, jns, layers, args, &plan);
+  if (rc) return rc;
+  const int N = g->n_junctions, nl = plan.n_layers, top = g->top_layer;
+  const int per = (N + world - 1) / world;
+  const int e_lo = std::min(N, rank * per), e_hi = std::min(N, e_lo + per), own = e_hi - e_lo;
+  const int64_t NS = plan.n_samples;
+  const bool do_log = args->log_mode == CMTJB_LOG_FULL && jlog;
+  /* the whole array is built so that partners carry their Ms / thickness / surface; only own elements hold real state */
+  std::vector<double> m_all((size_t)nl * 3 * N, 0.0);
+  for (int r = 0; r < nl * 3; r++)
+    for (int a = 0; a < own; a++) m_all[(size_t)r * N + e_lo + a] = m_state[(size_t)r * own + a];
+  SystemSim S;
+  rc = build_system(N, jns, layers, nullptr, 0, args, m_all.data(), N, 0, S);
+  if (rc) return rc;
+  std::vector<double> xbuf((size_t)world * 3 * per, 0.0);
+  auto publish = [&]() {
+    for (int a = 0; a < own; a++) {
+      const V3 m = S.j[e_lo + a].layers[top].mag;
+      double *q = xbuf.data() + (size_t)rank * 3 * per + a;
+      q[0] = m.x, q[per] = m.y, q[2 * per] = m.z;
+    }
+  };
+  auto absorb = [&]() {
+    for (int b = 0; b < N; b++) {
+      if (b >= e_lo && b < e_hi) continue;
+      const double *q = xbuf.data() + (size_t)(b / per) * 3 * per + (b % per);
+      S.j[b].layers[top].mag = v3(q[0], q[per], q[2 * per]);
+    }
+  };
+  publish();
+  if (exchange(ctx, xbuf.data(), (int64_t)3 * per, -1, stream)) return fail(CMTJB_ERUNTIME, "exchange callback failed");
+  absorb();
+  int64_t sample = 0;
+  bool nan = false;
+  const double dt = args->timeStep;
+  for (int64_t i = args->start_iteration; i < plan.total_iterations; i++) {
+    const double t = i * dt;
+    for (int a = e_lo; a < e_hi && !nan; a++) {
+      V3 H = v3(0, 0, 0);
+      for (int b = 0; b < N; b++) {
+        if (a == b) continue;
+        const V3 ra = arr3(g->coordinates + 3 * a), rb = arr3(g->coordinates + 3 * b);
+        const LayerSim &lb = S.j[b].layers[top];
+        if (g->interaction == CMTJB_INT_DIPOLE) H = H + dipole_kanao(ra, rb, lb);
+        else if (g->interaction == CMTJB_INT_DIPOLE_NOMURA) H = H + dipole_nomura(ra, rb, lb);
+      }
+      LayerSim &la = S.j[a].layers[top];
+      const double h[3] = {H.x, H.y, H.z};
+      for (int c = 0; c < 3; c++) {
+        cmtjb_driver_t &d = la.drv[CMTJB_SLOT_HRES_X + c];
+        std::memset(&d, 0, sizeof(d));
+        d.update = CMTJB_UPD_CONSTANT;
+        d.constantValue = h[c];
+      }
+    }
+    for (int a = e_lo; a < e_hi && !nan; a++)
+      if (!step_junction(S.j[a], S.solver, t, dt, i)) nan = true;
+    if (!(i % plan.write_every)) {
+      if (do_log && !nan)
+        for (int a = 0; a < own; a++) write_sample(S.j[e_lo + a], jlog, NS, own, sample, a);
+      sample++;
+    }
+    /* every rank keeps calling the collective for the full run, NaN or not (the others are waiting in it) */
+    publish();
+    if (exchange(ctx, xbuf.data(), (int64_t)3 * per, i, stream)) return fail(CMTJB_ERUNTIME, "exchange callback failed");
+    absorb();
+  }
+  for (int l = 0; l < nl; l++)
+    for (int a = 0; a < own; a++) {
+      const V3 m = S.j[e_lo + a].layers[l].mag;
+      m_state[(size_t)(l * 3 + 0) * own + a] = m.x;
+      m_state[(size_t)(l * 3 + 1) * own + a] = m.y;
+      m_state[(size_t)(l * 3 + 2) * own + a] = m.z;
+    }
+  for (int a = 0; a < own; a++)
+    if (status) status[a] = nan ? 1 : 0;
+  if (nan) return fail(CMTJB_ENAN, "NAN magnetisation");
+  return CMTJB_OK;
+}
+
+
 } /* extern "C" */
