@@ -517,7 +517,7 @@ void moment_tables(long long n, const MomentPlan &M, std::vector<double> &T, std
 // a sector come from neighbouring warps of one block and merge in L2.
 template <int D>
 __global__ void __launch_bounds__(kMomThreads, (D > 24 ? 2 : 3)) cheb_moments_kernel(const double *__restrict__ x, long long ld, long long b_lo,
-                                                                      long long b_hi, int n1, int n2, int q_per_block,
+                                                                      long long b_hi, int n1, int n2, int q0, int nq, int q_per_block,
                                                                       const double *__restrict__ Ttab, double2 *__restrict__ mom) {
   extern __shared__ double sT[];  // [(n2 + 1) / 2][D]
   const int rows = (n2 + 1) / 2;
@@ -528,8 +528,8 @@ __global__ void __launch_bounds__(kMomThreads, (D > 24 ? 2 : 3)) cheb_moments_ke
   if (b >= b_hi) return;
   const int half = n2 / 2;
   for (int it = 0; it < q_per_block; it += kMomThreads / 32) {
-    const int q = blockIdx.y * q_per_block + it + warp;
-    if (q >= n1) break;
+    const int q = blockIdx.y * q_per_block + it + warp;  // relative to the chunk: x's row 0 is the first sample of block q0
+    if (q >= nq) break;
     const double *lo = x + (long long)n2 * q * ld + b;
     const double *hi = lo + (long long)(n2 - 1) * ld;
     double c[D];
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kMomThreads, (D > 24 ? 2 : 3)) cheb_moments_ke
 #pragma unroll
       for (int d = 0; d < D; d += 2) c[d] = fma(sT[half * D + d], a0, c[d]);
     }
-    double2 *m = mom + ((b - b_lo) * (D / 2)) * (long long)n1 + q;
+    double2 *m = mom + ((b - b_lo) * (D / 2)) * (long long)n1 + q0 + q;
 #pragma unroll
     for (int p = 0; p < D / 2; p++) m[(long long)p * n1] = make_double2(c[2 * p], c[2 * p + 1]);
   }
@@ -579,8 +579,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <int D>
 __global__ void __launch_bounds__(kMomThreads, 1) cheb_moments_async_kernel(const double *__restrict__ x, long long ld, int n1, int n2,
-                                                                            int S, int q_per_warp, const double *__restrict__ Ttab,
-                                                                            double2 *__restrict__ mom) {
+                                                                            int q0, int nq, int S, int q_per_warp,
+                                                                            const double *__restrict__ Ttab, double2 *__restrict__ mom) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const int rows_T = (n2 + 1) / 2;
   const int stage_rows = 2 * S + 1;
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kMomThreads, 1) cheb_moments_async_kernel(cons
   const int half = n2 / 2;
   const int nst = (half + S - 1) / S;  // stages per block of samples
   const int q_begin = (blockIdx.y * (kMomThreads / 32) + warp) * q_per_warp;
-  const int q_end = min(n1, q_begin + q_per_warp);
+  const int q_end = min(nq, q_begin + q_per_warp);  // block indices relative to the chunk (q0 is even: pairs stay sector-aligned)
   if (q_begin >= q_end) return;
   const int total = (q_end - q_begin) * nst;
   const double *xt = x + (long long)blockIdx.x * 32 + 2 * (lane & 15);  // this lane's 16 bytes of the tile's rows
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(kMomThreads, 1) cheb_moments_async_kernel(cons
   double c[D], cprev[D];
 #pragma unroll
   for (int d = 0; d < D; d++) c[d] = 0.0, cprev[d] = 0.0;
-  double2 *mrow = mom + ((long long)blockIdx.x * 32 + lane) * (D / 2) * (long long)n1;
+  double2 *mrow = mom + ((long long)blockIdx.x * 32 + lane) * (D / 2) * (long long)n1 + q0;
   for (int t = 0; t < total; t++) {
     const int q = q_begin + t / nst, k = t - (t / nst) * nst;
     const int j0 = k * S, cnt = min(S, half - j0);
@@ -733,12 +733,12 @@ __global__ void __launch_bounds__(kPrunedThreads, 3) cheb_combine_kernel(const d
 }
 
 template <int D>
-cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long long b_hi, int n1, int n2, const double *Ttab,
-                           double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream) {
+cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long long b_hi, int n1, int n2, int q0, int nq,
+                           const double *Ttab, double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream) {
   const int rows_T = (n2 + 1) / 2;
   long long full_tiles = 0;
   // asynchronous-copy form: whole 32-series tiles whose rows start on 16-byte boundaries
-  if (allow_tma && (ld % 2) == 0 && (reinterpret_cast<uintptr_t>(x + b_lo) % 16) == 0 && n2 >= 4) {
+  if (allow_tma && (ld % 2) == 0 && (reinterpret_cast<uintptr_t>(x + b_lo) % 16) == 0 && n2 >= 4 && (q0 % 2) == 0) {
     const size_t t_bytes = (((size_t)rows_T * D * sizeof(double)) + 127) / 128 * 128;
     const size_t bar_bytes = 0;
     const size_t avail = (size_t)max_smem > t_bytes + bar_bytes + 1024 ? (size_t)max_smem - t_bytes - bar_bytes - 1024 : 0;
@@ -756,9 +756,9 @@ cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long l
       if (full_tiles > 0) {
         // an even number of blocks per warp, enough warps for every SM: ~4 waves of 148 blocks at least when the slab allows
         int q_per_warp = 8;
-        while (q_per_warp > 2 && full_tiles * ((n1 + 8 * q_per_warp - 1) / (8 * q_per_warp)) < 4 * 148) q_per_warp -= 2;
-        const dim3 grid((unsigned)full_tiles, (unsigned)((n1 + 8 * q_per_warp - 1) / (8 * q_per_warp)));
-        cheb_moments_async_kernel<D><<<grid, kMomThreads, smem, stream>>>(x + b_lo, ld, n1, n2, S, q_per_warp, Ttab, mom);
+        while (q_per_warp > 2 && full_tiles * ((nq + 8 * q_per_warp - 1) / (8 * q_per_warp)) < 4 * 148) q_per_warp -= 2;
+        const dim3 grid((unsigned)full_tiles, (unsigned)((nq + 8 * q_per_warp - 1) / (8 * q_per_warp)));
+        cheb_moments_async_kernel<D><<<grid, kMomThreads, smem, stream>>>(x + b_lo, ld, n1, n2, q0, nq, S, q_per_warp, Ttab, mom);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         g_launches++;
@@ -771,11 +771,25 @@ cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long l
   cudaError_t e = cudaFuncSetAttribute(cheb_moments_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int per_block = 4 * (kMomThreads / 32);  // four blocks of samples per warp: the table load is amortised over 32 of them
-  const dim3 grid((unsigned)((b_hi - b_rest + 31) / 32), (unsigned)((n1 + per_block - 1) / per_block));
-  cheb_moments_kernel<D><<<grid, kMomThreads, smem, stream>>>(x, ld, b_rest, b_hi, n1, n2, per_block, Ttab,
+  const dim3 grid((unsigned)((b_hi - b_rest + 31) / 32), (unsigned)((nq + per_block - 1) / per_block));
+  cheb_moments_kernel<D><<<grid, kMomThreads, smem, stream>>>(x, ld, b_rest, b_hi, n1, n2, q0, nq, per_block, Ttab,
                                                               mom + full_tiles * 32 * (D / 2) * (long long)n1);
   g_launches++;
   return cudaGetLastError();
+}
+
+cudaError_t launch_moments_D(int D, const double *x, long long ld, long long b_lo, long long b_hi, int n1, int n2, int q0, int nq,
+                             const double *Ttab, double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream) {
+  switch (D) {
+  case 4: return launch_moments<4>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  case 8: return launch_moments<8>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  case 12: return launch_moments<12>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  case 16: return launch_moments<16>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  case 20: return launch_moments<20>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  case 24: return launch_moments<24>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  case 28: return launch_moments<28>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  default: return launch_moments<32>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  }
 }
 
 // n = n1 n2 with K <= n1 <= n1_max and n1 a product of 2, 3, 4, 5: the smallest such n1, or false
@@ -893,6 +907,71 @@ extern "C" int cmtjb_rfft_abs_device(const double *x, int64_t n, int64_t B, int6
   return cmtjb_rfft_abs_device_ws(x, n, B, ld, K, out, device, stream_, nullptr, 0);
 }
 
+// ---- the same spectrum, streamed: the series arrive in time chunks and are never resident as a whole --------------------
+extern "C" int cmtjb_spectrum_stream_plan(int64_t n, int64_t K, int device, int64_t *block_len, int64_t *bytes_per_series) {
+  if (!block_len || !bytes_per_series || n <= 0 || K < 0) return fail(CMTJB_EINVAL, "bad argument");
+  *block_len = 0, *bytes_per_series = 0;
+  if (K == 0 || !moments_wanted()) return CMTJB_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaError_t e;
+  const MomentTables *t = moment_tables_for(n, K, device, max_smem, &e);
+  if (e != cudaSuccess) return cuda_fail(e, "moment tables");
+  if (t) {
+    *block_len = t->M.fft.n2;
+    *bytes_per_series = (int64_t)(t->M.D / 2) * t->M.fft.n1 * (int64_t)sizeof(double2);
+  }
+  return CMTJB_OK;
+}
+
+extern "C" int cmtjb_spectrum_stream_moments(const double *x_chunk, int64_t ld, int64_t B, int64_t n, int64_t K, int64_t q0,
+                                             int64_t nq, void *moments, int device, void *stream_) {
+  if (!x_chunk || !moments || B <= 0 || ld < B || n <= 0 || K <= 0 || q0 < 0 || nq < 0) return fail(CMTJB_EINVAL, "bad argument");
+  if (nq == 0) return CMTJB_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaError_t e;
+  const MomentTables *mt = moment_tables_for(n, K, device, max_smem, &e);
+  if (e != cudaSuccess) return cuda_fail(e, "moment tables");
+  if (!mt) return fail(CMTJB_ENOTSUP, "no streaming plan for this (n, K): see cmtjb_spectrum_stream_plan");
+  const MomentPlan &M = mt->M;
+  if (q0 + nq > M.fft.n1) return fail(CMTJB_EINVAL, "block range beyond the series");
+  if ((reinterpret_cast<uintptr_t>(moments) % 32) != 0) return fail(CMTJB_EINVAL, "moments must be 32-byte aligned");
+  const char *tma_env = std::getenv("CMTJB_SPECTRUM_TMA");
+  const bool allow_tma = !(tma_env && tma_env[0] == '0');
+  e = launch_moments_D(M.D, x_chunk, ld, 0, B, M.fft.n1, M.fft.n2, (int)q0, (int)nq, mt->d_T, reinterpret_cast<double2 *>(moments), max_smem,
+                       allow_tma, (cudaStream_t)stream_);
+  if (e != cudaSuccess) return cuda_fail(e, "cheb_moments_kernel (streamed)");
+  return CMTJB_OK;
+}
+
+extern "C" int cmtjb_spectrum_stream_finish(const void *moments, int64_t n, int64_t B, int64_t K, double *out, int device, void *stream_) {
+  if (!moments || !out || B <= 0 || n <= 0 || K <= 0) return fail(CMTJB_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaError_t e;
+  const MomentTables *mt = moment_tables_for(n, K, device, max_smem, &e);
+  if (e != cudaSuccess) return cuda_fail(e, "moment tables");
+  if (!mt) return fail(CMTJB_ENOTSUP, "no streaming plan for this (n, K): see cmtjb_spectrum_stream_plan");
+  const MomentPlan &M = mt->M;
+  const int n1 = M.fft.n1;
+  const size_t smem_c = (2 * (size_t)n1 + (size_t)K) * sizeof(double2) + (size_t)n1 * sizeof(unsigned short) + 16;
+  e = cudaFuncSetAttribute(cheb_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+  const long long step = 1 << 20;  // grid.x limit is 2^31 - 1; keep launches modest
+  for (long long b_lo = 0; b_lo < B && e == cudaSuccess; b_lo += step) {
+    const long long cnt = std::min<long long>(step, B - b_lo);
+    cheb_combine_kernel<<<(unsigned)cnt, kPrunedThreads, smem_c, (cudaStream_t)stream_>>>(
+        reinterpret_cast<const double2 *>(moments) + b_lo * (long long)(M.D / 2) * n1, b_lo, M.D / 2, M.fft, mt->d_w, mt->d_ab, out);
+    g_launches++;
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "cheb_combine_kernel (streamed)");
+  return CMTJB_OK;
+}
+
 extern "C" int cmtjb_rfft_abs_device_ws(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
                                         void *stream_, void *workspace, int64_t workspace_bytes) {
   if (!x || !out || n <= 0 || B <= 0 || ld < B || K < 0 || K > n / 2 + 1) return fail(CMTJB_EINVAL, "bad argument");
@@ -938,16 +1017,7 @@ extern "C" int cmtjb_rfft_abs_device_ws(const double *x, int64_t n, int64_t B, i
       e = cudaFuncSetAttribute(cheb_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
       for (long long b_lo = 0; b_lo < B && e == cudaSuccess; b_lo += slab) {
         const long long b_hi = std::min<long long>(B, b_lo + slab);
-        switch (D) {
-        case 4: e = launch_moments<4>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        case 8: e = launch_moments<8>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        case 12: e = launch_moments<12>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        case 16: e = launch_moments<16>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        case 20: e = launch_moments<20>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        case 24: e = launch_moments<24>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        case 28: e = launch_moments<28>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        default: e = launch_moments<32>(x, ld, b_lo, b_hi, n1, n2, d_T, d_mom, max_smem, allow_tma, stream); break;
-        }
+        e = launch_moments_D(D, x, ld, b_lo, b_hi, n1, n2, 0, n1, d_T, d_mom, max_smem, allow_tma, stream);
         if (e != cudaSuccess) break;
         cheb_combine_kernel<<<(unsigned)(b_hi - b_lo), kPrunedThreads, smem_c, stream>>>(d_mom, b_lo, Pn, M.fft, mt->d_w, mt->d_ab, out);
         g_launches++;

@@ -24,6 +24,7 @@ Everything else -- arguments, validation, return shapes -- follows the reference
 from __future__ import annotations
 
 import functools
+import os as _os
 import warnings
 
 import math
@@ -134,6 +135,100 @@ def spectrum_device(signal, int_step: float, max_frequency: float):
     stream = torch.cuda.current_stream(signal.device).cuda_stream
     be.check(f(signal.data_ptr(), n, B, ld, K, out.data_ptr(), dev, C.c_void_p(stream), ws_ptr, ws_bytes))
     return out, freqs
+
+
+class _SpectrumStream:
+    """|FFT| of B series that arrive in time chunks (``cmtjb_spectrum_stream_*``): a sweep's full-rate projection log
+    (1e5 points x 2e5 steps: 160 GB) is never resident -- each chunk is reduced to its Chebyshev block moments right after
+    the time loop has written it, and the moments (a third of the log here) are transformed at the end."""
+
+    def __init__(self, n: int, B: int, int_step: float, max_frequency: float, device: int):
+        import ctypes as C
+
+        torch = _torch()
+        self.n, self.B, self.device = int(n), int(B), int(device)
+        findx, self.freqs = _spectrum_bins(self.n, int_step, max_frequency)
+        self.K = int(findx.size)
+        self.block_len = 0
+        if self.K == 0 or self.B == 0 or self.n <= 0:
+            return
+        self.be = _abi.cuda_backend()
+        f = self.be.lib.cmtjb_spectrum_stream_plan
+        f.restype = C.c_int
+        f.argtypes = [C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        bl, per = C.c_int64(0), C.c_int64(0)
+        self.be.check(f(self.n, self.K, self.device, C.byref(bl), C.byref(per)))
+        self.block_len, self.bytes_per_series = int(bl.value), int(per.value)
+        self.n_blocks = self.n // self.block_len if self.block_len else 0
+        self.moments = None
+        self._C = C
+
+    def allocate(self):
+        torch = _torch()
+        self.moments = torch.empty(self.B * self.bytes_per_series, dtype=torch.uint8, device=torch.device("cuda", self.device))
+
+    def add(self, chunk, q0: int, nq: int) -> None:
+        """chunk: device tensor [nq * block_len, B] (row 0 = first sample of block q0), reduced on the current stream"""
+        C, torch = self._C, _torch()
+        assert chunk.dtype == torch.float64 and chunk.stride(1) == 1 and chunk.shape[1] == self.B and chunk.shape[0] >= nq * self.block_len
+        f = self.be.lib.cmtjb_spectrum_stream_moments
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+        stream = torch.cuda.current_stream(chunk.device).cuda_stream
+        self.be.check(f(chunk.data_ptr(), int(chunk.stride(0)), self.B, self.n, self.K, int(q0), int(nq), self.moments.data_ptr(),
+                        self.device, C.c_void_p(stream)))
+
+    def finish(self):
+        C, torch = self._C, _torch()
+        dev = torch.device("cuda", self.device)
+        out = torch.empty((self.B, self.K), dtype=torch.float64, device=dev)
+        f = self.be.lib.cmtjb_spectrum_stream_finish
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self.be.check(f(self.moments.data_ptr(), self.n, self.B, self.K, out.data_ptr(), self.device, C.c_void_p(stream)))
+        return out
+
+
+class _Rows(list):
+    """The per-point lists the reference's procedures return (one ``output["Rx"].append(...)`` per field point,
+    procedures.py:183-193) for a whole batch: a ``list`` of row views of ONE [n_points, ...] array, materialised when it
+    is first used as a list -- a 1e5-point sweep does not pay for 4e5 Python objects it may never look at
+    (``np.asarray(rows)`` hands back the array itself)."""
+
+    def __init__(self, array: np.ndarray):
+        super().__init__()
+        self._array = array  # None once the rows exist as list items
+
+    def _fill(self) -> None:
+        if self._array is not None:
+            a, self._array = self._array, None
+            list.extend(self, a)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._array if self._array is not None else np.array(list(self))
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __reduce__(self):
+        self._fill()
+        return (list, (list(self),))
+
+
+def _filled(name):
+    inner = getattr(list, name)
+
+    def method(self, *a, **k):
+        self._fill()
+        return inner(self, *a, **k)
+
+    method.__name__ = name
+    return method
+
+
+for _n in ("__len__", "__getitem__", "__iter__", "__contains__", "__reversed__", "__eq__", "__ne__", "__lt__", "__le__", "__gt__", "__ge__",
+           "__add__", "__mul__", "__rmul__", "__repr__", "__setitem__", "__delitem__", "__iadd__", "__imul__", "index", "count", "copy",
+           "append", "extend", "insert", "pop", "remove", "clear", "sort", "reverse"):
+    setattr(_Rows, _n, _filled(_n))
 
 
 def _to_host(t):
@@ -255,13 +350,54 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
         proj[0, 3 * l + comp] = weights[l]
         if full_output and not static_only:
             proj[1 + l, 3 * l + comp] = weights[l]
-    proj_log = torch.empty((n_proj, n_total, B), dtype=torch.float64, device=dev) if n_proj else None
+    # where the transformed series starts (procedures.py:148: the samples with time >= wait_time)
+    n0 = min(n_total, max(0, int(math.ceil(wait_time / int_step)) - 2))
+    while n0 < n_total and n0 * float(int_step) < wait_time:
+        n0 += 1
+    # streamed spectrum: the projected signal goes through a chunk buffer and is reduced chunk by chunk
+    stream = None
+    if n_proj == 1 and n_total - n0 > 0 and not _os.environ.get("CMTJB_PIMM_RESIDENT_LOG"):
+        stream = _SpectrumStream(n_total - n0, B, int_step, max_frequency, device)
+        chunk_bytes = float(_os.environ.get("CMTJB_PIMM_CHUNK_MB", 10240)) * 2.0**20
+        chunks: List[Tuple[int, int]] = []
+        if stream.block_len:
+            cq = max(2, int(chunk_bytes // (8.0 * stream.block_len * B)) // 2 * 2)  # blocks per chunk, even
+            if cq >= 64:
+                cq = cq // 64 * 64  # the moments kernel hands 8 x 8 blocks to a thread block: whole ones only
+            chunks = [(q0, min(cq, stream.n_blocks - q0)) for q0 in range(0, stream.n_blocks, cq)]
+            if len(chunks) > 1 and chunks[-1][1] * stream.block_len < n_last:  # the last-n log must not straddle chunks
+                (qa, na), (_, nb) = chunks[-2], chunks[-1]
+                chunks[-2:] = [(qa, na + nb)]
+            if chunks[-1][1] * stream.block_len < n_last:
+                chunks = []
+        if not chunks:
+            stream = None  # resident log instead
+    if stream is not None:
+        stream.allocate()
+        proj_log = torch.empty((1, max(nq for _, nq in chunks) * stream.block_len, B), dtype=torch.float64, device=dev)
+    else:
+        proj_log = torch.empty((n_proj, n_total, B), dtype=torch.float64, device=dev) if n_proj else None
 
     def spec(sample0):
         return PostSpec(proj=proj[:n_proj], proj_log=proj_log, proj_sample0=sample0) if n_proj else None
 
     ph.mark("set-up (batch, inputs, projection log buffer)")
-    if full_output and not static_only:
+    if stream is not None:
+        n_a = n_total - n_last
+        if n0 > 0:
+            batch.run_device(_time_for_steps(n0, int_step), int_step, int_step, log=False)
+        L2 = stream.block_len
+        for q0, nq in chunks:
+            t0, t1 = n0 + q0 * L2, n0 + (q0 + nq) * L2
+            if t1 <= n_a:
+                batch.run_device(_time_for_steps(t1, int_step), int_step, int_step, log=False, post=spec(0), start_iteration=t0)
+            else:  # the last chunk: its final n_last steps also log every layer's m (static resistances)
+                if n_a > t0:
+                    batch.run_device(_time_for_steps(n_a, int_step), int_step, int_step, log=False, post=spec(0), start_iteration=t0)
+                res = batch.run_device(simulation_duration, int_step, int_step, post=spec(max(n_a, t0) - t0), start_iteration=max(n_a, t0))
+                log_last = res["_log"][:, res["_log"].shape[1] - n_last :, :]
+            stream.add(proj_log[0], q0, nq)
+    elif full_output and not static_only:
         res = batch.run_device(simulation_duration, int_step, int_step, post=spec(0))
         log_all = res["_log"]
         log_last = log_all[:, n_total - n_last :, :]
@@ -296,9 +432,10 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
     out["m_final"] = _to_host(final.contiguous())  # [L,3,B]
     ph.mark("static resistances + final state to the host")
     if not static_only:
-        time = np.arange(n_total, dtype=np.float64) * float(int_step)
-        n0 = int(np.argwhere(time >= wait_time).ravel()[0]) if np.any(time >= wait_time) else n_total
-        yf, freqs = spectrum_device(proj_log[0, n0:, :], int_step, max_frequency)
+        if stream is not None:
+            yf, freqs = stream.finish(), stream.freqs
+        else:
+            yf, freqs = spectrum_device(proj_log[0, n0:, :], int_step, max_frequency)
         ph.mark("spectrum (batched FFT)")
         out["spectrum"] = _to_host(yf)  # [B,K]
         out["freqs"] = freqs
@@ -381,6 +518,13 @@ def PIMM_procedure(
         # device bytes per instance: the projection log(s), the full-rate log when full_output, the last-n log
         # (twice: the weighted m_traj copy handed back to the host is staged on the device)
         per_inst = 8.0 * n_total * (n_series + (2.0 * (3 * L + 3) if full_output else 0.0)) + 8.0 * 200 * (3 * L + 3)
+        if n_series == 1 and not _os.environ.get("CMTJB_PIMM_RESIDENT_LOG"):
+            # streamed spectrum (_SpectrumStream): block moments instead of the log, plus one chunk buffer for the batch
+            n0 = int(np.searchsorted(np.arange(n_total, dtype=np.float64) * float(int_step), wait_time, side="left"))
+            probe = _SpectrumStream(n_total - n0, 1, int_step, max_frequency, device) if n_total > n0 else None
+            if probe is not None and probe.block_len and probe.block_len >= min(int(take_last_n), n_total):
+                per_inst = float(probe.bytes_per_series) + 8.0 * 200 * (3 * L + 3) + 8.0 * max(take_last_n, 100) * (3 * L + 3)
+                memory_budget = max(memory_budget - float(_os.environ.get("CMTJB_PIMM_CHUNK_MB", 10240)) * 2.0**20, 0.5 * memory_budget)
         for lo, hi in _instance_chunks(Hvecs.shape[0], per_inst, memory_budget):
             parts.append(run(Hvecs[lo:hi], {k: v[lo:hi] for k, v in m0.items()}))
         if parts:
@@ -402,16 +546,16 @@ def PIMM_procedure(
     # the reference appends one entry per field point (procedures.py:183-193); same lists, assembled
     # from whole-batch arrays (row views) instead of 1e5 Python-level appends
     n = sum(r["Rx"].shape[0] for r in parts)
-    output["H"] = list(Hvecs[:n])
-    output["Rx"] = list(cat("Rx"))
-    output["Ry"] = list(cat("Ry"))
-    output["m_avg"] = list(cat("m_avg"))
+    output["H"] = _Rows(Hvecs[:n])
+    output["Rx"] = _Rows(cat("Rx"))
+    output["Ry"] = _Rows(cat("Ry"))
+    output["m_avg"] = _Rows(cat("m_avg"))
     spectrum_arr = np.squeeze(np.asarray(spectrum))
     if not static_only:
         freqs = parts[-1]["freqs"]
         spectrum_arr = np.squeeze(cat("spectrum")[:, :, None])
         if full_output:
-            output["m_traj"] = list(cat("m_traj"))
+            output["m_traj"] = _Rows(cat("m_traj"))
             for li, lid in enumerate(layer_ids):
                 output[lid] = np.concatenate([r["layer_spectra"][li] for r in parts], axis=0)[:, :, None].squeeze()
     return spectrum_arr, freqs, output

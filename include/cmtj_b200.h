@@ -343,6 +343,18 @@ int cmtjb_rfft_abs_workspace(int64_t n, int64_t K, int device, int64_t *bytes_pe
 int cmtjb_rfft_abs_device_ws(const double *x, int64_t n, int64_t B, int64_t ld, int64_t K, double *out, int device,
                              void *stream, void *workspace, int64_t workspace_bytes);
 
+/* The same spectrum for series that are produced in TIME CHUNKS and never resident as a whole (a sweep's projection log at
+ * full rate is 160 GB for 1e5 points x 2e5 steps).  cmtjb_spectrum_stream_plan reports the block length L the series must
+ * be cut into and the bytes of moment storage one series needs (block_len = 0: no streaming plan for this (n, K); use
+ * cmtjb_rfft_abs_device).  The caller owns moments[B * bytes_per_series] (DEVICE, 32-byte aligned) and, for every chunk of
+ * nq whole blocks starting at block q0 (q0 even), passes the chunk's rows x_chunk[(t - q0 * L) * ld + b] to
+ * cmtjb_spectrum_stream_moments (one pass over the chunk, any order of chunks, stream-ordered); when blocks
+ * 0 .. n / L - 1 are all in, cmtjb_spectrum_stream_finish writes |FFT(x_b)[k]|, k < K, to out [B][K] (DEVICE). */
+int cmtjb_spectrum_stream_plan(int64_t n, int64_t K, int device, int64_t *block_len, int64_t *bytes_per_series);
+int cmtjb_spectrum_stream_moments(const double *x_chunk, int64_t ld, int64_t B, int64_t n, int64_t K, int64_t q0, int64_t nq,
+                                  void *moments, int device, void *stream);
+int cmtjb_spectrum_stream_finish(const void *moments, int64_t n, int64_t B, int64_t K, double *out, int device, void *stream);
+
 /* Number of kernels this library has launched in this process (monotonic). */
 long long cmtjb_launch_count(void);
 /* Name of the kernel variant (layer count / solver / compiled term set) the calling thread's last sweep launch

@@ -216,6 +216,57 @@ def test_spectrum_device_shapes(on_cuda, monkeypatch, n, B, K_freq, pitch, mode)
     assert np.max(np.abs(yf.cpu().numpy() - want) / scale) < 1e-12
 
 
+@pytest.mark.parametrize("B,chunk_mb,wait,last_n", [
+    (40, 0.2, 0.0, 20),      # 40 series x 5000 steps in chunks of a few blocks (one full 32-series tile + 8 ragged)
+    (70, 0.5, 0.1e-9, 100),  # wait_time > 0: the series starts inside the run; last-n longer than a block (merged tail chunk)
+    (3, 8192, 0.0, 20),      # one chunk
+])
+def test_pimm_streamed_spectrum_equals_resident_log(on_cuda, monkeypatch, B, chunk_mb, wait, last_n):
+    """PIMM_batch reduces the projected signal chunk by chunk (_SpectrumStream: block moments, no resident log); the
+    result must equal the whole-log path (CMTJB_PIMM_RESIDENT_LOG=1) to rounding, and numpy's rfft of that log."""
+    rng = np.random.default_rng(B)
+    H = rng.uniform(-300e3, 300e3, (B, 3))
+    kw = dict(int_step=1e-13, resistance_params=ps.rparams(P, 2), simulation_duration=0.5e-9, take_last_n=last_n, max_frequency=80e9,
+              Hoe_excitation=500, wait_time=wait, disturbance=0, disable_tqdm=True)
+    monkeypatch.setenv("CMTJB_PIMM_CHUNK_MB", str(chunk_mb))
+    calls = []
+    orig = P._SpectrumStream.add
+    monkeypatch.setattr(P._SpectrumStream, "add", lambda self, chunk, q0, nq: (calls.append((q0, nq)), orig(self, chunk, q0, nq))[1])
+    s1, f1, o1 = P.PIMM_batch(helpers.two_layer_mtj(cm), H, **kw)
+    assert calls  # the streamed path ran
+    if chunk_mb < 1:
+        assert len(calls) > 1, calls
+    monkeypatch.setenv("CMTJB_PIMM_RESIDENT_LOG", "1")
+    n_calls = len(calls)
+    s2, f2, o2 = P.PIMM_batch(helpers.two_layer_mtj(cm), H, **kw)
+    assert len(calls) == n_calls  # the resident path did not stream
+    np.testing.assert_array_equal(f1, f2)
+    scale = np.abs(s2).max(axis=1, keepdims=True)
+    assert np.max(np.abs(s1 - s2) / scale) < 1e-12
+    for k in ("Rx", "Ry", "m_avg"):
+        np.testing.assert_array_equal(np.asarray(o1[k]), np.asarray(o2[k]))  # the trajectories themselves are the same launches' work
+
+
+def test_spectrum_stream_chunks_in_any_order(on_cuda):
+    import torch
+
+    n, B = 6000, 37
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(n, B)) + 2.0 * np.sin(2 * np.pi * np.arange(n)[:, None] * (3.5 + np.arange(B)[None, :]) / n)
+    st = P._SpectrumStream(n, B, 1e-13, 1e11, 0)
+    assert st.block_len > 0 and st.n_blocks * st.block_len == n
+    st.allocate()
+    xd = torch.from_numpy(x).cuda()
+    L = st.block_len
+    cuts = [0, 2, 6, st.n_blocks - (st.n_blocks % 2 or 2), st.n_blocks]
+    spans = [(a, b - a) for a, b in zip(cuts, cuts[1:]) if b > a]
+    for q0, nq in reversed(spans):
+        st.add(xd[q0 * L : (q0 + nq) * L].contiguous(), q0, nq)
+    got = st.finish().cpu().numpy()
+    want = np.abs(np.fft.rfft(x, axis=0))[: st.K].T
+    assert np.max(np.abs(got - want) / np.abs(want).max(axis=1, keepdims=True)) < 1e-12
+
+
 def test_distribute_covers_the_product(on_cuda, oracle):
     j = helpers.two_layer_mtj(cm)
     Hx, Hz = [-100e3, 50e3, 200e3], [0.0, 30e3]

@@ -98,7 +98,7 @@ def s4_batch(cm, n, select=None, device=0):
 
 
 # ---- S5 ---------------------------------------------------------------------------------------------------------
-S5G_SIDE, S5G_STEPS = 64, 2000
+S5G_SIDE, S5G_STEPS = 64, 20000
 S5S_STACKS, S5S_JUNCTIONS, S5S_STEPS = 4096, 64, 2000
 
 
