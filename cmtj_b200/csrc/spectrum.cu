@@ -390,6 +390,7 @@ bool plan_grouped(long long n, long long K, int n1_max, PrunedPlan *P) {
 //     S[k] += alpha_p[k] Z_p[k] + beta_p[k] conj Z_p[-k],  alpha, beta = (-1)^p (a_2p -+ a_2p+1) / 2,  a_d = eps_d J_d(phi_k)
 // ).  The tail bound is evaluated on the host (Miller recurrence in long double) and D chosen for 2e-17.
 constexpr int kMomThreads = 256;
+constexpr int kBgThreads = 128;
 constexpr int kMomMaxD = 32;
 
 struct MomentPlan {
@@ -557,6 +558,57 @@ __global__ void __launch_bounds__(kMomThreads, (D > 24 ? 2 : 3)) cheb_moments_ke
     double2 *m = mom + ((b - b_lo) * (D / 2)) * (long long)n1 + q0 + q;
 #pragma unroll
     for (int p = 0; p < D / 2; p++) m[(long long)p * n1] = make_double2(c[2 * p], c[2 * p + 1]);
+  }
+}
+
+// ---- the BACKGROUND form: reduces chunk c on a second stream while the time loop integrates chunk c + 1 ---------------
+// llgs_balanced_kernel keeps 16 warps x 88 registers on every SM and pins its own occupancy by claiming the SM's shared
+// memory (launch_fixed), which leaves 20 K registers and no shared memory.  This kernel is sized for exactly that hole:
+// ONE block of 128 threads x <= 160 registers per SM (a persistent grid of one block per SM; a second block does not fit
+// beside the time loop), no shared memory (the table is read through L1, one broadcast load per warp and entry), a
+// grid-stride walk over the (32-series tile, block q) tasks with q fastest, so that the 16-byte halves of a moment sector
+// still come from neighbouring warps.  Its FP64 instructions fill issue slots the time loop leaves idle (~21 % of them).
+template <int D>
+__global__ void __maxnreg__(160) cheb_moments_bg_kernel(const double *__restrict__ x, long long ld, long long B,
+                                                                                      int n1, int n2, int q0, int nq,
+                                                                                      const double *__restrict__ Ttab, double2 *__restrict__ mom) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long tiles = (B + 31) / 32, total = tiles * nq;
+  const int half = n2 / 2;
+  for (long long u = (long long)blockIdx.x * (kBgThreads / 32) + warp; u < total; u += (long long)gridDim.x * (kBgThreads / 32)) {
+    const long long tile = u / nq;
+    const int q = (int)(u - tile * nq);
+    const long long b_raw = tile * 32 + lane;
+    const long long b = b_raw < B ? b_raw : B - 1;
+    const double *lo = x + (long long)n2 * q * ld + b;
+    const double *hi = lo + (long long)(n2 - 1) * ld;
+    double c[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) c[d] = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < half; j++) {
+      const double a0 = __ldcs(lo), a1 = __ldcs(hi);
+      lo += ld;
+      hi -= ld;
+      const double e = a0 + a1, o = a0 - a1;
+      const double2 *t2 = reinterpret_cast<const double2 *>(Ttab + j * D);
+#pragma unroll
+      for (int d = 0; d < D; d += 2) {
+        const double2 t = __ldg(t2 + d / 2);
+        c[d] = fma(t.x, e, c[d]);
+        c[d + 1] = fma(t.y, o, c[d + 1]);
+      }
+    }
+    if (n2 & 1) {
+      const double a0 = __ldcs(lo);
+#pragma unroll
+      for (int d = 0; d < D; d += 2) c[d] = fma(__ldg(Ttab + half * D + d), a0, c[d]);
+    }
+    if (b_raw < B) {
+      double2 *m = mom + (b * (D / 2)) * (long long)n1 + q0 + q;
+#pragma unroll
+      for (int p = 0; p < D / 2; p++) m[(long long)p * n1] = make_double2(c[2 * p], c[2 * p + 1]);
+    }
   }
 }
 
@@ -734,9 +786,20 @@ __global__ void __launch_bounds__(kPrunedThreads, 3) cheb_combine_kernel(const d
 
 template <int D>
 cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long long b_hi, int n1, int n2, int q0, int nq,
-                           const double *Ttab, double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream) {
+                           const double *Ttab, double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream, bool background = false) {
   const int rows_T = (n2 + 1) / 2;
   long long full_tiles = 0;
+  if (background) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // the time loop beside it runs with the SM's carve-out at its maximum (its occupancy pin); an SM only changes its
+    // carve-out when idle, so this kernel must ask for the same one or the two kernels exclude each other
+    cudaFuncSetAttribute(cheb_moments_bg_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cheb_moments_bg_kernel<D><<<(unsigned)sms, kBgThreads, 0, stream>>>(x + b_lo, ld, b_hi - b_lo, n1, n2, q0, nq, Ttab, mom);
+    g_launches++;
+    return cudaGetLastError();
+  }
   // asynchronous-copy form: whole 32-series tiles whose rows start on 16-byte boundaries
   if (allow_tma && (ld % 2) == 0 && (reinterpret_cast<uintptr_t>(x + b_lo) % 16) == 0 && n2 >= 4 && (q0 % 2) == 0) {
     const size_t t_bytes = (((size_t)rows_T * D * sizeof(double)) + 127) / 128 * 128;
@@ -779,16 +842,16 @@ cudaError_t launch_moments(const double *x, long long ld, long long b_lo, long l
 }
 
 cudaError_t launch_moments_D(int D, const double *x, long long ld, long long b_lo, long long b_hi, int n1, int n2, int q0, int nq,
-                             const double *Ttab, double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream) {
+                             const double *Ttab, double2 *mom, int max_smem, bool allow_tma, cudaStream_t stream, bool background = false) {
   switch (D) {
-  case 4: return launch_moments<4>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
-  case 8: return launch_moments<8>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
-  case 12: return launch_moments<12>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
-  case 16: return launch_moments<16>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
-  case 20: return launch_moments<20>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
-  case 24: return launch_moments<24>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
-  case 28: return launch_moments<28>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
-  default: return launch_moments<32>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream);
+  case 4: return launch_moments<4>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
+  case 8: return launch_moments<8>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
+  case 12: return launch_moments<12>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
+  case 16: return launch_moments<16>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
+  case 20: return launch_moments<20>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
+  case 24: return launch_moments<24>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
+  case 28: return launch_moments<28>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
+  default: return launch_moments<32>(x, ld, b_lo, b_hi, n1, n2, q0, nq, Ttab, mom, max_smem, allow_tma, stream, background);
   }
 }
 
@@ -926,7 +989,7 @@ extern "C" int cmtjb_spectrum_stream_plan(int64_t n, int64_t K, int device, int6
 }
 
 extern "C" int cmtjb_spectrum_stream_moments(const double *x_chunk, int64_t ld, int64_t B, int64_t n, int64_t K, int64_t q0,
-                                             int64_t nq, void *moments, int device, void *stream_) {
+                                             int64_t nq, void *moments, int32_t background, int device, void *stream_) {
   if (!x_chunk || !moments || B <= 0 || ld < B || n <= 0 || K <= 0 || q0 < 0 || nq < 0) return fail(CMTJB_EINVAL, "bad argument");
   if (nq == 0) return CMTJB_OK;
   CUDA_TRY(cudaSetDevice(device));
@@ -942,7 +1005,7 @@ extern "C" int cmtjb_spectrum_stream_moments(const double *x_chunk, int64_t ld, 
   const char *tma_env = std::getenv("CMTJB_SPECTRUM_TMA");
   const bool allow_tma = !(tma_env && tma_env[0] == '0');
   e = launch_moments_D(M.D, x_chunk, ld, 0, B, M.fft.n1, M.fft.n2, (int)q0, (int)nq, mt->d_T, reinterpret_cast<double2 *>(moments), max_smem,
-                       allow_tma, (cudaStream_t)stream_);
+                       allow_tma, (cudaStream_t)stream_, background != 0);
   if (e != cudaSuccess) return cuda_fail(e, "cheb_moments_kernel (streamed)");
   return CMTJB_OK;
 }

@@ -167,16 +167,18 @@ class _SpectrumStream:
         torch = _torch()
         self.moments = torch.empty(self.B * self.bytes_per_series, dtype=torch.uint8, device=torch.device("cuda", self.device))
 
-    def add(self, chunk, q0: int, nq: int) -> None:
-        """chunk: device tensor [nq * block_len, B] (row 0 = first sample of block q0), reduced on the current stream"""
+    def add(self, chunk, q0: int, nq: int, background: bool = False) -> None:
+        """chunk: device tensor [nq * block_len, B] (row 0 = first sample of block q0), reduced on the current stream;
+        ``background``: the low-footprint kernel that fits beside a resident time-loop kernel (see the C header)"""
         C, torch = self._C, _torch()
         assert chunk.dtype == torch.float64 and chunk.stride(1) == 1 and chunk.shape[1] == self.B and chunk.shape[0] >= nq * self.block_len
         f = self.be.lib.cmtjb_spectrum_stream_moments
         f.restype = C.c_int
-        f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+        f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int,
+                      C.c_void_p]
         stream = torch.cuda.current_stream(chunk.device).cuda_stream
         self.be.check(f(chunk.data_ptr(), int(chunk.stride(0)), self.B, self.n, self.K, int(q0), int(nq), self.moments.data_ptr(),
-                        self.device, C.c_void_p(stream)))
+                        1 if background else 0, self.device, C.c_void_p(stream)))
 
     def finish(self):
         C, torch = self._C, _torch()
@@ -374,29 +376,73 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
             stream = None  # resident log instead
     if stream is not None:
         stream.allocate()
-        proj_log = torch.empty((1, max(nq for _, nq in chunks) * stream.block_len, B), dtype=torch.float64, device=dev)
+        # two chunk buffers: the moments of chunk c are reduced (second stream, background kernel) while chunk c + 1 integrates
+        overlap = len(chunks) > 1 and not _os.environ.get("CMTJB_PIMM_NO_OVERLAP")
+        ring = torch.empty((2 if overlap else 1, 1, max(nq for _, nq in chunks) * stream.block_len, B), dtype=torch.float64, device=dev)
+        proj_log = ring[0]
     else:
         proj_log = torch.empty((n_proj, n_total, B), dtype=torch.float64, device=dev) if n_proj else None
 
-    def spec(sample0):
-        return PostSpec(proj=proj[:n_proj], proj_log=proj_log, proj_sample0=sample0) if n_proj else None
+    def spec(sample0, buf=None):
+        return PostSpec(proj=proj[:n_proj], proj_log=proj_log if buf is None else buf, proj_sample0=sample0) if n_proj else None
 
     ph.mark("set-up (batch, inputs, projection log buffer)")
     if stream is not None:
         n_a = n_total - n_last
-        if n0 > 0:
-            batch.run_device(_time_for_steps(n0, int_step), int_step, int_step, log=False)
+        cur = torch.cuda.current_stream(dev)
+        if overlap:
+            # the time loop on a high-priority stream (its blocks are placed first and keep their share of every SM), the
+            # reductions on a second one: they fill the registers the time-loop kernel leaves free
+            s_int, s_mom = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev)
+            s_int.wait_stream(cur)
+            s_mom.wait_stream(cur)
+        else:
+            s_int = s_mom = cur
+        slot_free = [None] * ring.shape[0]
+        marks = []
+        if ph.on:
+            ev_start = torch.cuda.Event(enable_timing=True)
+            ev_start.record(s_int)
+            h_start = ph.time.perf_counter()
+        with torch.cuda.stream(s_int):
+            if n0 > 0:
+                batch.run_device(_time_for_steps(n0, int_step), int_step, int_step, log=False)
         L2 = stream.block_len
-        for q0, nq in chunks:
+        for c, (q0, nq) in enumerate(chunks):
             t0, t1 = n0 + q0 * L2, n0 + (q0 + nq) * L2
-            if t1 <= n_a:
-                batch.run_device(_time_for_steps(t1, int_step), int_step, int_step, log=False, post=spec(0), start_iteration=t0)
-            else:  # the last chunk: its final n_last steps also log every layer's m (static resistances)
-                if n_a > t0:
-                    batch.run_device(_time_for_steps(n_a, int_step), int_step, int_step, log=False, post=spec(0), start_iteration=t0)
-                res = batch.run_device(simulation_duration, int_step, int_step, post=spec(max(n_a, t0) - t0), start_iteration=max(n_a, t0))
-                log_last = res["_log"][:, res["_log"].shape[1] - n_last :, :]
-            stream.add(proj_log[0], q0, nq)
+            k = c % ring.shape[0]
+            buf = ring[k]
+            with torch.cuda.stream(s_int):
+                if slot_free[k] is not None:
+                    s_int.wait_event(slot_free[k])
+                if t1 <= n_a:
+                    batch.run_device(_time_for_steps(t1, int_step), int_step, int_step, log=False, post=spec(0, buf), start_iteration=t0)
+                else:  # the last chunk: its final n_last steps also log every layer's m (static resistances)
+                    if n_a > t0:
+                        batch.run_device(_time_for_steps(n_a, int_step), int_step, int_step, log=False, post=spec(0, buf), start_iteration=t0)
+                    res = batch.run_device(simulation_duration, int_step, int_step, post=spec(max(n_a, t0) - t0, buf),
+                                           start_iteration=max(n_a, t0))
+                    log_last = res["_log"][:, res["_log"].shape[1] - n_last :, :]
+                    log_last.record_stream(cur)
+                done = torch.cuda.Event(enable_timing=ph.on)
+                done.record(s_int)
+            with torch.cuda.stream(s_mom):
+                s_mom.wait_event(done)
+                stream.add(buf[0], q0, nq, background=overlap and c + 1 < len(chunks))
+                slot_free[k] = torch.cuda.Event(enable_timing=ph.on)
+                slot_free[k].record(s_mom)
+            if ph.on:
+                marks.append((ph.time.perf_counter(), done, slot_free[k]))
+        if overlap:
+            cur.wait_stream(s_int)
+            cur.wait_stream(s_mom)
+        if ph.on and marks:
+            torch.cuda.synchronize()
+            print("[cmtjb] PIMM batch chunks: host enqueue done / time loop done / moments done, ms after the phase started "
+                  f"(host wall until everything had finished: {1e3 * (ph.time.perf_counter() - h_start):.1f}):", flush=True)
+            for i, (h, e_int, e_mom) in enumerate(marks):
+                print(f"[cmtjb]   chunk {i:3d}: {1e3 * (h - h_start):8.1f} {ev_start.elapsed_time(e_int):8.1f} {ev_start.elapsed_time(e_mom):8.1f}",
+                      flush=True)
     elif full_output and not static_only:
         res = batch.run_device(simulation_duration, int_step, int_step, post=spec(0))
         log_all = res["_log"]

@@ -349,10 +349,12 @@ int cmtjb_rfft_abs_device_ws(const double *x, int64_t n, int64_t B, int64_t ld, 
  * cmtjb_rfft_abs_device).  The caller owns moments[B * bytes_per_series] (DEVICE, 32-byte aligned) and, for every chunk of
  * nq whole blocks starting at block q0 (q0 even), passes the chunk's rows x_chunk[(t - q0 * L) * ld + b] to
  * cmtjb_spectrum_stream_moments (one pass over the chunk, any order of chunks, stream-ordered); when blocks
- * 0 .. n / L - 1 are all in, cmtjb_spectrum_stream_finish writes |FFT(x_b)[k]|, k < K, to out [B][K] (DEVICE). */
+ * 0 .. n / L - 1 are all in, cmtjb_spectrum_stream_finish writes |FFT(x_b)[k]|, k < K, to out [B][K] (DEVICE).
+ * background != 0 selects a low-footprint form of the reduction (128 threads, <= 128 registers per block) meant to run on a
+ * second stream WHILE the next chunk integrates: it fits into the registers a resident time-loop kernel leaves free. */
 int cmtjb_spectrum_stream_plan(int64_t n, int64_t K, int device, int64_t *block_len, int64_t *bytes_per_series);
 int cmtjb_spectrum_stream_moments(const double *x_chunk, int64_t ld, int64_t B, int64_t n, int64_t K, int64_t q0, int64_t nq,
-                                  void *moments, int device, void *stream);
+                                  void *moments, int32_t background, int device, void *stream);
 int cmtjb_spectrum_stream_finish(const void *moments, int64_t n, int64_t B, int64_t K, double *out, int device, void *stream);
 
 /* Number of kernels this library has launched in this process (monotonic). */

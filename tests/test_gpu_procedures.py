@@ -216,12 +216,13 @@ def test_spectrum_device_shapes(on_cuda, monkeypatch, n, B, K_freq, pitch, mode)
     assert np.max(np.abs(yf.cpu().numpy() - want) / scale) < 1e-12
 
 
-@pytest.mark.parametrize("B,chunk_mb,wait,last_n", [
-    (40, 0.2, 0.0, 20),      # 40 series x 5000 steps in chunks of a few blocks (one full 32-series tile + 8 ragged)
-    (70, 0.5, 0.1e-9, 100),  # wait_time > 0: the series starts inside the run; last-n longer than a block (merged tail chunk)
-    (3, 8192, 0.0, 20),      # one chunk
+@pytest.mark.parametrize("B,chunk_mb,wait,last_n,overlap", [
+    (40, 0.2, 0.0, 20, True),      # 40 series x 5000 steps in chunks of a few blocks (one full 32-series tile + 8 ragged)
+    (70, 0.5, 0.1e-9, 100, True),  # wait_time > 0: the series starts inside the run; last-n longer than a block (merged tail chunk)
+    (40, 0.2, 0.0, 20, False),     # the same chunks on one stream, foreground kernels only
+    (3, 8192, 0.0, 20, True),      # one chunk
 ])
-def test_pimm_streamed_spectrum_equals_resident_log(on_cuda, monkeypatch, B, chunk_mb, wait, last_n):
+def test_pimm_streamed_spectrum_equals_resident_log(on_cuda, monkeypatch, B, chunk_mb, wait, last_n, overlap):
     """PIMM_batch reduces the projected signal chunk by chunk (_SpectrumStream: block moments, no resident log); the
     result must equal the whole-log path (CMTJB_PIMM_RESIDENT_LOG=1) to rounding, and numpy's rfft of that log."""
     rng = np.random.default_rng(B)
@@ -231,11 +232,16 @@ def test_pimm_streamed_spectrum_equals_resident_log(on_cuda, monkeypatch, B, chu
     monkeypatch.setenv("CMTJB_PIMM_CHUNK_MB", str(chunk_mb))
     calls = []
     orig = P._SpectrumStream.add
-    monkeypatch.setattr(P._SpectrumStream, "add", lambda self, chunk, q0, nq: (calls.append((q0, nq)), orig(self, chunk, q0, nq))[1])
+    monkeypatch.setattr(P._SpectrumStream, "add",
+                        lambda self, chunk, q0, nq, background=False: (calls.append((q0, nq, background)), orig(self, chunk, q0, nq, background))[1])
+    if not overlap:
+        monkeypatch.setenv("CMTJB_PIMM_NO_OVERLAP", "1")
     s1, f1, o1 = P.PIMM_batch(helpers.two_layer_mtj(cm), H, **kw)
-    assert calls  # the streamed path ran
+    assert calls and sum(nq for _, nq, _ in calls) > 0  # the streamed path ran
     if chunk_mb < 1:
         assert len(calls) > 1, calls
+        # every chunk but the last is reduced by the background kernel while the next one integrates
+        assert [bg for _, _, bg in calls] == [overlap] * (len(calls) - 1) + [False]
     monkeypatch.setenv("CMTJB_PIMM_RESIDENT_LOG", "1")
     n_calls = len(calls)
     s2, f2, o2 = P.PIMM_batch(helpers.two_layer_mtj(cm), H, **kw)
@@ -260,8 +266,8 @@ def test_spectrum_stream_chunks_in_any_order(on_cuda):
     L = st.block_len
     cuts = [0, 2, 6, st.n_blocks - (st.n_blocks % 2 or 2), st.n_blocks]
     spans = [(a, b - a) for a, b in zip(cuts, cuts[1:]) if b > a]
-    for q0, nq in reversed(spans):
-        st.add(xd[q0 * L : (q0 + nq) * L].contiguous(), q0, nq)
+    for i, (q0, nq) in enumerate(reversed(spans)):
+        st.add(xd[q0 * L : (q0 + nq) * L].contiguous(), q0, nq, background=bool(i % 2))  # both forms of the reduction
     got = st.finish().cpu().numpy()
     want = np.abs(np.fft.rfft(x, axis=0))[: st.K].T
     assert np.max(np.abs(got - want) / np.abs(want).max(axis=1, keepdims=True)) < 1e-12
