@@ -17,32 +17,44 @@ local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-T = steps * 1e-13 * (1 + 1e-9)
-out = {}
-for rep in range(2):  # the first pass pays NCCL's lazy channel set-up
-    g = lattice_group(n)
-    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    g.run_sharded(T, 1e-13, 1e-12, seed=7, gather=True)
-    torch.cuda.synchronize(); dist.barrier(); out["sharded_s"] = time.perf_counter() - t0
+def T_of(k):
+    return k * 1e-13 * (1 + 1e-9)
+
+
+def timed(fn):
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    fn()
+    torch.cuda.synchronize(); dist.barrier()
+    return time.perf_counter() - t0
+
+
+T = T_of(steps)
+short = max(10, steps // 5)
+g = lattice_group(n)
+g.run_sharded(T_of(10), 1e-13, 1e-12, seed=7, gather=False)  # NCCL's lazy channel set-up
+# marginal time per step: (long run - short run) / (steps - short); the fixed part is packing and uploading n junction models
+t_short = timed(lambda: lattice_group(n).run_sharded(T_of(short), 1e-13, 1e-12, seed=7, gather=False))
+g = lattice_group(n)
+t_long = timed(lambda: g.run_sharded(T, 1e-13, 1e-12, seed=7, gather=True))
+out = {"what": "GroupInteraction.run_sharded, NCCL all-gather of the top-layer m per step", "elements": n, "steps": steps, "world": world,
+       "us_per_step_sharded": 1e6 * (t_long - t_short) / (steps - short), "fixed_s_sharded": t_short - short * (t_long - t_short) / (steps - short)}
 if rank == 0:
-    for rep in range(2):
-        one = lattice_group(n)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        one.run_sharded(T, 1e-13, 1e-12, rank=0, world=1, seed=7)
-        torch.cuda.synchronize(); out["single_s"] = time.perf_counter() - t0
+    one = lattice_group(n)
+    t1s = time.perf_counter(); lattice_group(n).run_sharded(T_of(short), 1e-13, 1e-12, rank=0, world=1, seed=7); torch.cuda.synchronize(); t1s = time.perf_counter() - t1s
+    t1l = time.perf_counter(); one.run_sharded(T, 1e-13, 1e-12, rank=0, world=1, seed=7); torch.cuda.synchronize(); t1l = time.perf_counter() - t1l
+    out["us_per_step_world_1"] = 1e6 * (t1l - t1s) / (steps - short)
     a, b = logs_of(g), logs_of(one)
     same = all(np.array_equal(a[k][name], b[k][name]) for k in range(n) for name in b[k])
     coop = lattice_group(n)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    coop.runSimulation(T, 1e-13, 1e-12)
-    torch.cuda.synchronize(); out["cooperative_single_gpu_s"] = time.perf_counter() - t0
+    tcs = time.perf_counter(); lattice_group(n).runSimulation(T_of(short), 1e-13, 1e-12); torch.cuda.synchronize(); tcs = time.perf_counter() - tcs
+    tcl = time.perf_counter(); coop.runSimulation(T, 1e-13, 1e-12); torch.cuda.synchronize(); tcl = time.perf_counter() - tcl
+    out["us_per_step_cooperative_kernel_one_gpu"] = 1e6 * (tcl - tcs) / (steps - short)
     c = logs_of(coop)
     scale = max(np.max(np.abs(c[k][nm])) for k in range(n) for nm in c[k] if nm != "time")
     err = max(np.max(np.abs(a[k][nm] - c[k][nm])) for k in range(n) for nm in c[k] if nm != "time") / scale
-    print(json.dumps({"what": "GroupInteraction.run_sharded, NCCL all-gather of the top-layer m per step", "elements": n, "steps": steps,
-                      "world": world, "bit_identical_to_world_1": bool(same), "max_rel_diff_vs_cooperative_kernel": float(err),
-                      "us_per_step_sharded": 1e6 * out["sharded_s"] / steps, "us_per_step_world_1": 1e6 * out["single_s"] / steps,
-                      "us_per_step_cooperative_kernel_incl_host": 1e6 * out["cooperative_single_gpu_s"] / steps}), flush=True)
+    out["bit_identical_to_world_1"] = bool(same)
+    out["max_rel_diff_vs_cooperative_kernel"] = float(err)
+    print(json.dumps(out), flush=True)
     assert same
 dist.barrier()
 dist.destroy_process_group()
