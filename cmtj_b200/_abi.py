@@ -351,6 +351,20 @@ class Backend:
             C.c_void_p(m_state_ptr), C.c_void_p(jlog_ptr), C.c_void_p(status_ptr), int(device), C.c_void_p(stream),
         )  # fmt: skip
 
+    def group_run_sharded_peer(self, g, jns, layers, args, rank, world, areas, m_state_ptr, jlog_ptr, status_ptr, device=0, stream=0) -> int:
+        """``cmtjb_group_run_sharded_peer``: the exchange over peer memory; ``areas`` = the ``world`` exchange-area addresses
+        as seen from this process."""
+        f = self._fn(
+            "group_run_sharded_peer",
+            [_P(Group), C.c_void_p, C.c_void_p, _P(RunArgs), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)] + [C.c_void_p] * 3
+            + [C.c_int, C.c_void_p],
+        )  # fmt: skip
+        arr = (C.c_void_p * int(world))(*[int(a) for a in areas])
+        return f(
+            C.byref(g), C.cast(jns, C.c_void_p), C.cast(layers, C.c_void_p), C.byref(args), int(rank), int(world), arr,
+            C.c_void_p(m_state_ptr), C.c_void_p(jlog_ptr), C.c_void_p(status_ptr), int(device), C.c_void_p(stream),
+        )  # fmt: skip
+
     def last_error(self) -> str:
         s = self._last_error()
         return s.decode("utf-8", "replace") if s else ""

@@ -629,10 +629,11 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
 // for this rank's elements only.
 template <int NL>
 int group_shard_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a,
-                       const Common &c, int rank, int world, cmtjb_exchange_fn exchange, void *ctx, double *m_state, double *jlog,
-                       int32_t *status, int device, cudaStream_t stream) {
+                       const Common &c, int rank, int world, cmtjb_exchange_fn exchange, void *ctx, void *const *areas, double *m_state,
+                       double *jlog, int32_t *status, int device, cudaStream_t stream) {
   const int N = g->n_junctions;
   const int per = (N + world - 1) / world;
+  const bool peer = areas != nullptr;  // peer-memory exchange (coupled_kernels.cuh: PeerPush) instead of the callback
   const int e_lo = std::min(N, rank * per), e_hi = std::min(N, e_lo + per), own = e_hi - e_lo;
   RunParams R;
   std::memset(&R, 0, sizeof(R));
@@ -659,18 +660,45 @@ int group_shard_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, cons
   if (e == cudaSuccess) e = upload(pos.data(), pos.size(), &d_pos, stream);
   if (e == cudaSuccess) e = upload(pref.data(), pref.size(), &d_pref, stream);
   if (e == cudaSuccess) e = upload(&R, 1, &d_R, stream);
-  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_x, (size_t)world * 3 * per * sizeof(double), stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_x, 0, (size_t)world * 3 * per * sizeof(double), stream);
+  if (e == cudaSuccess && !peer) e = cudaMallocAsync((void **)&d_x, (size_t)world * 3 * per * sizeof(double), stream);
+  if (e == cudaSuccess && !peer) e = cudaMemsetAsync(d_x, 0, (size_t)world * 3 * per * sizeof(double), stream);
   if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_hpart, (size_t)P * 3 * std::max(own, 1) * sizeof(double), stream);
   int rc = (e == cudaSuccess) ? CMTJB_OK : cuda_fail(e, "sharded group set-up");
   double *x_own = d_x ? d_x + (size_t)rank * 3 * per : nullptr;
+  // layout of an exchange area (peer mode): X[2][world][3][per], arrived[world], blocks_done, error
+  const size_t x_doubles = (size_t)world * 3 * per;
+  auto area_x = [&](int r, int parity) { return reinterpret_cast<double *>(areas[r]) + (size_t)parity * x_doubles; };
+  auto area_arrived = [&](int r) { return reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(areas[r]) + 2 * x_doubles); };
+  unsigned int *own_words = peer ? reinterpret_cast<unsigned int *>(area_arrived(rank) + world) : nullptr;  // blocks_done, error
+  unsigned long long timeout_ns = 20ull * 1000000000ull;
+  if (const char *cto = std::getenv("CMTJB_PEER_TIMEOUT_MS")) timeout_ns = (unsigned long long)std::max(1, std::atoi(cto)) * 1000000ull;
+  PeerPush push;
+  std::memset(&push, 0, sizeof(push));
+  auto aim = [&](int parity, unsigned long long epoch) {  // this rank's rows of buffer `parity` in every area
+    push.n = world, push.rank = rank, push.epoch = epoch, push.blocks_done = own_words;
+    for (int r = 0; r < world; r++) {
+      push.x[r] = area_x(r, parity) + (size_t)rank * 3 * per;
+      push.arrived[r] = area_arrived(r) + rank;
+    }
+  };
   // initial exchange: the top-layer rows of the incoming state
-  for (int cpt = 0; cpt < 3 && rc == CMTJB_OK && own > 0; cpt++) {
-    e = cudaMemcpyAsync(x_own + (size_t)cpt * per, m_state + (size_t)(3 * g->top_layer + cpt) * own, (size_t)own * sizeof(double),
-                        cudaMemcpyDeviceToDevice, stream);
-    if (e != cudaSuccess) rc = cuda_fail(e, "sharded group initial state");
+  if (peer) {
+    if (rc == CMTJB_OK) {
+      aim(0, 1);
+      const double *mx = m_state + (size_t)(3 * g->top_layer) * own;
+      group_peer_publish_kernel<<<(unsigned)std::max(1, (own + 127) / 128), 128, 0, stream>>>(mx, mx + own, mx + 2 * (size_t)own, own, per, push);
+      g_launches++;
+      e = cudaGetLastError();
+      if (e != cudaSuccess) rc = cuda_fail(e, "group_peer_publish_kernel");
+    }
+  } else {
+    for (int cpt = 0; cpt < 3 && rc == CMTJB_OK && own > 0; cpt++) {
+      e = cudaMemcpyAsync(x_own + (size_t)cpt * per, m_state + (size_t)(3 * g->top_layer + cpt) * own, (size_t)own * sizeof(double),
+                          cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) rc = cuda_fail(e, "sharded group initial state");
+    }
+    if (rc == CMTJB_OK && exchange(ctx, d_x, (int64_t)3 * per, (int64_t)-1, (void *)stream) != 0) rc = fail(CMTJB_ERUNTIME, "exchange callback failed");
   }
-  if (rc == CMTJB_OK && exchange(ctx, d_x, (int64_t)3 * per, (int64_t)-1, (void *)stream) != 0) rc = fail(CMTJB_ERUNTIME, "exchange callback failed");
   const bool rk4 = (c.solver == CMTJB_RK4);
   const bool lean = own > 0 && lean_ok(system_features(own, NL, jns + e_lo, layers + (size_t)e_lo * NL, nullptr, 0, a, c.solver, false));
   PairShardParams Q;
@@ -679,11 +707,20 @@ int group_shard_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, cons
   GroupStepParams G;
   std::memset(&G, 0, sizeof(G));
   G.N = own, G.P = P, G.interaction = g->interaction, G.top = g->top_layer, G.inst = 0, G.Hpart = d_hpart;
-  G.xout = x_own, G.xpitch = per;
+  G.xout = peer ? nullptr : x_own, G.xpitch = per;
   long long sample = R.first_sample;
+  long long step_no = 0;  // steps of THIS call (exchange epochs count from the call's initial publish)
   const long long we = R.write_every;
   const long long pair_blocks = ((long long)tiles * 32 * P + 255) / 256;
-  for (long long it = R.it_begin; it < R.it_end && rc == CMTJB_OK; it++) {
+  for (long long it = R.it_begin; it < R.it_end && rc == CMTJB_OK; it++, step_no++) {
+    if (peer) {
+      // slices number step_no + 1 of every rank must be in before the pair sums read buffer step_no % 2
+      group_peer_wait_kernel<<<1, 32, 0, stream>>>(area_arrived(rank), world, (unsigned long long)step_no + 1, own_words + 1, timeout_ns);
+      g_launches++;
+      Q.xbuf = area_x(rank, (int)(step_no & 1));
+      aim((int)((step_no + 1) & 1), (unsigned long long)step_no + 2);
+      G.push = push;
+    }
     if (own > 0) {
       if (g->interaction != CMTJB_INT_NULL) {
         group_pair_shard_kernel<<<(unsigned)pair_blocks, 256, 0, stream>>>(Q);
@@ -704,8 +741,27 @@ int group_shard_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, cons
       e = cudaGetLastError();
       if (e != cudaSuccess) rc = cuda_fail(e, "sharded group pair/step kernels");
     }
+    else if (peer) {  // a rank without elements still takes part in the hand-shake
+      group_peer_publish_kernel<<<1, 128, 0, stream>>>(nullptr, nullptr, nullptr, 0, per, push);
+      g_launches++;
+    }
     if (it % we == 0) sample++;
-    if (rc == CMTJB_OK && exchange(ctx, d_x, (int64_t)3 * per, (int64_t)it, (void *)stream) != 0) rc = fail(CMTJB_ERUNTIME, "exchange callback failed");
+    if (!peer && rc == CMTJB_OK && exchange(ctx, d_x, (int64_t)3 * per, (int64_t)it, (void *)stream) != 0)
+      rc = fail(CMTJB_ERUNTIME, "exchange callback failed");
+  }
+  if (peer && rc == CMTJB_OK) {
+    // the last slices must have left before anybody frees an area, and a peer that never arrived is an error, not a hang
+    group_peer_wait_kernel<<<1, 32, 0, stream>>>(area_arrived(rank), world, (unsigned long long)step_no + 1, own_words + 1, timeout_ns);
+    g_launches++;
+    unsigned int err = 0;
+    e = cudaMemcpyAsync(&err, own_words + 1, sizeof(err), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "sharded group (peer exchange)");
+    else if (err) {
+      char buf[128];
+      std::snprintf(buf, sizeof(buf), "peer exchange: rank %u did not deliver its slice within the time limit", err - 1);
+      rc = fail(CMTJB_ERUNTIME, buf);
+    }
   }
   cudaFreeAsync(d_models, stream);
   cudaFreeAsync(d_pos, stream);
@@ -897,10 +953,75 @@ int cmtjb_group_run_sharded(const cmtjb_group_t *g, const cmtjb_junction_t *jns,
       return fail(CMTJB_ENOTSUP, "1/f noise is not supported for sharded arrays");
   CUDA_TRY(cudaSetDevice(device));
   switch (c.nl) {
-  case 1: return group_shard_launch<1>(g, jns, layers, args, c, rank, world, exchange, ctx, m_state, junction_log, status, device, (cudaStream_t)stream);
-  case 2: return group_shard_launch<2>(g, jns, layers, args, c, rank, world, exchange, ctx, m_state, junction_log, status, device, (cudaStream_t)stream);
+  case 1: return group_shard_launch<1>(g, jns, layers, args, c, rank, world, exchange, ctx, nullptr, m_state, junction_log, status, device, (cudaStream_t)stream);
+  case 2: return group_shard_launch<2>(g, jns, layers, args, c, rank, world, exchange, ctx, nullptr, m_state, junction_log, status, device, (cudaStream_t)stream);
   default: return fail(CMTJB_ENOTSUP, "dipole-coupled junctions with more than 2 layers are not supported by this build");
   }
+}
+
+int64_t cmtjb_group_peer_area_bytes(int32_t n_junctions, int32_t world) {
+  if (n_junctions <= 0 || world <= 0) return 0;
+  const int64_t per = (n_junctions + world - 1) / world;
+  return 2 * (int64_t)world * 3 * per * (int64_t)sizeof(double) + (int64_t)world * (int64_t)sizeof(unsigned long long) + 64;
+}
+
+int cmtjb_group_run_sharded_peer(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                                 const cmtjb_run_args_t *args, int32_t rank, int32_t world, void *const *areas, double *m_state,
+                                 double *junction_log, int32_t *status, int device, void *stream) {
+  if (!areas || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(CMTJB_EINVAL, "bad rank / world (at most 16 ranks) / areas");
+  for (int r = 0; r < world; r++)
+    if (!areas[r]) return fail(CMTJB_EINVAL, "null exchange area");
+  if (!args || args->n_instances != 1) return fail(CMTJB_EINVAL, "a sharded array is one instance");
+  Common c;
+  int rc = validate_group(g, jns, layers, args, &c);
+  if (rc) return rc;
+  if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
+  if (args->onef_buffer) return fail(CMTJB_ENOTSUP, "1/f noise buffers are not supported for sharded arrays");
+  for (long long k = 0; k < (long long)g->n_junctions * c.nl; k++)
+    if (layers[k].noiseScale != 0.0) return fail(CMTJB_ENOTSUP, "1/f noise is not supported for sharded arrays");
+  CUDA_TRY(cudaSetDevice(device));
+  switch (c.nl) {
+  case 1: return group_shard_launch<1>(g, jns, layers, args, c, rank, world, nullptr, nullptr, areas, m_state, junction_log, status, device, (cudaStream_t)stream);
+  case 2: return group_shard_launch<2>(g, jns, layers, args, c, rank, world, nullptr, nullptr, areas, m_state, junction_log, status, device, (cudaStream_t)stream);
+  default: return fail(CMTJB_ENOTSUP, "dipole-coupled junctions with more than 2 layers are not supported by this build");
+  }
+}
+
+/* device memory every process of the box can map (cudaMalloc, zero-filled: stream-ordered pool memory cannot be exported) */
+int cmtjb_peer_alloc(int device, int64_t bytes, void **ptr) {
+  if (!ptr || bytes <= 0) return fail(CMTJB_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMalloc(ptr, (size_t)bytes));
+  CUDA_TRY(cudaMemset(*ptr, 0, (size_t)bytes));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return CMTJB_OK;
+}
+int cmtjb_peer_free(int device, void *ptr) {
+  CUDA_TRY(cudaSetDevice(device));
+  if (ptr) CUDA_TRY(cudaFree(ptr));
+  return CMTJB_OK;
+}
+int cmtjb_peer_export(int device, void *ptr, unsigned char *handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!ptr || !handle64) return fail(CMTJB_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+  std::memcpy(handle64, &h, 64);
+  return CMTJB_OK;
+}
+int cmtjb_peer_open(int device, const unsigned char *handle64, void **ptr) {
+  if (!ptr || !handle64) return fail(CMTJB_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return CMTJB_OK;
+}
+int cmtjb_peer_close(int device, void *ptr) {
+  CUDA_TRY(cudaSetDevice(device));
+  if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return CMTJB_OK;
 }
 
 } /* extern "C" */

@@ -651,6 +651,79 @@ __global__ void __launch_bounds__(256) group_pair_kernel(const __grid_constant__
   }
 }
 
+// ---- peer-memory exchange of a sharded array (no collective library, no host in the time loop) ---------------------------
+// Every rank owns an exchange AREA in its own device memory that all ranks of the box can address (CUDA IPC over NVLink):
+//     double             X[2][world][3][per]   top-layer m of every element, double-buffered by step parity
+//     unsigned long long arrived[world]        arrived[r] = number of slices rank r has delivered into THIS area
+//     unsigned int       blocks_done, error
+// A rank's step kernel stores its new m rows into X[(s + 1) % 2][rank] of EVERY area (remote stores for the peers') and the
+// last of its blocks to finish -- system-scope fences on both sides of a block counter -- raises arrived[rank] to s + 2 in
+// every area.  Before the pair kernel of step s a one-warp kernel waits until arrived[r] >= s + 1 for all r in its OWN area.
+// Buffer parity is safe with two buffers: a rank writes X[(s + 1) % 2] only after its own wait for step s, i.e. after every
+// peer has finished step s - 1, whose pair kernel was the last reader of that buffer.
+constexpr int kMaxPeers = 16;
+struct PeerPush {
+  int n;                               // ranks (0: no peer exchange)
+  int rank;
+  double *x[kMaxPeers];                // this rank's rows [3][per] of the buffer being written, in every area
+  unsigned long long *arrived[kMaxPeers];  // &arrived[rank] in every area
+  unsigned long long epoch;            // value to publish
+  unsigned int *blocks_done;           // own area
+};
+
+__device__ __forceinline__ void peer_signal(const PeerPush &P) {
+  // every thread's remote stores are ordered before its block's increment of the counter ...
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    if (atomicAdd(P.blocks_done, 1u) == total - 1) {
+      *P.blocks_done = 0;  // next launch (stream-ordered)
+      __threadfence_system();  // ... and the last block's flag stores after everybody's data
+      for (int r = 0; r < P.n; r++) *reinterpret_cast<volatile unsigned long long *>(P.arrived[r]) = P.epoch;
+    }
+  }
+}
+
+// initial state: the top-layer rows of m_state into X[0][rank] of every area
+__global__ void __launch_bounds__(128) group_peer_publish_kernel(const double *__restrict__ mx, const double *__restrict__ my,
+                                                                 const double *__restrict__ mz, int own, int per,
+                                                                 const __grid_constant__ PeerPush P) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < own) {
+    const double x = mx[a], y = my[a], z = mz[a];
+    for (int r = 0; r < P.n; r++) {
+      P.x[r][a] = x;
+      P.x[r][per + a] = y;
+      P.x[r][2 * per + a] = z;
+    }
+  }
+  peer_signal(P);
+}
+
+// wait until every rank has delivered slice number `epoch` into this area (one thread per rank); gives up after timeout_ns
+__global__ void group_peer_wait_kernel(const unsigned long long *arrived, int world, unsigned long long epoch, unsigned int *error,
+                                       unsigned long long timeout_ns) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  if (*reinterpret_cast<volatile unsigned int *>(error)) return;  // an earlier wait of this call already gave up: do not wait again
+  const volatile unsigned long long *f = arrived + r;
+  unsigned long long t0 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  unsigned int spins = 0;
+  while (*f < epoch) {
+    if ((++spins & 1023u) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) {
+        atomicExch(error, 1u + (unsigned)r);
+        break;
+      }
+    }
+  }
+  __threadfence_system();  // the data behind the flag is read after this point
+}
+
 struct GroupStepParams {
   int N, P, interaction, top;
   long long inst;          // instance of the batch (state rows inst*N .. inst*N + N - 1)
@@ -659,6 +732,7 @@ struct GroupStepParams {
   const double *Hpart;     // [P][3][N]
   double *xout;            // sharded arrays: this rank's rows [3][xpitch] of the exchange buffer (else null)
   int xpitch;
+  PeerPush push;           // sharded arrays, peer-memory exchange: where else the rows go, and whom to tell (n = 0: nobody)
 };
 
 // ---- one array sharded over several GPUs (reservoir.hpp:129-152 with the elements split into contiguous ranges) ---------
@@ -714,40 +788,50 @@ template <int NL, int SOLVER, uint32_t F, bool UNIFORM>
 __global__ void __launch_bounds__(128) group_step_kernel(const DevModel<NL> *__restrict__ models, const RunParams *__restrict__ Rp,
                                                          const __grid_constant__ GroupStepParams G) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= G.N) return;
-  const int N = G.N;
-  const long long i = G.inst * N + a;
-  const RunParams &R = *Rp;
-  const DevModel<NL> &M = models[UNIFORM ? 0 : a];
-  State<NL> S;
-  load_state<NL>(R, i, S);
-  d3 H = mk(0, 0, 0);
-  if (G.interaction != CMTJB_INT_NULL) {
-    for (int p = 0; p < G.P; p++) {
-      const double *q = G.Hpart + (size_t)p * 3 * N + a;
-      H = H + mk(q[0], q[N], q[2 * N]);
+  if (a < G.N) {
+    const int N = G.N;
+    const long long i = G.inst * N + a;
+    const RunParams &R = *Rp;
+    const DevModel<NL> &M = models[UNIFORM ? 0 : a];
+    State<NL> S;
+    load_state<NL>(R, i, S);
+    d3 H = mk(0, 0, 0);
+    if (G.interaction != CMTJB_INT_NULL) {
+      for (int p = 0; p < G.P; p++) {
+        const double *q = G.Hpart + (size_t)p * 3 * N + a;
+        H = H + mk(q[0], q[N], q[2 * N]);
+      }
+      if (G.interaction == CMTJB_INT_DIPOLE_NOMURA) H = H * (1.0 / (4.0 * M_PI));
     }
-    if (G.interaction == CMTJB_INT_DIPOLE_NOMURA) H = H * (1.0 / (4.0 * M_PI));
+    d3 Hl[NL];
+  #pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const d3 Hc = constant_field(M.L[l], R, i);
+      Hl[l] = (l == G.top) ? Hc + H : Hc;  // setLayerReservedInteractionField(topId, ...) (reservoir.hpp:145-146)
+    }
+    coupled_step<NL, SOLVER, F>(M, R, i, G.it, (double)G.it * R.dt, S, Hl, NoExt());
+    store_state<NL>(R, i, S);  // the next pair kernel reads the top layer's rows from here
+    if (G.xout) {
+      const d3 mt = layer_m2<NL>(S, G.top);
+      G.xout[a] = mt.x;
+      G.xout[G.xpitch + a] = mt.y;
+      G.xout[2 * G.xpitch + a] = mt.z;
+    }
+    if (G.push.n > 0) {
+      const d3 mt = layer_m2<NL>(S, G.top);
+      for (int r = 0; r < G.push.n; r++) {  // NVLink stores into the peers' areas (and a local one into our own)
+        G.push.x[r][a] = mt.x;
+        G.push.x[r][G.xpitch + a] = mt.y;
+        G.push.x[r][2 * G.xpitch + a] = mt.z;
+      }
+    }
+    if (G.write && R.log) write_sample<NL>(M, R, S, G.sample, i);
+    if (R.status) {
+      const int st = nan_status<NL, SOLVER>(S);
+      if (G.it == 0 || st) R.status[i] = st;
+    }
   }
-  d3 Hl[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) {
-    const d3 Hc = constant_field(M.L[l], R, i);
-    Hl[l] = (l == G.top) ? Hc + H : Hc;  // setLayerReservedInteractionField(topId, ...) (reservoir.hpp:145-146)
-  }
-  coupled_step<NL, SOLVER, F>(M, R, i, G.it, (double)G.it * R.dt, S, Hl, NoExt());
-  store_state<NL>(R, i, S);  // the next pair kernel reads the top layer's rows from here
-  if (G.xout) {
-    const d3 mt = layer_m2<NL>(S, G.top);
-    G.xout[a] = mt.x;
-    G.xout[G.xpitch + a] = mt.y;
-    G.xout[2 * G.xpitch + a] = mt.z;
-  }
-  if (G.write && R.log) write_sample<NL>(M, R, S, G.sample, i);
-  if (R.status) {
-    const int st = nan_status<NL, SOLVER>(S);
-    if (G.it == 0 || st) R.status[i] = st;
-  }
+  if (G.push.n > 0) peer_signal(G.push);  // every thread of the block, owners of an element or not
 }
 
 }  // namespace cmtjb

@@ -135,7 +135,9 @@ class GroupInteraction:
         seed: Optional[int] = None,
         exchange: Optional[Callable] = None,
         gather: bool = True,
+        transport: str = "auto",
         _host_memory: bool = False,
+        _peer_areas: Optional[Callable] = None,
     ) -> Dict[str, np.ndarray]:
         """``runSimulation`` for an array split over the ranks of a ``torch.distributed`` job, one process per GPU
         (core/reservoir.hpp:129-152 with the element loop cut into contiguous ranges of ceil(N / world)).  Every rank
@@ -144,6 +146,10 @@ class GroupInteraction:
         synchronisation inside the time loop).  The pair sums are accumulated in an order that depends on N alone, so
         the trajectories are bit-identical for every world size.
 
+        ``transport``: ``"peer"`` -- the step kernels store their slice straight into every rank's exchange area over
+        NVLink (CUDA IPC mappings, set up here through ``torch.distributed``) and hand-shake through arrival counters: no
+        collective, no host in the time loop; ``"nccl"`` -- the all-gather above; ``"auto"`` -- peer memory when the job
+        runs NCCL on one node with at most 16 ranks, else the collective.
         ``exchange(buf_address, count, step, stream_address) -> 0`` replaces the collective (tests, other transports).
         With ``gather`` every rank ends up with all junction logs, as after the reference's runSimulation; without it
         only this rank's junctions are written back.  Returns this rank's ``{"lo", "hi", "m_state", "log"}``."""
@@ -185,10 +191,26 @@ class GroupInteraction:
             stream = torch.cuda.Stream(tdev)
             stream_ptr = stream.cuda_stream
             with torch.cuda.stream(stream):
-                m_dev = torch.from_numpy(m_host).to(tdev)
+                m_dev = torch.from_numpy(m_host if own > 0 else np.zeros((m_host.shape[0], 1))).to(tdev)  # never a null pointer
                 jlog_dev = torch.zeros((ch, max(ns, 1), max(own, 1)), dtype=torch.float64, device=tdev)
                 st_dev = torch.zeros(max(own, 1), dtype=torch.int32, device=tdev)
             addr = lambda t: t.data_ptr()  # noqa: E731
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        use_peer = (transport == "peer") or (
+            transport == "auto" and exchange is None and not _host_memory and world > 1 and world <= 16
+            and dist is not None and dist.get_backend() == "nccl" and _single_node()
+        )
+        if use_peer and (_host_memory or exchange is not None):
+            raise ValueError("the peer-memory transport takes no exchange callback")
+        if use_peer:
+            peers = (_peer_areas or _ipc_peer_areas)(be, dist, rank, world, dev, N)
+            try:
+                rc = be.group_run_sharded_peer(g, jns, layers, a, rank, world, peers.areas, addr(m_dev), addr(jlog_dev), addr(st_dev), dev, stream_ptr)
+                stream.synchronize()
+            finally:
+                peers.close()  # barrier, then unmap and free
+            return self._finish_sharded(be, rc, dist, rank, world, dev, nl, ch, ns, N, per, lo, hi, own, m_dev, jlog_dev, plan, timeStep, gather, torch)
         failure: List[BaseException] = []
         if exchange is None:
             exchange = _collective_exchange(dist, rank, world, None if _host_memory else dev)
@@ -204,9 +226,16 @@ class GroupInteraction:
         rc = be.group_run_sharded(g, jns, layers, a, rank, world, cb, addr(m_dev), addr(jlog_dev), addr(st_dev), dev, stream_ptr)
         if failure:
             raise failure[0]
-        if torch is not None:
+        return self._finish_sharded(be, rc, dist, rank, world, dev, nl, ch, ns, N, per, lo, hi, own, m_dev, jlog_dev, plan, timeStep, gather, torch,
+                                    stream if torch is not None else None)
+
+    def _finish_sharded(self, be, rc, dist, rank, world, dev, nl, ch, ns, N, per, lo, hi, own, m_dev, jlog_dev, plan, timeStep, gather, torch,
+                        stream=None):
+        """results of this rank to the host, the optional gather of every rank's logs, write-back into the junction objects"""
+        if torch is not None and stream is not None:
             stream.synchronize()
-            m_own, jlog_own = m_dev.cpu().numpy(), jlog_dev.cpu().numpy()[:, :ns, :own]
+        if torch is not None:
+            m_own, jlog_own = m_dev.cpu().numpy()[:, :own], jlog_dev.cpu().numpy()[:, :ns, :own]
         else:
             m_own, jlog_own = m_dev, jlog_dev[:, :ns, :own]
         times = _coupled.sample_times(plan, timeStep)[:ns]
@@ -323,3 +352,52 @@ def _collective_exchange(dist, rank: int, world: int, device: Optional[int]):
         return 0
 
     return device_exchange
+
+
+def _single_node() -> bool:
+    import os
+
+    return int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0) == int(os.environ.get("WORLD_SIZE", "-1") or -1)
+
+
+class _PeerAreas:
+    """The exchange areas of a peer-memory run as seen from this process: ``areas[r]`` for every rank, own one included."""
+
+    def __init__(self, be, device, own_ptr, areas, opened, barrier):
+        self.be, self.device, self.own_ptr, self.areas, self.opened, self.barrier = be, device, own_ptr, areas, opened, barrier
+
+    def close(self):
+        import ctypes as C
+
+        self.barrier()  # nobody unmaps or frees while a peer may still store into an area
+        lib = self.be.lib
+        for p in self.opened:
+            lib.cmtjb_peer_close(C.c_int(self.device), C.c_void_p(p))
+        self.barrier()
+        lib.cmtjb_peer_free(C.c_int(self.device), C.c_void_p(self.own_ptr))
+
+
+def _ipc_peer_areas(be, dist, rank: int, world: int, device: int, n_elements: int) -> _PeerAreas:
+    """Allocate this rank's exchange area, trade CUDA IPC handles through ``torch.distributed`` and map the peers' areas."""
+    import ctypes as C
+
+    lib = be.lib
+    lib.cmtjb_group_peer_area_bytes.restype = C.c_int64
+    nbytes = int(lib.cmtjb_group_peer_area_bytes(C.c_int32(n_elements), C.c_int32(world)))
+    own = C.c_void_p()
+    be.check(lib.cmtjb_peer_alloc(C.c_int(device), C.c_int64(nbytes), C.byref(own)))
+    handle = (C.c_ubyte * 64)()
+    be.check(lib.cmtjb_peer_export(C.c_int(device), own, handle))
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(handle))  # also the barrier after which every area exists and is zero
+    areas, opened = [], []
+    for r in range(world):
+        if r == rank:
+            areas.append(own.value)
+            continue
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+        be.check(lib.cmtjb_peer_open(C.c_int(device), h, C.byref(p)))
+        areas.append(p.value)
+        opened.append(p.value)
+    return _PeerAreas(be, device, own.value, areas, opened, dist.barrier)

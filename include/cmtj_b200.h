@@ -482,6 +482,27 @@ int cmtjb_group_run_sharded(const cmtjb_group_t *g, const cmtjb_junction_t *jns,
                             const cmtjb_run_args_t *args, int32_t rank, int32_t world, cmtjb_exchange_fn exchange, void *ctx,
                             double *m_state, double *junction_log, int32_t *status, int device, void *stream);
 
+/* The same array with the exchange done by the kernels themselves over PEER MEMORY (NVLink / NVSwitch): no collective
+ * library and no host in the time loop.  Every rank owns an exchange area of cmtjb_group_peer_area_bytes(n_junctions, world)
+ * bytes in its own device memory (cmtjb_peer_alloc: cudaMalloc, zero-filled) that the other ranks have mapped
+ * (cmtjb_peer_export -> 64-byte CUDA IPC handle, sent by any means -> cmtjb_peer_open in the other processes; ranks that are
+ * threads of one process pass each other's pointers directly).  areas[r] is rank r's area as addressable from THIS process,
+ * areas[rank] the own one.  Each step's kernel stores the rank's new top-layer magnetisations into every area and raises a
+ * per-rank arrival counter there behind a system-scope fence; a one-warp kernel waits on the own area's counters before the
+ * next pair sums (no deadlock: a rank never waits for anything a peer has not already been able to launch; a peer that
+ * does not arrive within CMTJB_PEER_TIMEOUT_MS, default 20000, is CMTJB_ERUNTIME).  All areas must be allocated (and zero)
+ * before any rank calls, and freed only after every rank has returned: two barriers of the caller's.  An area serves ONE call.
+ * At most 16 ranks.  Results are bit-identical to cmtjb_group_run_sharded and to a single rank. */
+int64_t cmtjb_group_peer_area_bytes(int32_t n_junctions, int32_t world);
+int cmtjb_group_run_sharded_peer(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
+                                 const cmtjb_run_args_t *args, int32_t rank, int32_t world, void *const *areas, double *m_state,
+                                 double *junction_log, int32_t *status, int device, void *stream);
+int cmtjb_peer_alloc(int device, int64_t bytes, void **ptr);
+int cmtjb_peer_free(int device, void *ptr);
+int cmtjb_peer_export(int device, void *ptr, unsigned char *handle64);
+int cmtjb_peer_open(int device, const unsigned char *handle64, void **ptr);
+int cmtjb_peer_close(int device, void *ptr);
+
 /* RNG test hooks.  cmtjb_philox_host: one Philox4x32-10 block for counter ctr[4] / key key[2]
  * (known-answer tests).  cmtjb_normals_host: the N(0,1) triples the stochastic steppers draw for
  * instances inst0..inst0+n_inst-1, layer `layer`, steps step0..step0+n_steps-1 under `seed`

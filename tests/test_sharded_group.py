@@ -210,3 +210,79 @@ def test_sharded_cuda_array_thermal_is_keyed_by_global_element():
         for name, v in one[k].items():
             assert np.array_equal(got[k][name], v), (k, name)
     assert np.std(one[5]["free_mx"]) > 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+def thread_peer_areas_factory(shared, barrier):
+    """ranks as threads of one process: the 'peers' are each other's plain device pointers (no IPC needed)"""
+    import ctypes as C
+
+    from cmtj_b200.reservoir import _PeerAreas
+
+    def make(be, dist, rank, world, device, n):
+        lib = be.lib
+        lib.cmtjb_group_peer_area_bytes.restype = C.c_int64
+        own = C.c_void_p()
+        be.check(lib.cmtjb_peer_alloc(C.c_int(device), C.c_int64(lib.cmtjb_group_peer_area_bytes(C.c_int32(n), C.c_int32(world))), C.byref(own)))
+        shared["bufs"][rank] = own.value
+        barrier.wait()
+        return _PeerAreas(be, device, own.value, list(shared["bufs"]), [], barrier.wait)
+
+    return make
+
+
+def threaded_peer_ranks(world, make, T):
+    groups = [make() for _ in range(world)]
+    errs = []
+    shared = {"bufs": [None] * world}
+    barrier = threading.Barrier(world)
+    factory = thread_peer_areas_factory(shared, barrier)
+
+    def work(r):
+        try:
+            groups[r].run_sharded(T, 1e-13, 1e-12, rank=r, world=world, transport="peer", gather=False, seed=7, _peer_areas=factory)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0]
+    return groups
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,world,inter,two,temperature", [
+    (400, 2, None, False, 0.0),
+    (150, 3, "computeDipoleInteractionNoumra", True, 0.0),
+    (5, 4, None, False, 0.0),       # the last rank owns nothing and still takes part in the hand-shake
+    (96, 3, None, False, 300.0),    # thermal noise keyed by the global element index
+])
+def test_peer_memory_exchange_is_bit_identical_to_one_rank(monkeypatch, n, world, inter, two, temperature):
+    """cmtjb_group_run_sharded_peer: the step kernels push their slice into every rank's exchange area and hand-shake
+    through arrival counters (ranks = threads sharing this GPU, each on its own stream); same bits as world = 1."""
+    monkeypatch.setenv("CMTJB_PEER_TIMEOUT_MS", "8000")  # a scheduling dead-end on the shared GPU fails instead of hanging
+
+    def make():
+        g = lattice_group(n, temperature, two_layers=two)
+        if inter:
+            g.setInteractionFunction(getattr(m.reservoir, inter))
+        return g
+
+    T = 0.03e-9
+    one = make()
+    one.run_sharded(T, 1e-13, 1e-12, rank=0, world=1, seed=7)
+    one = logs_of(one)
+    got = merged_logs(threaded_peer_ranks(world, make, T), world)
+    for k in range(n):
+        for name, v in one[k].items():
+            assert np.array_equal(got[k][name], v), (world, k, name)
+    # world = 1 through the peer path as well (an area of one's own)
+    alone = threaded_peer_ranks(1, make, T)
+    for k in range(n):
+        for name, v in one[k].items():
+            assert np.array_equal(logs_of(alone[0])[k][name], v), (k, name)

@@ -31,13 +31,20 @@ def timed(fn):
 T = T_of(steps)
 short = max(10, steps // 5)
 g = lattice_group(n)
-g.run_sharded(T_of(10), 1e-13, 1e-12, seed=7, gather=False)  # NCCL's lazy channel set-up
+g.run_sharded(T_of(10), 1e-13, 1e-12, seed=7, gather=False, transport="nccl")  # NCCL's lazy channel set-up
 # marginal time per step: (long run - short run) / (steps - short); the fixed part is packing and uploading n junction models
-t_short = timed(lambda: lattice_group(n).run_sharded(T_of(short), 1e-13, 1e-12, seed=7, gather=False))
-g = lattice_group(n)
-t_long = timed(lambda: g.run_sharded(T, 1e-13, 1e-12, seed=7, gather=True))
-out = {"what": "GroupInteraction.run_sharded, NCCL all-gather of the top-layer m per step", "elements": n, "steps": steps, "world": world,
-       "us_per_step_sharded": 1e6 * (t_long - t_short) / (steps - short), "fixed_s_sharded": t_short - short * (t_long - t_short) / (steps - short)}
+out = {"what": "GroupInteraction.run_sharded: one dipole array over the GPUs of a box, top-layer m exchanged every step", "elements": n,
+       "steps": steps, "world": world}
+for transport in ("nccl", "peer"):
+    t_short = timed(lambda: lattice_group(n).run_sharded(T_of(short), 1e-13, 1e-12, seed=7, gather=False, transport=transport))
+    g = lattice_group(n)
+    t_long = timed(lambda: g.run_sharded(T, 1e-13, 1e-12, seed=7, gather=True, transport=transport))
+    out["us_per_step_" + transport] = 1e6 * (t_long - t_short) / (steps - short)
+    if transport == "nccl":
+        g_nccl = logs_of(g)
+if rank == 0:
+    a0, b0 = g_nccl, logs_of(g)
+    out["peer_bit_identical_to_nccl"] = bool(all(np.array_equal(a0[k][name], b0[k][name]) for k in range(len(b0)) for name in b0[k]))
 if rank == 0:
     one = lattice_group(n)
     t1s = time.perf_counter(); lattice_group(n).run_sharded(T_of(short), 1e-13, 1e-12, rank=0, world=1, seed=7); torch.cuda.synchronize(); t1s = time.perf_counter() - t1s
