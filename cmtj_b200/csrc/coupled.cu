@@ -712,6 +712,12 @@ int group_shard_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, cons
   long long step_no = 0;  // steps of THIS call (exchange epochs count from the call's initial publish)
   const long long we = R.write_every;
   const long long pair_blocks = ((long long)tiles * 32 * P + 255) / 256;
+  const bool trace = std::getenv("CMTJB_TRACE_SHARD") != nullptr;  // device time of the step loop, printed per rank
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (trace) {
+    cudaEventCreate(&ev0), cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
   for (long long it = R.it_begin; it < R.it_end && rc == CMTJB_OK; it++, step_no++) {
     if (peer) {
       // slices number step_no + 1 of every rank must be in before the pair sums read buffer step_no % 2
@@ -748,6 +754,14 @@ int group_shard_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, cons
     if (it % we == 0) sample++;
     if (!peer && rc == CMTJB_OK && exchange(ctx, d_x, (int64_t)3 * per, (int64_t)it, (void *)stream) != 0)
       rc = fail(CMTJB_ERUNTIME, "exchange callback failed");
+  }
+  if (trace) {
+    cudaEventRecord(ev1, stream);
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess && step_no > 0)
+      std::fprintf(stderr, "[cmtjb] sharded group rank %d/%d (%s): %lld steps, %.2f us per step on the device\n", rank, world,
+                   peer ? "peer memory" : "exchange callback", step_no, 1e3 * ms / (double)step_no);
+    cudaEventDestroy(ev0), cudaEventDestroy(ev1);
   }
   if (peer && rc == CMTJB_OK) {
     // the last slices must have left before anybody frees an area, and a peer that never arrived is an error, not a hang
