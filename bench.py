@@ -530,14 +530,14 @@ def main():
     # what the pipe sustains by operand shape (cmtjb_fp64_pipe_probe): independent DFMA chains on fixed
     # register triplets at 8 resident warps per sub-partition (the pipe's practical peak) and a loop of the LLG right-hand
     # side's shape -- three different live register pairs per DFMA -- at the S1 kernel's 4 warps (its ceiling)
-    probe = {}
+    pipe_probe = {}
     pf = lib.cmtjb_fp64_pipe_probe
     pf.restype = C.c_int
     pf.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name, kind, warps, iters in (("dfma_3reg_8warps", 1, 8, 100000), ("rhs_shape_4warps", 3, 4, 200000), ("rhs_shape_two_vectors_4warps", 4, 4, 200000)):
         fr, mh = C.c_double(), C.c_double()
         if pf(local_rank, kind, warps, iters, C.byref(fr), C.byref(mh)) == 0:
-            probe[name] = round(fr.value, 4)
+            pipe_probe[name] = round(fr.value, 4)
 
     # ---- device-resident leg ("value") --------------------------------------------------------------------
     b = fresh_batch()
@@ -826,9 +826,9 @@ def main():
                 },
                 "fp64_peak_microbenchmark": {"tflops": fp64_peak / 1e12, "sm_mhz_in_kernel": fp64_peak_mhz,
                                              "nominal_tflops_at_sampled_clock": nominal / 1e12},
-                "pipe_probe_issue_slot_frac": probe,
-                "frac_of_rhs_shape_ceiling": (frac / max(probe.get("rhs_shape_4warps", 0), probe.get("rhs_shape_two_vectors_4warps", 0)))
-                if frac and probe.get("rhs_shape_4warps") else None,
+                "pipe_probe_issue_slot_frac": pipe_probe,
+                "frac_of_rhs_shape_ceiling": (frac / max(pipe_probe.get("rhs_shape_4warps", 0), pipe_probe.get("rhs_shape_two_vectors_4warps", 0)))
+                if frac and pipe_probe.get("rhs_shape_4warps") else None,
                 "hbm": {
                     "achieved_gbs": log_bytes / kern_s / 1e9,
                     "peak_gbs": hbm_peak,
