@@ -189,7 +189,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 os.environ.get("BENCH_SAMPLER_MS", "100")],
                 stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL,
                 text=True,
@@ -254,6 +255,8 @@ def pimm_leg(args, cm, torch, dist, dev, local_rank, rank, world, barrier, H, st
     # warm-up like the full-log leg: W calls at least, up to W + 6 while a call is still > 10 % faster than the one before
     # (the first calls page-lock the host result buffers that torch's pinned allocator then reuses, and allocate the
     # device moment storage that its caching allocator then reuses)
+    sampler = ClockSampler(local_rank)  # started before the warm-up, see the full-log leg
+    sampler.start()
     n_warm, prev = 0, None
     while True:
         t_w = time.perf_counter()
@@ -268,8 +271,6 @@ def pimm_leg(args, cm, torch, dist, dev, local_rank, rank, world, barrier, H, st
             improving = bool(flag.item() > 0)
         if n_warm >= max(args.warmup, 3) and (not improving or n_warm >= max(args.warmup, 3) + 6):
             break
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     t0 = time.perf_counter()
     each = []
@@ -551,10 +552,10 @@ def main():
         b._m_dev.copy_(m0_dev)  # every step integrates the same 20 ns from the same initial state
         b.run_device(T, DT, wf, out=logbuf)
 
-    for _ in range(max(args.warmup - 1, 0)):
-        one_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(max(args.warmup - 1, 0)):
+        one_step()
     barrier()
     stream = torch.cuda.current_stream(dev)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -616,7 +617,12 @@ def main():
             return bh.run(T, DT, wf, out=host_log)
 
         # warm-up: the pinned allocation above leaves the GPU idle for seconds; W untimed steps bring the
-        # clocks back up before the timed region (sampled below like the device leg)
+        # clocks back up before the timed region (sampled below like the device leg).  The clock sampler starts BEFORE the
+        # warm-up: nvidia-smi's start-up (NVML initialisation over every GPU of the box) holds driver locks for some hundred
+        # milliseconds, which used to land on the first timed step (its copies stalled: 750-1090 ms against 380 ms for the
+        # steps after it); its rows are filtered to the timed region by time stamp.
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
         n_warm, prev = 0, None
         while True:
             t_w = time.perf_counter()
@@ -634,8 +640,6 @@ def main():
                 improving = bool(flag.item() > 0)
             if n_warm >= max(args.warmup, 3) and (not improving or n_warm >= max(args.warmup, 3) + 6):
                 break
-        sampler2 = ClockSampler(local_rank)
-        sampler2.start()
         barrier()
         t0 = time.perf_counter()
         each = []
