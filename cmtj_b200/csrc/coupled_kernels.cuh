@@ -191,7 +191,7 @@ enum { STACK_KCL = 0, STACK_DELAYED = 1, STACK_SEQUENTIAL = 2 };
 // it is then passed by value like in the sweep kernels and its parameters are constant-bank operands
 // instead of registers loaded from models[j].
 template <int NL, int SOLVER, uint32_t F, bool UNIFORM, int MODE>
-__global__ void __maxnreg__((F == F_COUPLED_LEAN && UNIFORM) ? 96 : 128) stack_kernel(const DevModel<NL> *__restrict__ models,
+__global__ void __maxnreg__((F == F_COUPLED_LEAN && UNIFORM) ? 88 : 128) stack_kernel(const DevModel<NL> *__restrict__ models,
                                                                  const __grid_constant__ DevModel<NL> Mu,
                                                                  const __grid_constant__ StackParams SP,
                                                                  const __grid_constant__ RunParams R) {

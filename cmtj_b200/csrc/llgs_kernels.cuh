@@ -417,7 +417,7 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
 // Register budget: left to the compiler for every variant.  Tried and dropped (round 2): capping the stochastic single-
 // layer kernels at 64 registers for 8 warps per sub-partition instead of 5 (ncu: `wait` is their top stall) made
 // them slower, 7.3 -> 6.5e10 (Heun) and 9.0 -> 8.2e10 (Euler-Heun) layer-steps/s: the spilled state costs more than
-// the extra warps hide.  NB a second __launch_bounds__ argument of 1 is NOT neutral: it lifts the S1 kernel from 87 to
+// the extra warps hide; at 80 registers (6 warps, 20-160 bytes of spills) still 6 % slower, 7.29 -> 6.87e10 and 8.55 -> 8.10e10.  NB a second __launch_bounds__ argument of 1 is NOT neutral: it lifts the S1 kernel from 87 to
 // 116 registers and the 3-layer Heun kernel from 120 to 192, 9 % slower each.
 constexpr int min_blocks(int, int, int, uint32_t) { return 0; }  // 0 = no constraint
 
