@@ -28,6 +28,7 @@ from .core import (  # noqa: F401
     posSineDriver,
     pulseDriver,
     seed,
+    thermal_normals,
     sineDriver,
     stepDriver,
     trapezoidDriver,

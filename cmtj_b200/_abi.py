@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LAYERS = 8
 NSLOTS = 30
 
@@ -150,6 +150,8 @@ class RunArgs(C.Structure):
         ("onef_buffer", C.c_void_p),
         ("custom_table", C.c_void_p),
         ("n_custom", C.c_int64),
+        ("thermal_normals", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

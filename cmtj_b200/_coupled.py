@@ -8,6 +8,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _abi
+from . import core as _core
 from .core import Junction, _next_seed
 
 
@@ -34,6 +35,7 @@ def pack_junctions(junctions: Sequence[Junction]):
 
 def run_args(totalTime, timeStep, writeFrequency, n_instances, log=True, seed=None, instance_offset=0) -> _abi.RunArgs:
     a = _abi.RunArgs()
+    a.thermal_normals = _core._thermal_normals
     a.totalTime = float(totalTime)
     a.timeStep = float(timeStep)
     a.writeFrequency = float(writeFrequency)

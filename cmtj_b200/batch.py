@@ -23,6 +23,7 @@ from typing import Dict, List, Optional, Sequence, Union
 import numpy as np
 
 from . import _abi
+from . import core as _core
 from .core import CVector, Junction, SolverMode, _next_seed
 
 _FIELD_INDEX = {n: i for i, n in enumerate(_abi.FIELD_NAMES)}
@@ -165,6 +166,7 @@ class JunctionBatch:
     # ---- shared plumbing -------------------------------------------------------------------------------
     def _args(self, totalTime, timeStep, writeFrequency, solverMode, log, seed, onef, start_iteration=0) -> _abi.RunArgs:
         a = _abi.RunArgs()
+        a.thermal_normals = _core._thermal_normals
         a.totalTime = float(totalTime)
         a.timeStep = float(timeStep)
         a.writeFrequency = float(writeFrequency)

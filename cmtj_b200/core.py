@@ -1261,6 +1261,7 @@ class Junction:
         t0 = _time.perf_counter()
         jn, layers = self._pack()
         args = _abi.RunArgs()
+        args.thermal_normals = _thermal_normals
         args.totalTime = float(totalTime)
         args.timeStep = float(timeStep)
         args.writeFrequency = float(writeFrequency)
@@ -1318,6 +1319,22 @@ def seed(value: Optional[int] = None) -> None:
     (``None`` = OS entropy).  An addition: the reference cannot repeat a stochastic run."""
     global _seed_rng
     _seed_rng = np.random.default_rng(value)
+
+
+_thermal_normals = 0
+
+
+def thermal_normals(precision: Optional[str] = None) -> str:
+    """Precision of the Langevin normals of all subsequent stochastic runs of this process: ``"float32"`` (default: Philox +
+    Box-Muller on the SFU, absolute error 2^-21, tail to 6.7 sigma) or ``"float64"`` (53-bit uniforms, double-precision
+    Box-Muller, tail to 8.6 sigma; the reference draws ``std::normal_distribution<double>``).  Returns the current setting.
+    An addition (``cmtjb_run_args_t::thermal_normals``)."""
+    global _thermal_normals
+    if precision is not None:
+        if precision not in ("float32", "float64"):
+            raise ValueError("precision must be 'float32' or 'float64'")
+        _thermal_normals = 1 if precision == "float64" else 0
+    return "float64" if _thermal_normals else "float32"
 
 
 def _next_seed() -> int:

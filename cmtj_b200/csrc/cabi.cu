@@ -486,6 +486,7 @@ void fill_run_params(RunParams &R, const cmtjb_junction_t *jn, int NL, const cmt
   R.write_frequency = a->writeFrequency;
   R.seed = a->seed;
   R.pk = make_philox_keys(a->seed);
+  R.normals64 = a->thermal_normals == 1 ? 1 : 0;
   if (const char *c = std::getenv("CMTJB_TUNE")) R.tune_flags = std::atoi(c);
   if (post) {
     PostParams &P = R.post;
@@ -917,12 +918,13 @@ __global__ void philox_kernel(uint4 ctr, uint2 key, uint32_t *out) {
   out[3] = r.w;
 }
 __global__ void normals_kernel(unsigned long long seed, long long inst0, long long n_inst, unsigned layer, long long step0,
-                               long long n_steps, double *out) {
+                               long long n_steps, double *out, int f64) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_inst * n_steps) return;
   const long long st = q / n_inst, i = q - st * n_inst;
   const PhiloxKeys K = philox_keys(seed);
-  const d3 v = normal3(K, (unsigned long long)(inst0 + i), layer, (unsigned long long)(step0 + st));
+  const d3 v = f64 ? normal3_f64(K.x[0], K.y[0], (unsigned long long)(inst0 + i), layer, (unsigned long long)(step0 + st))
+                   : normal3(K, (unsigned long long)(inst0 + i), layer, (unsigned long long)(step0 + st));
   out[3 * q + 0] = v.x;
   out[3 * q + 1] = v.y;
   out[3 * q + 2] = v.z;
@@ -1518,12 +1520,17 @@ int cmtjb_philox_host(const uint32_t *ctr, const uint32_t *key, uint32_t *out, i
 
 int cmtjb_normals_host(uint64_t seed, int64_t inst0, int64_t n_inst, int32_t layer, int64_t step0, int64_t n_steps,
                        double *out, int device) {
+  return cmtjb_normals_host_ex(seed, inst0, n_inst, layer, step0, n_steps, 0, out, device);
+}
+
+int cmtjb_normals_host_ex(uint64_t seed, int64_t inst0, int64_t n_inst, int32_t layer, int64_t step0, int64_t n_steps,
+                          int32_t thermal_normals, double *out, int device) {
   if (!out || n_inst <= 0 || n_steps <= 0) return fail(CMTJB_EINVAL, "bad argument");
   CUDA_TRY(cudaSetDevice(device));
   const long long n = n_inst * n_steps;
   double *d = nullptr;
   CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(double)));
-  normals_kernel<<<(unsigned)((n + 255) / 256), 256>>>(seed, inst0, n_inst, (unsigned)layer, step0, n_steps, d);
+  normals_kernel<<<(unsigned)((n + 255) / 256), 256>>>(seed, inst0, n_inst, (unsigned)layer, step0, n_steps, d, thermal_normals == 1 ? 1 : 0);
   cudaError_t e = cudaMemcpy(out, d, 3 * n * sizeof(double), cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return cuda_fail(e, "normals_kernel");

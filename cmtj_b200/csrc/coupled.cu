@@ -249,6 +249,7 @@ void fill_run_params(RunParams &R, const Common &c, const cmtjb_run_args_t *a, l
   R.write_frequency = a->writeFrequency;
   R.seed = a->seed;
   R.pk = make_philox_keys(a->seed);
+  R.normals64 = a->thermal_normals == 1 ? 1 : 0;
 }
 
 // stream-ordered upload of a small host array

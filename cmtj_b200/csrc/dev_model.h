@@ -175,6 +175,7 @@ struct RunParams {
   double dt, sqrt_dt, total_time, write_frequency;
   unsigned long long seed;
   PhiloxKeys pk;             // round keys of `seed` (thermal noise)
+  int normals64;             // 1: double-precision thermal normals (normal3_f64), 0: the float32 SFU stream
   int32_t tune_flags;        // CMTJB_TUNE bits (experiments): 1 = stateless thermal normals in the sweep kernels
   PostParams post;
 };

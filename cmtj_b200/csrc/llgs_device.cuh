@@ -587,6 +587,31 @@ __device__ __forceinline__ d3 normal3_carried(const PhiloxKeys &K, unsigned long
   return out;
 }
 
+// ---- double-precision alternative (cmtjb_run_args_t::thermal_normals = 1) ---------------------------------------------
+// The reference draws std::normal_distribution<double>.  The default stream above is float32 (absolute error 2^-21 per
+// normal, radius tail ending at 6.7 sigma): more than any Langevin statistic tested resolves, but a caller who studies rare
+// events can ask for this one instead: two Philox blocks per layer-step (sub-counters 8 and 9, disjoint from the float32
+// stream's 0..2), 53-bit uniforms u = (k + 1) 2^-53 in (0, 1], Box-Muller with the double-precision library log / sqrt /
+// sincospi: relative error ~1e-16, tail to 8.6 sigma.  Out of line and cold: the default path pays one predicate for it.
+static __device__ __noinline__ d3 normal3_f64(uint32_t kx, uint32_t ky, unsigned long long inst, unsigned layer, unsigned long long step) {
+  double n[4];
+#pragma unroll
+  for (unsigned b = 0; b < 2; b++) {
+    const uint4 ctr = make_uint4((uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)step,
+                                 ((uint32_t)(step >> 32) << 8) | ((8u + b) << 4) | (layer & 0xFu));
+    const uint4 r = philox4x32_10(ctr, make_uint2(kx, ky));
+    const unsigned long long k1 = (((unsigned long long)r.x << 32) | r.y) >> 11, k2 = (((unsigned long long)r.z << 32) | r.w) >> 11;
+    const double u1 = ((double)k1 + 1.0) * 1.1102230246251565e-16;  // (0, 1]
+    const double u2 = (double)k2 * 1.1102230246251565e-16;          // [0, 1)
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    n[2 * b] = rad * cs;
+    n[2 * b + 1] = rad * sn;
+  }
+  return mk(n[0], n[1], n[2]);
+}
+
 // the step's noise vector dW (junction.hpp:1121-1136): Langevin + 1/f^alpha buffer
 template <uint32_t F, int NL>
 __device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, int l, long long i, long long it, StageTime t,
@@ -602,7 +627,8 @@ __device__ __forceinline__ d3 noise_dW(const DevLayer &Lr, const RunParams &R, i
         sigma = sqrt(Lr.sigma_c * T);
       }
       const unsigned long long inst = (unsigned long long)(R.inst_offset + i);
-      dW = (nc ? normal3_carried(R.pk, inst, (unsigned)l, (unsigned long long)it, *nc) : normal3(R.pk, inst, (unsigned)l, (unsigned long long)it)) * sigma;
+      if (R.normals64) dW = normal3_f64(R.pk.x[0], R.pk.y[0], inst, (unsigned)l, (unsigned long long)it) * sigma;
+      else dW = (nc ? normal3_carried(R.pk, inst, (unsigned)l, (unsigned long long)it, *nc) : normal3(R.pk, inst, (unsigned)l, (unsigned long long)it)) * sigma;
     }
   }
   if constexpr ((F & F_ONEF) != 0) {

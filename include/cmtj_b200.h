@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CMTJB_ABI_VERSION 4
+#define CMTJB_ABI_VERSION 5
 #define CMTJB_MAX_LAYERS 8
 
 /* ---- error codes --------------------------------------------------------------- */
@@ -187,6 +187,14 @@ typedef struct cmtjb_run_args {
    * Dormand-Prince, junctions of more than 4 layers, Stack and GroupInteraction (CMTJB_ENOTSUP). */
   const double *custom_table;
   int64_t n_custom;
+  /* Thermal (Langevin) normals, replacing std::normal_distribution<double> over mt19937 (core/junction.hpp:174-175,
+   * :1111-1119).  0 (default): Philox4x32-10 + Box-Muller in float32 on the SFU -- absolute error 2^-21 per normal, radius
+   * tail ending at 6.7 sigma (a 32-bit uniform); 0.75 hashes per layer-step.  1: the same generator with 53-bit uniforms
+   * and double-precision log / sqrt / sincospi -- relative error ~1e-16, tail to 8.6 sigma; two hashes and ~300 more
+   * instructions per layer-step.  Both are pure functions of (seed, global instance, layer, step); the two streams are
+   * different numbers. */
+  int32_t thermal_normals;
+  int32_t reserved0;
 } cmtjb_run_args_t;
 
 enum cmtjb_log_mode {
@@ -511,6 +519,9 @@ int cmtjb_peer_close(int device, void *ptr);
 int cmtjb_philox_host(const uint32_t *ctr, const uint32_t *key, uint32_t *out, int device);
 int cmtjb_normals_host(uint64_t seed, int64_t inst0, int64_t n_inst, int32_t layer, int64_t step0, int64_t n_steps,
                        double *out, int device);
+/* the same for either stream: thermal_normals as in cmtjb_run_args_t */
+int cmtjb_normals_host_ex(uint64_t seed, int64_t inst0, int64_t n_inst, int32_t layer, int64_t step0, int64_t n_steps,
+                          int32_t thermal_normals, double *out, int device);
 
 /* FP64 FMA-pipe microbenchmark used for the roofline denominator: runs `iters` dependent
  * DFMA chains on every SM and returns achieved FLOP/s in *flops (2 flop per DFMA). */

@@ -79,6 +79,46 @@ def test_normal_stream_moments_and_independence():
     assert not np.array_equal(_normals(12346, 0, 8, 0, 0, 3), z[:3, :8])
 
 
+def test_float64_normal_stream():
+    """thermal_normals = 1: 53-bit uniforms, double-precision Box-Muller (cmtjb_normals_host_ex).  Same distributional
+    checks as the float32 stream; the values are full-precision doubles (not representable in float32), a different stream
+    from the default one, a pure function of (seed, instance, layer, step), and the radius tail is not cut at 6.7 sigma."""
+    lib = _abi.load_library()
+    f = lib.cmtjb_normals_host_ex
+    f.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int]
+
+    def normals64(seed, inst0, n_inst, layer, step0, n_steps, prec=1):
+        out = np.zeros((n_steps, n_inst, 3))
+        assert f(seed, inst0, n_inst, layer, step0, n_steps, prec, out.ctypes.data, 0) == 0
+        return out
+
+    z = normals64(777, 0, 4096, 0, 0, 256)
+    flat = z.ravel()
+    n = flat.size
+    assert abs(flat.mean()) < 4 / math.sqrt(n)
+    assert abs(flat.var() - 1) < 4 * math.sqrt(2 / n)
+    assert abs((flat**3).mean()) < 4 * math.sqrt(15 / n)
+    assert abs((flat**4).mean() - 3) < 4 * math.sqrt(96 / n)
+    p3 = 2.699796e-3
+    assert abs((np.abs(flat) > 3).mean() - p3) < 4 * math.sqrt(p3 / n)
+    from scipy import special
+
+    sub = np.sort(flat[::16])
+    cdf = 0.5 * (1 + special.erf(sub / math.sqrt(2)))
+    d = np.max(np.abs(cdf - (np.arange(1, len(sub) + 1) - 0.5) / len(sub)))
+    assert d < 2.23 / math.sqrt(len(sub)) + 0.5 / len(sub)
+    s4 = 4 / math.sqrt(z.shape[0] * z.shape[1])
+    assert abs((z[..., 0] * z[..., 1]).mean()) < s4 and abs((z[..., 0] * z[..., 2]).mean()) < s4
+    assert abs((z[:-1, :, 1] * z[1:, :, 1]).mean()) < s4
+    # full double precision: (almost) none of the values survives a round trip through float32
+    assert (flat.astype(np.float32).astype(np.float64) == flat).mean() < 1e-3
+    assert (_normals(777, 0, 64, 0, 0, 4).astype(np.float32).astype(np.float64) == _normals(777, 0, 64, 0, 0, 4)).all()  # the default stream is float32
+    # a different stream from the float32 one, reproducible, continued by instance_offset
+    assert not np.array_equal(z[:4, :64], _normals(777, 0, 64, 0, 0, 4))
+    assert np.array_equal(normals64(777, 1000, 8, 0, 5, 3), z[5:8, 1000:1008])
+    assert np.array_equal(normals64(777, 0, 8, 0, 0, 3, prec=0), _normals(777, 0, 8, 0, 0, 3))
+
+
 # ---- sLLGS dynamics vs the reference ---------------------------------------------------------------
 @pytest.fixture(scope="module", autouse=True)
 def _pool(ref):
@@ -91,10 +131,19 @@ def _pool(ref):
 FIELDS = [-260e3, -280e3, -300e3, -320e3, -340e3]
 
 
-@pytest.mark.parametrize("mode", ["Heun", "EulerHeun"])
-def test_switching_probability_curve(ref, mode):
+@pytest.fixture
+def normals_precision(request):
+    prev = m.thermal_normals()
+    m.thermal_normals(request.param)
+    yield request.param
+    m.thermal_normals(prev)
+
+
+@pytest.mark.parametrize("mode,normals_precision", [("Heun", "float32"), ("EulerHeun", "float32"), ("Heun", "float64")],
+                         indirect=["normals_precision"])
+def test_switching_probability_curve(ref, mode, normals_precision):
     """P(m_x < 0 after 0.5 ns) vs opposing field at 300 K: 20000 GPU trials per field in ONE batch against
-    4096 reference trials per field; two-proportion z-test per point."""
+    4096 reference trials per field; two-proportion z-test per point.  Both precisions of the Langevin normals."""
     n_gpu, n_ref, steps = 20000, 4096, 5000
     j = ref_pool.pbit(m)
     b = m.JunctionBatch(j, n_gpu * len(FIELDS))
@@ -110,7 +159,7 @@ def test_switching_probability_curve(ref, mode):
         r = ref_pool.run(ref_pool.switching_trials, n_ref, Hx, steps, mode)
         z, d, se = sh.z_proportions(int((mx[k] < 0).sum()), n_gpu, int((r < 0).sum()), n_ref)
         zs.append(z)
-        record(f"switching probability {mode} H={Hx:g}", z=z, bound=sh.Z_BOUND, estimate=d, se=se, n_gpu=n_gpu, n_ref=n_ref)
+        record(f"switching probability {mode}{'' if normals_precision == 'float32' else ' (float64 normals)'} H={Hx:g}", z=z, bound=sh.Z_BOUND, estimate=d, se=se, n_gpu=n_gpu, n_ref=n_ref)
     assert np.all(np.abs(zs) <= sh.Z_BOUND), (zs, p_gpu)
     # the curve is a curve: monotone in the field and spanning the transition
     assert p_gpu[0] < 0.35 and p_gpu[-1] > 0.65 and np.all(np.diff(p_gpu) > 0), p_gpu
