@@ -177,9 +177,11 @@ def main():
         json.dump(info, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     for cfg, title in (("s3", "S3 p-bit: 1-layer STT, 300 K, Heun (first captured launch), 1e5 instances x 5000 steps"),
                        ("s4", "S4 CIMS: 3-layer Heun with SOT step drivers, reduced grid"),
-                       ("s5s", "S5 SeriesStack of 64 MTJs, 1024 stacks x 2000 steps"),
-                       ("s5g", "S5 GroupInteraction lattice (cooperative grid kernel), reduced lattice")):
-        ncu_full(tag, f"prof_{cfg}.ncu-rep", title)
+                       ("s5s", "S5 SeriesStack of 64 MTJs, batch of stacks x 2000 steps"),
+                       ("s5g", "S5 GroupInteraction 64 x 64 lattice (cooperative grid kernel)"),
+                       ("mombg", "PIMM_batch: background Chebyshev-moment kernel of one chunk, running beside the time loop of the next")):
+        if os.path.exists(os.path.join(OUT, f"prof_{cfg}.ncu-rep")):
+            ncu_full(tag, f"prof_{cfg}.ncu-rep", title)
     print("wrote", sorted(os.listdir(PROF)))
 
 
