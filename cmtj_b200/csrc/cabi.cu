@@ -38,6 +38,20 @@ int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
+void keep_pool_memory() {
+  static std::atomic<unsigned long long> done{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  if (done.load(std::memory_order_relaxed) & (1ull << dev)) return;
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done.fetch_or(1ull << dev, std::memory_order_relaxed);
+}
+
 int cuda_fail(cudaError_t e, const char *what) {
   return fail(CMTJB_ECUDA, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
 }
@@ -221,11 +235,18 @@ uint32_t needed_features(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers
 // `need`: union of the layers' needs plus launch-wide bits (F_POST, forced F_ALL); `per_layer`: each layer's own
 // needs, or null.  A plain variant covers the model if it contains `need`; a split variant (F_SPLIT) if every
 // layer's needs are contained in the term set that variant compiles for that layer.
+const Variant *pick_variant_exact(int nl, int solver, uint32_t need, const uint32_t *per_layer);
 const Variant *pick_variant(int nl, int solver, uint32_t need, const uint32_t *per_layer = nullptr) {
+  const Variant *v = pick_variant_exact(nl, solver, need, per_layer);
+  // projection-only needs are also covered by the full post-processing variants
+  if (!v && (need & F_PROJ)) v = pick_variant_exact(nl, solver, (need & ~(uint32_t)F_PROJ) | F_POST, per_layer);
+  return v;
+}
+const Variant *pick_variant_exact(int nl, int solver, uint32_t need, const uint32_t *per_layer) {
   const Variant *tab = nullptr;
   int n = 0;
   switch (solver) {
-  case CMTJB_RK4: n = (need & F_POST) ? variants_post(&tab) : variants_rk4(&tab); break;
+  case CMTJB_RK4: n = (need & (F_POST | F_PROJ)) ? variants_post(&tab) : variants_rk4(&tab); break;
   case CMTJB_HEUN: n = variants_heun(&tab); break;
   case CMTJB_EULER_HEUN: n = variants_euler_heun(&tab); break;
   case CMTJB_DORMAND_PRINCE: n = variants_dopri(&tab); break;
@@ -239,7 +260,7 @@ const Variant *pick_variant(int nl, int solver, uint32_t need, const uint32_t *p
     if (v.features & F_SPLIT) {
       if (!per_layer) continue;
       const uint32_t launch_wide = need & ~F_BASEMASK;  // none today besides what F_BASEMASK already holds
-      if (launch_wide || (need & F_POST) != (v.features & F_POST)) continue;
+      if (launch_wide || (need & F_POST) != (v.features & F_POST) || (need & F_PROJ)) continue;
       bool ok = true;
       for (int l = 0; l < nl && ok; l++) {
         const uint32_t have = layer_mask(v.features, l) & ~(uint32_t)F_POST;
@@ -669,8 +690,10 @@ int launch_span(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const c
   if (force && std::strcmp(force, "full") == 0) need = F_ALL, split_ok = false;
   if (force && std::strcmp(force, "nosplit") == 0) split_ok = false;
   if (a->log_mode == CMTJB_LOG_ENERGY) need = F_ALL, split_ok = false;  // the energy log lives in the general variants only
-  if (post) need |= F_POST;
-  if (post && need_fast) need_fast |= F_POST;
+  // projection log without spin-diode reduction: the lean F_PROJ form (pick_variant falls back to F_POST variants)
+  const uint32_t post_bit = (post && post->sd_mode == CMTJB_SD_NONE && post->n_proj > 0) ? F_PROJ : F_POST;
+  if (post) need |= post_bit;
+  if (post && need_fast) need_fast |= post_bit;
   {
     int max_col = -1;
     for (int l = 0; l < jn->n_layers; l++)
@@ -804,6 +827,7 @@ int run_device_impl(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, con
                     const cmtjb_run_args_t *a, double *m_state, double *log, int32_t *status, int32_t *n_samples_out,
                     double *time_log, cudaStream_t stream, cmtjb_plan_t *plan_out, const Span *span_in = nullptr,
                     const cmtjb_post_t *post = nullptr) {
+  keep_pool_memory();
   cmtjb_plan_t plan;
   int rc = make_plan(jn, layers, a, &plan);
   if (rc) return rc;

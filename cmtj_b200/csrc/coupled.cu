@@ -254,6 +254,7 @@ void fill_run_params(RunParams &R, const Common &c, const cmtjb_run_args_t *a, l
 
 // stream-ordered upload of a small host array
 template <class T> cudaError_t upload(const T *src, size_t n, T **dst, cudaStream_t st) {
+  keep_pool_memory();
   cudaError_t e = cudaMallocAsync((void **)dst, std::max<size_t>(n, 1) * sizeof(T), st);
   if (e != cudaSuccess) return e;
   if (n) e = cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);

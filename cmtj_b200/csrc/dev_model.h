@@ -51,7 +51,11 @@ enum : uint32_t {
   // per-instance waveform parameter belongs to it (a VSD map: Oersted sine with per-instance frequency).  The
   // driver is resolved once per launch (resolve_fast) and added to the field at the three stage times, so
   // the loop body is compiled WITHOUT inline-driver and override machinery (F_DYNI / F_OVR).
-  F_FAST = 1u << 20
+  F_FAST = 1u << 20,
+  // Projection-only post-processing: the projection log of F_POST without the spin-diode filter and its per-thread
+  // state (a PIMM sweep writes one projected double per step and nothing else: 87 registers like the plain RK4 kernel
+  // instead of the 108 of the F_POST form, whose double-precision sine also brings a stack frame).
+  F_PROJ = 1u << 21
 };
 #define CMTJB_SPLIT(heavy_layers) (cmtjb::F_SPLIT | ((uint32_t)(heavy_layers) << cmtjb::F_HEAVY_SHIFT))
 // the term set compiled into layer l of a variant

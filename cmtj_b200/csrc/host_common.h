@@ -20,6 +20,11 @@ int cuda_fail(cudaError_t e, const char *what);
     if (_e != cudaSuccess) return ::cmtjb::cuda_fail(_e, #expr); \
   } while (0)
 
+// The library's small per-launch scratch (models, stage tables, scheduler tickets) comes from the device's stream-ordered
+// pool.  By default that pool hands its memory back to the OS at every synchronisation, so each call of a sweep loop pays
+// the driver's map / unmap again; this sets the current device's pool to keep what it has (once per device and process).
+void keep_pool_memory();
+
 // validation + derived quantities (cabi.cu)
 int make_plan(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtjb_run_args_t *a, cmtjb_plan_t *p);
 void derive_layer(const cmtjb_junction_t &J, const cmtjb_layer_t &L, DevLayer &D);

@@ -81,7 +81,7 @@ __device__ __forceinline__ double sd_resistance(const DevModel<NL> &M, const Pos
   return parallel ? 1.0 / acc : acc;
 }
 
-template <int NL>
+template <int NL, bool SD = true>
 __device__ __forceinline__ void post_sample(const DevModel<NL> &M, const RunParams &R, const State<NL> &S, PostState &ps,
                                             double t, long long sample, long long i) {
   const PostParams &P = R.post;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void post_sample(const DevModel<NL> &M, const RunPara
   // spin-diode mixing + low-pass (compute_sd, resistance.py:12-22): scipy's lfilter recurrence
   // in its own operation order, without FMA contraction (the filter is ill-conditioned: its poles
   // sit 6e-6 from the unit circle, so the operation order is visible in the fifth digit).
-  if (P.sd_mode != CMTJB_SD_NONE) {
+  if (SD && P.sd_mode != CMTJB_SD_NONE) {
     const double x = -sin(ps.omega * t) * sd_resistance<NL>(M, P, S);
     const double y = __dadd_rn(ps.z0, __dmul_rn(P.sd_b[0], x));
     ps.z0 = __dsub_rn(__dadd_rn(ps.z1, __dmul_rn(x, P.sd_b[1])), __dmul_rn(y, P.sd_a[1]));
@@ -377,7 +377,8 @@ __device__ __forceinline__ void run_span(const DevModel<NL> &M, const RunParams 
     }
     if (until_write == 0) {
       if (logging) write_sample<NL>(M, R, S, sample, i);
-      if constexpr ((F & F_POST) != 0) post_sample<NL>(M, R, S, ps, t, sample, i);
+      if constexpr ((F & F_POST) != 0) post_sample<NL, true>(M, R, S, ps, t, sample, i);
+      else if constexpr ((F & F_PROJ) != 0) post_sample<NL, false>(M, R, S, ps, t, sample, i);
       if constexpr (F == F_ALL) {
         if (logging && R.elog_ch0 >= 0)
           write_energy<NL, F>(M, R, Em, Enb, SOLVER == CMTJB_EULER_HEUN ? t : t + R.dt,

@@ -562,9 +562,9 @@ __global__ void __launch_bounds__(kMomThreads, (D > 24 ? 2 : 3)) cheb_moments_ke
 }
 
 // ---- the BACKGROUND form: reduces chunk c on a second stream while the time loop integrates chunk c + 1 ---------------
-// llgs_balanced_kernel keeps 16 warps x 88 registers on every SM and pins its own occupancy by claiming the SM's shared
-// memory (launch_fixed), which leaves 20 K registers and no shared memory.  This kernel is sized for exactly that hole:
-// ONE block of 128 threads x <= 160 registers per SM (a persistent grid of one block per SM; a second block does not fit
+// EXPERIMENT (CMTJB_PIMM_OVERLAP=1; measured, not the default: see DESIGN.md section 7).  llgs_balanced_kernel keeps 16 warps
+// on every SM and pins its own occupancy by claiming the SM's shared memory (launch_fixed), which leaves a quarter of the
+// registers and no shared memory.  This kernel is sized for that hole: ONE block of 128 threads x <= 160 registers per SM (a persistent grid of one block per SM; a second block does not fit
 // beside the time loop), no shared memory (the table is read through L1, one broadcast load per warp and entry), a
 // grid-stride walk over the (32-series tile, block q) tasks with q fastest, so that the 16-byte halves of a moment sector
 // still come from neighbouring warps.  Its FP64 instructions fill issue slots the time loop leaves idle (~21 % of them).

@@ -4,6 +4,8 @@
 #include "variants.h"
 namespace cmtjb {
 static const Variant kTable[] = {
+    CMTJB_FIXED(1, CMTJB_RK4, F_PROJ),            // projection log only (PIMM): relaxation segment, no spin-diode state
+    CMTJB_FIXED(2, CMTJB_RK4, F_IEC | F_PROJ),    // ... of the two-layer MTJ (the S1 sweep through PIMM_batch)
     CMTJB_FIXED(1, CMTJB_RK4, F_POST),            // the relaxation segment after the pulse window (constant drivers)
     CMTJB_FIXED(1, CMTJB_RK4, F_DYN | F_POST),    // PIMM / VSD of a single layer, batch-uniform excitation
     CMTJB_FIXED(1, CMTJB_RK4, F_FAST | F_POST),           // VSD with a per-instance excitation frequency (resolved once)

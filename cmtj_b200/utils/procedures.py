@@ -376,8 +376,12 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
             stream = None  # resident log instead
     if stream is not None:
         stream.allocate()
-        # two chunk buffers: the moments of chunk c are reduced (second stream, background kernel) while chunk c + 1 integrates
-        overlap = len(chunks) > 1 and not _os.environ.get("CMTJB_PIMM_NO_OVERLAP")
+        # Default: one stream, one chunk buffer -- the time loop of chunk c, then its reduction (4.3 ms per 10 GB chunk).
+        # CMTJB_PIMM_OVERLAP=1: two buffers, the reduction of chunk c on a second stream (low-footprint background
+        # kernel) while chunk c + 1 integrates.  Measured on B200 at 1e5 x 2e5: 465 ms of device time against 470 ms for
+        # the default -- the reduction's FP64 instructions compete with the time loop for the same pipe (each chunk's
+        # time loop slows from 24 to 27 ms), so hiding it buys nothing; kept as a measured experiment.
+        overlap = len(chunks) > 1 and bool(_os.environ.get("CMTJB_PIMM_OVERLAP"))
         ring = torch.empty((2 if overlap else 1, 1, max(nq for _, nq in chunks) * stream.block_len, B), dtype=torch.float64, device=dev)
         proj_log = ring[0]
     else:

@@ -219,7 +219,7 @@ def test_spectrum_device_shapes(on_cuda, monkeypatch, n, B, K_freq, pitch, mode)
 @pytest.mark.parametrize("B,chunk_mb,wait,last_n,overlap", [
     (40, 0.2, 0.0, 20, True),      # 40 series x 5000 steps in chunks of a few blocks (one full 32-series tile + 8 ragged)
     (70, 0.5, 0.1e-9, 100, True),  # wait_time > 0: the series starts inside the run; last-n longer than a block (merged tail chunk)
-    (40, 0.2, 0.0, 20, False),     # the same chunks on one stream, foreground kernels only
+    (40, 0.2, 0.0, 20, False),     # the default: the same chunks on one stream, foreground kernels only
     (3, 8192, 0.0, 20, True),      # one chunk
 ])
 def test_pimm_streamed_spectrum_equals_resident_log(on_cuda, monkeypatch, B, chunk_mb, wait, last_n, overlap):
@@ -234,8 +234,8 @@ def test_pimm_streamed_spectrum_equals_resident_log(on_cuda, monkeypatch, B, chu
     orig = P._SpectrumStream.add
     monkeypatch.setattr(P._SpectrumStream, "add",
                         lambda self, chunk, q0, nq, background=False: (calls.append((q0, nq, background)), orig(self, chunk, q0, nq, background))[1])
-    if not overlap:
-        monkeypatch.setenv("CMTJB_PIMM_NO_OVERLAP", "1")
+    if overlap:
+        monkeypatch.setenv("CMTJB_PIMM_OVERLAP", "1")  # the two-stream experiment: background reduction kernel
     s1, f1, o1 = P.PIMM_batch(helpers.two_layer_mtj(cm), H, **kw)
     assert calls and sum(nq for _, nq, _ in calls) > 0  # the streamed path ran
     if chunk_mb < 1:
