@@ -1,12 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-echo "== pytest -m gpu (all)"; S=$(date +%s); timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? wall $(( $(date +%s) - S )) s"; tail -4 gpurun_out/pytest_gpu.log
-echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -1
-echo "== bench"; S=$(date +%s); timeout 1500 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$? wall $(( $(date +%s) - S )) s"; tail -3 gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/bench.json') if l.startswith('{')][-1])
-print('value',d['value'],'e2e',d['e2e']['value'],[round(x) for x in d['e2e']['ms_each']],'pimm',d['e2e_pimm']['value'],[round(x) for x in d['e2e_pimm']['ms_each']])
-for k,v in d['secondary'].items(): print(k[:70], '%.3e'%v.get('value',0))
-PY
+echo "== compute-sanitizer memcheck: streamed spectrum + F_PROJ + background kernel"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/sanitizer_proc.log python -m pytest tests/test_gpu_procedures.py -m gpu -q -x -k "stream or streamed" 2>&1 | tail -3; echo "rc=$?"; tail -4 gpurun_out/sanitizer_proc.log
+echo "== compute-sanitizer memcheck: sharded arrays (callback + peer memory)"
+CMTJB_PEER_TIMEOUT_MS=60000 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/sanitizer_group.log python -m pytest tests/test_sharded_group.py -m gpu -q -x -k "peer and 400 or thermal" 2>&1 | tail -3; echo "rc=$?"; tail -4 gpurun_out/sanitizer_group.log
+echo "== compute-sanitizer memcheck: float64 normals"
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/sanitizer_noise.log python -m pytest tests/test_stochastic_gpu.py -m gpu -q -x -k "float64_normal or philox" 2>&1 | tail -3; echo "rc=$?"; tail -3 gpurun_out/sanitizer_noise.log
