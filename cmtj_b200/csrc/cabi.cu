@@ -45,7 +45,9 @@ void keep_pool_memory() {
   if (done.load(std::memory_order_relaxed) & (1ull << dev)) return;
   cudaMemPool_t pool = nullptr;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
-    unsigned long long keep = ~0ull;
+    // enough for every per-launch scratch block; the large stream-ordered allocations (generated 1/f^alpha buffers, spectrum
+    // slabs) still go back to the OS at the next synchronisation, where torch's own allocator can have them
+    unsigned long long keep = 256ull << 20;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   cudaGetLastError();

@@ -22,7 +22,7 @@ int cuda_fail(cudaError_t e, const char *what);
 
 // The library's small per-launch scratch (models, stage tables, scheduler tickets) comes from the device's stream-ordered
 // pool.  By default that pool hands its memory back to the OS at every synchronisation, so each call of a sweep loop pays
-// the driver's map / unmap again; this sets the current device's pool to keep what it has (once per device and process).
+// the driver's map / unmap again; this lets the current device's pool keep up to 256 MB (once per device and process).
 void keep_pool_memory();
 
 // validation + derived quantities (cabi.cu)
