@@ -55,6 +55,22 @@ _INTERACTIONS = {
 }
 
 
+class _Shard:
+    """This rank's slice of a sharded array and the sizes of its buffers."""
+
+    def __init__(self, n_elements: int, rank: int, world: int, n_layers: int, n_channels: int, n_samples: int):
+        self.N, self.rank, self.world = int(n_elements), int(rank), int(world)
+        self.nl, self.ch, self.ns = int(n_layers), int(n_channels), int(n_samples)
+        self.per = -(-self.N // self.world)  # ceil(N / world): contiguous ranges, the last ones may be short or empty
+        self.lo = min(self.N, self.rank * self.per)
+        self.hi = min(self.N, self.lo + self.per)
+        self.own = self.hi - self.lo
+
+    def range_of(self, r: int):
+        lo = min(self.N, r * self.per)
+        return lo, min(self.N, lo + self.per)
+
+
 class GroupInteraction:
     def __init__(self, coordinateMatrix: Sequence, junctionList: Sequence[Junction], topId: str = "free"):
         coords = [CVector._coerce(c).copy() for c in coordinateMatrix]
@@ -172,11 +188,16 @@ class GroupInteraction:
         plan = be.group_plan(g, jns, layers, a)
         if plan.solver_overridden and rank == 0:
             print("[WARNING] Solver automatically changed to Euler Heun for stochastic calculation.")
-        N, ns, ch = self.noElements, int(plan.n_samples), int(plan.n_junction_channels)
-        per = -(-N // world)
-        lo = min(N, rank * per)
-        hi = min(N, lo + per)
-        own = hi - lo
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        use_peer = (transport == "peer") or (
+            transport == "auto" and exchange is None and not _host_memory and world > 1 and world <= 16
+            and dist is not None and dist.get_backend() == "nccl" and _single_node()
+        )
+        if use_peer and (_host_memory or exchange is not None):
+            raise ValueError("the peer-memory transport takes no exchange callback")
+        sh = _Shard(self.noElements, rank, world, nl, int(plan.n_junction_channels), int(plan.n_samples))
+        N, ns, ch, own, lo, hi = sh.N, sh.ns, sh.ch, sh.own, sh.lo, sh.hi
         m_host = np.ascontiguousarray(_coupled.initial_state(self.junctionList, 1)[:, lo:hi])
         if _host_memory:  # a host-memory stand-in for the library (CPU tests of this plumbing)
             torch = None
@@ -195,14 +216,6 @@ class GroupInteraction:
                 jlog_dev = torch.zeros((ch, max(ns, 1), max(own, 1)), dtype=torch.float64, device=tdev)
                 st_dev = torch.zeros(max(own, 1), dtype=torch.int32, device=tdev)
             addr = lambda t: t.data_ptr()  # noqa: E731
-        if transport not in ("auto", "peer", "nccl"):
-            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
-        use_peer = (transport == "peer") or (
-            transport == "auto" and exchange is None and not _host_memory and world > 1 and world <= 16
-            and dist is not None and dist.get_backend() == "nccl" and _single_node()
-        )
-        if use_peer and (_host_memory or exchange is not None):
-            raise ValueError("the peer-memory transport takes no exchange callback")
         if use_peer:
             peers = (_peer_areas or _ipc_peer_areas)(be, dist, rank, world, dev, N)
             try:
@@ -210,7 +223,7 @@ class GroupInteraction:
                 stream.synchronize()
             finally:
                 peers.close()  # barrier, then unmap and free
-            return self._finish_sharded(be, rc, dist, rank, world, dev, nl, ch, ns, N, per, lo, hi, own, m_dev, jlog_dev, plan, timeStep, gather, torch)
+            return self._finish_sharded(be, rc, dist, sh, dev, m_dev, jlog_dev, plan, timeStep, gather, torch)
         failure: List[BaseException] = []
         if exchange is None:
             exchange = _collective_exchange(dist, rank, world, None if _host_memory else dev)
@@ -226,12 +239,11 @@ class GroupInteraction:
         rc = be.group_run_sharded(g, jns, layers, a, rank, world, cb, addr(m_dev), addr(jlog_dev), addr(st_dev), dev, stream_ptr)
         if failure:
             raise failure[0]
-        return self._finish_sharded(be, rc, dist, rank, world, dev, nl, ch, ns, N, per, lo, hi, own, m_dev, jlog_dev, plan, timeStep, gather, torch,
-                                    stream if torch is not None else None)
+        return self._finish_sharded(be, rc, dist, sh, dev, m_dev, jlog_dev, plan, timeStep, gather, torch, stream if torch is not None else None)
 
-    def _finish_sharded(self, be, rc, dist, rank, world, dev, nl, ch, ns, N, per, lo, hi, own, m_dev, jlog_dev, plan, timeStep, gather, torch,
-                        stream=None):
+    def _finish_sharded(self, be, rc, dist, sh: _Shard, dev, m_dev, jlog_dev, plan, timeStep, gather, torch, stream=None):
         """results of this rank to the host, the optional gather of every rank's logs, write-back into the junction objects"""
+        world, nl, ch, ns, N, per, lo, hi, own = sh.world, sh.nl, sh.ch, sh.ns, sh.N, sh.per, sh.lo, sh.hi, sh.own
         if torch is not None and stream is not None:
             stream.synchronize()
         if torch is not None:
@@ -254,8 +266,7 @@ class GroupInteraction:
             parts = [_t.empty_like(t) for _ in range(world)]
             dist.all_gather(parts, t)
             for r, part in enumerate(parts):
-                r_lo = min(N, r * per)
-                r_hi = min(N, r_lo + per)
+                r_lo, r_hi = sh.range_of(r)
                 if r_hi > r_lo:
                     pr = part.cpu().numpy()[:, : r_hi - r_lo]
                     _coupled.write_back(self.junctionList[r_lo:r_hi], pr[: 3 * nl], pr[3 * nl :].reshape(ch, ns, r_hi - r_lo), times)
