@@ -180,16 +180,43 @@ class _SpectrumStream:
         self.be.check(f(chunk.data_ptr(), int(chunk.stride(0)), self.B, self.n, self.K, int(q0), int(nq), self.moments.data_ptr(),
                         1 if background else 0, self.device, C.c_void_p(stream)))
 
-    def finish(self):
+    def _combine(self, b_lo: int, b_hi: int, out) -> None:
+        """series [b_lo, b_hi): moments -> |X[k]|, k < K, into out[b_lo:b_hi] (device), on the current stream"""
         C, torch = self._C, _torch()
-        dev = torch.device("cuda", self.device)
-        out = torch.empty((self.B, self.K), dtype=torch.float64, device=dev)
         f = self.be.lib.cmtjb_spectrum_stream_finish
         f.restype = C.c_int
         f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        self.be.check(f(self.moments.data_ptr(), self.n, self.B, self.K, out.data_ptr(), self.device, C.c_void_p(stream)))
+        stream = torch.cuda.current_stream(out.device).cuda_stream
+        self.be.check(f(self.moments.data_ptr() + b_lo * self.bytes_per_series, self.n, b_hi - b_lo, self.K,
+                        out.data_ptr() + b_lo * self.K * 8, self.device, C.c_void_p(stream)))
+
+    def finish(self):
+        """[B, K] spectra on the device"""
+        torch = _torch()
+        out = torch.empty((self.B, self.K), dtype=torch.float64, device=torch.device("cuda", self.device))
+        self._combine(0, self.B, out)
         return out
+
+    def finish_to_host(self, n_slabs: int = 4) -> np.ndarray:
+        """[B, K] spectra in page-locked host memory: the series are transformed in slabs and the copy of one slab to the
+        host runs (second stream) while the next is transformed"""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        out = torch.empty((self.B, self.K), dtype=torch.float64, device=dev)
+        host = torch.empty((self.B, self.K), dtype=torch.float64, pin_memory=True)
+        cur, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+        step = max(1, -(-self.B // max(1, n_slabs)))
+        for b_lo in range(0, self.B, step):
+            b_hi = min(self.B, b_lo + step)
+            self._combine(b_lo, b_hi, out)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                host[b_lo:b_hi].copy_(out[b_lo:b_hi], non_blocking=True)
+        side.synchronize()
+        out.record_stream(side)
+        return host.numpy()
 
 
 class _Rows(list):
@@ -483,11 +510,11 @@ def _pimm_batch(junction, Hc, m0, int_step, res_rows, kind, resistance_fn, resis
     ph.mark("static resistances + final state to the host")
     if not static_only:
         if stream is not None:
-            yf, freqs = stream.finish(), stream.freqs
+            out["spectrum"], freqs = stream.finish_to_host(), stream.freqs  # [B,K]
         else:
             yf, freqs = spectrum_device(proj_log[0, n0:, :], int_step, max_frequency)
-        ph.mark("spectrum (batched FFT)")
-        out["spectrum"] = _to_host(yf)  # [B,K]
+            ph.mark("spectrum (batched FFT)")
+            out["spectrum"] = _to_host(yf)  # [B,K]
         out["freqs"] = freqs
         ph.mark("spectrum to the host")
         if full_output:

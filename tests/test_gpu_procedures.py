@@ -269,6 +269,7 @@ def test_spectrum_stream_chunks_in_any_order(on_cuda):
     for i, (q0, nq) in enumerate(reversed(spans)):
         st.add(xd[q0 * L : (q0 + nq) * L].contiguous(), q0, nq, background=bool(i % 2))  # both forms of the reduction
     got = st.finish().cpu().numpy()
+    assert np.array_equal(st.finish_to_host(n_slabs=3), got)  # slab-wise transform with the copies overlapped: same numbers
     want = np.abs(np.fft.rfft(x, axis=0))[: st.K].T
     assert np.max(np.abs(got - want) / np.abs(want).max(axis=1, keepdims=True)) < 1e-12
 
