@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LAYERS = 8
 NSLOTS = 30
 
@@ -172,7 +172,7 @@ class Plan(C.Structure):
 
 LAYER_SYSTEM = -2
 STACK_SERIES, STACK_PARALLEL = 0, 1
-INT_NULL, INT_DIPOLE, INT_DIPOLE_NOMURA = 0, 1, 2
+INT_NULL, INT_DIPOLE, INT_DIPOLE_NOMURA, INT_TABLE = 0, 1, 2, 3
 
 
 class Stack(C.Structure):
@@ -199,6 +199,7 @@ class Group(C.Structure):
         ("top_layer", C.c_int32),
         ("reserved", C.c_int32),
         ("coordinates", C.c_void_p),
+        ("pair_table", C.c_void_p),
     ]
 
 

@@ -413,7 +413,8 @@ int validate_group(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cm
   if (rc) return rc;
   if (c->nl > 4) return fail(CMTJB_ENOTSUP, "coupled junctions with more than 4 layers are not supported by this build");
   if (g->top_layer < 0 || g->top_layer >= c->nl) return fail(CMTJB_EINVAL, "layer index out of range");
-  if (g->interaction < CMTJB_INT_NULL || g->interaction > CMTJB_INT_DIPOLE_NOMURA) return fail(CMTJB_EINVAL, "unknown interaction function");
+  if (g->interaction < CMTJB_INT_NULL || g->interaction > CMTJB_INT_TABLE) return fail(CMTJB_EINVAL, "unknown interaction function");
+  if (g->interaction == CMTJB_INT_TABLE && !g->pair_table) return fail(CMTJB_EINVAL, "CMTJB_INT_TABLE without a pair table");
   // reservoir.hpp:171-177 (unique coordinates) and the per-pair distance guards (:84-87, :39-42): the reference tests
   // every pair; points closer than `lim` are adjacent in x within `lim`, so a sort and a sliding window find them
   const double lim = (g->interaction == CMTJB_INT_DIPOLE_NOMURA) ? 1e-14 : 1e-10;
@@ -432,7 +433,8 @@ int validate_group(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cm
       const double dx = r[3 * j] - r[3 * i], dy = r[3 * i + 1] - r[3 * j + 1], dz = r[3 * i + 2] - r[3 * j + 2];
       if (dx > lim && dx != 0) break;
       if (dx == 0 && dy == 0 && dz == 0) return fail(CMTJB_ERUNTIME, "Coordinate vectors must be unique!");
-      if (g->interaction != CMTJB_INT_NULL && std::sqrt(dx * dx + dy * dy + dz * dz) < lim) too_close = true;
+      if ((g->interaction == CMTJB_INT_DIPOLE || g->interaction == CMTJB_INT_DIPOLE_NOMURA) && std::sqrt(dx * dx + dy * dy + dz * dz) < lim)
+        too_close = true;
     }
   if (too_close) return fail(CMTJB_ERUNTIME, "Points are too close for stable dipole calculation");
   return CMTJB_OK;
@@ -493,7 +495,8 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
   const bool lean = lean_ok(system_features(N, NL, jns, layers, ovr, n_ovr, a, c.solver, false));
   const bool uni = lean && models_uniform<NL>(models);
   DevModel<NL> M0 = models[0];
-  if (!group_uses_grid<NL>(N)) {
+  const bool table = g->interaction == CMTJB_INT_TABLE;  // tabulated interaction: the two-kernel form for every N
+  if (!table && !group_uses_grid<NL>(N)) {
     GP.P = std::min(32, pow2_floor(kCoupledBlockMax / N));
     const int threads = ((N * GP.P + 31) / 32) * 32;
     const size_t smem = 13 * (size_t)N * sizeof(double);
@@ -511,7 +514,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
     if (e != cudaSuccess) rc = cuda_fail(e, "group_block_kernel");
   } else {
     const char *two_env = std::getenv("CMTJB_GROUP_TWO_KERNEL");
-    if (two_env && two_env[0] == '1') {
+    if (table || (two_env && two_env[0] == '1')) {
       // EXPERIMENT (off by default, measured slower: 79 vs 61 us per step at N = 4096): two kernels per step,
       // the pair sum at full occupancy, then the per-element step (coupled_kernels.cuh)
       int sms = 148;
@@ -519,10 +522,11 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
       const int tiles = (N + 31) / 32;
       const long long want_threads = (long long)sms * 2048;  // every SM full
       const int P = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(64, N), want_threads / ((long long)tiles * 32)));
-      double *d_hpart = nullptr;
+      double *d_hpart = nullptr, *d_table = nullptr;
       RunParams *d_R = nullptr;
       e = cudaMallocAsync((void **)&d_hpart, (size_t)P * 3 * N * sizeof(double), stream);
       if (e == cudaSuccess) e = upload(&R, 1, &d_R, stream);
+      if (e == cudaSuccess && table) e = upload(g->pair_table, (size_t)N * 12 * N, &d_table, stream);
       if (e != cudaSuccess) rc = cuda_fail(e, "cudaMallocAsync(pair-field partials)");
       const long long we = R.write_every;
       const long long Btot = R.B;
@@ -547,7 +551,12 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
         long long sample = R.first_sample;
         const long long pair_blocks = ((long long)tiles * 32 * P + 255) / 256;
         for (long long it = R.it_begin; it < R.it_end && rc == CMTJB_OK; it++) {
-          if (g->interaction != CMTJB_INT_NULL) {
+          if (table) {
+            PairTableParams QT;
+            QT.N = N, QT.P = P, QT.table = d_table, QT.mx = Q.mx, QT.my = Q.my, QT.mz = Q.mz, QT.Hpart = d_hpart;
+            group_pair_table_kernel<<<(unsigned)pair_blocks, 256, 0, stream>>>(QT);
+            g_launches++;
+          } else if (g->interaction != CMTJB_INT_NULL) {
             group_pair_kernel<<<(unsigned)pair_blocks, 256, 0, stream>>>(Q);
             g_launches++;
           }
@@ -572,6 +581,7 @@ int group_launch(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtj
       }
       if (d_hpart) cudaFreeAsync(d_hpart, stream);
       if (d_R) cudaFreeAsync(d_R, stream);
+      if (d_table) cudaFreeAsync(d_table, stream);
     } else {
     // one array across the grid: cooperative launch, one block per SM, every block the same share of the N^2 pairs
     // lean single-layer arrays (the reservoir case) run 768 threads per block; CMTJB_GROUP_THREADS=512 forces the 512 form
@@ -964,6 +974,7 @@ int cmtjb_group_run_sharded(const cmtjb_group_t *g, const cmtjb_junction_t *jns,
   if (rc) return rc;
   if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
   if (args->onef_buffer) return fail(CMTJB_ENOTSUP, "1/f noise buffers are not supported for sharded arrays");
+  if (g->interaction == CMTJB_INT_TABLE) return fail(CMTJB_ENOTSUP, "tabulated interaction functions are not supported for sharded arrays");
   for (long long k = 0; k < (long long)g->n_junctions * c.nl; k++)
     if (layers[k].noiseScale != 0.0)
       return fail(CMTJB_ENOTSUP, "1/f noise is not supported for sharded arrays");
@@ -993,6 +1004,7 @@ int cmtjb_group_run_sharded_peer(const cmtjb_group_t *g, const cmtjb_junction_t 
   if (rc) return rc;
   if (!m_state) return fail(CMTJB_EINVAL, "m_state is null");
   if (args->onef_buffer) return fail(CMTJB_ENOTSUP, "1/f noise buffers are not supported for sharded arrays");
+  if (g->interaction == CMTJB_INT_TABLE) return fail(CMTJB_ENOTSUP, "tabulated interaction functions are not supported for sharded arrays");
   for (long long k = 0; k < (long long)g->n_junctions * c.nl; k++)
     if (layers[k].noiseScale != 0.0) return fail(CMTJB_ENOTSUP, "1/f noise is not supported for sharded arrays");
   CUDA_TRY(cudaSetDevice(device));

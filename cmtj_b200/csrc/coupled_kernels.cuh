@@ -651,6 +651,46 @@ __global__ void __launch_bounds__(256) group_pair_kernel(const __grid_constant__
   }
 }
 
+// CMTJB_INT_TABLE: a tabulated affine interaction, H_a += c[a][b] + T[a][b] m_b (include/cmtj_b200.h).  Same decomposition
+// as group_pair_kernel (a warp = 32 consecutive elements a sharing one partner slice); the table is [b][12][a], so the 12
+// loads of a pair are coalesced over the warp's elements.  The a == b entries are zero by construction.
+struct PairTableParams {
+  int N, P;
+  const double *table;         // device [N b][12][N a]
+  const double *mx, *my, *mz;  // device [N] each
+  double *Hpart;               // device [P][3][N]
+};
+__global__ void __launch_bounds__(256) group_pair_table_kernel(const __grid_constant__ PairTableParams Q) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = Q.N;
+  const int tiles = (N + 31) / 32;
+  const long long w = gt >> 5;
+  const int p = (int)(w / tiles);
+  if (p >= Q.P) return;
+  const int a_raw = (int)(w - (long long)p * tiles) * 32 + (int)(gt & 31);
+  const int a = a_raw < N ? a_raw : N - 1;
+  const int per = (N + Q.P - 1) / Q.P;
+  const int b0 = p * per, b1 = (b0 + per < N) ? b0 + per : N;
+  d3 H = mk(0, 0, 0);
+  for (int b = b0; b < b1; b++) {
+    const double *t = Q.table + (size_t)b * 12 * N + a;
+    const d3 m = mk(Q.mx[b], Q.my[b], Q.mz[b]);
+    double e[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) e[k] = __ldg(t + (size_t)k * N);
+    // the oracle's operation order: offset + (row . m), no contraction across the parenthesis
+    H.x += e[9] + __dadd_rn(__dadd_rn(__dmul_rn(e[0], m.x), __dmul_rn(e[1], m.y)), __dmul_rn(e[2], m.z));
+    H.y += e[10] + __dadd_rn(__dadd_rn(__dmul_rn(e[3], m.x), __dmul_rn(e[4], m.y)), __dmul_rn(e[5], m.z));
+    H.z += e[11] + __dadd_rn(__dadd_rn(__dmul_rn(e[6], m.x), __dmul_rn(e[7], m.y)), __dmul_rn(e[8], m.z));
+  }
+  if (a_raw < N) {
+    double *o = Q.Hpart + (size_t)p * 3 * N + a;
+    o[0] = H.x;
+    o[N] = H.y;
+    o[2 * N] = H.z;
+  }
+}
+
 // ---- peer-memory exchange of a sharded array (no collective library, no host in the time loop) ---------------------------
 // Every rank owns an exchange AREA in its own device memory that all ranks of the box can address (CUDA IPC over NVLink):
 //     double             X[2][world][3][per]   top-layer m of every element, double-buffered by step parity

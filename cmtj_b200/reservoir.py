@@ -87,13 +87,61 @@ class GroupInteraction:
         if len(np.unique(xyz, axis=0)) != len(xyz):
             raise RuntimeError("Coordinate vectors must be unique!")
         self._interaction = _abi.INT_DIPOLE
+        self._custom_interaction: Optional[Callable] = None
+        self._pair_table: Optional[np.ndarray] = None
 
     def setInteractionFunction(self, interactionFunc: Callable) -> None:
-        if interactionFunc not in _INTERACTIONS:
+        """``GroupInteraction::setInteractionFunction`` (core/reservoir.hpp:181, python/cmtj.cpp:438).  The three built-in
+        functions run as device code.  Any other callable ``f(r1, r2, layer1, layer2) -> CVector`` is accepted if it is
+        AFFINE in the partner's magnetisation ``layer2.mag`` and does not depend on ``layer1.mag`` (every linear-response
+        coupling is): it is probed once per ordered pair at run time -- ``layer2.mag`` = 0, e_x, e_y, e_z -- and the device
+        evaluates the resulting 3x3 tensor + offset, instead of the reference's N^2 Python calls per step.  A callable that
+        fails the affinity check at a random magnetisation raises ``NotImplementedError`` when the simulation starts."""
+        if interactionFunc in _INTERACTIONS:
+            self._interaction, self._custom_interaction = _INTERACTIONS[interactionFunc], None
+        elif callable(interactionFunc):
+            self._interaction, self._custom_interaction = _abi.INT_TABLE, interactionFunc
+        else:
+            raise TypeError("interactionFunc must be callable")
+
+    def _probe_interaction(self) -> np.ndarray:
+        """[N b][12][N a] table of the custom interaction: T[a][b] (rows 0..8, row-major) and c[a][b] (rows 9..11)."""
+        f, n = self._custom_interaction, self.noElements
+        tops = [j.getLayer(self.topId) for j in self.junctionList]
+        table = np.zeros((n, 12, n), dtype=np.float64)
+        rng = np.random.default_rng(12345)
+        basis = [CVector(0, 0, 0), CVector(1, 0, 0), CVector(0, 1, 0), CVector(0, 0, 1)]
+
+        def call(a, b, mag_b, mag_a=None):
+            l1, l2 = tops[a]._clone(), tops[b]._clone()
+            l2.mag = mag_b
+            if mag_a is not None:
+                l1.mag = mag_a
+            return np.array(CVector._coerce(f(self.coordinateMatrix[a].copy(), self.coordinateMatrix[b].copy(), l1, l2)).tolist())
+
+        worst, scale = 0.0, 0.0
+        for a in range(n):
+            for b in range(n):
+                if a == b:
+                    continue
+                c, ex, ey, ez = (call(a, b, m.copy()) for m in basis)
+                T = np.stack([ex - c, ey - c, ez - c], axis=1)  # columns = responses to the unit vectors
+                table[b, 0:9, a] = T.reshape(9)
+                table[b, 9:12, a] = c
+                if (a + b) % max(1, n // 4) == 0 or n <= 8:  # affinity / independence of layer1.mag, on a sample of the pairs
+                    v = rng.normal(size=3)
+                    v /= np.linalg.norm(v)
+                    w = rng.normal(size=3)
+                    w /= np.linalg.norm(w)
+                    got = call(a, b, CVector(*v), CVector(*w))
+                    worst = max(worst, float(np.abs(got - (c + T @ v)).max()))
+                    scale = max(scale, float(np.abs(got).max()), float(np.abs(c).max()))
+        if worst > 1e-9 * max(scale, 1e-300):
             raise NotImplementedError(
-                "only nullDipoleInteraction, computeDipoleInteraction and computeDipoleInteractionNoumra run on the device"
+                "the interaction function is not affine in layer2.mag (or depends on layer1.mag): only such functions, and "
+                "nullDipoleInteraction / computeDipoleInteraction / computeDipoleInteractionNoumra, run on the device"
             )
-        self._interaction = _INTERACTIONS[interactionFunc]
+        return table
 
     def clearLogs(self) -> None:
         for j in self.junctionList:
@@ -120,6 +168,10 @@ class GroupInteraction:
         g.top_layer = ids.index(self.topId)
         xyz = np.ascontiguousarray([c.tolist() for c in self.coordinateMatrix], dtype=np.float64)
         g.coordinates = xyz.ctypes.data
+        self._pair_table = None
+        if self._interaction == _abi.INT_TABLE:
+            self._pair_table = np.ascontiguousarray(self._probe_interaction())  # kept alive on the object for the call
+            g.pair_table = self._pair_table.ctypes.data
         return g, jns, layers, nl, xyz
 
     def runSimulation(self, totalTime: float, timeStep: float = 1e-13, writeFrequency: float = 1e-11) -> None:

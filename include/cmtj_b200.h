@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CMTJB_ABI_VERSION 5
+#define CMTJB_ABI_VERSION 6
 #define CMTJB_MAX_LAYERS 8
 
 /* ---- error codes --------------------------------------------------------------- */
@@ -432,7 +432,17 @@ typedef struct cmtjb_stack {
 } cmtjb_stack_t;
 
 /* reservoir.hpp:63-120 */
-enum cmtjb_interaction { CMTJB_INT_NULL = 0, CMTJB_INT_DIPOLE = 1, CMTJB_INT_DIPOLE_NOMURA = 2 };
+enum cmtjb_interaction {
+  CMTJB_INT_NULL = 0,
+  CMTJB_INT_DIPOLE = 1,
+  CMTJB_INT_DIPOLE_NOMURA = 2,
+  /* Any interaction function that is AFFINE in the partner's magnetisation (every linear-response coupling is):
+   *     H_a += c[a][b] + T[a][b] m_b        for every partner b != a,
+   * with the 3x3 tensors and offsets tabulated by the caller -- the binding obtains them by probing the user's callable
+   * (GroupInteraction::setInteractionFunction, reservoir.hpp:181; python/cmtj.cpp:438) with m_b = 0, e_x, e_y, e_z once
+   * per ordered pair instead of calling it N^2 times per step.  cmtjb_group_t::pair_table. */
+  CMTJB_INT_TABLE = 3
+};
 
 typedef struct cmtjb_group {
   int32_t n_junctions;
@@ -440,6 +450,9 @@ typedef struct cmtjb_group {
   int32_t top_layer;     /* index of the layer called topId inside each junction */
   int32_t reserved;
   const double *coordinates; /* HOST pointer, [n_junctions][3] */
+  /* CMTJB_INT_TABLE only (else NULL): HOST pointer, [n_junctions b][12][n_junctions a] doubles -- for the field at a from
+   * partner b: rows 0..8 the tensor T[a][b] row-major, rows 9..11 the offset c[a][b]; the a == b entries are ignored. */
+  const double *pair_table;
 } cmtjb_group_t;
 
 typedef struct cmtjb_coupled_plan {

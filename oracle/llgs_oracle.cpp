@@ -938,6 +938,15 @@ int oracle_stack_run_host(const cmtjb_stack_t *st, const cmtjb_junction_t *jns, 
   return CMTJB_OK;
 }
 
+/* CMTJB_INT_TABLE: the tabulated affine interaction c[a][b] + T[a][b] m_b (include/cmtj_b200.h) */
+static V3 pair_table_field(const cmtjb_group_t *g, int a, int b, V3 m) {
+  const size_t n = (size_t)g->n_junctions;
+  const double *t = g->pair_table + (size_t)b * 12 * n + (size_t)a;
+  auto e = [&](int k) { return t[(size_t)k * n]; };
+  return v3(e(9) + (e(0) * m.x + e(1) * m.y + e(2) * m.z), e(10) + (e(3) * m.x + e(4) * m.y + e(5) * m.z),
+            e(11) + (e(6) * m.x + e(7) * m.y + e(8) * m.z));
+}
+
 int oracle_group_plan(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const cmtjb_layer_t *layers,
                       const cmtjb_run_args_t *args, cmtjb_coupled_plan_t *plan) {
   if (!g || !jns || !layers || !args || !plan) return fail(CMTJB_EINVAL, "null argument");
@@ -949,7 +958,8 @@ int oracle_group_plan(const cmtjb_group_t *g, const cmtjb_junction_t *jns, const
     for (int j = i + 1; j < n; j++) {
       const V3 d = arr3(g->coordinates + 3 * i) - arr3(g->coordinates + 3 * j);
       if (d.x == 0 && d.y == 0 && d.z == 0) return fail(CMTJB_ERUNTIME, "Coordinate vectors must be unique!");
-      if (g->interaction != CMTJB_INT_NULL && vlen(d) < lim) return fail(CMTJB_ERUNTIME, "Points are too close for stable dipole calculation");
+      if ((g->interaction == CMTJB_INT_DIPOLE || g->interaction == CMTJB_INT_DIPOLE_NOMURA) && vlen(d) < lim)
+        return fail(CMTJB_ERUNTIME, "Points are too close for stable dipole calculation");
     }
   SystemSim S;
   std::vector<double> m0((size_t)jns[0].n_layers * 3 * n, 0.0);
@@ -994,6 +1004,7 @@ int oracle_group_run_host(const cmtjb_group_t *g, const cmtjb_junction_t *jns, c
           const LayerSim &lb = S.j[b].layers[g->top_layer];
           if (g->interaction == CMTJB_INT_DIPOLE) H = H + dipole_kanao(ra, rb, lb);
           else if (g->interaction == CMTJB_INT_DIPOLE_NOMURA) H = H + dipole_nomura(ra, rb, lb);
+          else if (g->interaction == CMTJB_INT_TABLE) H = H + pair_table_field(g, a, b, lb.mag);
         }
         LayerSim &la = S.j[a].layers[g->top_layer];
         const double h[3] = {H.x, H.y, H.z};
@@ -1079,6 +1090,7 @@ int oracle_group_run_sharded(const cmtjb_group_t *g, const cmtjb_junction_t *jns
         const LayerSim &lb = S.j[b].layers[top];
         if (g->interaction == CMTJB_INT_DIPOLE) H = H + dipole_kanao(ra, rb, lb);
         else if (g->interaction == CMTJB_INT_DIPOLE_NOMURA) H = H + dipole_nomura(ra, rb, lb);
+        else if (g->interaction == CMTJB_INT_TABLE) H = H + pair_table_field(g, a, b, lb.mag);
       }
       LayerSim &la = S.j[a].layers[top];
       const double h[3] = {H.x, H.y, H.z};

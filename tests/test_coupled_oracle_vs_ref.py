@@ -207,3 +207,51 @@ def test_stack_batch_equals_single_runs(on_oracle):
             assert np.array_equal(out[k][:, i], log[k]), (i, k)
         j1 = helpers.log_arrays(s1.getLog(1))
         assert np.array_equal(out["1/free_mx"][:, i], j1["free_mx"])
+
+
+def _scaled_cutoff(res):
+    """A user-written interaction in the only form the reference's Python API allows (its Layer exposes no `mag`): a
+    composition of the built-in functions -- here Kanao's dipole field, halved, cut off beyond 250 nm."""
+
+    def f(r1, r2, layer1, layer2):
+        if (r1 - r2).length() > 2.5e-7:
+            return res.nullDipoleInteraction(r1, r2, layer1, layer2)
+        return res.computeDipoleInteraction(r1, r2, layer1, layer2) * 0.5
+
+    return f
+
+
+def test_custom_python_interaction_matches_reference(ref, on_oracle):
+    """setInteractionFunction with an arbitrary callable (reservoir.hpp:181, cmtj.cpp:438): the reference calls it N^2
+    times per step; here it is probed once per ordered pair and evaluated as a tabulated affine map (CMTJB_INT_TABLE).
+    Not the same floating-point expression, so: 1e-10 relative instead of bit-exact."""
+    gs = []
+    for m, _, res in _mods(ref):
+        g = _group(m, res, n=7, Ms=1.2)  # kA/m dipole fields: a regular array, so a tolerance means something
+        g.setInteractionFunction(_scaled_cutoff(res))
+        g.runSimulation(0.2e-9, 1e-13, 2e-13)
+        gs.append(g)
+    r, o = gs
+    for k in range(7):
+        a, b = helpers.log_arrays(r.getLog(k)), helpers.log_arrays(o.getLog(k))
+        for name in a:
+            assert helpers.max_rel_err(b[name], a[name]) <= 1e-10, (k, name)
+    # the cutoff matters (element 6 is beyond it from element 0) and so does the interaction
+    plain = _group(cmtj_b200, cmtj_b200.reservoir, n=7, Ms=1.2)
+    plain.setInteractionFunction(cmtj_b200.reservoir.nullDipoleInteraction)
+    plain.runSimulation(0.2e-9, 1e-13, 2e-13)
+    assert helpers.max_rel_err(helpers.log_arrays(plain.getLog(0))["free_mx"], helpers.log_arrays(o.getLog(0))["free_mx"]) > 1e-6
+
+
+def test_non_affine_interaction_is_rejected(on_oracle):
+    m = cmtj_b200
+
+    def f(r1, r2, layer1, layer2):
+        return m.reservoir.computeDipoleInteraction(r1, r2, layer1, layer2) * (1.0 + layer2.mag.x ** 2)
+
+    g = _group(m, m.reservoir, n=4)
+    g.setInteractionFunction(f)
+    with pytest.raises(NotImplementedError):
+        g.runSimulation(1e-12, 1e-13, 1e-13)
+    with pytest.raises(TypeError):
+        g.setInteractionFunction(3)

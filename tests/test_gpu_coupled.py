@@ -278,3 +278,27 @@ def test_group_two_kernel_experiment_matches_the_oracle(monkeypatch):
 
     g, w, p = _three(fn)
     _check(g, w, p)
+
+
+@pytest.mark.parametrize("n", [7, 144])
+def test_group_custom_interaction_table(n):
+    """A user-supplied interaction callable (probed into a tensor table, CMTJB_INT_TABLE; group_pair_table_kernel +
+    group_step_kernel) against the oracle evaluating the same table."""
+
+    def halved(r1, r2, l1, l2):
+        return m.reservoir.computeDipoleInteraction(r1, r2, l1, l2) * 0.5
+
+    def fn(eps):
+        if n == 7:
+            g = T._group(m, m.reservoir, n=7)
+            if eps:
+                _perturb(g.junctionList[0], eps)
+        else:
+            g = _lattice_group(12, eps)  # 144 elements: several warp tiles and partner slices
+        g.setInteractionFunction(halved)
+        out = g.run_batch(1, 0.03e-9, 1e-13, 1e-12)
+        out.pop("m_state")
+        return out
+
+    g, w, p = _three(fn)
+    _check(g, w, p)
