@@ -606,8 +606,9 @@ int run_wide(const cmtjb_junction_t *jn, const cmtjb_layer_t *layers, const cmtj
   std::vector<DevLayer> L(NL);
   for (int l = 0; l < NL; l++) {
     for (int s = 0; s < CMTJB_NSLOTS; s++)
-      if (layers[l].drivers[s].update == CMTJB_UPD_CUSTOM)
-        return fail(CMTJB_ENOTSUP, "custom (Python callback) drivers support junctions of at most 4 layers");
+      if (layers[l].drivers[s].update == CMTJB_UPD_CUSTOM &&
+          (!a->custom_table || layers[l].drivers[s].custom_column < 0 || layers[l].drivers[s].custom_column >= a->n_custom))
+        return fail(CMTJB_EINVAL, "custom driver: custom_table is null or has too few columns");
     derive_layer(*jn, layers[l], L[l]);
     set_step_products(L[l], a->timeStep);
   }

@@ -529,25 +529,30 @@ __global__ void __launch_bounds__(128) llgs_wide_kernel(const __grid_constant__ 
     bot = l > 0 ? b : zero;
     top = l < NL - 1 ? t : zero;
   };
-  auto rhs = [&](double t, d3 mm, d3 bot, d3 top) { return llg_u<F, true, true>(Lr, R, l, i, StageTime{t, nullptr}, mm, bot, top, Hc); };
+  // `stage` (0, 1, 2 = t, t + dt/2, t + dt) selects the row of the caller's custom-driver table for this step, if any
+  const double *crow = nullptr;
+  auto rhs = [&](double t, int stage, d3 mm, d3 bot, d3 top) {
+    return llg_u<F, true, true>(Lr, R, l, i, StageTime{t, crow ? crow + stage * R.n_custom : nullptr}, mm, bot, top, Hc);
+  };
   const long long we = R.write_every;
   long long until_write = (we - (R.it_begin % we)) % we;
   long long sample = R.first_sample;
   const long long cs = R.n_samples * R.B;
   for (long long it = R.it_begin; it < R.it_end; ++it) {
     const double t = (double)it * R.dt;
+    crow = R.custom ? R.custom + 3 * it * R.n_custom : nullptr;
     d3 bot, top;
     neighbours(m, bot, top);
     if constexpr (SOLVER == CMTJB_RK4) {
-      const d3 u1 = rhs(t, m, bot, top);
-      const d3 u2 = rhs(t + 0.5 * R.dt, axpy(u1, Lr.h_half, m), bot, top);
-      const d3 u3 = rhs(t + 0.5 * R.dt, axpy(u2, Lr.h_half, m), bot, top);
-      const d3 u4 = rhs(t + R.dt, axpy(u3, Lr.h, m), bot, top);
+      const d3 u1 = rhs(t, 0, m, bot, top);
+      const d3 u2 = rhs(t + 0.5 * R.dt, 1, axpy(u1, Lr.h_half, m), bot, top);
+      const d3 u3 = rhs(t + 0.5 * R.dt, 1, axpy(u2, Lr.h_half, m), bot, top);
+      const d3 u4 = rhs(t + R.dt, 2, axpy(u3, Lr.h, m), bot, top);
       const d3 acc = mk(fma(2.0, u2.x + u3.x, u1.x + u4.x), fma(2.0, u2.y + u3.y, u1.y + u4.y), fma(2.0, u2.z + u3.z, u1.z + u4.z));
       m = normalize3(axpy(acc, Lr.h_sixth, m));
     } else if constexpr (SOLVER == CMTJB_EULER_HEUN) {
-      const StageTime t0{t, nullptr};
-      const d3 f = rhs(t, m, bot, top);
+      const StageTime t0{t, crow};
+      const d3 f = rhs(t, 0, m, bot, top);
       d3 mn = axpy(f, Lr.llg * R.dt, m);
       const d3 dW = noise_dW<F, 1>(Lr, R, l, i, it, t0);
       const double gs = Lr.llg * R.sqrt_dt;
@@ -556,14 +561,14 @@ __global__ void __launch_bounds__(128) llgs_wide_kernel(const __grid_constant__ 
       mn = axpy(g + gp, 0.5 * gs, mn);
       m = normalize3(mn);
     } else {  // Heun: predictor with the current neighbours, corrector with the PREDICTED ones (junction.hpp:1756-1815)
-      const StageTime t0{t, nullptr};
-      const d3 f = rhs(t, m, bot, top);
+      const StageTime t0{t, crow};
+      const d3 f = rhs(t, 0, m, bot, top);
       const d3 dW = noise_dW<F, 1>(Lr, R, l, i, it, t0);
       const d3 g = stoch_u(Lr, m, dW);
       const d3 mp = axpy(g, Lr.llg * R.sqrt_dt, axpy(f, Lr.llg * R.dt, m));
       d3 pb, pt;
       neighbours(mp, pb, pt);
-      const d3 f2 = rhs(t + R.dt, mp, pb, pt);
+      const d3 f2 = rhs(t + R.dt, 2, mp, pb, pt);
       const d3 g2 = stoch_u(Lr, mp, dW);
       d3 mn = axpy(f + f2, 0.5 * (Lr.llg * R.dt), m);
       mn = axpy(g + g2, 0.5 * (Lr.llg * R.sqrt_dt), mn);

@@ -184,7 +184,7 @@ typedef struct cmtjb_run_args {
    * :1020-1033; Heun reads stages 0 and 2, Euler-Heun stage 0).  As in the reference the callback's
    * value IS the driver's value (constantValue and amplitude are ignored).  Host or device pointer
    * according to the entry point; NULL when the model has no custom driver.  Not available for
-   * Dormand-Prince, junctions of more than 4 layers, Stack and GroupInteraction (CMTJB_ENOTSUP). */
+   * Dormand-Prince, Stack and GroupInteraction (CMTJB_ENOTSUP). */
   const double *custom_table;
   int64_t n_custom;
   /* Thermal (Langevin) normals, replacing std::normal_distribution<double> over mt19937 (core/junction.hpp:174-175,

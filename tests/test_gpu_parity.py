@@ -399,6 +399,16 @@ def test_many_layer_junctions_lane_per_layer_kernel(n, strip, mode):
     _check(g, w)
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_many_layer_junction_with_custom_python_drivers(mode):
+    """Python-callback drivers (getCustomDriver) on a 6-layer junction: the lane-per-layer kernel reads the pre-evaluated
+    stage table like the per-thread kernels do."""
+    import test_oracle_vs_ref as t
+
+    (g, jg), (w, _) = _both(helpers.multi_layer, 0.2e-9, 1e-13, 4e-13, mode, t._custom_tweak, n=6)
+    _check(g, w)
+
+
 def test_many_layer_batch_with_overrides():
     """A 7-layer junction swept over per-instance fields and a per-instance anisotropy (ragged last warp:
     45 instances x 8 lanes)."""

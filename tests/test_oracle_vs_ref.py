@@ -293,6 +293,13 @@ def test_custom_python_callback_drivers_bit_exact(ref, on_oracle, build, mode):
     _assert_same_logs(jr, jo)
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_custom_python_callback_drivers_on_a_six_layer_junction_bit_exact(ref, on_oracle, mode):
+    """the same for a junction beyond four layers (the lane-per-layer kernel's case on the GPU)"""
+    jr, jo = _run_both(ref, helpers.multi_layer, T=0.2e-9, wf=4e-13, mode=mode, tweak=_custom_tweak, n=6)
+    _assert_same_logs(jr, jo)
+
+
 def test_custom_driver_errors(on_oracle):
     j = helpers.single_layer_mtj(cmtj_b200)
     j.setLayerCurrentDriver("free", cmtj_b200.ScalarDriver.getCustomDriver(lambda t: 1 / 0))
