@@ -441,6 +441,32 @@ def secondary_block(cm, torch, lib, local_rank):
               stacks=n_inst, junctions=N, steps=steps)
 
     guarded("S5s", s5s)
+
+    # the spin-diode procedure end to end (configs[0]'s kind of sweep, as one batch): 256 fields x 64 frequencies x 10 ns
+    def vsd():
+        import helpers
+
+        P = cm.utils.procedures
+        rp = [P.ResistanceParameters(Rxx0=100, Rxy0=1, Rahe=1, Rsmr=-0.2, Ramr=0.5, w=3e-5, l=2e-5),
+              P.ResistanceParameters(Rxx0=80, Rxy0=2, Rahe=-0.5, Rsmr=0.1, Ramr=-0.3, w=3e-5, l=2e-5)]
+        nH, nF, steps = 256, 64, 100000
+        Hv = np.zeros((nH, 3))
+        Hv[:, 0] = np.linspace(50e3, 400e3, nH)
+        Hv[:, 2] = 20e3
+        fs = np.linspace(2e9, 20e9, nF)
+        shape = []
+
+        def run():
+            vm = P.VSD_batch(helpers.two_layer_mtj(cm), Hv, fs, DT, rp, simulation_duration=wl.exact(steps), Rtype="Rz", disable_tqdm=True,
+                             device=local_rank)
+            shape[:] = list(np.asarray(vm).shape)
+
+        secs, clocks = _timed(torch, run, local_rank)
+        entry("VSD_batch end to end: 2-layer MTJ, 256 fields x 64 frequencies x 10 ns, spin-diode map on the host (mixing, low-pass "
+              "and mean inside the time loop)", N_LAYERS * nH * nF * steps, "layer-timesteps/s", secs, clocks, instances=nH * nF, steps=steps,
+              map_shape=shape, variant=_abi.last_variant())
+
+    guarded("VSD", vsd)
     return out
 
 
