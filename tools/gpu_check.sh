@@ -1,13 +1,11 @@
 #!/bin/bash
-# final-state check: whole GPU suite, smoke, the bench line
 set -u
 mkdir -p gpurun_out
-echo "== pytest -m gpu (all)"; S=$(date +%s); timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? wall $(( $(date +%s) - S )) s"; tail -4 gpurun_out/pytest_gpu.log
-echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -1
-echo "== bench"; S=$(date +%s); timeout 1500 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$? wall $(( $(date +%s) - S )) s"; tail -3 gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open('gpurun_out/bench.json') if l.startswith('{')][-1])
-print('value',d['value'],'e2e',d['e2e']['value'],[round(x) for x in d['e2e']['ms_each']],'pimm',d['e2e_pimm']['value'],[round(x) for x in d['e2e_pimm']['ms_each']])
-for k,v in d['secondary'].items(): print(k[:70], '%.3e'%v.get('value',0))
-PY
+for L in 32 16 8 auto; do
+  echo "== lanes per warp: $L"
+  if [ "$L" = "auto" ]; then unset CMTJB_LANES; else export CMTJB_LANES=$L; fi
+  timeout 300 python tools/vsd_run.py 256 64 100000 2>&1 | tail -1
+  timeout 300 python tools/bench_configs.py s2 1 2>&1 | grep config | cut -c1-170
+done
+unset CMTJB_LANES
+echo "== parity quick (auto lanes)"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_procedures.py tests/test_gpu_balanced.py -m gpu -q -x 2>&1 | tail -3
